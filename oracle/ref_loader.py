@@ -1,0 +1,122 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the *unmodified* reference modules for oracle pinning.
+
+Imports VideoSys' OpenSora hot-path modules straight from ``/root/reference`` (read-only) by
+registering a bare ``videosys`` namespace package (skipping ``videosys/__init__.py:1-12`` which
+pulls every pipeline -> diffusers) and stubbing the third-party names that are not installed in
+this image (timm ``Mlp``/``DropPath``, colossalai ``ProcessGroupMesh``, diffusers ``Attention``,
+``rotary_embedding_torch.RotaryEmbedding``, imageio, omegaconf).  Recipe: SURVEY.md Appendix C.
+
+Only ``tests/`` and ``oracle/gen_golden.py`` may import this file, and only inside the authoring
+container: ``/root/reference`` does not exist on the GPU box, ``available()`` says so.
+"""
+import importlib
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+
+REF = os.environ.get("VSB_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF, "videosys"))
+
+
+def _mod(name, **kw):
+    m = types.ModuleType(name)
+    m.__dict__.update(kw)
+    sys.modules[name] = m
+    return m
+
+
+class _Mlp(nn.Module):
+    """timm.models.vision_transformer.Mlp semantics: fc2(act(fc1(x))), biases on, dropout 0."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.0, **_):
+        super().__init__()
+        out_features = out_features or in_features
+        hidden_features = hidden_features or in_features
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features, out_features)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class _RotaryEmbedding(nn.Module):
+    """rotary_embedding_torch.RotaryEmbedding(dim) ('lang' freqs, theta 1e4), rotate_queries_or_keys only."""
+
+    def __init__(self, dim, theta=10000):
+        super().__init__()
+        self.freqs = nn.Parameter(
+            1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim)), requires_grad=False
+        )
+
+    def rotate_queries_or_keys(self, t, seq_dim=-2):
+        n = t.shape[seq_dim]
+        pos = torch.arange(n, device=t.device, dtype=torch.float32)
+        f = torch.einsum("i,j->ij", pos, self.freqs.float()).repeat_interleave(2, dim=-1)
+        x1, x2 = t.reshape(*t.shape[:-1], -1, 2).unbind(-1)
+        rh = torch.stack((-x2, x1), -1).flatten(-2)
+        return (t * f.cos() + rh * f.sin()).type(t.dtype)
+
+
+_LOADED = {}
+
+
+def load():
+    """Returns a namespace with the reference modules (cached)."""
+    if _LOADED:
+        return types.SimpleNamespace(**_LOADED)
+    if not available():
+        raise RuntimeError(f"reference tree not present at {REF}")
+    import transformers  # noqa: F401  (must be imported before timm is stubbed)
+
+    pkg = _mod("videosys")
+    pkg.__path__ = [REF + "/videosys"]
+    _mod("timm")
+    _mod("timm.models")
+    _mod("timm.models.layers", DropPath=nn.Identity)
+    _mod("timm.models.vision_transformer", Mlp=_Mlp)
+    _mod("colossalai")
+    _mod("colossalai.cluster")
+    _mod(
+        "colossalai.cluster.process_group_mesh",
+        ProcessGroupMesh=type("ProcessGroupMesh", (), {"__init__": lambda s, *a: None}),
+    )
+    _mod("diffusers")
+    _mod("diffusers.models")
+    _mod("diffusers.models.attention", Attention=object)
+    _mod("diffusers.models.attention_processor", AttnProcessor=object)
+    _mod("imageio")
+    _mod("omegaconf", DictConfig=dict, ListConfig=list, OmegaConf=object)
+    _mod("rotary_embedding_torch", RotaryEmbedding=_RotaryEmbedding)
+    _LOADED["stdit3"] = importlib.import_module("videosys.models.transformers.open_sora_transformer_3d")
+    _LOADED["attentions"] = importlib.import_module("videosys.models.modules.attentions")
+    _LOADED["normalization"] = importlib.import_module("videosys.models.modules.normalization")
+    _LOADED["pab_mgr"] = importlib.import_module("videosys.core.pab.pab_mgr")
+    _LOADED["comm"] = importlib.import_module("videosys.core.distributed.comm")
+    _LOADED["rflow"] = importlib.import_module("videosys.schedulers.scheduling_rflow_open_sora")
+    return types.SimpleNamespace(**_LOADED)
+
+
+class SingleRankPM:
+    """Stand-in for ParallelManager on one rank (parallel_mgr.py:14-39)."""
+
+    sp_size = 1
+    cp_size = 1
+    sp_group = None
+    cp_group = None
+
+
+def build_stdit3(depth=1, hidden_size=1152, num_heads=16, dtype=torch.float32, **kw):
+    ref = load()
+    M = ref.stdit3
+    net = M.STDiT3(M.STDiT3Config(depth=depth, hidden_size=hidden_size, num_heads=num_heads, **kw)).eval().to(dtype)
+    net.parallel_manager = SingleRankPM()
+    for b in [*net.spatial_blocks, *net.temporal_blocks]:
+        b.parallel_manager = SingleRankPM()
+    return net

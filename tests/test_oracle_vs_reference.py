@@ -1,0 +1,163 @@
+"""Pins the oracle by EXECUTING THE UNMODIFIED REFERENCE (only where /root/reference exists: the
+authoring container).  On the GPU box these skip; the golden vectors carry the pin there."""
+import threading
+
+import pytest
+import torch
+
+from oracle import cases, dsp_oracle, pab_oracle, ref_loader, stdit3_oracle as O, synth
+
+pytestmark = pytest.mark.skipif(not ref_loader.available(), reason="reference tree not mounted")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_forward_bit_exact(dtype):
+    c = cases.small_model_cfg(depth=2)
+    net = ref_loader.build_stdit3(dtype=dtype, **c)
+    sd = synth.fill_state_dict(net.state_dict(), "vsref.")
+    net.load_state_dict(sd)
+    inp = cases.forward_inputs(dtype)
+    with torch.no_grad():
+        ref = net(inp["x"], inp["timestep"], inp["y"], mask=inp["mask"], x_mask=inp["x_mask"], fps=inp["fps"],
+                  height=inp["height"], width=inp["width"])
+        out = O.stdit3_forward(sd, cases.oracle_cfg(c), **inp)
+    assert torch.equal(ref, out)
+
+
+def test_forward_with_pab_bit_exact_over_steps():
+    """PAB on (attn + cross broadcast; mlp_broadcast=False, the only mode the reference can run for
+    OpenSora): reuse-by-reference semantics and counters over 8 consecutive steps."""
+    ref = ref_loader.load()
+    P = ref.pab_mgr
+    dtype = torch.bfloat16
+    c = cases.small_model_cfg(depth=2)
+    net = ref_loader.build_stdit3(dtype=dtype, **c)
+    sd = synth.fill_state_dict(net.state_dict(), "vsref.")
+    net.load_state_dict(sd)
+    steps = [1000, 900, 860, 800, 700, 600, 500, 300]
+    P.set_pab_manager(P.PABConfig(spatial_broadcast=True, spatial_threshold=[450, 930], spatial_range=2,
+                                  temporal_broadcast=True, temporal_threshold=[450, 930], temporal_range=4,
+                                  cross_broadcast=True, cross_threshold=[450, 930], cross_range=6))
+    P.update_steps(len(steps))
+    gate = pab_oracle.opensora_default(len(steps))
+    states = {k: [O.BlockPABState() for _ in range(2)] for k in ("spatial", "temporal")}
+    inp = cases.forward_inputs(dtype)
+    try:
+        with torch.no_grad():
+            for i, t in enumerate(steps):
+                inp["x"] = synth.normalish(f"pab.x{i}", tuple(inp["x"].shape))
+                inp["timestep"] = torch.tensor([float(t)] * 2)
+                r = net(inp["x"], inp["timestep"], inp["y"], mask=inp["mask"], x_mask=inp["x_mask"], fps=inp["fps"],
+                        height=inp["height"], width=inp["width"])
+                o = O.stdit3_forward(sd, cases.oracle_cfg(c), pab=gate, pab_states=states, **inp)
+                assert torch.equal(r, o), f"step {i} t={t}"
+    finally:
+        P.PAB_MANAGER = None
+
+
+def test_pab_gate_matches_reference_manager():
+    P = ref_loader.load().pab_mgr
+    import random
+
+    rnd = random.Random(0)
+    try:
+        for _ in range(20):
+            kw = {}
+            spec = {}
+            for k in ("spatial", "temporal", "cross"):
+                on = rnd.random() < 0.7
+                lo = rnd.randrange(0, 600)
+                hi = lo + rnd.randrange(1, 500)
+                rg = rnd.randrange(1, 7)
+                kw.update({f"{k}_broadcast": on, f"{k}_threshold": [lo, hi], f"{k}_range": rg})
+                spec[k] = (on, (lo, hi), rg)
+            steps = rnd.randrange(1, 40)
+            P.set_pab_manager(P.PABConfig(**kw))
+            P.update_steps(steps)
+            g = pab_oracle.PABGate(steps=steps, **spec)
+            for k, fn in (("spatial", P.if_broadcast_spatial), ("temporal", P.if_broadcast_temporal), ("cross", P.if_broadcast_cross)):
+                c1 = c2 = 0
+                for _ in range(3 * steps):
+                    t = rnd.choice([None, rnd.randrange(0, 1100)])
+                    f1, c1 = fn(t, c1)
+                    f2, c2 = g.gate(k, t, c2)
+                    assert (f1, c1) == (f2, c2)
+    finally:
+        P.PAB_MANAGER = None
+
+
+class _FakeDist:
+    """Thread-per-rank stand-in for torch.distributed so the reference comm functions run on CPU."""
+
+    def __init__(self, sp):
+        self.sp = sp
+        self.board = [None] * sp
+        self.bar = threading.Barrier(sp)
+        self.local = threading.local()
+        self.ProcessGroup = object
+
+    def get_world_size(self, group=None):
+        return self.sp
+
+    def get_rank(self, group=None):
+        return self.local.rank
+
+    def all_to_all(self, output_list, input_list, group=None):
+        r = self.local.rank
+        self.board[r] = input_list
+        self.bar.wait()
+        for src in range(self.sp):
+            output_list[src].copy_(self.board[src][r])
+        self.bar.wait()
+
+
+def _run_ranks(sp, fn):
+    fake = _FakeDist(sp)
+    comm = ref_loader.load().comm
+    old = comm.dist
+    comm.dist = fake
+    outs, errs = [None] * sp, []
+
+    def body(r):
+        fake.local.rank = r
+        try:
+            outs[r] = fn(comm, r)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+            fake.bar.abort()
+
+    try:
+        th = [threading.Thread(target=body, args=(r,)) for r in range(sp)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+    finally:
+        comm.dist = old
+    assert not errs, errs
+    return outs
+
+
+@pytest.mark.parametrize("sp,T,S", [(2, 5, 9), (4, 5, 9), (8, 20, 24), (4, 4, 8), (2, 15, 405)])
+def test_dsp_reshard_matches_reference_comm(sp, T, S):
+    B, C = 2, 16
+    full = synth.normalish(f"dsp{sp}{T}{S}", (B, T, S, C))
+    tp, spd = dsp_oracle.pad_amount(T, sp), dsp_oracle.pad_amount(S, sp)
+    res = dsp_oracle.split_sequence(full, sp, dim=2)
+
+    def fn(comm, r):
+        x = comm._split_sequence_func(full, None, 2, spd)
+        a = comm.all_to_all_with_pad(x, None, scatter_dim=1, gather_dim=2, scatter_pad=tp, gather_pad=spd)
+        b = comm.all_to_all_with_pad(a, None, scatter_dim=2, gather_dim=1, scatter_pad=spd, gather_pad=tp)
+        return x, a, b
+
+    outs = _run_ranks(sp, fn)
+    parts = [p.reshape(B, -1, C) for p in res]
+    sw, new_s, new_t = dsp_oracle.dynamic_switch(parts, T, S, to_spatial_shard=False)
+    back, s2, t2 = dsp_oracle.dynamic_switch(sw, T, S, to_spatial_shard=True)
+    padded_t = torch.cat([full, torch.zeros(B, tp, S, C)], 1)
+    for r in range(sp):
+        x, a, b = outs[r]
+        assert torch.equal(x, res[r])
+        assert torch.equal(a.reshape(B, -1, C), sw[r]) and (a.shape[1], a.shape[2]) == (new_t, new_s)
+        assert torch.equal(a, padded_t[:, r * new_t:(r + 1) * new_t])  # Appendix E: a slice of the T-padded tensor
+        assert torch.equal(b.reshape(B, -1, C), back[r]) and torch.equal(b, x)
+    assert torch.equal(dsp_oracle.gather_sequence([o[2] for o in outs], 2, spd), full)
