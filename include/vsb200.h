@@ -1,0 +1,129 @@
+/* vsb200.h -- C-ABI of libvsb200.so: the B200-native (sm_100a) kernels behind the VideoSys DiT denoising hot path.
+ *
+ * The reference (NUS-HPC-AI-Lab/VideoSys @ 4cce4778) is pure Python and exposes no FFI/plugin boundary
+ * (SURVEY.md section 8b); this header is the boundary a maintainer binds with ctypes (INTEGRATION.md shows the
+ * stub).  Each entry cites the reference code it replaces (paths relative to /root/reference/videosys/).
+ *
+ * Conventions
+ *   - plain pointers and sizes; every pointer is DEVICE memory unless named host_*; bf16 = uint16 storage.
+ *   - all kernels are asynchronous on `stream` (a cudaStream_t passed as void*); no allocation, no host sync.
+ *   - return 0 on success, a negative vsb_status otherwise; vsb_last_error() gives the text (per host thread).
+ *   - no CPU fallback and no multi-backend dispatch: unsupported shape/alignment = VSB_ERR_UNSUPPORTED.
+ *   - one process per GPU; entries are not re-entrant per device (same as one torch stream).
+ */
+#ifndef VSB200_H_
+#define VSB200_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  VSB_OK = 0,
+  VSB_ERR_INVALID = -1,     /* bad argument (null pointer, non-positive size) */
+  VSB_ERR_UNSUPPORTED = -2, /* shape / alignment outside what the sm_100a kernels handle */
+  VSB_ERR_CUDA = -3,        /* CUDA runtime / driver error (text in vsb_last_error) */
+  VSB_ERR_NO_DEVICE = -4    /* no sm_100 device: the library never falls back to the CPU */
+} vsb_status;
+
+typedef uint16_t vsb_bf16;
+
+int vsb_version(void);
+const char* vsb_last_error(void);
+/* Checks that `device` is compute capability 10.x and loads cuTensorMapEncodeTiled. */
+int vsb_init(int device);
+/* Number of kernels this library has launched since load (all entries); bench.py reports the delta. */
+unsigned long long vsb_launch_count(void);
+
+/* ---- AdaLN: LayerNorm(eps, no affine) -> x*(1+scale)+shift with per-frame t / t0 select --------------------
+ * replaces norm1/norm2 + t2i_modulate + t_mask_select: models/transformers/open_sora_transformer_3d.py:47-48,
+ * :152-160, :196-200, :260-264.  Rounds to bf16 at the same points as the eager chain (after LN, after 1+scale,
+ * after the multiply, after the add).
+ *   x, out   [B, T, S, C] bf16 (out may alias x)
+ *   mod      [2, B, 6, C] bf16: mod[0] = scale_shift_table + t, mod[1] = table + t0 (see vsb_modulation_table)
+ *   x_mask   [B, T] uint8 (nonzero -> use mod[0]) or NULL (always mod[0])
+ *   shift_row/scale_row: which of the 6 rows (0,1 for attention; 3,4 for the MLP) */
+int vsb_ln_modulate(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask, int shift_row,
+                    int scale_row, int B, int T, int S, int C, float eps, void* stream);
+
+/* mod[0,b,r,:] = bf16(table[r,:] + t[b, r*C:(r+1)*C]); mod[1] likewise from t0 (t0 may be NULL -> mod[1]=mod[0]).
+ * replaces open_sora_transformer_3d.py:177-184.  table [6,C], t/t0 [B,6C], mod [2,B,6,C]. */
+int vsb_modulation_table(const vsb_bf16* table, const vsb_bf16* t, const vsb_bf16* t0, vsb_bf16* mod, int B, int C,
+                         int rows, void* stream);
+
+/* ---- gate * y (+ per-frame select) + residual, optional PAB cache write ---------------------------------------
+ * replaces open_sora_transformer_3d.py:219-228 and :270-284.  gated = bf16(gate*y); out = bf16(x + gated).
+ *   cache_out (nullable): receives `gated` (what the reference keeps as last_attn, :224-225). */
+int vsb_gate_residual(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* out, vsb_bf16* cache_out, const vsb_bf16* mod,
+                      const uint8_t* x_mask, int gate_row, int B, int T, int S, int C, void* stream);
+
+/* out = bf16(x + y) over n elements: cross-attention residual (:240) and PAB replay of a cached tensor
+ * (:192-193 -> :228, :234-235).  One coalesced pass: 2 reads + 1 write. */
+int vsb_residual_add(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* out, size_t n, void* stream);
+
+/* ---- per-head RMSNorm of q and k inside a packed qkv buffer (spatial blocks, no RoPE) -------------------------
+ * replaces LlamaRMSNorm on q,k: models/modules/normalization.py:28-33 via attentions.py:75.
+ *   qkv [rows, 3, H, D] bf16, normalised in place for the q and k thirds; wq, wk [D] bf16. */
+int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D, float eps,
+                   void* stream);
+
+/* ---- short-sequence attention (n < 30): RMSNorm(q,k) -> [RoPE] -> native_attention, one warp per (seq, head) --
+ * replaces OpenSoraAttention.forward's N<30 path: attentions.py:59-78,95-97,111-120 with the reference's op order
+ * (bf16(q*scale), bf16 scores, fp32 softmax, bf16 probs).  Reads the packed qkv of the token-major activation
+ * without any rearrange: sequence (o,i) token j lives at row o*outer_stride + i*inner_stride + j*tok_stride.
+ *   qkv [rows,3,H,D] bf16; out [rows,H*D] bf16; rope_cos/rope_sin [n, D] fp32 or NULL; n == 1 copies v (:65-66). */
+int vsb_attn_short(const vsb_bf16* qkv, vsb_bf16* out, const vsb_bf16* wq, const vsb_bf16* wk, const float* rope_cos,
+                   const float* rope_sin, int n_outer, int n_inner, long long outer_stride, long long inner_stride,
+                   long long tok_stride, int n, int H, int D, float eps, float scale, void* stream);
+
+/* ---- GEMM on tcgen05: out[M,N] = act(A[M,K] @ W[N,K]^T + bias[N]) ---------------------------------------------
+ * replaces every nn.Linear on the path (attentions.py:59,107,156-157; timm Mlp fc1/fc2) and the tanh-GELU between
+ * fc1 and fc2 (models/modules/activations.py:3).  bf16 in, fp32 accumulate in TMEM, bf16 out.
+ *   act: 0 = none, 1 = gelu_tanh applied to bf16(acc+bias) (the eager rounding point).
+ *   Requirements: K % 8 == 0, N % 8 == 0, 16-byte aligned pointers, row-major contiguous. */
+int vsb_gemm_bias_act(const vsb_bf16* A, const vsb_bf16* W, const vsb_bf16* bias, vsb_bf16* out, int M, int N, int K,
+                      int act, void* stream);
+
+/* ---- flash attention on tcgen05 (spatial self-attention and text cross-attention) -------------------------------
+ * replaces F.scaled_dot_product_attention at attentions.py:100 and :268 (bool key mask = per-batch key count).
+ * q/k/v are strided views: element (b, n, h, d) at base + b*batch_stride + n*row_stride + h*D + d (strides in
+ * elements, multiples of 8).  out [nb, nq, H*D] contiguous.  kv_lens (host int array, nullable) = valid keys per
+ * batch (<= nk).  D must be 72 or 64. */
+int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb, int nq, int nk,
+                   int H, int D, long long q_row_stride, long long q_batch_stride, long long kv_row_stride,
+                   long long kv_batch_stride, const int* host_kv_lens, float scale, void* stream);
+
+/* ---- Pyramid Attention Broadcast gate (host integer logic, bit-exact) -------------------------------------------
+ * replaces PABManager.if_broadcast_{spatial,temporal,cross}: core/pab/pab_mgr.py:54-91.
+ * Returns 1 (reuse the cached tensor) or 0; *count advances on every call and wraps modulo steps.
+ * has_timestep = 0 models `timestep is None`. */
+int vsb_pab_gate(int broadcast_on, int has_timestep, int timestep, int* count, int range, int lo, int hi, int steps);
+
+/* ---- DSP reshard (dimension switch) over NVLink peer memory ----------------------------------------------------
+ * replaces STDiT3Block.dynamic_switch -> all_to_all_with_pad -> _all_to_all_func:
+ * open_sora_transformer_3d.py:288-315, core/distributed/comm.py:282-304,104-108.
+ * One kernel packs each destination rank's slice and stores it straight into that rank's receive window with
+ * 128-bit peer stores (no staging copies, zero padding synthesised on the fly), then signals a per-peer flag.
+ *   peer_recv[r]   device pointer (peer-mapped) to rank r's receive window for this direction
+ *   peer_flags[r]  device pointer (peer-mapped) to rank r's flag array [world] (uint32 epoch counters)
+ *   to_spatial_shard = 0: local [B, T, Sl, C] (S-sharded) -> recv [B, Tp/sp, Sp, C] (T-sharded)
+ *   to_spatial_shard = 1: local [B, Tl, S(+pad), C] -> recv [B, Tp, Sl, C]
+ * vsb_dsp_wait blocks the stream until all `world` peers have delivered epoch `epoch`. */
+int vsb_dsp_scatter(const vsb_bf16* local, void* const* host_peer_recv, void* const* host_peer_flags, int rank,
+                    int world, int to_spatial_shard, int B, int T, int S, int C, unsigned epoch, void* stream);
+int vsb_dsp_wait(const void* my_flags, int world, unsigned epoch, void* stream);
+
+/* Symmetric receive windows for the reshard: cudaMalloc'ed (zeroed) here so that a CUDA IPC handle maps the exact
+ * base address; handles (64 bytes) are exchanged once at initialize() over the process group's store.
+ * replaces nothing in the reference (NCCL owns its buffers); this is the B200-native plumbing for P2P stores. */
+int vsb_dsp_alloc(void** out, size_t bytes);
+int vsb_dsp_free(void* p);
+int vsb_ipc_get_handle(void* devptr, void* out_handle64);
+int vsb_ipc_open_handle(const void* handle64, void** out_devptr);
+int vsb_ipc_close_handle(void* devptr);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSB200_H_ */

@@ -1,0 +1,271 @@
+"""Parity of every sm_100a kernel (through the C-ABI) against the oracle's leaf ops on identical bf16 inputs.
+
+Tolerances (rtol 1e-3 is below one bf16 ulp, so per-kernel parity is stated as):
+  - elementwise kernels: >= 99 % bit-equal, the rest within 1 bf16 ulp (reduction-order flips at a rounding edge);
+  - GEMM / attention: within 2 bf16 ulps of the oracle's bf16 result AND closer to the fp32-exact result than
+    1 bf16 ulp of the output magnitude (accumulation order differs from the CPU library).
+"""
+import math
+
+import pytest
+import torch
+
+from oracle import stdit3_oracle as O, synth
+
+gpu = pytest.mark.gpu
+pytestmark = gpu
+BF = torch.bfloat16
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _bf16_ulp(x):
+    """Spacing of bf16 numbers at |x| (8-bit significand): 2^(floor(log2|x|) - 7)."""
+    _, e = torch.frexp(x.abs().clamp_min(2.0**-126))  # |x| = m * 2^e, m in [0.5, 1)
+    return torch.ldexp(torch.ones_like(x), e - 8)
+
+
+def _ulp_report(name, got, want, min_equal=0.99, max_ulps=1.0, row_floor=0.0):
+    """bit-equal fraction + max error in TRUE bf16 ulps.  row_floor > 0 measures the ulp at
+    max(|want|, row_floor * rowmax|want|): outputs of a reduction carry the rounding error of the
+    row's magnitude even where the result itself cancels to ~0."""
+    got = got.float().cpu()
+    want = want.float().cpu()
+    eq = (got == want).float().mean().item()
+    mag = want.abs()
+    if row_floor > 0:
+        mag = torch.maximum(mag, row_floor * want.abs().amax(dim=-1, keepdim=True))
+    rel = ((got - want).abs() / _bf16_ulp(mag)).max().item()
+    print(f"[parity] {name}: bit-equal {eq*100:.3f} %  max diff {rel:.2f} ulp  max abs {(got-want).abs().max().item():.3e}")
+    assert eq >= min_equal, f"{name}: only {eq*100:.2f} % bit-equal"
+    assert rel <= max_ulps + 1e-3, f"{name}: {rel:.2f} ulp"
+    return eq, rel
+
+
+def _mask_u8(x_mask, dev):
+    return x_mask.to(torch.uint8).contiguous().to(dev)
+
+
+@pytest.mark.parametrize("B,T,S,C", [(2, 5, 36, 288), (2, 3, 50, 1152), (1, 2, 7, 1920)])
+def test_ln_modulate(B, T, S, C):
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    x = (synth.normalish("lnm.x", (B, T * S, C)) * 2 + 0.3).to(BF)
+    table = synth.normalish("lnm.tab", (6, C), std=0.3).to(BF)
+    t = synth.normalish("lnm.t", (B, 6 * C), std=0.5).to(BF)
+    t0 = synth.normalish("lnm.t0", (B, 6 * C), std=0.5).to(BF)
+    x_mask = torch.ones(B, T, dtype=torch.bool)
+    x_mask[0, 0] = False
+    x_mask[B - 1, T - 1] = False
+    mods = (table[None] + t.reshape(B, 6, -1)).chunk(6, dim=1)
+    mods0 = (table[None] + t0.reshape(B, 6, -1)).chunk(6, dim=1)
+    mod = K.modulation_table(table.to(dev), t.to(dev), t0.to(dev))
+    want_mod = torch.stack([torch.cat(mods, 1), torch.cat(mods0, 1)])
+    assert torch.equal(mod.cpu(), want_mod)
+    for (sh, sc) in ((0, 1), (3, 4)):
+        n = O.layer_norm_noaffine(x)
+        want = O.frame_select(x_mask, O.t2i_modulate(n, mods[sh], mods[sc]), O.t2i_modulate(n, mods0[sh], mods0[sc]), T, S)
+        got = K.ln_modulate(x.to(dev), mod, _mask_u8(x_mask, dev), sh, sc, B, T, S)
+        _ulp_report(f"ln_modulate C={C} rows=({sh},{sc})", got, want)
+        got2 = K.ln_modulate(x.to(dev), mod, None, sh, sc, B, T, S)
+        _ulp_report(f"ln_modulate nomask C={C}", got2, O.t2i_modulate(n, mods[sh], mods[sc]))
+
+
+@pytest.mark.parametrize("B,T,S,C", [(2, 5, 36, 288), (2, 3, 50, 1152)])
+def test_gate_residual_and_add(B, T, S, C):
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    x = synth.normalish("gr.x", (B, T * S, C)).to(BF)
+    y = synth.normalish("gr.y", (B, T * S, C)).to(BF)
+    table = synth.normalish("gr.tab", (6, C), std=0.3).to(BF)
+    t = synth.normalish("gr.t", (B, 6 * C), std=0.5).to(BF)
+    t0 = synth.normalish("gr.t0", (B, 6 * C), std=0.5).to(BF)
+    x_mask = torch.ones(B, T, dtype=torch.bool)
+    x_mask[0, 1] = False
+    mods = (table[None] + t.reshape(B, 6, -1)).chunk(6, dim=1)
+    mods0 = (table[None] + t0.reshape(B, 6, -1)).chunk(6, dim=1)
+    mod = K.modulation_table(table.to(dev), t.to(dev), t0.to(dev))
+    for g in (2, 5):
+        gated = O.frame_select(x_mask, mods[g] * y, mods0[g] * y, T, S)
+        want = x + gated
+        cache = torch.empty_like(x, device=dev)
+        got = K.gate_residual(x.to(dev), y.to(dev), mod, _mask_u8(x_mask, dev), g, B, T, S, cache_out=cache)
+        assert torch.equal(got.cpu(), want), "gate_residual must be bit-exact"
+        assert torch.equal(cache.cpu(), gated), "PAB cache value must be bit-exact"
+    assert torch.equal(K.residual_add(x.to(dev), y.to(dev)).cpu(), x + y)
+
+
+@pytest.mark.parametrize("rows,H,D", [(77, 4, 72), (405, 16, 72), (50, 30, 64)])
+def test_qk_rmsnorm(rows, H, D):
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    qkv = (synth.normalish("rms.qkv", (rows, 3, H, D)) * 1.7).to(BF)
+    wq = (1 + 0.2 * synth.uniform("rms.wq", (D,))).to(BF)
+    wk = (1 + 0.2 * synth.uniform("rms.wk", (D,))).to(BF)
+    want = qkv.clone()
+    want[:, 0] = O.llama_rms_norm(qkv[:, 0], wq)
+    want[:, 1] = O.llama_rms_norm(qkv[:, 1], wk)
+    got = K.qk_rmsnorm_(qkv.clone().to(dev), wq.to(dev), wk.to(dev), H, D)
+    assert torch.equal(got[:, 2].cpu(), qkv[:, 2]), "v must be untouched"
+    _ulp_report(f"qk_rmsnorm D={D}", got, want)
+
+
+def _rope_tables(n, D, dtype=BF):
+    freqs = O.rope_freqs(D).to(dtype).float()
+    ang = torch.einsum("i,j->ij", torch.arange(n, dtype=torch.float32), freqs).repeat_interleave(2, dim=-1)
+    return ang.cos().contiguous(), ang.sin().contiguous()
+
+
+@pytest.mark.parametrize("B,T,S,H,D,temporal", [(2, 5, 36, 4, 72, True), (2, 15, 20, 16, 72, True), (2, 20, 9, 16, 72, True),
+                                                (2, 3, 12, 4, 72, False), (1, 1, 6, 4, 72, True)])
+def test_attn_short(B, T, S, H, D, temporal):
+    """Temporal self-attention core (RMSNorm -> RoPE -> native_attention), token-major in / out, no rearrange."""
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    C = H * D
+    qkv = synth.normalish(f"as.qkv{T}{S}", (B, T, S, 3, H, D)).to(BF)
+    wq = (1 + 0.2 * synth.uniform("as.wq", (D,))).to(BF)
+    wk = (1 + 0.2 * synth.uniform("as.wk", (D,))).to(BF)
+    freqs = O.rope_freqs(D).to(BF)
+    if temporal:  # sequences run over T for each (b, s)
+        seq = qkv.permute(0, 2, 1, 3, 4, 5).reshape(B * S, T, 3, H, D)
+    else:  # short spatial sequences (only in tiny configs): over S for each (b, t)
+        seq = qkv.reshape(B * T, S, 3, H, D)
+    q, k, v = seq.permute(2, 0, 3, 1, 4).unbind(0)
+    n = q.shape[2]
+    if n == 1:
+        o = v
+    else:
+        qn, kn = O.llama_rms_norm(q, wq), O.llama_rms_norm(k, wk)
+        if temporal:
+            qn, kn = O.rotate_queries_or_keys(qn, freqs), O.rotate_queries_or_keys(kn, freqs)
+        o = O.native_attention(qn, kn, v, D**-0.5)
+    o = o.transpose(1, 2).reshape(seq.shape[0], n, C)
+    if temporal:
+        want = o.reshape(B, S, T, C).permute(0, 2, 1, 3).reshape(B * T * S, C)
+    else:
+        want = o.reshape(B * T * S, C)
+    cos, sin = _rope_tables(n, D) if temporal else (None, None)
+    args = (B, S, T * S, 1, S, T) if temporal else (B * T, 1, S, 0, 1, S)
+    got = K.attn_short(qkv.to(dev).reshape(-1, 3, H, D), wq.to(dev), wk.to(dev),
+                       None if cos is None else cos.to(dev), None if sin is None else sin.to(dev), *args, H, D, D**-0.5)
+    _ulp_report(f"attn_short T={T} S={S} temporal={temporal}", got, want, min_equal=0.97, max_ulps=2.0, row_floor=0.5)
+
+
+def _gemm_check(name, M, N, K_, act):
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    a = synth.normalish(f"{name}.a", (M, K_)).to(BF)
+    w = synth.normalish(f"{name}.w", (N, K_), std=0.05).to(BF)
+    b = (0.1 * synth.uniform(f"{name}.b", (N,))).to(BF)
+    exact = a.double() @ w.double().t() + b.double()
+    want = torch.nn.functional.linear(a, w, b)  # oracle op (bf16 CPU)
+    if act:
+        exact = torch.nn.functional.gelu(exact.to(BF).double(), approximate="tanh")
+        want = O.gelu_tanh(want)
+    got = K.gemm_bias_act(a.to(dev), w.to(dev), b.to(dev), act=act).cpu()
+    err_exact = (got.double() - exact).abs()
+    # one bf16 rounding of the result (half an ulp) + fp32 accumulation noise; with the GELU epilogue the
+    # pre-activation is itself rounded to bf16 first (the eager rounding point), so a flip there moves the
+    # output by up to ~1.1 pre-activation ulps more
+    tol = _bf16_ulp(exact.float().clamp_min(0.05)).double() * (0.51 if not act else 2.2) + 1e-3
+    bad = err_exact > tol
+    if bad.any():
+        idx = bad.nonzero()
+        print(f"[gemm {name}] {bad.float().mean().item()*100:.3f} % outside tolerance; first: ",
+              [(int(r), int(c), float(got[r, c]), float(exact[r, c])) for r, c in idx[:8]])
+        rows_bad = bad.any(1).nonzero().flatten()
+        cols_bad = bad.any(0).nonzero().flatten()
+        print("   bad rows (first 16):", rows_bad[:16].tolist(), " count", len(rows_bad), "of", M)
+        print("   bad cols (first 16):", cols_bad[:16].tolist(), " count", len(cols_bad), "of", N)
+        print("   bad by row%8:", [int(bad[r::8].sum()) for r in range(8)], " by col%64/8:", [int(bad[:, c * 8:(c + 1) * 8].sum()) for c in range(min(8, N // 8))])
+    assert not bad.any(), f"gemm {name}: mismatch vs fp64-exact"
+    eq = (got == want).float().mean().item()
+    print(f"[parity] gemm {name} M={M} N={N} K={K_} act={act}: bit-equal to oracle bf16 {eq*100:.2f} %, "
+          f"max |err| vs exact {err_exact.max().item():.3e}")
+    assert eq > 0.9
+
+
+@pytest.mark.parametrize("M,N,K_,act", [
+    (128, 64, 64, 0),      # one tile, one k-block
+    (128, 192, 128, 0),    # one tile, two k-blocks
+    (300, 288, 288, 0),    # M/N/K tails (small test config: hidden 288)
+    (200, 864, 288, 0),
+    (1000, 3456, 1152, 0),  # qkv projection
+    (777, 1152, 1152, 0),   # proj / q_linear
+    (40, 2304, 1152, 0),    # kv_linear (few text tokens)
+    (515, 4608, 1152, 1),   # fc1 + tanh-GELU
+    (515, 1152, 4608, 0),   # fc2
+    (260, 256, 512, 0),     # BN=256 path
+    (130, 128, 96, 1),      # BN=128 path, K tail
+])
+def test_gemm(M, N, K_, act):
+    _gemm_check(f"g{M}x{N}x{K_}", M, N, K_, act)
+
+
+def test_gemm_many_tiles_persistent():
+    """More tiles than SMs so every CTA loops over several tiles (accumulator double-buffer phases)."""
+    _gemm_check("gbig", 128 * 40, 192 * 8, 320, 0)
+
+
+def _flash_check(name, nb, nq, nk, H, D, lens=None, packed_qkv=True):
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    C = H * D
+    scale = D**-0.5
+    if packed_qkv:
+        assert nq == nk
+        qkv = synth.normalish(f"{name}.qkv", (nb, nq, 3, H, D)).to(BF)
+        q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)  # [nb, H, n, D]
+        gq = qkv.to(dev)
+        got = K.attn_flash(gq[:, :, 0], gq[:, :, 1], gq[:, :, 2], nb, nq, nk, H, D, 3 * C, nq * 3 * C, 3 * C, nk * 3 * C, scale)
+    else:
+        qt = synth.normalish(f"{name}.q", (nb, nq, H, D)).to(BF)
+        kv = synth.normalish(f"{name}.kv", (nb, nk, 2, H, D)).to(BF)
+        q = qt.permute(0, 2, 1, 3)
+        k, v = kv.permute(2, 0, 3, 1, 4).unbind(0)
+        gkv = kv.to(dev)
+        got = K.attn_flash(qt.to(dev), gkv[:, :, 0], gkv[:, :, 1], nb, nq, nk, H, D, C, nq * C, 2 * C, nk * 2 * C, scale, kv_lens=lens)
+    mask = None
+    if lens is not None:
+        mask = torch.zeros(nb, 1, nq, nk, dtype=torch.bool)
+        for i, m in enumerate(lens):
+            mask[i, :, :, :m] = True
+    want = torch.nn.functional.scaled_dot_product_attention(q, k, v, attn_mask=mask)  # oracle op
+    exact = torch.nn.functional.scaled_dot_product_attention(q.double(), k.double(), v.double(), attn_mask=mask)
+    want = want.transpose(1, 2).reshape(nb, nq, C)
+    exact = exact.transpose(1, 2).reshape(nb, nq, C)
+    got = got.cpu()
+    err = (got.double() - exact).abs()
+    err_or = (want.double() - exact).abs()
+    print(f"[parity] attn_flash {name}: max|err| vs fp64 {err.max().item():.3e} (oracle bf16: {err_or.max().item():.3e}), "
+          f"mean {err.mean().item():.3e} (oracle {err_or.mean().item():.3e}), bit-equal to oracle {(got == want).float().mean().item()*100:.1f} %")
+    tol = 2.0**-7 * exact.abs().clamp_min(0.02) + 2e-3
+    bad = err > tol
+    if bad.any():
+        idx = bad.nonzero()
+        print("   first bad (b, row, col, got, exact):", [(int(a), int(r), int(c), float(got[a, r, c]), float(exact[a, r, c])) for a, r, c in idx[:8]])
+        print("   bad fraction", bad.float().mean().item(), " bad rows", bad.any(2).sum().item(), " bad head-cols by d:",
+              [int(bad.reshape(nb, nq, H, D)[..., d].sum()) for d in range(0, D, 8)])
+    assert not bad.any()
+    assert err.mean().item() <= 2.0 * err_or.mean().item() + 1e-5
+
+
+@pytest.mark.parametrize("nb,n,H,D", [(1, 128, 1, 72), (2, 36, 4, 72), (3, 405, 16, 72), (1, 700, 2, 72), (2, 300, 3, 64)])
+def test_attn_flash_self(nb, n, H, D):
+    _flash_check(f"self{n}x{H}x{D}", nb, n, n, H, D)
+
+
+@pytest.mark.parametrize("nb,nq,nk,H,D,lens", [(2, 500, 300, 16, 72, None), (2, 257, 300, 4, 72, [300, 120]), (2, 180, 15, 4, 72, [15, 15])])
+def test_attn_flash_cross(nb, nq, nk, H, D, lens):
+    _flash_check(f"cross{nq}x{nk}", nb, nq, nk, H, D, lens=lens, packed_qkv=False)

@@ -1,0 +1,189 @@
+"""Dynamic Sequence Parallelism communication -- host-side mirror of videosys/core/distributed/comm.py.
+
+Same function names / argument meaning as the reference (set_pad/get_pad :268-279, split_sequence /
+gather_sequence :148-190,256-261, all_to_all_with_pad :282-304, all_to_all_comm :139-140,
+split/gather_from_second_dim :307-318), inference only (no autograd functions).
+
+Two transports for the dimension switch:
+  * ``DspP2P`` (B200 path): one sm_100a kernel stores every 16-byte vector straight into the destination rank's
+    receive window over NVLink (CUDA-IPC mapped peer memory), flags + a wait kernel order the streams; no staging
+    copies, no NCCL launch (csrc/dsp_p2p.cu, C-ABI vsb_dsp_scatter / vsb_dsp_wait).
+  * ``torch.distributed.all_to_all_single`` (NCCL on GPU, gloo on CPU for the host-logic tests): the fallback
+    north_star allows "where the fused P2P kernel is not taken".
+"""
+import ctypes as C
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+PAD_DICT: Dict[str, int] = {}
+
+
+def set_pad(name: str, dim_size: int, parallel_group) -> None:
+    sp = dist.get_world_size(parallel_group)
+    PAD_DICT[name] = (sp - (dim_size % sp)) % sp
+
+
+def get_pad(name: str) -> int:
+    return PAD_DICT[name]
+
+
+def _append(x: torch.Tensor, dim: int, n: int, value: float = 0.0) -> torch.Tensor:
+    shape = list(x.shape)
+    shape[dim] = n
+    return torch.cat([x, x.new_full(shape, value)], dim=dim)
+
+
+def split_sequence(input_, process_group, dim, grad_scale=1.0, pad=0, pad_val=0):
+    """This rank's equal chunk along ``dim`` after appending ``pad`` entries of ``pad_val`` (no communication)."""
+    world = dist.get_world_size(process_group)
+    if world == 1:
+        return input_
+    if pad > 0:
+        input_ = _append(input_, dim, pad, pad_val)
+    size = input_.size(dim)
+    assert size % world == 0, f"dim_size ({size}) is not divisible by world_size ({world})"
+    step = size // world
+    rank = dist.get_rank(process_group)
+    return input_.narrow(dim, rank * step, step).contiguous()
+
+
+def gather_sequence(input_, process_group, dim, grad_scale=1.0, pad=0):
+    """all_gather along ``dim`` then drop the trailing ``pad`` entries."""
+    world = dist.get_world_size(process_group)
+    input_ = input_.contiguous()
+    if world == 1:
+        return input_
+    parts = [torch.empty_like(input_) for _ in range(world)]
+    dist.all_gather(parts, input_, group=process_group)
+    out = torch.cat(parts, dim=dim)
+    return out.narrow(dim, 0, out.size(dim) - pad) if pad > 0 else out
+
+
+def all_to_all_comm(input_, process_group=None, scatter_dim=2, gather_dim=1):
+    """Scatter ``scatter_dim`` / gather ``gather_dim`` across the group with one all_to_all_single."""
+    world = dist.get_world_size(process_group)
+    if world == 1:
+        return input_
+    assert input_.shape[scatter_dim] % world == 0
+    # [.., world, chunk, ..] -> leading 'destination rank' axis, contiguous send buffer
+    send = torch.stack(torch.tensor_split(input_, world, scatter_dim), dim=0).contiguous()
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=process_group)
+    return torch.cat(list(recv.unbind(0)), dim=gather_dim).contiguous()
+
+
+def all_to_all_with_pad(input_, process_group, scatter_dim: int = 2, gather_dim: int = 1, scatter_pad: int = 0,
+                        gather_pad: int = 0):
+    if scatter_pad > 0:
+        input_ = _append(input_, scatter_dim, scatter_pad, 0.0)
+    world = dist.get_world_size(process_group)
+    assert input_.shape[scatter_dim] % world == 0, (
+        f"Dimension to scatter ({input_.shape[scatter_dim]}) is not divisible by world size ({world})"
+    )
+    out = all_to_all_comm(input_, process_group, scatter_dim, gather_dim)
+    if gather_pad > 0:
+        out = out.narrow(gather_dim, 0, out.size(gather_dim) - gather_pad)
+    return out
+
+
+def split_from_second_dim(x, batch_size, parallel_group):
+    x = x.view(batch_size, -1, *x.shape[1:])
+    x = split_sequence(x, parallel_group, dim=1, grad_scale="down", pad=get_pad("temporal"))
+    return x.reshape(-1, *x.shape[2:])
+
+
+def gather_from_second_dim(x, batch_size, parallel_group):
+    x = x.view(batch_size, -1, *x.shape[1:])
+    x = gather_sequence(x, parallel_group, dim=1, grad_scale="up", pad=get_pad("temporal"))
+    return x.reshape(-1, *x.shape[2:])
+
+
+class DspP2P:
+    """Symmetric receive windows + flags for the P2P dimension switch (one instance per process / sp group).
+
+    ``switch(x, T, S, to_spatial_shard)`` is the B200 replacement of STDiT3Block.dynamic_switch
+    (open_sora_transformer_3d.py:288-315): x is the local [B, t, s, C] tensor, the result is a view of this rank's
+    receive window in the new layout.  The two directions own separate windows and flag arrays; stream order plus
+    the data dependencies of the block make one window per direction sufficient.
+    """
+
+    def __init__(self, process_group, max_elems: int, device: torch.device):
+        from ... import _lib
+
+        self._libmod = _lib
+        self.lib = _lib.load()
+        self.group = process_group
+        self.world = dist.get_world_size(process_group)
+        self.rank = dist.get_rank(process_group)
+        self.device = device
+        self.max_elems = int(max_elems)
+        self.epoch = [0, 0]
+        self._own = []
+        self._peer_recv: List[List[int]] = [[], []]
+        self._peer_flag: List[List[int]] = [[], []]
+        self._opened = []
+        handles = []
+        for d in range(2):
+            buf = C.c_void_p()
+            _lib.check(self.lib.vsb_dsp_alloc(C.byref(buf), self.max_elems * 2), "dsp_alloc")
+            flg = C.c_void_p()
+            _lib.check(self.lib.vsb_dsp_alloc(C.byref(flg), 64 * 4), "dsp_alloc")
+            self._own.append((buf.value, flg.value))
+            hb, hf = C.create_string_buffer(64), C.create_string_buffer(64)
+            _lib.check(self.lib.vsb_ipc_get_handle(buf, hb), "ipc_get_handle")
+            _lib.check(self.lib.vsb_ipc_get_handle(flg, hf), "ipc_get_handle")
+            handles.append((hb.raw, hf.raw))
+        everyone: List[Optional[list]] = [None] * self.world
+        dist.all_gather_object(everyone, handles, group=process_group)
+        for d in range(2):
+            for r in range(self.world):
+                if r == self.rank:
+                    self._peer_recv[d].append(self._own[d][0])
+                    self._peer_flag[d].append(self._own[d][1])
+                    continue
+                pb, pf = C.c_void_p(), C.c_void_p()
+                _lib.check(self.lib.vsb_ipc_open_handle(everyone[r][d][0], C.byref(pb)), "ipc_open_handle")
+                _lib.check(self.lib.vsb_ipc_open_handle(everyone[r][d][1], C.byref(pf)), "ipc_open_handle")
+                self._opened += [pb.value, pf.value]
+                self._peer_recv[d].append(pb.value)
+                self._peer_flag[d].append(pf.value)
+        self._recv_arr = [(C.c_void_p * self.world)(*self._peer_recv[d]) for d in range(2)]
+        self._flag_arr = [(C.c_void_p * self.world)(*self._peer_flag[d]) for d in range(2)]
+        dist.barrier(group=process_group)
+
+    def _window(self, d: int, shape) -> torch.Tensor:
+        n = 1
+        for s in shape:
+            n *= s
+        assert n <= self.max_elems, "DSP window too small"
+        from ..._cuda_view import device_view
+
+        return device_view(self._own[d][0], shape, torch.bfloat16, self.device)
+
+    def switch(self, x: torch.Tensor, T: int, S: int, to_spatial_shard: bool) -> torch.Tensor:
+        """x: local [B, T, Sl, C] (to_spatial_shard=False) or [B, Tl, S, C] (True); T, S are GLOBAL extents."""
+        d = 1 if to_spatial_shard else 0
+        B, Cc = x.shape[0], x.shape[-1]
+        w = self.world
+        Tl, Sl = -(-T // w), -(-S // w)
+        out_shape = (B, T, Sl, Cc) if to_spatial_shard else (B, Tl, S, Cc)
+        self.epoch[d] += 1
+        st = torch.cuda.current_stream().cuda_stream
+        self._libmod.check(
+            self.lib.vsb_dsp_scatter(x.data_ptr(), self._recv_arr[d], self._flag_arr[d], self.rank, w, d, B, T, S, Cc,
+                                     self.epoch[d], st),
+            "dsp_scatter",
+        )
+        self._libmod.check(self.lib.vsb_dsp_wait(self._own[d][1], w, self.epoch[d], st), "dsp_wait")
+        return self._window(d, out_shape)
+
+    def close(self):
+        for p in self._opened:
+            self.lib.vsb_ipc_close_handle(p)
+        self._opened = []
+        for buf, flg in self._own:
+            self.lib.vsb_dsp_free(buf)
+            self.lib.vsb_dsp_free(flg)
+        self._own = []

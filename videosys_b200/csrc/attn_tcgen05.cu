@@ -1,0 +1,337 @@
+// vsb200 -- flash attention forward on tcgen05 for head_dim 72 (STDiT3) and 64 (CogVideoX).
+//
+// One CTA per SM-slot handles TWO 128-row query tiles (A, B) of one (batch, head) against all key tiles of 128:
+//   warp 0        TMA producer: Q tiles once, K/V tiles through a 3-deep mbarrier ring
+//   warp 1        MMA issuer  : S_X = Q_X K^T  (SS, fp32 in TMEM),  O_X += P_X V (TS: P read from TMEM, V MN-major)
+//   warp 2        TMEM allocator (512 columns: S_A|S_B 128 each, O_A|O_B 80 each; bf16 P aliases the head of S)
+//   warps 4..7    softmax warpgroup A (thread = query row; tcgen05.ld 32x32b, no shuffles needed)
+//   warps 8..11   softmax warpgroup B
+// The two query tiles ping-pong: while warpgroup A runs exp2 on S_A(j) the tensor core does PV_B(j-1) / S_B(j).
+//
+// head_dim 72 is not a multiple of the 128-byte swizzle span: every operand tile is staged as a 64-wide
+// SWIZZLE_128B chunk plus a 16-wide SWIZZLE_32B chunk (columns 64..79; the tensor map's inner extent is 72, so
+// TMA zero-fills 72..79).  QK^T runs 4+1 K-steps, PV runs two N-slices (64 and 16) per K-step.
+#include "vsb_common.cuh"
+#include "vsb_host.h"
+
+namespace vsb {
+
+constexpr int kAttnThreads = 384;
+constexpr int kKvStages = 3;
+constexpr int kTileA = 128 * 128;  // bytes: 128 rows x 64 bf16 (SWIZZLE_128B)
+constexpr int kTileB = 128 * 32;   // bytes: 128 rows x 16 bf16 (SWIZZLE_32B)
+constexpr int kQBytes = kTileA + kTileB;
+constexpr int kKvStageBytes = 2 * (kTileA + kTileB);
+constexpr int kAttnSmem = 2 * kQBytes + kKvStages * kKvStageBytes + 1024 + 256;
+
+// TMEM columns
+__host__ __device__ constexpr uint32_t col_s(int x) { return uint32_t(x) * 128u; }        // S_A, S_B
+__host__ __device__ constexpr uint32_t col_o(int x) { return 256u + uint32_t(x) * 80u; }  // O_A, O_B: 64 + 16 columns
+
+struct AttnParams {
+  bf16* out;
+  int nb, nq, nk, H;
+  float scale_log2;  // softmax scale * log2(e)
+  int has_lens;
+  int lens[8];
+};
+
+template <int D>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qb,
+                  const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_kb,
+                  const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_vb,
+                  const __grid_constant__ AttnParams p) {
+  constexpr bool kHasB = (D > 64);
+  constexpr int kQTx = kHasB ? kQBytes : kTileA;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;                       // [2][Q_A | Q_B]
+  unsigned char* sKV = smem + 2 * kQBytes;        // [stages][K_A | K_B | V_A | V_B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + kKvStages * kKvStageBytes);
+  uint64_t* q_full = bars;                 // [1]
+  uint64_t* k_full = bars + 1;             // [stages]
+  uint64_t* v_full = k_full + kKvStages;   // [stages]
+  uint64_t* kv_empty = v_full + kKvStages; // [stages]
+  uint64_t* s_full = kv_empty + kKvStages; // [2]
+  uint64_t* p_full = s_full + 2;           // [2]
+  uint64_t* o_full = p_full + 2;           // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int kv_len = p.has_lens ? p.lens[b] : p.nk;
+  const int n_tiles = (kv_len + 127) / 128;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    if (kHasB) {
+      tma_prefetch_desc(&tm_qb);
+      tma_prefetch_desc(&tm_kb);
+      tma_prefetch_desc(&tm_vb);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kKvStages; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);  // one arrival per softmax warp
+      mbar_init(&o_full[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * kQTx);
+      for (int x = 0; x < 2; ++x) {
+        tma_load_4d(&tm_q, q_full, sQ + x * kQBytes, 0, h, q0 + x * 128, b);
+        if (kHasB) tma_load_4d(&tm_qb, q_full, sQ + x * kQBytes + kTileA, 64, h, q0 + x * 128, b);
+      }
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % kKvStages;
+        const uint32_t ph = (j / kKvStages) & 1;
+        mbar_wait(&kv_empty[s], ph ^ 1);
+        unsigned char* st = sKV + s * kKvStageBytes;
+        mbar_arrive_expect_tx(&k_full[s], kQTx);
+        tma_load_4d(&tm_k, &k_full[s], st, 0, h, j * 128, b);
+        if (kHasB) tma_load_4d(&tm_kb, &k_full[s], st + kTileA, 64, h, j * 128, b);
+        mbar_arrive_expect_tx(&v_full[s], kQTx);
+        tma_load_4d(&tm_v, &v_full[s], st + kQBytes, 0, h, j * 128, b);
+        if (kHasB) tma_load_4d(&tm_vb, &v_full[s], st + kQBytes + kTileA, 64, h, j * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T, both K-major
+      constexpr uint32_t idesc_o64 = umma_idesc_bf16(128, 64, 0, 1);  // O[:, 0:64]  += P V, V MN-major
+      constexpr uint32_t idesc_o16 = umma_idesc_bf16(128, 16, 0, 1);  // O[:, 64:80] += P V
+      auto issue_S = [&](int x, int stage) {
+        const uint32_t qa = smem_u32(sQ + x * kQBytes);
+        const uint32_t ka = smem_u32(sKV + stage * kKvStageBytes);
+        const uint32_t d = tmem_base + col_s(x);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss(d, umma_smem_desc(qa + k * 32, 16, 1024, kSwz128), umma_smem_desc(ka + k * 32, 16, 1024, kSwz128),
+                  idesc_s, k > 0 ? 1u : 0u);
+        if (kHasB)
+          umma_ss(d, umma_smem_desc(qa + kTileA, 16, 256, kSwz32), umma_smem_desc(ka + kTileA, 16, 256, kSwz32),
+                  idesc_s, 1u);
+        umma_commit(&s_full[x]);
+      };
+      auto issue_PV = [&](int x, int stage, bool accumulate) {
+        const uint32_t va = smem_u32(sKV + stage * kKvStageBytes + kQBytes);
+        const uint32_t pt = tmem_base + col_s(x);  // bf16 P aliases the first 64 columns of S_x
+        const uint32_t d = tmem_base + col_o(x);
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {  // 16 keys per step
+          const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
+          umma_ts(d, pt + ks * 8, umma_smem_desc(va + ks * 2048, 16384, 1024, kSwz128), idesc_o64, acc);
+          if (kHasB)
+            umma_ts(d + 64, pt + ks * 8, umma_smem_desc(va + kTileA + ks * 512, 4096, 256, kSwz32), idesc_o16, acc);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_S(0, 0);
+      issue_S(1, 0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j % kKvStages;
+        const uint32_t ph = (j / kKvStages) & 1;
+        const int s1 = (j + 1) % kKvStages;
+        const uint32_t ph1 = ((j + 1) / kKvStages) & 1;
+        for (int x = 0; x < 2; ++x) {
+          mbar_wait(&p_full[x], j & 1);
+          if (x == 0) mbar_wait(&v_full[s], ph);
+          tc_fence_after();
+          issue_PV(x, s, j > 0);
+          if (x == 1) umma_commit(&kv_empty[s]);  // K_j and V_j fully consumed by both query tiles
+          if (j + 1 < n_tiles) {
+            if (x == 0) {
+              mbar_wait(&k_full[s1], ph1);
+              tc_fence_after();
+            }
+            issue_S(x, s1);
+          } else {
+            umma_commit(&o_full[x]);
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== softmax warpgroups ===============================
+    const int x = (warp - 4) >> 2;          // query tile 0/1
+    const int ew = warp & 3;                // TMEM lane quarter
+    const int row = ew * 32 + lane;
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + col_s(x);
+    const uint32_t tO = tmem_base + lane_off + col_o(x);
+    const float sl2 = p.scale_log2;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[x], j & 1);
+      tc_fence_after();
+      const int valid = min(128, kv_len - j * 128);  // columns >= valid are masked
+      // ---- pass 1: row max ----
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + c * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = __uint_as_float(r[i]);
+          if (c * 32 + i < valid) mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = fast_exp2((m_run - m_new) * sl2);  // m_run = -inf -> 0
+      // ---- rescale O (quiescent: S_x(j) complete implies PV_x(j-1) complete) ----
+      if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
+#pragma unroll 1
+        for (int c = 0; c < (kHasB ? 5 : 4); ++c) {
+          uint32_t r[16];
+          tmem_ld16(tO + c * 16, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+          tmem_st16(tO + c * 16, r);
+        }
+      }
+      m_run = m_new;
+      const float mb = m_new * sl2;
+      // ---- pass 2: p = exp2(s*sl2 - m*sl2), row sum, bf16 P -> TMEM (aliasing consumed S columns) ----
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tS + c * 32, r);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = (c * 32 + i < valid) ? fast_exp2(fmaf(__uint_as_float(r[i]), sl2, -mb)) : 0.f;
+          float p1 = (c * 32 + i + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(r[i + 1]), sl2, -mb)) : 0.f;
+          sum += p0 + p1;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(tS + c * 16, pk);
+      }
+      l_run = l_run * alpha + sum;
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);
+    }
+    // ---- epilogue: O / l -> bf16 -> global ----
+    mbar_wait(&o_full[x], 0);
+    tc_fence_after();
+    const int qrow = q0 + x * 128 + row;
+    const float inv = 1.f / l_run;
+    bf16* dst = p.out + ((size_t)((size_t)b * p.nq + (qrow < p.nq ? qrow : 0)) * p.H + h) * D;
+#pragma unroll 1
+    for (int c = 0; c < D / 8; ++c) {
+      uint32_t r[8];
+      tmem_ld8(tO + c * 8, r);
+      tmem_wait_ld();
+      if (qrow < p.nq) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+        *reinterpret_cast<uint4*>(dst + c * 8) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace vsb
+
+using namespace vsb;
+
+extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb, int nq,
+                              int nk, int H, int D, long long q_row_stride, long long q_batch_stride,
+                              long long kv_row_stride, long long kv_batch_stride, const int* host_kv_lens, float scale,
+                              void* stream) {
+  if (!q || !k || !v || !out || nb <= 0 || nq <= 0 || nk <= 0 || H <= 0) return fail(VSB_ERR_INVALID, "attn_flash: bad args");
+  if (D != 72 && D != 64) return fail(VSB_ERR_UNSUPPORTED, "attn_flash: head_dim %d (72 or 64 only)", D);
+  if ((q_row_stride % 8) || (q_batch_stride % 8) || (kv_row_stride % 8) || (kv_batch_stride % 8) || !aligned16(q) ||
+      !aligned16(k) || !aligned16(v) || !aligned16(out))
+    return fail(VSB_ERR_UNSUPPORTED, "attn_flash: strides must be multiples of 8 elements and pointers 16B-aligned");
+  if (host_kv_lens && nb > 8) return fail(VSB_ERR_UNSUPPORTED, "attn_flash: per-batch key lengths need nb <= 8");
+  if (nb > 65535 || H > 65535) return fail(VSB_ERR_UNSUPPORTED, "attn_flash: grid too large");
+  AttnParams prm;
+  prm.out = (bf16*)out;
+  prm.nb = nb;
+  prm.nq = nq;
+  prm.nk = nk;
+  prm.H = H;
+  prm.scale_log2 = scale * 1.4426950408889634f;
+  prm.has_lens = host_kv_lens ? 1 : 0;
+  for (int i = 0; i < 8; ++i) prm.lens[i] = 0;
+  if (host_kv_lens)
+    for (int i = 0; i < nb; ++i) {
+      if (host_kv_lens[i] < 1 || host_kv_lens[i] > nk) return fail(VSB_ERR_INVALID, "attn_flash: kv_lens[%d]=%d", i, host_kv_lens[i]);
+      prm.lens[i] = host_kv_lens[i];
+    }
+  // Two tensor maps per operand: the 64-wide SWIZZLE_128B chunk and (head_dim 72 only) the 16-wide SWIZZLE_32B
+  // chunk at d = 64..79.  The inner extent is D, so TMA zero-fills 72..79 and rows past nq / nk.
+  CUtensorMap tm[6];
+  const vsb_bf16* base[3] = {q, k, v};
+  for (int i = 0; i < 3; ++i) {
+    const long long rs = i == 0 ? q_row_stride : kv_row_stride, bs = i == 0 ? q_batch_stride : kv_batch_stride;
+    unsigned long long dims[4] = {(unsigned long long)D, (unsigned long long)H, (unsigned long long)(i == 0 ? nq : nk),
+                                  (unsigned long long)nb};
+    unsigned long long str[3] = {(unsigned long long)D * 2, (unsigned long long)rs * 2, (unsigned long long)bs * 2};
+    unsigned boxA[4] = {64, 1, 128, 1}, boxB[4] = {16, 1, 128, 1};
+    int rc = make_tmap_bf16(&tm[2 * i], base[i], 4, dims, str, boxA, CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc) return rc;
+    if (D == 72) {
+      rc = make_tmap_bf16(&tm[2 * i + 1], base[i], 4, dims, str, boxB, CU_TENSOR_MAP_SWIZZLE_32B);
+      if (rc) return rc;
+    } else {
+      tm[2 * i + 1] = tm[2 * i];  // unused by the head_dim-64 instantiation
+    }
+  }
+  dim3 grid((nq + 255) / 256, H, nb);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 72) {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash: smem attr: %s", cudaGetErrorString(e));
+      attr = true;
+    }
+    attn_flash_kernel<72><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash: smem attr: %s", cudaGetErrorString(e));
+      attr = true;
+    }
+    attn_flash_kernel<64><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+  }
+  return check_launch("attn_flash");
+}

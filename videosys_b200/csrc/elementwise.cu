@@ -1,0 +1,302 @@
+// vsb200 -- HBM-bound kernels of the STDiT3 block: AdaLN modulate, gate+residual, residual add, q/k RMSNorm.
+// One pass over the activation each (128-bit coalesced loads/stores, fp32 math, bf16 rounding at the eager
+// op boundaries so results track the reference's eager chain bit-for-bit wherever the reduction order allows).
+#include "vsb_common.cuh"
+#include "vsb_host.h"
+
+namespace vsb {
+
+union Vec8 {
+  uint4 u;
+  __nv_bfloat162 h[4];
+};
+
+__device__ __forceinline__ uint4 ld_stream(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void st_stream(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LayerNorm (no affine) + modulate + per-frame select.  One warp per token row; the row lives in registers.
+// kMaxVec: max 16-byte vectors per lane (C <= kMaxVec*32*8).
+// ---------------------------------------------------------------------------------------------------------
+template <int kMaxVec>
+__global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
+                                                          const bf16* __restrict__ mod,
+                                                          const uint8_t* __restrict__ x_mask, int shift_row,
+                                                          int scale_row, int B, int T, int S, int C, float eps,
+                                                          long long rows) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
+       row += (long long)gridDim.x * warps_per_block) {
+    const long long bt = row / S;
+    const int b = int(bt / T);
+    const int sel = (x_mask != nullptr && x_mask[bt] == 0) ? 1 : 0;
+    const bf16* shift = mod + ((size_t)(sel * B + b) * 6 + shift_row) * C;
+    const bf16* scale = mod + ((size_t)(sel * B + b) * 6 + scale_row) * C;
+    const bf16* xr = x + (size_t)row * C;
+    Vec8 v[kMaxVec];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int vi = lane + i * 32;
+      if (vi < nvec) {
+        v[i].u = ld_stream(xr + vi * 8);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(v[i].h[j]);
+          sum += f.x + f.y;
+        }
+      }
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int vi = lane + i * 32;
+      if (vi < nvec) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(v[i].h[j]);
+          float a = f.x - mean, c = f.y - mean;
+          sq += a * a + c * c;
+        }
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+    bf16* orow = out + (size_t)row * C;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      int vi = lane + i * 32;
+      if (vi < nvec) {
+        Vec8 sh, sc, o;
+        sh.u = __ldg(reinterpret_cast<const uint4*>(shift + vi * 8));
+        sc.u = __ldg(reinterpret_cast<const uint4*>(scale + vi * 8));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(v[i].h[j]);
+          float2 fs = __bfloat1622float2(sc.h[j]);
+          float2 fh = __bfloat1622float2(sh.h[j]);
+          // eager chain: n = bf16(LN(x)); g = bf16(1 + scale); m = bf16(n * g); out = bf16(m + shift)
+          float n0 = rbf((f.x - mean) * rstd), n1 = rbf((f.y - mean) * rstd);
+          float g0 = rbf(1.f + fs.x), g1 = rbf(1.f + fs.y);
+          float m0 = rbf(n0 * g0), m1 = rbf(n1 * g1);
+          o.h[j] = __floats2bfloat162_rn(m0 + fh.x, m1 + fh.y);
+        }
+        st_stream(orow + vi * 8, o.u);
+      }
+    }
+  }
+}
+
+__global__ void modulation_table_kernel(const bf16* __restrict__ table, const bf16* __restrict__ t,
+                                        const bf16* __restrict__ t0, bf16* __restrict__ mod, int B, int C, int rows) {
+  // mod[s, b, r, c] = bf16(table[r, c] + (s ? t0 : t)[b, r*C + c])
+  const int total = 2 * B * rows * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int c = i % C;
+    int r = (i / C) % rows;
+    int b = (i / (C * rows)) % B;
+    int s = i / (C * rows * B);
+    const bf16* src = (s == 1 && t0 != nullptr) ? t0 : t;
+    float v = __bfloat162float(table[r * C + c]) + __bfloat162float(src[(size_t)b * rows * C + r * C + c]);
+    mod[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// out = x + bf16(gate * y), gate row selected per frame; optional cache of the gated value.
+__global__ void __launch_bounds__(256) gate_residual_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
+                                                            bf16* __restrict__ out, bf16* __restrict__ cache,
+                                                            const bf16* __restrict__ mod,
+                                                            const uint8_t* __restrict__ x_mask, int gate_row, int B,
+                                                            int T, int S, int C, long long nvec_total) {
+  const int nvec = C >> 3;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec_total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / nvec;
+    const int vi = int(i - row * nvec);
+    const long long bt = row / S;
+    const int b = int(bt / T);
+    const int sel = (x_mask != nullptr && x_mask[bt] == 0) ? 1 : 0;
+    const bf16* gate = mod + ((size_t)(sel * B + b) * 6 + gate_row) * C;
+    Vec8 vx, vy, vg, o, g;
+    vx.u = ld_stream(x + i * 8);
+    vy.u = ld_stream(y + i * 8);
+    vg.u = __ldg(reinterpret_cast<const uint4*>(gate + vi * 8));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 fx = __bfloat1622float2(vx.h[j]), fy = __bfloat1622float2(vy.h[j]), fg = __bfloat1622float2(vg.h[j]);
+      g.h[j] = __floats2bfloat162_rn(fg.x * fy.x, fg.y * fy.y);
+      float2 gg = __bfloat1622float2(g.h[j]);
+      o.h[j] = __floats2bfloat162_rn(fx.x + gg.x, fx.y + gg.y);
+    }
+    if (cache != nullptr) st_stream(cache + i * 8, g.u);
+    st_stream(out + i * 8, o.u);
+  }
+}
+
+__global__ void __launch_bounds__(256) residual_add_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y,
+                                                           bf16* __restrict__ out, long long nvec_total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec_total;
+       i += (long long)gridDim.x * blockDim.x) {
+    Vec8 vx, vy, o;
+    vx.u = ld_stream(x + i * 8);
+    vy.u = ld_stream(y + i * 8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float2 fx = __bfloat1622float2(vx.h[j]), fy = __bfloat1622float2(vy.h[j]);
+      o.h[j] = __floats2bfloat162_rn(fx.x + fy.x, fx.y + fy.y);
+    }
+    st_stream(out + i * 8, o.u);
+  }
+}
+
+// In-place RMSNorm of the q and k heads of a packed [rows, 3, H, D] buffer.  A group of D/8 lanes owns one
+// (row, q|k, head) vector of D elements (D=72 -> 9 lanes, D=64 -> 8 lanes); groups are packed 3 per warp.
+template <int D>
+__global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ wq,
+                                                         const bf16* __restrict__ wk, long long rows, int H,
+                                                         float eps) {
+  constexpr int LPG = D / 8;        // lanes per group
+  constexpr int GPW = 32 / LPG;     // groups per warp (3 for D=72, 4 for D=64)
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPG, l = lane % LPG;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long ngroups = rows * 2 * H;  // (row, which in {q,k}, head)
+  unsigned member = 0;                     // lanes of my group
+  for (int i = 0; i < LPG; ++i) member |= 1u << (g * LPG + i);
+  for (long long base = warp * GPW; base < ngroups; base += nwarps * GPW) {
+    const long long gi = base + g;
+    const bool active = (g < GPW) && (gi < ngroups);
+    Vec8 v;
+    float ss = 0.f;
+    bf16* p = nullptr;
+    int which = 0;
+    if (active) {
+      const long long row = gi / (2 * H);
+      const int rem = int(gi - row * 2 * H);
+      which = rem / H;
+      const int h = rem - which * H;
+      p = qkv + ((size_t)row * 3 + which) * H * D + (size_t)h * D + l * 8;
+      v.u = *reinterpret_cast<const uint4*>(p);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(v.h[j]);
+        ss += f.x * f.x + f.y * f.y;
+      }
+    }
+    // reduce within the group (groups never straddle: lanes g*LPG .. g*LPG+LPG-1); all lanes take part in shuffles
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < LPG; ++i) tot += __shfl_sync(0xffffffffu, ss, (g < GPW ? g : 0) * LPG + i);
+    if (active) {
+      const float r = rsqrtf(tot / (float)D + eps);
+      Vec8 w, o;
+      w.u = __ldg(reinterpret_cast<const uint4*>((which ? wk : wq) + l * 8));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(v.h[j]), fw = __bfloat1622float2(w.h[j]);
+        // eager: h = bf16(x * rstd); out = bf16(w * h)
+        o.h[j] = __floats2bfloat162_rn(fw.x * rbf(f.x * r), fw.y * rbf(f.y * r));
+      }
+      *reinterpret_cast<uint4*>(p) = o.u;
+    }
+  }
+}
+
+static int grid_for(long long work_items, int per_block) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace vsb
+
+using namespace vsb;
+
+extern "C" int vsb_ln_modulate(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
+                               int shift_row, int scale_row, int B, int T, int S, int C, float eps, void* stream) {
+  if (!x || !out || !mod || B <= 0 || T <= 0 || S <= 0 || C <= 0) return fail(VSB_ERR_INVALID, "ln_modulate: bad args");
+  if (C % 8 || C > 2048 || !aligned16(x) || !aligned16(out) || !aligned16(mod))
+    return fail(VSB_ERR_UNSUPPORTED, "ln_modulate: need C %% 8 == 0, C <= 2048, 16B-aligned pointers (C=%d)", C);
+  if (shift_row < 0 || shift_row > 5 || scale_row < 0 || scale_row > 5) return fail(VSB_ERR_INVALID, "ln_modulate: row");
+  long long rows = (long long)B * T * S;
+  int grid = grid_for(rows, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 1280)
+    ln_modulate_kernel<5><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, (const bf16*)mod, x_mask, shift_row,
+                                                 scale_row, B, T, S, C, eps, rows);
+  else
+    ln_modulate_kernel<8><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, (const bf16*)mod, x_mask, shift_row,
+                                                 scale_row, B, T, S, C, eps, rows);
+  return check_launch("ln_modulate");
+}
+
+extern "C" int vsb_modulation_table(const vsb_bf16* table, const vsb_bf16* t, const vsb_bf16* t0, vsb_bf16* mod,
+                                    int B, int C, int rows, void* stream) {
+  if (!table || !t || !mod || B <= 0 || C <= 0 || rows <= 0) return fail(VSB_ERR_INVALID, "modulation_table: bad args");
+  int total = 2 * B * rows * C;
+  modulation_table_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const bf16*)table, (const bf16*)t,
+                                                                                  (const bf16*)t0, (bf16*)mod, B, C,
+                                                                                  rows);
+  return check_launch("modulation_table");
+}
+
+extern "C" int vsb_gate_residual(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* out, vsb_bf16* cache_out,
+                                 const vsb_bf16* mod, const uint8_t* x_mask, int gate_row, int B, int T, int S, int C,
+                                 void* stream) {
+  if (!x || !y || !out || !mod || B <= 0 || T <= 0 || S <= 0 || C <= 0)
+    return fail(VSB_ERR_INVALID, "gate_residual: bad args");
+  if (C % 8 || !aligned16(x) || !aligned16(y) || !aligned16(out) || !aligned16(mod) || (cache_out && !aligned16(cache_out)))
+    return fail(VSB_ERR_UNSUPPORTED, "gate_residual: need C %% 8 == 0 and 16B-aligned pointers");
+  long long nvec = (long long)B * T * S * (C / 8);
+  gate_residual_kernel<<<grid_for(nvec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)x, (const bf16*)y, (bf16*)out, (bf16*)cache_out, (const bf16*)mod, x_mask, gate_row, B, T, S, C,
+      nvec);
+  return check_launch("gate_residual");
+}
+
+extern "C" int vsb_residual_add(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* out, size_t n, void* stream) {
+  if (!x || !y || !out || n == 0) return fail(VSB_ERR_INVALID, "residual_add: bad args");
+  if (n % 8 || !aligned16(x) || !aligned16(y) || !aligned16(out))
+    return fail(VSB_ERR_UNSUPPORTED, "residual_add: need n %% 8 == 0 and 16B-aligned pointers");
+  long long nvec = (long long)(n / 8);
+  residual_add_kernel<<<grid_for(nvec, 256 * 4), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (const bf16*)y,
+                                                                                  (bf16*)out, nvec);
+  return check_launch("residual_add");
+}
+
+extern "C" int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D,
+                              float eps, void* stream) {
+  if (!qkv || !wq || !wk || rows == 0 || H <= 0) return fail(VSB_ERR_INVALID, "qk_rmsnorm: bad args");
+  if (!aligned16(qkv) || !aligned16(wq) || !aligned16(wk)) return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: alignment");
+  long long groups = (long long)rows * 2 * H;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 72)
+    qk_rmsnorm_kernel<72><<<grid_for(groups, 8 * 3), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)wk,
+                                                                     (long long)rows, H, eps);
+  else if (D == 64)
+    qk_rmsnorm_kernel<64><<<grid_for(groups, 8 * 4), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)wk,
+                                                                     (long long)rows, H, eps);
+  else
+    return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: head_dim %d (72 or 64 only)", D);
+  return check_launch("qk_rmsnorm");
+}

@@ -1,0 +1,150 @@
+"""Thin torch-tensor front end of the C-ABI (videosys_b200/_lib.py): pointer + shape marshalling only.
+
+Every function enqueues exactly one sm_100a kernel on the current CUDA stream.  CPU tensors are rejected:
+there is no fallback path.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+_initialised = set()
+
+
+def _init_dev(lib, dev):
+    if dev not in _initialised:
+        _lib.check(lib.vsb_init(dev), "init")
+        _initialised.add(dev)
+
+
+def _prep(*tensors):
+    lib = _lib.load()
+    dev = None
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.VsbError("vsb200 kernels need CUDA tensors (no CPU fallback)")
+        if not t.is_contiguous():
+            raise _lib.VsbError("vsb200 kernels need contiguous tensors")
+        dev = t.device.index if dev is None else dev
+    _init_dev(lib, dev)
+    return lib, torch.cuda.current_stream().cuda_stream
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _bf16(t, name):
+    if t is not None and t.dtype != torch.bfloat16:
+        raise _lib.VsbError(f"{name} must be bfloat16")
+
+
+def launch_count() -> int:
+    return int(_lib.load().vsb_launch_count())
+
+
+def modulation_table(table: torch.Tensor, t: torch.Tensor, t0: Optional[torch.Tensor]) -> torch.Tensor:
+    """[2, B, rows, C] = table + t (and + t0); rows = table.shape[0] (6 for blocks, 2 for the final layer)."""
+    lib, st = _prep(table, t, t0)
+    rows, Cc = table.shape
+    B = t.shape[0]
+    mod = torch.empty(2, B, rows, Cc, dtype=torch.bfloat16, device=table.device)
+    _lib.check(lib.vsb_modulation_table(_p(table), _p(t), _p(t0), _p(mod), B, Cc, rows, st), "modulation_table")
+    return mod
+
+
+def ln_modulate(x, mod, x_mask_u8, shift_row, scale_row, B, T, S, out=None, eps=1e-6):
+    lib, st = _prep(x, mod, x_mask_u8, out)
+    _bf16(x, "x")
+    Cc = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(
+        lib.vsb_ln_modulate(_p(x), _p(out), _p(mod), _p(x_mask_u8), shift_row, scale_row, B, T, S, Cc, eps, st),
+        "ln_modulate",
+    )
+    return out
+
+
+def gate_residual(x, y, mod, x_mask_u8, gate_row, B, T, S, out=None, cache_out=None):
+    lib, st = _prep(x, y, mod, x_mask_u8, out, cache_out)
+    Cc = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(
+        lib.vsb_gate_residual(_p(x), _p(y), _p(out), _p(cache_out), _p(mod), _p(x_mask_u8), gate_row, B, T, S, Cc, st),
+        "gate_residual",
+    )
+    return out
+
+
+def residual_add(x, y, out=None):
+    lib, st = _prep(x, y, out)
+    out = torch.empty_like(x) if out is None else out
+    _lib.check(lib.vsb_residual_add(_p(x), _p(y), _p(out), x.numel(), st), "residual_add")
+    return out
+
+
+def qk_rmsnorm_(qkv, wq, wk, H, D, eps=1e-6):
+    lib, st = _prep(qkv, wq, wk)
+    rows = qkv.numel() // (3 * H * D)
+    _lib.check(lib.vsb_qk_rmsnorm(_p(qkv), _p(wq), _p(wk), rows, H, D, eps, st), "qk_rmsnorm")
+    return qkv
+
+
+def attn_short(qkv, wq, wk, rope_cos, rope_sin, n_outer, n_inner, outer_stride, inner_stride, tok_stride, n, H, D,
+               scale, out=None, eps=1e-6):
+    lib, st = _prep(qkv, wq, wk, rope_cos, rope_sin, out)
+    rows = qkv.numel() // (3 * H * D)
+    out = torch.empty(rows, H * D, dtype=torch.bfloat16, device=qkv.device) if out is None else out
+    _lib.check(
+        lib.vsb_attn_short(_p(qkv), _p(out), _p(wq), _p(wk), _p(rope_cos), _p(rope_sin), n_outer, n_inner,
+                           outer_stride, inner_stride, tok_stride, n, H, D, eps, scale, st),
+        "attn_short",
+    )
+    return out
+
+
+def gemm_bias_act(a, w, bias=None, act: int = 0, out=None):
+    """out[..., N] = act(a[..., K] @ w[N, K]^T + bias)."""
+    lib, st = _prep(a, w, bias, out)
+    _bf16(a, "a"), _bf16(w, "w"), _bf16(bias, "bias")
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise _lib.VsbError("gemm: K mismatch")
+    out = torch.empty(*a.shape[:-1], N, dtype=torch.bfloat16, device=a.device) if out is None else out
+    _lib.check(lib.vsb_gemm_bias_act(_p(a), _p(w), _p(bias), _p(out), M, N, K, act, st), "gemm_bias_act")
+    return out
+
+
+def attn_flash(q, k, v, nb, nq, nk, H, D, q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, scale,
+               kv_lens: Optional[Sequence[int]] = None, out=None):
+    """q/k/v: tensors whose data_ptr() is the first element of the strided view (may be slices of one buffer)."""
+    lib = _lib.load()
+    if not q.is_cuda:
+        raise _lib.VsbError("vsb200 kernels need CUDA tensors (no CPU fallback)")
+    _init_dev(lib, q.device.index)
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.empty(nb, nq, H * D, dtype=torch.bfloat16, device=q.device) if out is None else out
+    lens = None
+    if kv_lens is not None:
+        lens = (C.c_int * len(kv_lens))(*[int(v_) for v_ in kv_lens])
+    _lib.check(
+        lib.vsb_attn_flash(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), nb, nq, nk, H, D, q_row_stride,
+                           q_batch_stride, kv_row_stride, kv_batch_stride, lens, scale, st),
+        "attn_flash",
+    )
+    return out
+
+
+def pab_gate(on: bool, timestep: Optional[int], count: int, rng: int, lo: int, hi: int, steps: int):
+    lib = _lib.load()
+    c = C.c_int(count)
+    rc = lib.vsb_pab_gate(int(bool(on)), int(timestep is not None), int(timestep or 0), C.byref(c), int(rng or 1),
+                          int(lo), int(hi), int(steps))
+    _lib.check(rc, "pab_gate")
+    return bool(rc), c.value

@@ -1,0 +1,491 @@
+"""STDiT3 (OpenSora v1.2) denoiser whose block forward runs on the vsb200 sm_100a kernels.
+
+Drop-in for videosys/models/transformers/open_sora_transformer_3d.py: ``STDiT3Config`` / ``STDiT3`` keep the
+constructor arguments, the ``forward(x, timestep, y, all_timesteps, mask, x_mask, fps, height, width)`` signature,
+``enable_parallel`` and the exact ``state_dict`` key set / shapes, so reference checkpoints
+load with ``load_state_dict``.  What differs is *how* a step executes:
+
+  * every Linear is ``vsb_gemm_bias_act`` (tcgen05, bias / tanh-GELU fused in the epilogue);
+  * LayerNorm + AdaLN modulate + the t/t0 frame select is ONE pass (``vsb_ln_modulate``), gate + select +
+    residual (+ PAB cache write) is ONE pass (``vsb_gate_residual``);
+  * spatial / cross attention run ``vsb_attn_flash`` straight on the packed qkv / kv buffers (strided TMA views);
+    temporal attention runs ``vsb_attn_short`` on the token-major tensor -- no ``rearrange`` copies anywhere;
+  * the PAB gate is evaluated once per block from a HOST integer timestep (one D2H sync per step instead of
+    up to three per block: reference :188,190,232), cached tensors are replayed with one ``vsb_residual_add``;
+  * the DSP dimension switch is a peer-store kernel (``DspP2P``) with NCCL ``all_to_all_single`` as fallback.
+
+The embedders / final layer (< 2 % of the step) stay as torch ops.
+There is no CPU execution path: ``forward`` raises on CPU tensors.
+"""
+import math
+import os
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ... import kernels
+from ...core.distributed import comm
+from ...core.distributed.parallel_mgr import ParallelManager
+from ...core.pab import pab_mgr
+
+
+class STDiT3Config:
+    model_type = "STDiT3"
+
+    def __init__(
+        self,
+        input_size=(None, None, None),
+        input_sq_size=512,
+        in_channels=4,
+        patch_size=(1, 2, 2),
+        hidden_size=1152,
+        depth=28,
+        num_heads=16,
+        mlp_ratio=4.0,
+        class_dropout_prob=0.1,
+        pred_sigma=True,
+        drop_path=0.0,
+        caption_channels=4096,
+        model_max_length=300,
+        qk_norm=True,
+        enable_flash_attn=False,
+        only_train_temporal=False,
+        freeze_y_embedder=False,
+        skip_y_embedder=False,
+        **kwargs,
+    ):
+        args = dict(locals())
+        args.pop("self"), args.pop("kwargs")
+        for k, v in args.items():
+            setattr(self, k, v)
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+
+# ---- parameter holders (names/shapes = the reference modules; no forward logic lives here) -------------------
+class _NormWeight(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim))
+
+
+class _SelfAttnParams(nn.Module):
+    def __init__(self, dim, qk_norm, head_dim):
+        super().__init__()
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.q_norm = _NormWeight(head_dim) if qk_norm else nn.Identity()
+        self.k_norm = _NormWeight(head_dim) if qk_norm else nn.Identity()
+        self.proj = nn.Linear(dim, dim)
+
+
+class _CrossAttnParams(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.q_linear = nn.Linear(dim, dim)
+        self.kv_linear = nn.Linear(dim, dim * 2)
+        self.proj = nn.Linear(dim, dim)
+
+
+class _MlpParams(nn.Module):
+    def __init__(self, fin, hidden, fout=None):
+        super().__init__()
+        self.fc1 = nn.Linear(fin, hidden)
+        self.fc2 = nn.Linear(hidden, fout or fin)
+
+
+class STDiT3Block(nn.Module):
+    """Parameters + PAB state of one block (reference :99-150); the forward lives in STDiT3._run_block."""
+
+    def __init__(self, hidden_size, num_heads, mlp_ratio=4.0, qk_norm=False, temporal=False, block_idx=None):
+        super().__init__()
+        self.temporal = temporal
+        self.hidden_size = hidden_size
+        self.num_heads = num_heads
+        self.attn = _SelfAttnParams(hidden_size, qk_norm, hidden_size // num_heads)
+        self.cross_attn = _CrossAttnParams(hidden_size)
+        self.mlp = _MlpParams(hidden_size, int(hidden_size * mlp_ratio))
+        self.scale_shift_table = nn.Parameter(torch.randn(6, hidden_size) / hidden_size**0.5)
+        self.parallel_manager: Optional[ParallelManager] = None
+        self.block_idx = block_idx
+        self.reset_pab()
+
+    def reset_pab(self):
+        self.attn_count = 0
+        self.cross_count = 0
+        self.last_attn = None
+        self.last_cross = None
+
+
+class _Embed2(nn.Module):
+    """Linear -> SiLU -> Linear on a 256-wide sinusoid (TimestepEmbedder / SizeEmbedder parameters)."""
+
+    def __init__(self, hidden):
+        super().__init__()
+        self.mlp = nn.Sequential(nn.Linear(256, hidden), nn.SiLU(), nn.Linear(hidden, hidden))
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch, cin, hidden):
+        super().__init__()
+        self.proj = nn.Conv3d(cin, hidden, kernel_size=patch, stride=patch)
+
+
+class _Caption(nn.Module):
+    def __init__(self, cin, hidden, tokens):
+        super().__init__()
+        self.y_proj = _MlpParams(cin, hidden, hidden)
+        self.register_buffer("y_embedding", torch.randn(tokens, cin) / cin**0.5)
+
+
+class _Final(nn.Module):
+    def __init__(self, hidden, out_features):
+        super().__init__()
+        self.linear = nn.Linear(hidden, out_features)
+        self.scale_shift_table = nn.Parameter(torch.randn(2, hidden) / hidden**0.5)
+
+
+class _Rope(nn.Module):
+    def __init__(self, dim, theta=10000.0):
+        super().__init__()
+        self.freqs = nn.Parameter(1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim)), requires_grad=False)
+
+
+def _sinusoid(t: torch.Tensor, dim: int = 256) -> torch.Tensor:
+    half = dim // 2
+    f = torch.exp(-math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=t.device) / half)
+    a = t[:, None].float() * f[None]
+    return torch.cat([a.cos(), a.sin()], dim=-1)
+
+
+class STDiT3(nn.Module):
+    config_class = STDiT3Config
+
+    def __init__(self, config: STDiT3Config):
+        super().__init__()
+        self.config = config
+        C = config.hidden_size
+        self.pred_sigma = config.pred_sigma
+        self.in_channels = config.in_channels
+        self.out_channels = config.in_channels * 2 if config.pred_sigma else config.in_channels
+        self.depth, self.hidden_size, self.num_heads = config.depth, C, config.num_heads
+        self.mlp_ratio = config.mlp_ratio
+        self.patch_size = tuple(config.patch_size)
+        self.input_sq_size = config.input_sq_size
+
+        self.rope = _Rope(C // config.num_heads)
+        self.x_embedder = _PatchEmbed(self.patch_size, config.in_channels, C)
+        self.t_embedder = _Embed2(C)
+        self.fps_embedder = _Embed2(C)
+        self.t_block = nn.Sequential(nn.SiLU(), nn.Linear(C, 6 * C, bias=True))
+        self.y_embedder = _Caption(config.caption_channels, C, config.model_max_length)
+        mk = lambda temporal: nn.ModuleList(  # noqa: E731
+            [STDiT3Block(C, config.num_heads, config.mlp_ratio, config.qk_norm, temporal, i) for i in range(config.depth)]
+        )
+        self.spatial_blocks = mk(False)
+        self.temporal_blocks = mk(True)
+        self.final_layer = _Final(C, int(math.prod(self.patch_size)) * self.out_channels)
+        self.initialize_weights()
+        self.parallel_manager: Optional[ParallelManager] = None
+        self._dsp: Optional[comm.DspP2P] = None
+        self._pos_cache = {}
+        self._rope_cache = {}
+
+    # ------------------------------------------------------------------------------------------------------
+    def initialize_weights(self):
+        """Same scheme as the reference (:491-511): xavier-uniform Linears, zero biases, fps_embedder tail and the
+        temporal blocks' output projections zero."""
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.xavier_uniform_(m.weight)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+        nn.init.normal_(self.fps_embedder.mlp[0].weight, std=0.02)
+        nn.init.zeros_(self.fps_embedder.mlp[2].weight)
+        for blk in self.temporal_blocks:
+            nn.init.zeros_(blk.attn.proj.weight)
+            nn.init.zeros_(blk.cross_attn.proj.weight)
+            nn.init.zeros_(blk.mlp.fc2.weight)
+
+    def enable_parallel(self, dp_size=None, sp_size=None, enable_cp=None, parallel_mgr=None):
+        if parallel_mgr is not None:
+            self.parallel_manager = parallel_mgr
+        else:
+            cp_size = 1
+            if enable_cp and sp_size % 2 == 0:
+                sp_size, cp_size = sp_size // 2, 2
+            self.parallel_manager = ParallelManager(dp_size, cp_size, sp_size)
+        for blk in [*self.spatial_blocks, *self.temporal_blocks]:
+            blk.parallel_manager = self.parallel_manager
+
+    def reset_pab_state(self):
+        for blk in [*self.spatial_blocks, *self.temporal_blocks]:
+            blk.reset_pab()
+
+    def get_dynamic_size(self, x):
+        _, _, T, H, W = x.size()
+        p = self.patch_size
+        return (-(-T // p[0]), -(-H // p[1]), -(-W // p[2]))
+
+    # ---- glue (torch ops; < 2 % of the step) ---------------------------------------------------------------
+    def _pos_embed(self, h, w, scale, base_size, dtype, device):
+        key = (h, w, float(scale), base_size, dtype, str(device))
+        if key not in self._pos_cache:
+            half = self.hidden_size // 2
+            # the reference keeps inv_freq as a module buffer, so model.to(bf16) rounds it (embeddings.py:236-237)
+            inv = (1.0 / (10000 ** (torch.arange(0, half, 2).float() / half))).to(dtype).to(device)
+            gh = torch.arange(h, device=device) / scale * (base_size / h)
+            gw = torch.arange(w, device=device) / scale * (base_size / w)
+            gh, gw = torch.meshgrid(gw, gh, indexing="ij")
+            gh, gw = gh.t().reshape(-1), gw.t().reshape(-1)
+            sc = lambda v: torch.cat((torch.sin(torch.einsum("i,d->id", v, inv)), torch.cos(torch.einsum("i,d->id", v, inv))), -1)  # noqa: E731
+            self._pos_cache[key] = torch.cat([sc(gh), sc(gw)], dim=-1).unsqueeze(0).to(dtype)
+        return self._pos_cache[key]
+
+    def _rope_tables(self, n, device):
+        key = (n, str(device))
+        if key not in self._rope_cache:
+            f = self.rope.freqs.float()
+            ang = torch.einsum("i,j->ij", torch.arange(n, dtype=torch.float32, device=device), f.to(device))
+            ang = ang.repeat_interleave(2, dim=-1)
+            self._rope_cache[key] = (ang.cos().contiguous(), ang.sin().contiguous())
+        return self._rope_cache[key]
+
+    def _embed(self, emb: _Embed2, v: torch.Tensor, dtype) -> torch.Tensor:
+        return emb.mlp(_sinusoid(v).to(dtype))
+
+    def encode_text(self, y, mask=None):
+        p = self.y_embedder.y_proj
+        y = F.linear(F.gelu(F.linear(y, p.fc1.weight, p.fc1.bias), approximate="tanh"), p.fc2.weight, p.fc2.bias)
+        if mask is not None:
+            if mask.shape[0] != y.shape[0]:
+                mask = mask.repeat(y.shape[0] // mask.shape[0], 1)
+            mask = mask.squeeze(1).squeeze(1)
+            y = y.squeeze(1).masked_select(mask.unsqueeze(-1) != 0).view(1, -1, self.hidden_size)
+            y_lens = mask.sum(dim=1).tolist()
+        else:
+            y_lens = [y.shape[2]] * y.shape[0]
+            y = y.squeeze(1).view(1, -1, self.hidden_size)
+        return y, y_lens
+
+    # ---- one block on the kernels ----------------------------------------------------------------------------
+    def _switch(self, x4: torch.Tensor, T: int, S: int, to_spatial_shard: bool) -> torch.Tensor:
+        """DSP dimension switch of a [B, t, s, C] tensor (global extents T, S)."""
+        pm = self.parallel_manager
+        if self._dsp is not None:
+            return self._dsp.switch(x4.contiguous(), T, S, to_spatial_shard)
+        if to_spatial_shard:
+            return comm.all_to_all_with_pad(x4, pm.sp_group, scatter_dim=2, gather_dim=1,
+                                            scatter_pad=comm.get_pad("spatial"), gather_pad=comm.get_pad("temporal"))
+        return comm.all_to_all_with_pad(x4, pm.sp_group, scatter_dim=1, gather_dim=2,
+                                        scatter_pad=comm.get_pad("temporal"), gather_pad=comm.get_pad("spatial"))
+
+    def _run_block(self, blk: STDiT3Block, x, y_tok, kv_lens, t_mlp, t0_mlp, mask_u8, B, T, S, Tg, Sg, ts_int):
+        """x: [B, T*S, C] resident layout (T full, S local); Tg/Sg are the global extents (== T, S when sp == 1)."""
+        K = kernels
+        C, H = self.hidden_size, self.num_heads
+        D = C // H
+        sp = self.parallel_manager.sp_size if self.parallel_manager is not None else 1
+        mod = K.modulation_table(blk.scale_shift_table, t_mlp, t0_mlp)
+        pab_on = pab_mgr.enable_pab()
+
+        # ---- self attention ----
+        reuse = False
+        if pab_on:
+            gate = pab_mgr.if_broadcast_temporal if blk.temporal else pab_mgr.if_broadcast_spatial
+            reuse, blk.attn_count = gate(ts_int, blk.attn_count)
+        if reuse:
+            K.residual_add(x, blk.last_attn, out=x)
+        else:
+            xm = K.ln_modulate(x, mod, mask_u8, 0, 1, B, T, S)
+            a = blk.attn
+            wq = a.q_norm.weight if hasattr(a.q_norm, "weight") else None
+            wk = a.k_norm.weight if hasattr(a.k_norm, "weight") else None
+            if wq is None:
+                raise RuntimeError("vsb200 STDiT3 kernels implement qk_norm=True (the OpenSora v1.2 configuration)")
+            if blk.temporal:
+                qkv = K.gemm_bias_act(xm, a.qkv.weight, a.qkv.bias)
+                cos, sin = self._rope_tables(T, x.device)
+                if T >= 30:
+                    raise RuntimeError("temporal sequences >= 30 frames are not supported by vsb_attn_short")
+                o = K.attn_short(qkv.view(-1, 3, H, D), wq, wk, cos, sin, B, S, T * S, 1, S, T, H, D, D**-0.5)
+            else:
+                if sp > 1:  # S-sharded -> T-sharded: attention needs every patch of a frame
+                    xm = self._switch(xm.view(B, T, S, C), Tg, Sg, to_spatial_shard=False)
+                    Ta, Sa = xm.shape[1], xm.shape[2]
+                    xm = xm.reshape(B, Ta * Sa, C)
+                else:
+                    Ta, Sa = T, S
+                qkv = K.gemm_bias_act(xm, a.qkv.weight, a.qkv.bias)
+                if Sa >= 30:
+                    K.qk_rmsnorm_(qkv, wq, wk, H, D)
+                    q3 = qkv.view(-1, 3, C)
+                    o = K.attn_flash(q3[:, 0], q3[:, 1], q3[:, 2], B * Ta, Sa, Sa, H, D, 3 * C, Sa * 3 * C, 3 * C,
+                                     Sa * 3 * C, D**-0.5)
+                else:
+                    o = K.attn_short(qkv.view(-1, 3, H, D), wq, wk, None, None, B * Ta, 1, Sa, 0, 1, Sa, H, D, D**-0.5)
+            y = K.gemm_bias_act(o.view(-1, C), a.proj.weight, a.proj.bias)
+            if not blk.temporal and sp > 1:
+                y = self._switch(y.view(B, Ta, Sa, C), Tg, Sg, to_spatial_shard=True)
+            cache = None
+            if pab_on:
+                if blk.last_attn is None or blk.last_attn.shape != x.shape:
+                    blk.last_attn = torch.empty_like(x)
+                cache = blk.last_attn
+            K.gate_residual(x, y.reshape(x.shape), mod, mask_u8, 2, B, T, S, out=x, cache_out=cache)
+
+        # ---- cross attention ----
+        reuse = False
+        if pab_on:
+            reuse, blk.cross_count = pab_mgr.if_broadcast_cross(ts_int, blk.cross_count)
+        if reuse:
+            K.residual_add(x, blk.last_cross, out=x)
+        else:
+            c = blk.cross_attn
+            q = K.gemm_bias_act(x, c.q_linear.weight, c.q_linear.bias)
+            kv = K.gemm_bias_act(y_tok, c.kv_linear.weight, c.kv_linear.bias)
+            Lv = kv.shape[-2] // B
+            kv2 = kv.view(-1, 2, C)
+            o = K.attn_flash(q, kv2[:, 0], kv2[:, 1], B, T * S, Lv, H, D, C, T * S * C, 2 * C, Lv * 2 * C, D**-0.5,
+                             kv_lens=kv_lens)
+            out = blk.last_cross if (pab_on and blk.last_cross is not None and blk.last_cross.shape == x.shape) else None
+            xc = K.gemm_bias_act(o, c.proj.weight, c.proj.bias, out=out)
+            if pab_on:
+                blk.last_cross = xc
+            K.residual_add(x, xc.view(x.shape), out=x)
+
+        # ---- MLP ----
+        xm = K.ln_modulate(x, mod, mask_u8, 3, 4, B, T, S)
+        h = K.gemm_bias_act(xm, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=1)
+        y = K.gemm_bias_act(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias)
+        K.gate_residual(x, y, mod, mask_u8, 5, B, T, S, out=x)
+        return x
+
+    # ---- STDiT3.forward --------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, timestep, y, all_timesteps=None, mask=None, x_mask=None, fps=None, height=None, width=None,
+                **kwargs):
+        if not x.is_cuda:
+            raise RuntimeError("videosys_b200.STDiT3 runs on sm_100a CUDA devices only (no CPU path)")
+        dtype = self.x_embedder.proj.weight.dtype
+        if dtype != torch.bfloat16:
+            raise RuntimeError("videosys_b200.STDiT3 kernels are bf16: call model.to(torch.bfloat16)")
+        pm = self.parallel_manager
+        sp = pm.sp_size if pm is not None else 1
+        if pm is not None and pm.cp_size > 1:
+            raise NotImplementedError("cp (CFG-batch split) is dormant in every reference pipeline (SURVEY 2.2)")
+        _, _, Tx, Hx, Wx = x.size()
+        T, Hn, Wn = self.get_dynamic_size(x)
+        B = x.size(0)
+        C = self.hidden_size
+        x = x.to(dtype)
+        timestep = timestep.to(dtype)
+        y = y.to(dtype)
+
+        S = Hn * Wn
+        base_size = round(S**0.5)
+        resolution_sq = (height[0].item() * width[0].item()) ** 0.5
+        pos = self._pos_embed(Hn, Wn, resolution_sq / self.input_sq_size, base_size, dtype, x.device)
+
+        t = self._embed(self.t_embedder, timestep, dtype)
+        f = fps.unsqueeze(1)
+        if f.shape[0] != B:
+            f = f.repeat(B // f.shape[0], 1)
+        fps_e = self._embed(self.fps_embedder, f.reshape(-1), dtype).reshape(B, -1)
+        t = t + fps_e
+        t_mlp = self.t_block(t)
+        t0 = t0_mlp = None
+        mask_u8 = None
+        if x_mask is not None:
+            t0 = self._embed(self.t_embedder, torch.zeros_like(timestep), dtype) + fps_e
+            t0_mlp = self.t_block(t0)
+            mask_u8 = x_mask.to(torch.uint8).contiguous()
+
+        if self.config.skip_y_embedder:
+            y_lens = mask.long().tolist() if isinstance(mask, torch.Tensor) else mask
+            y_tok = y
+        else:
+            y_tok, y_lens = self.encode_text(y, mask)
+        y_tok = y_tok.reshape(-1, C).contiguous()
+        Lv = y_tok.shape[0] // B
+        kv_lens = [min(int(m), Lv) for m in y_lens]
+        if min(kv_lens) < 1:
+            raise RuntimeError("cross attention needs at least one text token per sample")
+        if all(m == Lv for m in kv_lens):
+            kv_lens = None
+
+        # patch embed (right/bottom zero pad to the patch grid, then a strided conv)
+        p = self.patch_size
+        if Wx % p[2]:
+            x = F.pad(x, (0, p[2] - Wx % p[2]))
+        if Hx % p[1]:
+            x = F.pad(x, (0, 0, 0, p[1] - Hx % p[1]))
+        if Tx % p[0]:
+            x = F.pad(x, (0, 0, 0, 0, 0, p[0] - Tx % p[0]))
+        h = self.x_embedder.proj(x).flatten(2).transpose(1, 2)
+        h = h.reshape(B, T, S, C) + pos
+
+        Tg, Sg = T, S
+        if sp > 1:
+            comm.set_pad("temporal", T, pm.sp_group)
+            comm.set_pad("spatial", S, pm.sp_group)
+            comm.set_pad("batch", B, pm.sp_group)
+            h = comm.split_sequence(h, pm.sp_group, dim=2, grad_scale="down", pad=comm.get_pad("spatial"))
+            S = h.shape[2]
+            self._ensure_dsp(B, T, S, C, x.device)
+        h = h.reshape(B, T * S, C).contiguous()
+
+        ts_int = int(timestep[0]) if pab_mgr.enable_pab() else None
+        depth = kwargs.get("valid_depth", self.depth)
+        for d in range(depth):
+            h = self._run_block(self.spatial_blocks[d], h, y_tok, kv_lens, t_mlp, t0_mlp, mask_u8, B, T, S, Tg, Sg, ts_int)
+            h = self._run_block(self.temporal_blocks[d], h, y_tok, kv_lens, t_mlp, t0_mlp, mask_u8, B, T, S, Tg, Sg, ts_int)
+        if kwargs.get("return_tokens", False):
+            return h
+
+        if sp > 1:
+            h = comm.gather_sequence(h.reshape(B, T, S, C), pm.sp_group, dim=2, grad_scale="up", pad=comm.get_pad("spatial"))
+            S = h.shape[2]
+            h = h.reshape(B, T * S, C)
+
+        out = self._final_layer(h, t, x_mask, t0, B, T, S)
+        out = self.unpatchify(out, T, Hn, Wn, Tx, Hx, Wx)
+        return out.to(torch.float32)
+
+    def _ensure_dsp(self, B, T, Sl, C, device):
+        """Lazily build the P2P windows (largest of the two layouts, padded extents)."""
+        if self._dsp is not None or os.environ.get("VSB_DSP_P2P", "1") == "0":
+            return
+        pm = self.parallel_manager
+        w = pm.sp_size
+        Tl = -(-T // w)
+        elems = B * max(T * Sl, Tl * Sl * w) * C
+        self._dsp = comm.DspP2P(pm.sp_group, elems, device)
+
+    def _final_layer(self, x, t, x_mask, t0, B, T, S):
+        """T2IFinalLayer (reference :75-87), including its quirk: the t0 branch normalises the already
+        t-modulated tensor because line :81 rebinds x."""
+        fl = self.final_layer
+        C = self.hidden_size
+        ln = lambda v: F.layer_norm(v, (C,), None, None, 1e-6)  # noqa: E731
+        shift, scale = (fl.scale_shift_table[None] + t[:, None]).chunk(2, dim=1)
+        out = ln(x) * (1 + scale) + shift
+        if x_mask is not None:
+            shift0, scale0 = (fl.scale_shift_table[None] + t0[:, None]).chunk(2, dim=1)
+            out0 = ln(out) * (1 + scale0) + shift0
+            out = torch.where(x_mask[:, :, None, None], out.view(B, T, S, C), out0.view(B, T, S, C)).view(B, T * S, C)
+        return fl.linear(out)
+
+    def unpatchify(self, x, N_t, N_h, N_w, R_t, R_h, R_w):
+        B = x.shape[0]
+        Tp, Hp, Wp = self.patch_size
+        x = x.reshape(B, N_t, N_h, N_w, Tp, Hp, Wp, self.out_channels)
+        x = x.permute(0, 7, 1, 4, 2, 5, 3, 6).reshape(B, self.out_channels, N_t * Tp, N_h * Hp, N_w * Wp)
+        return x[:, :, :R_t, :R_h, :R_w]
+
+
+def STDiT3_XL_2(from_pretrained=None, **kwargs):
+    if from_pretrained is not None:
+        raise NotImplementedError("checkpoint download is out of scope; build the model and load_state_dict()")
+    return STDiT3(STDiT3Config(depth=28, hidden_size=1152, patch_size=(1, 2, 2), num_heads=16, **kwargs))
