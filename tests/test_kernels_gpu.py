@@ -71,9 +71,10 @@ def test_ln_modulate(B, T, S, C):
         n = O.layer_norm_noaffine(x)
         want = O.frame_select(x_mask, O.t2i_modulate(n, mods[sh], mods[sc]), O.t2i_modulate(n, mods0[sh], mods0[sc]), T, S)
         got = K.ln_modulate(x.to(dev), mod, _mask_u8(x_mask, dev), sh, sc, B, T, S)
-        _ulp_report(f"ln_modulate C={C} rows=({sh},{sc})", got, want)
+        # a 1-ulp flip of the product before the shift add is up to 2 ulps of a smaller sum: measure at row scale
+        _ulp_report(f"ln_modulate C={C} rows=({sh},{sc})", got, want, row_floor=0.25)
         got2 = K.ln_modulate(x.to(dev), mod, None, sh, sc, B, T, S)
-        _ulp_report(f"ln_modulate nomask C={C}", got2, O.t2i_modulate(n, mods[sh], mods[sc]))
+        _ulp_report(f"ln_modulate nomask C={C}", got2, O.t2i_modulate(n, mods[sh], mods[sc]), row_floor=0.25)
 
 
 @pytest.mark.parametrize("B,T,S,C", [(2, 5, 36, 288), (2, 3, 50, 1152)])
@@ -177,7 +178,7 @@ def _gemm_check(name, M, N, K_, act):
     # one bf16 rounding of the result (half an ulp) + fp32 accumulation noise; with the GELU epilogue the
     # pre-activation is itself rounded to bf16 first (the eager rounding point), so a flip there moves the
     # output by up to ~1.1 pre-activation ulps more
-    tol = _bf16_ulp(exact.float().clamp_min(0.05)).double() * (0.51 if not act else 2.2) + 1e-3
+    tol = _bf16_ulp(exact.float().abs().clamp_min(0.05)).double() * (0.51 if not act else 2.2) + 1e-3
     bad = err_exact > tol
     if bad.any():
         idx = bad.nonzero()
@@ -210,6 +211,26 @@ def _gemm_check(name, M, N, K_, act):
 ])
 def test_gemm(M, N, K_, act):
     _gemm_check(f"g{M}x{N}x{K_}", M, N, K_, act)
+
+
+@pytest.mark.parametrize("M,N,K_,act", [
+    (1024, 256, 128, 0),    # one CTA pair per tile, BN=256
+    (1100, 1152, 1152, 0),  # BN=192, M tail leaves the peer CTA of the last pair without rows
+    (1500, 3456, 1152, 0),
+    (1024, 4608, 1152, 1),  # BN=256 + GELU
+    (2000, 1152, 4608, 0),  # long K
+    (256 * 80, 768, 192, 0),  # more tiles than CTA pairs: accumulator / stage phases wrap
+])
+def test_gemm_cta_pair(M, N, K_, act):
+    """tcgen05 cta_group::2 variant (selected with vsb_set_option("gemm_2sm", 1))."""
+    from videosys_b200 import kernels as K
+
+    _dev()
+    K.set_option("gemm_2sm", 1)
+    try:
+        _gemm_check(f"p{M}x{N}x{K_}", M, N, K_, act)
+    finally:
+        K.set_option("gemm_2sm", 0)
 
 
 def test_gemm_many_tiles_persistent():

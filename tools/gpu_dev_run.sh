@@ -14,10 +14,31 @@ for g in "$@"; do
   case $g in
     elem)  run elem 300 tests/test_kernels_gpu.py -k "ln_modulate or gate_residual or qk_rmsnorm" ;;
     short) run short 300 tests/test_kernels_gpu.py -k "attn_short" ;;
-    gemm)  run gemm 300 tests/test_kernels_gpu.py -k "gemm" ;;
+    gemm)  run gemm 300 tests/test_kernels_gpu.py -k "gemm and not cta_pair" ;;
+    gemm2) run gemm2 300 tests/test_kernels_gpu.py -k "cta_pair" ;;
+    bench2sm) timeout 900 python bench.py --opt gemm_2sm=1 $BENCH_ARGS > gpurun_out/bench2sm.json 2> gpurun_out/bench2sm.err
+           echo "bench2sm exit $? : $(tail -c 300 gpurun_out/bench2sm.json)" | tee -a gpurun_out/summary.txt ;;
     flash) run flash 300 tests/test_kernels_gpu.py -k "attn_flash" ;;
     model) run model 600 tests/test_model_gpu.py ;;
     all)   run all 900 tests ;;
+    smoke) echo "=== smoke ===" | tee -a gpurun_out/summary.txt
+           timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
+           echo "exit $? : $(tail -n 1 gpurun_out/smoke.log)" | tee -a gpurun_out/summary.txt ;;
+    bench) echo "=== bench ===" | tee -a gpurun_out/summary.txt
+           timeout 900 python bench.py $BENCH_ARGS > gpurun_out/bench.json 2> gpurun_out/bench.err
+           echo "exit $? : $(tail -c 600 gpurun_out/bench.json)" | tee -a gpurun_out/summary.txt
+           tail -n 5 gpurun_out/bench.err ;;
+    bench240) timeout 600 python bench.py --workload opensora_240p_51f_30step $BENCH_ARGS > gpurun_out/bench240.json 2> gpurun_out/bench240.err
+           echo "exit $? : $(tail -c 400 gpurun_out/bench240.json)" | tee -a gpurun_out/summary.txt ;;
+    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+              python bench.py --steps 1 --warmup 1 --depth 2 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
+           echo "ncu_list exit $?" | tee -a gpurun_out/summary.txt ;;
+    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 14 -c 4 -o gpurun_out/prof_gemm -f \
+              python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
+           echo "ncu_gemm exit $?" | tee -a gpurun_out/summary.txt ;;
+    ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_flash -s 2 -c 2 -o gpurun_out/prof_attn -f \
+              python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline > gpurun_out/ncu_attn.log 2>&1
+           echo "ncu_attn exit $?" | tee -a gpurun_out/summary.txt ;;
     *)     run "custom" 600 $g ;;
   esac
 done

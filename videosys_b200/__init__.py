@@ -1,0 +1,10 @@
+"""vsb200: the VideoSys DiT denoising hot path, B200-native (sm_100a CUDA behind a C-ABI).
+
+Same top-level names as ``videosys/__init__.py:1-22`` for the path in scope (OpenSora); see DESIGN.md for scope.
+"""
+from .core.distributed.parallel_mgr import initialize  # noqa: F401
+from .core.engine.engine import VideoSysEngine  # noqa: F401
+from .core.pab.pab_mgr import PABConfig  # noqa: F401
+from .pipelines.open_sora.pipeline_open_sora import OpenSoraConfig, OpenSoraPABConfig, OpenSoraPipeline  # noqa: F401
+
+__all__ = ["initialize", "VideoSysEngine", "PABConfig", "OpenSoraConfig", "OpenSoraPABConfig", "OpenSoraPipeline"]

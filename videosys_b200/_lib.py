@@ -17,6 +17,7 @@ SIGNATURES = {
     "vsb_last_error": (C.c_char_p, []),
     "vsb_init": (_i, [_i]),
     "vsb_launch_count": (C.c_ulonglong, []),
+    "vsb_set_option": (_i, [C.c_char_p, _i]),
     "vsb_ln_modulate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "vsb_modulation_table": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "vsb_gate_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -77,6 +77,18 @@ extern "C" int vsb_init(int device) {
   return load_encode();
 }
 
+namespace vsb {
+extern int g_opt_gemm_2sm;
+}
+extern "C" int vsb_set_option(const char* name, int value) {
+  if (!name) return fail(VSB_ERR_INVALID, "set_option: null name");
+  if (!strcmp(name, "gemm_2sm")) {
+    g_opt_gemm_2sm = value;
+    return VSB_OK;
+  }
+  return fail(VSB_ERR_INVALID, "set_option: unknown option '%s'", name);
+}
+
 // core/pab/pab_mgr.py:54-91: flag = on && t is not None && count % range != 0 && lo < t < hi; count = (count+1) % steps
 extern "C" int vsb_pab_gate(int broadcast_on, int has_timestep, int timestep, int* count, int range, int lo, int hi,
                             int steps) {

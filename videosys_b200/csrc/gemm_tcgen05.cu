@@ -226,6 +226,10 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
   return check_launch("gemm_bf16_tn");
 }
 
+int gemm2_dispatch(const void* A, const void* W, const void* bias, void* out, int M, int N, int K, int act,
+                   cudaStream_t st);  // gemm_tcgen05_2sm.cu
+int g_opt_gemm_2sm = 0;  // vsb_set_option("gemm_2sm", 1): CTA-pair kernel for large problems
+
 }  // namespace vsb
 
 using namespace vsb;
@@ -236,6 +240,10 @@ extern "C" int vsb_gemm_bias_act(const vsb_bf16* A, const vsb_bf16* W, const vsb
   if (K % 8 || N % 8 || !aligned16(A) || !aligned16(W) || !aligned16(out))
     return fail(VSB_ERR_UNSUPPORTED, "gemm: need K %% 8 == 0, N %% 8 == 0, 16B-aligned pointers (M=%d N=%d K=%d)", M, N, K);
   if (act != 0 && act != 1) return fail(VSB_ERR_INVALID, "gemm: act=%d", act);
+  if (g_opt_gemm_2sm && M >= 1024) {
+    const int rc2 = gemm2_dispatch(A, W, bias, out, M, N, K, act, (cudaStream_t)stream);
+    if (rc2 <= 0) return rc2;  // 1 = not applicable -> single-CTA kernel below
+  }
   // tile width: 192 divides every STDiT3 width (1152, 2304, 3456, 4608); narrow outputs use 64/128
   const int BN = (N % 192 == 0) ? 192 : (N >= 256 && N % 256 == 0) ? 256 : (N >= 192 ? 192 : (N > 64 ? 128 : 64));
   CUtensorMap ta, tw, tc;

@@ -1,0 +1,268 @@
+// vsb200 -- bf16 TN GEMM, CTA-pair variant: tcgen05.mma.cta_group::2 (M = 256 across two SMs).
+//
+// Why: with one CTA per tile every SM pulls its own copy of the W tile through L2; at 128x192 the arithmetic
+// intensity is 38 MAC/B and the L2->SM fabric (not the tensor pipe) bounds the kernel.  A CTA pair shares the W tile:
+// each CTA stages 128 rows of A and HALF of the W tile (BN/2 rows); the leader's single thread issues
+// M=256 x N=BN x K=16 MMAs that read both CTAs' shared memory and write both CTAs' TMEM -> 55 (BN=192) / 64 (BN=256)
+// MAC per L2 byte and half the shared-memory operand traffic per SM.
+//
+// Protocol (cluster of 2, rank 0 = leader):
+//   full[s]    lives in the LEADER; the leader's producer arms it with the bytes of BOTH CTAs, both producers'
+//              TMA loads (.cta_group::2) complete_tx on it.
+//   empty[s]   one per CTA; the leader's MMA thread releases a stage in both CTAs with a multicast tcgen05.commit.
+//   tfull[a]   one per CTA (multicast commit), each CTA's epilogue drains its own 128 accumulator rows.
+//   tempty[a]  lives in the LEADER; 8 arrivals (4 epilogue warps x 2 CTAs, the peer's arrive remotely).
+#include "vsb_common.cuh"
+#include "vsb_host.h"
+
+namespace vsb {
+
+constexpr int k2BM = 128;  // rows per CTA (256 per pair)
+constexpr int k2BK = 64;
+constexpr int k2Threads = 256;
+
+template <int BN>
+struct Gemm2Cfg {
+  static constexpr int kABytes = k2BM * k2BK * 2;
+  static constexpr int kBBytes = (BN / 2) * k2BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kCBytes = k2BM * BN * 2;
+  static constexpr int kStages = (BN >= 256) ? 5 : 6;
+  static constexpr int kTmemCols = 512;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kCBytes + 1024 + 256;
+};
+
+__device__ __forceinline__ float gelu_tanh_f2(float x) {
+  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
+  const float inner = kBeta * (x + kKappa * x * x * x);
+  const float e = __expf(2.f * inner);
+  const float th = 1.f - __fdividef(2.f, e + 1.f);
+  return 0.5f * x * (1.f + th);
+}
+
+template <int BN, int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
+gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                     const __grid_constant__ CUtensorMap tm_c, const bf16* __restrict__ bias, int M, int N, int K) {
+  using Cfg = Gemm2Cfg<BN>;
+  constexpr int kStages = Cfg::kStages;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem_ab = smem;
+  unsigned char* smem_c = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_c + Cfg::kCBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tfull = bars + 2 * kStages;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();
+  const bool leader = (cta == 0);
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  const int tiles_m = (M + 2 * k2BM - 1) / (2 * k2BM), tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = (K + k2BK - 1) / k2BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_c);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm<Cfg::kTmemCols>(tmem_ptr);
+  tc_fence_before();
+  cluster_sync_all();  // barriers of BOTH CTAs are initialised before any remote arrive / TMA signal
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m0 = (tile / tiles_n) * (2 * k2BM) + int(cta) * k2BM;
+        const int n0 = (tile % tiles_n) * BN + int(cta) * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          unsigned char* sa = smem_ab + stage * Cfg::kStageBytes;
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+          const uint32_t fb = mapa_u32(&full[stage], 0);
+          tma_load_2d_2sm_to(&tm_a, fb, sa, kb * k2BK, m0);
+          tma_load_2d_2sm_to(&tm_w, fb, sa + Cfg::kABytes, kb * k2BK, n0);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * k2BM, BN, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem_ab + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+          for (int k = 0; k < k2BK / 16; ++k) {
+            const uint64_t da = umma_smem_desc(sa + k * 32, 16, 1024, kSwz128);
+            const uint64_t db = umma_smem_desc(sb + k * 32, 16, 1024, kSwz128);
+            umma_ss_2sm(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_2sm_mcast(&empty[stage], 0x3);  // frees the stage in both CTAs
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm_mcast(&tfull[acc], 0x3);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (both CTAs, own 128 rows) =====================
+    const int ew = warp - 4;
+    const int row = ew * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m0 = (tile / tiles_n) * (2 * k2BM) + int(cta) * k2BM;
+      const int n0 = (tile % tiles_n) * BN;
+      mbar_wait(&tfull[acc], acc_phase);
+      tc_fence_after();
+      if (threadIdx.x == 128) tma_store_wait_read0();
+      named_bar_sync(1, 128);
+      const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32(t_row + c * 64, r0);
+        tmem_ld32(t_row + c * 64 + 32, r1);
+        tmem_wait_ld();
+        if (c == BN / 64 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_u32(&tempty[acc], 0));
+        }
+        unsigned char* crow = smem_c + c * (k2BM * 128) + row * 128;
+        const int ncol0 = n0 + c * 64;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int col = j * 8 + e;
+            const float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]);
+            const int gcol = ncol0 + col;
+            const float b = (bias != nullptr && gcol < N) ? __bfloat162float(__ldg(bias + gcol)) : 0.f;
+            float x = a + b;
+            if (ACT == 1) x = gelu_tanh_f2(rbf(x));
+            v[e] = x;
+          }
+          uint4 u;
+          u.x = pack_bf16x2(v[0], v[1]);
+          u.y = pack_bf16x2(v[2], v[3]);
+          u.z = pack_bf16x2(v[4], v[5]);
+          u.w = pack_bf16x2(v[6], v[7]);
+          *reinterpret_cast<uint4*>(crow + ((j ^ (row & 7)) << 4)) = u;
+        }
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1, 128);
+      if (threadIdx.x == 128) {
+        if (m0 < M) {
+#pragma unroll 1
+          for (int c = 0; c < BN / 64; ++c)
+            if (n0 + c * 64 < N) tma_store_2d(&tm_c, smem_c + c * (k2BM * 128), n0 + c * 64, m0);
+        }
+        tma_store_commit();
+      }
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+    if (threadIdx.x == 128) tma_store_wait0();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // nobody leaves while the peer may still read my smem / signal my barriers
+  if (warp == 2) tmem_dealloc_2sm<Cfg::kTmemCols>(tmem_base);
+}
+
+template <int BN, int ACT>
+static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const bf16* bias, int M,
+                        int N, int K, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_bf16_tn_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "gemm2: smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  const int tiles = ((M + 2 * k2BM - 1) / (2 * k2BM)) * ((N + BN - 1) / BN);
+  int pairs = num_sms() / 2;
+  if (pairs > tiles) pairs = tiles;
+  gemm2_bf16_tn_kernel<BN, ACT><<<pairs * 2, k2Threads, Cfg::kSmemBytes, st>>>(ta, tw, tc, bias, M, N, K);
+  return check_launch("gemm2_bf16_tn");
+}
+
+// Called by vsb_gemm_bias_act (gemm_tcgen05.cu) for large problems.  Returns 1 if this variant does not apply.
+int gemm2_dispatch(const void* A, const void* W, const void* bias, void* out, int M, int N, int K, int act,
+                   cudaStream_t st) {
+  int BN;
+  if (N % 256 == 0)
+    BN = 256;
+  else if (N % 192 == 0)
+    BN = 192;
+  else
+    return 1;
+  CUtensorMap ta, tw, tc;
+  unsigned long long da[2] = {(unsigned long long)K, (unsigned long long)M};
+  unsigned long long sa[1] = {(unsigned long long)K * 2};
+  unsigned ba[2] = {k2BK, k2BM};
+  int rc = make_tmap_bf16(&ta, A, 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  unsigned long long dw[2] = {(unsigned long long)K, (unsigned long long)N};
+  unsigned bw[2] = {k2BK, (unsigned)(BN / 2)};
+  rc = make_tmap_bf16(&tw, W, 2, dw, sa, bw, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  unsigned long long dc[2] = {(unsigned long long)N, (unsigned long long)M};
+  unsigned long long sc[1] = {(unsigned long long)N * 2};
+  unsigned bc[2] = {64, k2BM};
+  rc = make_tmap_bf16(&tc, out, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  const bf16* b = (const bf16*)bias;
+  if (BN == 256)
+    return act ? launch_gemm2<256, 1>(ta, tw, tc, b, M, N, K, st) : launch_gemm2<256, 0>(ta, tw, tc, b, M, N, K, st);
+  return act ? launch_gemm2<192, 1>(ta, tw, tc, b, M, N, K, st) : launch_gemm2<192, 0>(ta, tw, tc, b, M, N, K, st);
+}
+
+}  // namespace vsb

@@ -12,6 +12,30 @@ from . import _lib
 
 _initialised = set()
 
+# bench.py sets this to a list to time individual launches with CUDA events on the launching stream:
+# entries are (kind, start_event, end_event, algorithmic_work) -- work = FLOPs for gemm/attn, bytes otherwise.
+PROFILE = None
+
+
+class _Timed:
+    __slots__ = ("kind", "work", "e0")
+
+    def __init__(self, kind, work):
+        self.kind, self.work = kind, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            PROFILE.append((self.kind, self.e0, e1, self.work))
+        return False
+
 
 def _init_dev(lib, dev):
     if dev not in _initialised:
@@ -43,6 +67,10 @@ def _bf16(t, name):
         raise _lib.VsbError(f"{name} must be bfloat16")
 
 
+def set_option(name: str, value: int) -> None:
+    _lib.check(_lib.load().vsb_set_option(name.encode(), int(value)), "set_option")
+
+
 def launch_count() -> int:
     return int(_lib.load().vsb_launch_count())
 
@@ -62,10 +90,11 @@ def ln_modulate(x, mod, x_mask_u8, shift_row, scale_row, B, T, S, out=None, eps=
     _bf16(x, "x")
     Cc = x.shape[-1]
     out = torch.empty_like(x) if out is None else out
-    _lib.check(
-        lib.vsb_ln_modulate(_p(x), _p(out), _p(mod), _p(x_mask_u8), shift_row, scale_row, B, T, S, Cc, eps, st),
-        "ln_modulate",
-    )
+    with _Timed("ln_modulate", 2 * x.numel() * 2):
+        _lib.check(
+            lib.vsb_ln_modulate(_p(x), _p(out), _p(mod), _p(x_mask_u8), shift_row, scale_row, B, T, S, Cc, eps, st),
+            "ln_modulate",
+        )
     return out
 
 
@@ -73,24 +102,28 @@ def gate_residual(x, y, mod, x_mask_u8, gate_row, B, T, S, out=None, cache_out=N
     lib, st = _prep(x, y, mod, x_mask_u8, out, cache_out)
     Cc = x.shape[-1]
     out = torch.empty_like(x) if out is None else out
-    _lib.check(
-        lib.vsb_gate_residual(_p(x), _p(y), _p(out), _p(cache_out), _p(mod), _p(x_mask_u8), gate_row, B, T, S, Cc, st),
-        "gate_residual",
-    )
+    with _Timed("gate_residual", (3 + (cache_out is not None)) * x.numel() * 2):
+        _lib.check(
+            lib.vsb_gate_residual(_p(x), _p(y), _p(out), _p(cache_out), _p(mod), _p(x_mask_u8), gate_row, B, T, S, Cc,
+                                  st),
+            "gate_residual",
+        )
     return out
 
 
 def residual_add(x, y, out=None):
     lib, st = _prep(x, y, out)
     out = torch.empty_like(x) if out is None else out
-    _lib.check(lib.vsb_residual_add(_p(x), _p(y), _p(out), x.numel(), st), "residual_add")
+    with _Timed("residual_add", 3 * x.numel() * 2):
+        _lib.check(lib.vsb_residual_add(_p(x), _p(y), _p(out), x.numel(), st), "residual_add")
     return out
 
 
 def qk_rmsnorm_(qkv, wq, wk, H, D, eps=1e-6):
     lib, st = _prep(qkv, wq, wk)
     rows = qkv.numel() // (3 * H * D)
-    _lib.check(lib.vsb_qk_rmsnorm(_p(qkv), _p(wq), _p(wk), rows, H, D, eps, st), "qk_rmsnorm")
+    with _Timed("qk_rmsnorm", 4 * rows * H * D * 2):
+        _lib.check(lib.vsb_qk_rmsnorm(_p(qkv), _p(wq), _p(wk), rows, H, D, eps, st), "qk_rmsnorm")
     return qkv
 
 
@@ -99,11 +132,12 @@ def attn_short(qkv, wq, wk, rope_cos, rope_sin, n_outer, n_inner, outer_stride, 
     lib, st = _prep(qkv, wq, wk, rope_cos, rope_sin, out)
     rows = qkv.numel() // (3 * H * D)
     out = torch.empty(rows, H * D, dtype=torch.bfloat16, device=qkv.device) if out is None else out
-    _lib.check(
-        lib.vsb_attn_short(_p(qkv), _p(out), _p(wq), _p(wk), _p(rope_cos), _p(rope_sin), n_outer, n_inner,
-                           outer_stride, inner_stride, tok_stride, n, H, D, eps, scale, st),
-        "attn_short",
-    )
+    with _Timed("attn_short", 4 * rows * H * D * 2):
+        _lib.check(
+            lib.vsb_attn_short(_p(qkv), _p(out), _p(wq), _p(wk), _p(rope_cos), _p(rope_sin), n_outer, n_inner,
+                               outer_stride, inner_stride, tok_stride, n, H, D, eps, scale, st),
+            "attn_short",
+        )
     return out
 
 
@@ -117,7 +151,8 @@ def gemm_bias_act(a, w, bias=None, act: int = 0, out=None):
     if w.shape[1] != K:
         raise _lib.VsbError("gemm: K mismatch")
     out = torch.empty(*a.shape[:-1], N, dtype=torch.bfloat16, device=a.device) if out is None else out
-    _lib.check(lib.vsb_gemm_bias_act(_p(a), _p(w), _p(bias), _p(out), M, N, K, act, st), "gemm_bias_act")
+    with _Timed("gemm", 2 * M * N * K):
+        _lib.check(lib.vsb_gemm_bias_act(_p(a), _p(w), _p(bias), _p(out), M, N, K, act, st), "gemm_bias_act")
     return out
 
 
@@ -133,11 +168,12 @@ def attn_flash(q, k, v, nb, nq, nk, H, D, q_row_stride, q_batch_stride, kv_row_s
     lens = None
     if kv_lens is not None:
         lens = (C.c_int * len(kv_lens))(*[int(v_) for v_ in kv_lens])
-    _lib.check(
-        lib.vsb_attn_flash(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), nb, nq, nk, H, D, q_row_stride,
-                           q_batch_stride, kv_row_stride, kv_batch_stride, lens, scale, st),
-        "attn_flash",
-    )
+    with _Timed("attn_flash", 4 * nb * H * nq * nk * D):
+        _lib.check(
+            lib.vsb_attn_flash(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), nb, nq, nk, H, D,
+                               q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, lens, scale, st),
+            "attn_flash",
+        )
     return out
 
 
