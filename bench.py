@@ -214,7 +214,9 @@ def run_ours(args):
         height=torch.tensor([W["h"]], device=dev, dtype=bf), width=torch.tensor([W["w"]], device=dev, dtype=bf),
         num_frames=torch.tensor([W["frames"]], device=dev, dtype=bf), fps=torch.tensor([24], device=dev, dtype=bf),
     )
-    timesteps = sched.prepare_timesteps(1, dev, margs)
+    # the timestep schedule is host arithmetic (50 tiny transforms): keep it off the GPU launch list
+    margs_cpu = {k: v.cpu() for k, v in margs.items() if k in ("height", "width", "num_frames")}
+    timesteps = [t.to(dev) for t in sched.prepare_timesteps(1, "cpu", margs_cpu)]
     fwd_args = {k: v for k, v in margs.items() if k != "num_frames"}
     fwd_args["x_mask"] = torch.ones(2, T, dtype=torch.bool, device=dev)  # generate() always passes an all-true mask
     n_ts = len(timesteps)

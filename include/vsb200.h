@@ -36,7 +36,8 @@ int vsb_init(int device);
 /* Number of kernels this library has launched since load (all entries); bench.py reports the delta. */
 unsigned long long vsb_launch_count(void);
 /* Run-time kernel selection knobs (not a backend switch: every choice is an sm_100a kernel of this library).
- *   "gemm_2sm" = 1: CTA-pair (tcgen05 cta_group::2, M = 256) GEMM for M >= 1024 when N % 192 == 0 or N % 256 == 0. */
+ *   "gemm_2sm" (default 1): CTA-pair (tcgen05 cta_group::2, M = 256) GEMM for M >= 1024 when N % 192 == 0 or
+ *   N % 256 == 0; 0 forces the single-CTA (M = 128) kernel everywhere. */
 int vsb_set_option(const char* name, int value);
 
 /* ---- AdaLN: LayerNorm(eps, no affine) -> x*(1+scale)+shift with per-frame t / t0 select --------------------

@@ -177,8 +177,8 @@ def _gemm_check(name, M, N, K_, act):
     err_exact = (got.double() - exact).abs()
     # one bf16 rounding of the result (half an ulp) + fp32 accumulation noise; with the GELU epilogue the
     # pre-activation is itself rounded to bf16 first (the eager rounding point), so a flip there moves the
-    # output by up to ~1.1 pre-activation ulps more
-    tol = _bf16_ulp(exact.float().abs().clamp_min(0.05)).double() * (0.51 if not act else 2.2) + 1e-3
+    # output by up to ~1.1 pre-activation ulps more (2x that across a binade edge)
+    tol = _bf16_ulp(exact.float().abs().clamp_min(0.05)).double() * (0.51 if not act else 3.3) + 1e-3
     bad = err_exact > tol
     if bad.any():
         idx = bad.nonzero()
@@ -227,10 +227,20 @@ def test_gemm_cta_pair(M, N, K_, act):
 
     _dev()
     K.set_option("gemm_2sm", 1)
+    _gemm_check(f"p{M}x{N}x{K_}", M, N, K_, act)
+
+
+@pytest.mark.parametrize("M,N,K_,act", [(1500, 3456, 1152, 0), (1024, 4608, 1152, 1)])
+def test_gemm_single_cta_large(M, N, K_, act):
+    """The 1-CTA kernel on shapes the CTA-pair kernel normally takes."""
+    from videosys_b200 import kernels as K
+
+    _dev()
+    K.set_option("gemm_2sm", 0)
     try:
-        _gemm_check(f"p{M}x{N}x{K_}", M, N, K_, act)
+        _gemm_check(f"s{M}x{N}x{K_}", M, N, K_, act)
     finally:
-        K.set_option("gemm_2sm", 0)
+        K.set_option("gemm_2sm", 1)
 
 
 def test_gemm_many_tiles_persistent():

@@ -15,7 +15,8 @@ for g in "$@"; do
     elem)  run elem 300 tests/test_kernels_gpu.py -k "ln_modulate or gate_residual or qk_rmsnorm" ;;
     short) run short 300 tests/test_kernels_gpu.py -k "attn_short" ;;
     gemm)  run gemm 300 tests/test_kernels_gpu.py -k "gemm and not cta_pair" ;;
-    gemm2) run gemm2 300 tests/test_kernels_gpu.py -k "cta_pair" ;;
+    gemm2) run gemm2 300 tests/test_kernels_gpu.py -k "cta_pair or single_cta" ;;
+    pipe)  run pipe 300 tests/test_pipeline_gpu.py ;;
     bench2sm) timeout 900 python bench.py --opt gemm_2sm=1 $BENCH_ARGS > gpurun_out/bench2sm.json 2> gpurun_out/bench2sm.err
            echo "bench2sm exit $? : $(tail -c 300 gpurun_out/bench2sm.json)" | tee -a gpurun_out/summary.txt ;;
     flash) run flash 300 tests/test_kernels_gpu.py -k "attn_flash" ;;
@@ -30,7 +31,7 @@ for g in "$@"; do
            tail -n 5 gpurun_out/bench.err ;;
     bench240) timeout 600 python bench.py --workload opensora_240p_51f_30step $BENCH_ARGS > gpurun_out/bench240.json 2> gpurun_out/bench240.err
            echo "exit $? : $(tail -c 400 gpurun_out/bench240.json)" | tee -a gpurun_out/summary.txt ;;
-    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \
+    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
               python bench.py --steps 1 --warmup 1 --depth 2 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
            echo "ncu_list exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 14 -c 4 -o gpurun_out/prof_gemm -f \

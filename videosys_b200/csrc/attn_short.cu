@@ -1,8 +1,13 @@
 // vsb200 -- short-sequence attention (n < 30 tokens): the temporal self-attention of STDiT3 (n = T = 15..20).
 //
-// FLOPs are negligible (3.7e11 per step at 720p); the kernel is HBM-bound on one read of q,k,v and one write
-// of o.  One warp owns one (sequence, head): it stages q,k,v rows in shared memory as bf16, applies the
-// per-head RMSNorm and RoPE in place, then lane i computes query row i with keys/values broadcast from smem.
+// FLOPs are negligible (3.7e11 per step at 720p); the kernel must be HBM-bound on one read of q,k,v and one write
+// of o.  One warp owns one (sequence, head):
+//   1. q,k,v rows (n x D each) -> per-warp shared memory (16-byte loads straight from the packed token-major qkv);
+//   2. lane = row: per-head RMSNorm (+ RoPE from a per-block smem table) in place on q and k, q scaled;
+//   3. S = Q K^T and O = P V on the warp-level tensor path (mma.sync m16n8k16 / m16n8k8 bf16, fp32 accumulate,
+//      ldmatrix fragments; P is re-packed from the S accumulators, FA2 style) -- the sequences are far too short for
+//      a tcgen05 tile (20 keys against a 128-key MMA would waste 84 % of the work);
+//   4. O staged through smem, written with 16-byte stores.
 // Rounding follows the reference's eager op order (attentions.py:111-120): bf16(q*scale), bf16(q@k^T),
 // fp32 softmax, bf16(probs), bf16(probs@v).
 #include "vsb_common.cuh"
@@ -13,19 +18,68 @@ namespace vsb {
 constexpr int kMaxN = 32;
 constexpr int kWarpsPerBlock = 4;
 
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x1(uint32_t& r, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x1.shared.b16 {%0}, [%1];" : "=r"(r) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
+               : "=r"(r[0]), "=r"(r[1])
+               : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void mma_k16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma_k8(float (&c)[4], const uint32_t (&a)[2], uint32_t b) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(b));
+}
+
 template <int D>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) attn_short_kernel(
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
     const bf16* __restrict__ qkv, bf16* __restrict__ out, const bf16* __restrict__ wq, const bf16* __restrict__ wk,
     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int n_outer, int n_inner,
     long long outer_stride, long long inner_stride, long long tok_stride, int n, int H, float eps, float scale) {
-  constexpr int VPR = D / 8;  // 16-byte vectors per head row
+  constexpr int VPR = D / 8;        // 16-byte vectors per head row
+  constexpr int K16 = D / 16;       // full k16 steps of Q K^T
+  constexpr bool K8 = (D % 16) != 0;  // one trailing k8 step (D = 72)
+  constexpr int ND = D / 8;         // n8 tiles of the output
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  bf16* sq = reinterpret_cast<bf16*>(smem_raw) + (size_t)warp * 3 * kMaxN * D;
+  // [rope cos | rope sin] (fp32, n x D each, shared by the block) then per warp q | k | v (bf16, 32 x D each)
+  float* s_cos = reinterpret_cast<float*>(smem_raw);
+  float* s_sin = s_cos + kMaxN * D;
+  bf16* sq = reinterpret_cast<bf16*>(s_sin + kMaxN * D) + (size_t)warp * 3 * kMaxN * D;
   bf16* sk = sq + kMaxN * D;
   bf16* sv = sk + kMaxN * D;
+  const bool has_rope = rope_cos != nullptr;
+  if (has_rope) {
+    for (int i = threadIdx.x; i < n * D; i += blockDim.x) {
+      s_cos[i] = rope_cos[i];
+      s_sin[i] = rope_sin[i];
+    }
+  }
+  // zero V's padding rows once (P is 0 there, but 0 * garbage could be NaN); loads below never touch them
+  for (int i = lane; i < (kMaxN - n) * VPR; i += 32)
+    *reinterpret_cast<uint4*>(sv + (size_t)n * D + i * 8) = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+
   const long long total = (long long)n_outer * n_inner * H;
   const int C = H * D;
+  const int nt = (n + 7) >> 3;   // key n8 tiles
+  const int kk = (n + 15) >> 4;  // key k16 steps of P V
+  const int g = lane >> 2, t = lane & 3;
 
   for (long long item = (long long)blockIdx.x * kWarpsPerBlock + warp; item < total;
        item += (long long)gridDim.x * kWarpsPerBlock) {
@@ -33,7 +87,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) attn_short_kernel(
     const long long seq = item / H;
     const long long row0 = (seq / n_inner) * outer_stride + (seq % n_inner) * inner_stride;
 
-    // ---- stage q,k,v rows (n x D each) ----
+    // ---- 1. stage q,k,v rows ----
     for (int idx = lane; idx < 3 * n * VPR; idx += 32) {
       const int which = idx / (n * VPR);
       const int rem = idx - which * n * VPR;
@@ -52,89 +106,167 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) attn_short_kernel(
       continue;
     }
 
-    // ---- RMSNorm(q), RMSNorm(k) (+RoPE) in place: lane i < n handles row i of q, lane 16+... would idle, so
-    //      do q rows then k rows with the same lanes ----
+    // ---- 2. RMSNorm (+RoPE) in place; lane = row, q then k ----
     if (lane < n) {
-#pragma unroll
+#pragma unroll 1
       for (int which = 0; which < 2; ++which) {
-        bf16* r = (which ? sk : sq) + lane * D;
-        const bf16* w = which ? wk : wq;
+        __nv_bfloat162* r2 = reinterpret_cast<__nv_bfloat162*>((which ? sk : sq) + lane * D);
+        const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(which ? wk : wq);
         float ss = 0.f;
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-          float f = __bfloat162float(r[d]);
-          ss += f * f;
+        for (int d = 0; d < D / 2; ++d) {
+          const float2 f = __bfloat1622float2(r2[d]);
+          ss += f.x * f.x + f.y * f.y;
         }
         const float rs = rsqrtf(ss / (float)D + eps);
-#pragma unroll
-        for (int d = 0; d < D; d += 2) {
+#pragma unroll 4
+        for (int d = 0; d < D / 2; ++d) {
+          const float2 f = __bfloat1622float2(r2[d]);
+          const float2 w = __bfloat1622float2(__ldg(w2 + d));
           // normalization.py:28-33: h = bf16(x*rstd); y = bf16(w*h)
-          float y0 = rbf(__bfloat162float(w[d]) * rbf(__bfloat162float(r[d]) * rs));
-          float y1 = rbf(__bfloat162float(w[d + 1]) * rbf(__bfloat162float(r[d + 1]) * rs));
-          if (rope_cos != nullptr) {
-            // rotate_queries_or_keys: out = t*cos + rotate_half(t)*sin in fp32, pairs (2i, 2i+1): rot = (-x2, x1)
-            const float c0 = rope_cos[lane * D + d], c1 = rope_cos[lane * D + d + 1];
-            const float s0 = rope_sin[lane * D + d], s1 = rope_sin[lane * D + d + 1];
-            const float o0 = __fadd_rn(__fmul_rn(y0, c0), __fmul_rn(-y1, s0));
-            const float o1 = __fadd_rn(__fmul_rn(y1, c1), __fmul_rn(y0, s1));
+          float y0 = rbf(w.x * rbf(f.x * rs));
+          float y1 = rbf(w.y * rbf(f.y * rs));
+          if (has_rope) {
+            // rotate_queries_or_keys: t*cos + rotate_half(t)*sin in fp32, pairs (2i, 2i+1): rot = (-x2, x1)
+            const float2 cs = *reinterpret_cast<const float2*>(s_cos + lane * D + 2 * d);
+            const float2 sn = *reinterpret_cast<const float2*>(s_sin + lane * D + 2 * d);
+            const float o0 = __fadd_rn(__fmul_rn(y0, cs.x), __fmul_rn(-y1, sn.x));
+            const float o1 = __fadd_rn(__fmul_rn(y1, cs.y), __fmul_rn(y0, sn.y));
             y0 = rbf(o0);
             y1 = rbf(o1);
           }
           if (which == 0) {  // q = bf16(q * scale)  (attentions.py:113)
-            y0 = rbf(y0 * scale);
-            y1 = rbf(y1 * scale);
+            y0 = y0 * scale;
+            y1 = y1 * scale;
           }
-          r[d] = __float2bfloat16_rn(y0);
-          r[d + 1] = __float2bfloat16_rn(y1);
+          r2[d] = __floats2bfloat162_rn(y0, y1);
         }
       }
     }
     __syncwarp();
 
-    // ---- lane i: scores over keys, softmax, PV ----
-    if (lane < n) {
-      float qreg[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) qreg[d] = __bfloat162float(sq[lane * D + d]);
-      float s[kMaxN];
-      float mx = -INFINITY;
+    // ---- 3. S = Q K^T (bf16 out), softmax fp32, P bf16, O = P V ----
 #pragma unroll 1
-      for (int j = 0; j < n; ++j) {
-        float acc = 0.f;
+    for (int mt = 0; mt < 2; ++mt) {
+      if (mt * 16 >= n) break;
+      float sacc[4][4];
 #pragma unroll
-        for (int d = 0; d < D; ++d) acc = fmaf(qreg[d], __bfloat162float(sk[j * D + d]), acc);
-        acc = rbf(acc);  // bf16 matmul output
-        s[j] = acc;
-        mx = fmaxf(mx, acc);
+      for (int j = 0; j < 4; ++j) sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+      const bf16* qa = sq + (size_t)(mt * 16 + (lane & 15)) * D + (lane >> 4) * 8;
+#pragma unroll
+      for (int ks = 0; ks < K16; ++ks) {
+        uint32_t a[4];
+        ldsm_x4(a, qa + ks * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nt) {
+            uint32_t b[2];
+            ldsm_x2(b, sk + (size_t)(j * 8 + (lane & 7)) * D + ks * 16 + ((lane >> 3) & 1) * 8);
+            mma_k16(sacc[j], a, b);
+          }
+        }
       }
-      float den = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) {
-        s[j] = expf(s[j] - mx);
-        den += s[j];
+      if (K8) {
+        uint32_t a[2];
+        ldsm_x2(a, sq + (size_t)(mt * 16 + (lane & 15)) * D + K16 * 16);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (j < nt) {
+            uint32_t b;
+            ldsm_x1(b, sk + (size_t)(j * 8 + (lane & 7)) * D + K16 * 16);
+            mma_k8(sacc[j], a, b);
+          }
+        }
       }
-      float o[D];
+      // rows g (c0,c1) and g+8 (c2,c3) of this m-tile; columns 8j + 2t, +1
+      float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int d = 0; d < D; ++d) o[d] = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < n; ++j) {
-        const float p = rbf(s[j] / den);  // softmax in fp32, cast to bf16
+      for (int j = 0; j < 4; ++j) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) o[d] = fmaf(p, __bfloat162float(sv[j * D + d]), o[d]);
+        for (int e = 0; e < 4; ++e) {
+          const int col = j * 8 + 2 * t + (e & 1);
+          const float v = (j < nt && col < n) ? rbf(sacc[j][e]) : -INFINITY;  // bf16 matmul output; mask pad keys
+          sacc[j][e] = v;
+          if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
+        }
       }
-      bf16* dst = out + (size_t)(row0 + (long long)lane * tok_stride) * C + (size_t)h * D;
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-      for (int d = 0; d < D; d += 8) {
-        uint4 u;
-        u.x = pack_bf16x2(o[d], o[d + 1]);
-        u.y = pack_bf16x2(o[d + 2], o[d + 3]);
-        u.z = pack_bf16x2(o[d + 4], o[d + 5]);
-        u.w = pack_bf16x2(o[d + 6], o[d + 7]);
-        *reinterpret_cast<uint4*>(dst + d) = u;
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float p = expf(sacc[j][e] - (e < 2 ? mx0 : mx1));  // exp(-inf) = 0 for masked keys
+          sacc[j][e] = p;
+          if (e < 2) d0 += p; else d1 += p;
+        }
+      }
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 1);
+      d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
+      d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+      // P (bf16) as A fragments of the two k16 steps
+      uint32_t pa[2][4];
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        pa[kb][0] = pack_bf16x2(sacc[2 * kb][0] / d0, sacc[2 * kb][1] / d0);
+        pa[kb][1] = pack_bf16x2(sacc[2 * kb][2] / d1, sacc[2 * kb][3] / d1);
+        pa[kb][2] = pack_bf16x2(sacc[2 * kb + 1][0] / d0, sacc[2 * kb + 1][1] / d0);
+        pa[kb][3] = pack_bf16x2(sacc[2 * kb + 1][2] / d1, sacc[2 * kb + 1][3] / d1);
+      }
+      float oacc[ND][4];
+#pragma unroll
+      for (int jd = 0; jd < ND; ++jd) oacc[jd][0] = oacc[jd][1] = oacc[jd][2] = oacc[jd][3] = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < 2; ++kb) {
+        if (kb < kk) {
+#pragma unroll
+          for (int jd = 0; jd < ND; ++jd) {
+            uint32_t b[2];
+            ldsm_x2_trans(b, sv + (size_t)(kb * 16 + (lane & 15)) * D + jd * 8);
+            mma_k16(oacc[jd], pa[kb], b);
+          }
+        }
+      }
+      // ---- 4. O (bf16) -> smem over this m-tile's Q rows (Q is dead for these rows) ----
+      __syncwarp();
+#pragma unroll
+      for (int jd = 0; jd < ND; ++jd) {
+        *reinterpret_cast<uint32_t*>(sq + (size_t)(mt * 16 + g) * D + jd * 8 + 2 * t) = pack_bf16x2(oacc[jd][0], oacc[jd][1]);
+        *reinterpret_cast<uint32_t*>(sq + (size_t)(mt * 16 + g + 8) * D + jd * 8 + 2 * t) = pack_bf16x2(oacc[jd][2], oacc[jd][3]);
       }
     }
     __syncwarp();
+    for (int idx = lane; idx < n * VPR; idx += 32) {
+      const int j = idx / VPR, c = idx - j * VPR;
+      *reinterpret_cast<uint4*>(out + (size_t)(row0 + (long long)j * tok_stride) * C + (size_t)h * D + c * 8) =
+          *reinterpret_cast<const uint4*>(sq + (size_t)j * D + c * 8);
+    }
+    __syncwarp();
   }
+}
+
+template <int D>
+static int launch_short(const bf16* qkv, bf16* out, const bf16* wq, const bf16* wk, const float* rc, const float* rs,
+                        int n_outer, int n_inner, long long os, long long is, long long ts, int n, int H, float eps,
+                        float scale, cudaStream_t st) {
+  const size_t smem = 2 * kMaxN * D * sizeof(float) + (size_t)kWarpsPerBlock * 3 * kMaxN * D * sizeof(bf16);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_short_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_short: smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  const long long total = (long long)n_outer * n_inner * H;
+  long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  const long long cap = (long long)num_sms() * 3 * 4;  // 3 resident blocks per SM, ~4 items per warp
+  if (blocks > cap) blocks = cap;
+  attn_short_kernel<D><<<(int)blocks, kWarpsPerBlock * 32, smem, st>>>(qkv, out, wq, wk, rc, rs, n_outer, n_inner, os,
+                                                                       is, ts, n, H, eps, scale);
+  return check_launch("attn_short");
 }
 
 }  // namespace vsb
@@ -150,33 +282,12 @@ extern "C" int vsb_attn_short(const vsb_bf16* qkv, vsb_bf16* out, const vsb_bf16
   if (n > kMaxN) return fail(VSB_ERR_UNSUPPORTED, "attn_short: n=%d > %d (use vsb_attn_flash)", n, kMaxN);
   if ((rope_cos == nullptr) != (rope_sin == nullptr)) return fail(VSB_ERR_INVALID, "attn_short: rope tables");
   if (!aligned16(qkv) || !aligned16(out)) return fail(VSB_ERR_UNSUPPORTED, "attn_short: alignment");
-  const long long total = (long long)n_outer * n_inner * H;
-  long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const long long cap = (long long)num_sms() * 16;
-  if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
-  if (D == 72) {
-    size_t smem = (size_t)kWarpsPerBlock * 3 * kMaxN * 72 * sizeof(bf16);
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(attn_short_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr = true;
-    }
-    attn_short_kernel<72><<<(int)blocks, kWarpsPerBlock * 32, smem, st>>>(
-        (const bf16*)qkv, (bf16*)out, (const bf16*)wq, (const bf16*)wk, rope_cos, rope_sin, n_outer, n_inner,
-        outer_stride, inner_stride, tok_stride, n, H, eps, scale);
-  } else if (D == 64) {
-    size_t smem = (size_t)kWarpsPerBlock * 3 * kMaxN * 64 * sizeof(bf16);
-    static bool attr = false;
-    if (!attr) {
-      cudaFuncSetAttribute(attn_short_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      attr = true;
-    }
-    attn_short_kernel<64><<<(int)blocks, kWarpsPerBlock * 32, smem, st>>>(
-        (const bf16*)qkv, (bf16*)out, (const bf16*)wq, (const bf16*)wk, rope_cos, rope_sin, n_outer, n_inner,
-        outer_stride, inner_stride, tok_stride, n, H, eps, scale);
-  } else {
-    return fail(VSB_ERR_UNSUPPORTED, "attn_short: head_dim %d (72 or 64 only)", D);
-  }
-  return check_launch("attn_short");
+  if (D == 72)
+    return launch_short<72>((const bf16*)qkv, (bf16*)out, (const bf16*)wq, (const bf16*)wk, rope_cos, rope_sin, n_outer,
+                            n_inner, outer_stride, inner_stride, tok_stride, n, H, eps, scale, st);
+  if (D == 64)
+    return launch_short<64>((const bf16*)qkv, (bf16*)out, (const bf16*)wq, (const bf16*)wk, rope_cos, rope_sin, n_outer,
+                            n_inner, outer_stride, inner_stride, tok_stride, n, H, eps, scale, st);
+  return fail(VSB_ERR_UNSUPPORTED, "attn_short: head_dim %d (72 or 64 only)", D);
 }

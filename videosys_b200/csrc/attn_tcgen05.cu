@@ -186,54 +186,81 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[x], j & 1);
       tc_fence_after();
-      const int valid = min(128, kv_len - j * 128);  // columns >= valid are masked
-      // ---- pass 1: row max ----
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + c * 32, r);
-        tmem_wait_ld();
+      const int valid = kv_len - j * 128;  // >= 128: full tile; columns >= valid are masked
+      // ---- all 128 scores of my row -> registers (4 loads in flight, one wait) ----
+      uint32_t a[4][32];
+      tmem_ld32(tS, a[0]);
+      tmem_ld32(tS + 32, a[1]);
+      tmem_ld32(tS + 64, a[2]);
+      tmem_ld32(tS + 96, a[3]);
+      tmem_wait_ld();
+      float mx;
+      if (valid >= 128) {
+        float m0 = fmax3(__uint_as_float(a[0][0]), __uint_as_float(a[0][1]), __uint_as_float(a[0][2]));
+        float m1 = fmax3(__uint_as_float(a[1][0]), __uint_as_float(a[1][1]), __uint_as_float(a[1][2]));
+        float m2 = fmax3(__uint_as_float(a[2][0]), __uint_as_float(a[2][1]), __uint_as_float(a[2][2]));
+        float m3 = fmax3(__uint_as_float(a[3][0]), __uint_as_float(a[3][1]), __uint_as_float(a[3][2]));
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = __uint_as_float(r[i]);
-          if (c * 32 + i < valid) mx = fmaxf(mx, v);
+        for (int i = 3; i < 31; i += 2) {
+          m0 = fmax3(m0, __uint_as_float(a[0][i]), __uint_as_float(a[0][i + 1]));
+          m1 = fmax3(m1, __uint_as_float(a[1][i]), __uint_as_float(a[1][i + 1]));
+          m2 = fmax3(m2, __uint_as_float(a[2][i]), __uint_as_float(a[2][i + 1]));
+          m3 = fmax3(m3, __uint_as_float(a[3][i]), __uint_as_float(a[3][i + 1]));
         }
+        m0 = fmaxf(m0, __uint_as_float(a[0][31]));
+        m1 = fmaxf(m1, __uint_as_float(a[1][31]));
+        m2 = fmaxf(m2, __uint_as_float(a[2][31]));
+        m3 = fmaxf(m3, __uint_as_float(a[3][31]));
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      } else {  // ragged last tile: masked columns never win the max and get p = 0 below
+        mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c * 32 + i >= valid) a[c][i] = 0xff800000u;  // -inf
+            mx = fmaxf(mx, __uint_as_float(a[c][i]));
+          }
       }
+      // ---- lazy rescale: keep the stale running max unless it grew by more than 2^8 (p stays <= 256) ----
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = fast_exp2((m_run - m_new) * sl2);  // m_run = -inf -> 0
-      // ---- rescale O (quiescent: S_x(j) complete implies PV_x(j-1) complete) ----
-      if (j > 0 && __any_sync(0xffffffffu, m_new > m_run)) {
+      const bool grow = (m_new - m_run) * sl2 > 8.f;  // first tile: m_run = -inf -> true
+      const float alpha = grow ? fast_exp2((m_run - m_new) * sl2) : 1.f;
+      if (j > 0 && __any_sync(0xffffffffu, grow)) {
+        // O is quiescent here: S_x(j) complete implies PV_x(j-1) complete (in-order tensor pipe)
 #pragma unroll 1
-        for (int c = 0; c < (kHasB ? 5 : 4); ++c) {
-          uint32_t r[16];
-          tmem_ld16(tO + c * 16, r);
+        for (int c = 0; c < (kHasB ? 5 : 4); ++c) {  // rare path: one 16-column chunk at a time (register budget)
+          uint32_t o[16];
+          tmem_ld16(tO + c * 16, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
-          tmem_st16(tO + c * 16, r);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tO + c * 16, o);
         }
       }
-      m_run = m_new;
-      const float mb = m_new * sl2;
-      // ---- pass 2: p = exp2(s*sl2 - m*sl2), row sum, bf16 P -> TMEM (aliasing consumed S columns) ----
-      float sum = 0.f;
-#pragma unroll 1
+      if (grow) m_run = m_new;
+      const float mb = m_run * sl2;
+      // ---- p = exp2(s*sl2 - m*sl2); row sum (4 chains); bf16 P -> TMEM over the consumed S columns ----
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tS + c * 32, r);
-        tmem_wait_ld();
         uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = (c * 32 + i < valid) ? fast_exp2(fmaf(__uint_as_float(r[i]), sl2, -mb)) : 0.f;
-          float p1 = (c * 32 + i + 1 < valid) ? fast_exp2(fmaf(__uint_as_float(r[i + 1]), sl2, -mb)) : 0.f;
-          sum += p0 + p1;
+        for (int i = 0; i < 32; i += 4) {
+          const float p0 = fast_exp2(fmaf(__uint_as_float(a[c][i]), sl2, -mb));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(a[c][i + 1]), sl2, -mb));
+          const float p2 = fast_exp2(fmaf(__uint_as_float(a[c][i + 2]), sl2, -mb));
+          const float p3 = fast_exp2(fmaf(__uint_as_float(a[c][i + 3]), sl2, -mb));
+          s0 += p0;
+          s1 += p1;
+          s2 += p2;
+          s3 += p3;
           pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
         }
         tmem_st16(tS + c * 16, pk);
       }
-      l_run = l_run * alpha + sum;
+      l_run = l_run * alpha + ((s0 + s1) + (s2 + s3));
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();

@@ -42,21 +42,32 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
-  for (long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); row < rows;
-       row += (long long)gridDim.x * warps_per_block) {
+  const long long stride = (long long)gridDim.x * warps_per_block;
+  long long row = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  Vec8 nxt[kMaxVec];
+  auto load_row = [&](long long r) {
+    const bf16* xr = x + (size_t)r * C;
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) nxt[i].u = ld_stream(xr + vi * 8);
+    }
+  };
+  if (row < rows) load_row(row);
+  for (; row < rows; row += stride) {
+    Vec8 v[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) v[i].u = nxt[i].u;
+    if (row + stride < rows) load_row(row + stride);  // keep the next row's 128-bit loads in flight
     const long long bt = row / S;
     const int b = int(bt / T);
     const int sel = (x_mask != nullptr && x_mask[bt] == 0) ? 1 : 0;
     const bf16* shift = mod + ((size_t)(sel * B + b) * 6 + shift_row) * C;
     const bf16* scale = mod + ((size_t)(sel * B + b) * 6 + scale_row) * C;
-    const bf16* xr = x + (size_t)row * C;
-    Vec8 v[kMaxVec];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
-      int vi = lane + i * 32;
-      if (vi < nvec) {
-        v[i].u = ld_stream(xr + vi * 8);
+      if (lane + i * 32 < nvec) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float2 f = __bfloat1622float2(v[i].h[j]);
@@ -68,8 +79,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
     float sq = 0.f;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
-      int vi = lane + i * 32;
-      if (vi < nvec) {
+      if (lane + i * 32 < nvec) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float2 f = __bfloat1622float2(v[i].h[j]);
@@ -82,7 +92,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
     bf16* orow = out + (size_t)row * C;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
-      int vi = lane + i * 32;
+      const int vi = lane + i * 32;
       if (vi < nvec) {
         Vec8 sh, sc, o;
         sh.u = __ldg(reinterpret_cast<const uint4*>(shift + vi * 8));
@@ -172,50 +182,62 @@ template <int D>
 __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ wq,
                                                          const bf16* __restrict__ wk, long long rows, int H,
                                                          float eps) {
-  constexpr int LPG = D / 8;        // lanes per group
-  constexpr int GPW = 32 / LPG;     // groups per warp (3 for D=72, 4 for D=64)
+  constexpr int LPG = D / 8;     // lanes per group
+  constexpr int GPW = 32 / LPG;  // groups per warp (3 for D=72, 4 for D=64)
+  constexpr int U = 4;           // independent head vectors in flight per lane
   const int lane = threadIdx.x & 31;
   const int g = lane / LPG, l = lane % LPG;
+  const int gs = (g < GPW ? g : 0) * LPG;  // first lane of my group (idle tail lanes shadow group 0)
   const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
   const long long ngroups = rows * 2 * H;  // (row, which in {q,k}, head)
-  unsigned member = 0;                     // lanes of my group
-  for (int i = 0; i < LPG; ++i) member |= 1u << (g * LPG + i);
-  for (long long base = warp * GPW; base < ngroups; base += nwarps * GPW) {
-    const long long gi = base + g;
-    const bool active = (g < GPW) && (gi < ngroups);
-    Vec8 v;
-    float ss = 0.f;
-    bf16* p = nullptr;
-    int which = 0;
-    if (active) {
-      const long long row = gi / (2 * H);
-      const int rem = int(gi - row * 2 * H);
-      which = rem / H;
-      const int h = rem - which * H;
-      p = qkv + ((size_t)row * 3 + which) * H * D + (size_t)h * D + l * 8;
-      v.u = *reinterpret_cast<const uint4*>(p);
+  Vec8 wv[2];
+  wv[0].u = __ldg(reinterpret_cast<const uint4*>(wq + l * 8));
+  wv[1].u = __ldg(reinterpret_cast<const uint4*>(wk + l * 8));
+  for (long long base = warp * (GPW * U); base < ngroups; base += nwarps * (GPW * U)) {
+    Vec8 v[U];
+    bf16* p[U];
+    int which[U];
+    bool active[U];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(v.h[j]);
-        ss += f.x * f.x + f.y * f.y;
+    for (int u = 0; u < U; ++u) {
+      const long long gi = base + (long long)u * GPW + g;
+      active[u] = (g < GPW) && (gi < ngroups);
+      p[u] = nullptr;
+      which[u] = 0;
+      if (active[u]) {
+        const long long row = gi / (2 * H);
+        const int rem = int(gi - row * 2 * H);
+        which[u] = rem / H;
+        const int h = rem - which[u] * H;
+        p[u] = qkv + ((size_t)row * 3 + which[u]) * H * D + (size_t)h * D + l * 8;
+        v[u].u = *reinterpret_cast<const uint4*>(p[u]);
       }
     }
-    // reduce within the group (groups never straddle: lanes g*LPG .. g*LPG+LPG-1); all lanes take part in shuffles
-    float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < LPG; ++i) tot += __shfl_sync(0xffffffffu, ss, (g < GPW ? g : 0) * LPG + i);
-    if (active) {
-      const float r = rsqrtf(tot / (float)D + eps);
-      Vec8 w, o;
-      w.u = __ldg(reinterpret_cast<const uint4*>((which ? wk : wq) + l * 8));
+    for (int u = 0; u < U; ++u) {
+      float ss = 0.f;
+      if (active[u]) {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(v.h[j]), fw = __bfloat1622float2(w.h[j]);
-        // eager: h = bf16(x * rstd); out = bf16(w * h)
-        o.h[j] = __floats2bfloat162_rn(fw.x * rbf(f.x * r), fw.y * rbf(f.y * r));
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(v[u].h[j]);
+          ss += f.x * f.x + f.y * f.y;
+        }
       }
-      *reinterpret_cast<uint4*>(p) = o.u;
+      float tot = 0.f;  // reduce within the group; every lane takes part in the shuffles
+#pragma unroll
+      for (int i = 0; i < LPG; ++i) tot += __shfl_sync(0xffffffffu, ss, gs + i);
+      if (active[u]) {
+        const float r = rsqrtf(tot / (float)D + eps);
+        Vec8 o;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float2 f = __bfloat1622float2(v[u].h[j]), fw = __bfloat1622float2(wv[which[u]].h[j]);
+          // eager: h = bf16(x * rstd); out = bf16(w * h)
+          o.h[j] = __floats2bfloat162_rn(fw.x * rbf(f.x * r), fw.y * rbf(f.y * r));
+        }
+        *reinterpret_cast<uint4*>(p[u]) = o.u;
+      }
     }
   }
 }
@@ -291,10 +313,10 @@ extern "C" int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16*
   long long groups = (long long)rows * 2 * H;
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 72)
-    qk_rmsnorm_kernel<72><<<grid_for(groups, 8 * 3), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)wk,
+    qk_rmsnorm_kernel<72><<<grid_for(groups, 8 * 3 * 4), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)wk,
                                                                      (long long)rows, H, eps);
   else if (D == 64)
-    qk_rmsnorm_kernel<64><<<grid_for(groups, 8 * 4), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)wk,
+    qk_rmsnorm_kernel<64><<<grid_for(groups, 8 * 4 * 4), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)wk,
                                                                      (long long)rows, H, eps);
   else
     return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: head_dim %d (72 or 64 only)", D);

@@ -228,7 +228,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
 
 int gemm2_dispatch(const void* A, const void* W, const void* bias, void* out, int M, int N, int K, int act,
                    cudaStream_t st);  // gemm_tcgen05_2sm.cu
-int g_opt_gemm_2sm = 0;  // vsb_set_option("gemm_2sm", 1): CTA-pair kernel for large problems
+int g_opt_gemm_2sm = 1;  // CTA-pair kernel for large problems (vsb_set_option("gemm_2sm", 0) selects 1-CTA tiles)
 
 }  // namespace vsb
 
