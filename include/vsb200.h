@@ -89,6 +89,16 @@ int vsb_attn_short(const vsb_bf16* qkv, vsb_bf16* out, const vsb_bf16* wq, const
 int vsb_gemm_bias_act(const vsb_bf16* A, const vsb_bf16* W, const vsb_bf16* bias, vsb_bf16* out, int M, int N, int K,
                       int act, void* stream);
 
+/* Same GEMM with the residual branch of the block fused into the epilogue:
+ *   y = bf16(A @ W^T + bias);  g = gate_row >= 0 ? bf16(gate * y) : y;  out = bf16(resid + g)
+ * gate = mod[sel(b,t), b, gate_row, :] with the per-frame t/t0 select of x_mask (as in vsb_gate_residual); M == B*T*S.
+ * replaces proj/fc2 Linear + open_sora_transformer_3d.py:219-228,:270-284 (gate_row 2 / 5) and cross proj + :240
+ * (gate_row -1).  out may alias resid.  Returns 1 WITHOUT launching when the CTA-pair kernel does not take the shape
+ * (M < 1024 or N not a multiple of 192/256): the caller then uses vsb_gemm_bias_act + vsb_gate_residual. */
+int vsb_gemm_bias_residual(const vsb_bf16* A, const vsb_bf16* W, const vsb_bf16* bias, const vsb_bf16* resid,
+                           vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask, int gate_row, int M, int N, int K,
+                           int B, int T, int S, void* stream);
+
 /* ---- flash attention on tcgen05 (spatial self-attention and text cross-attention) -------------------------------
  * replaces F.scaled_dot_product_attention at attentions.py:100 and :268 (bool key mask = per-batch key count).
  * q/k/v are strided views: element (b, n, h, d) at base + b*batch_stride + n*row_stride + h*D + d (strides in

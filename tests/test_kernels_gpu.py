@@ -243,6 +243,41 @@ def test_gemm_single_cta_large(M, N, K_, act):
         K.set_option("gemm_2sm", 1)
 
 
+@pytest.mark.parametrize("B,T,S,N,K_,gate_row", [(2, 4, 160, 1152, 1152, 2), (2, 3, 200, 1152, 4608, 5), (2, 4, 160, 1152, 1152, -1)])
+def test_gemm_fused_residual_epilogue(B, T, S, N, K_, gate_row):
+    """proj / fc2 GEMM with gate + per-frame select + residual in the epilogue == Linear then the eager chain."""
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    M = B * T * S
+    a = synth.normalish("fe.a", (M, K_)).to(BF)
+    w = synth.normalish("fe.w", (N, K_), std=0.05).to(BF)
+    bias = (0.1 * synth.uniform("fe.b", (N,))).to(BF)
+    x = synth.normalish("fe.x", (B, T * S, N)).to(BF)
+    table = synth.normalish("fe.tab", (6, N), std=0.3).to(BF)
+    t = synth.normalish("fe.t", (B, 6 * N), std=0.5).to(BF)
+    t0 = synth.normalish("fe.t0", (B, 6 * N), std=0.5).to(BF)
+    x_mask = torch.ones(B, T, dtype=torch.bool)
+    x_mask[0, 1] = False
+    y = torch.nn.functional.linear(a, w, bias).reshape(B, T * S, N)
+    if gate_row >= 0:
+        mods = (table[None] + t.reshape(B, 6, -1)).chunk(6, dim=1)
+        mods0 = (table[None] + t0.reshape(B, 6, -1)).chunk(6, dim=1)
+        want = x + O.frame_select(x_mask, mods[gate_row] * y, mods0[gate_row] * y, T, S)
+        mod = K.modulation_table(table.to(dev), t.to(dev), t0.to(dev))
+        xg = x.to(dev).clone()
+        got = K.gemm_bias_residual(a.to(dev), w.to(dev), bias.to(dev), xg, mod, _mask_u8(x_mask, dev), gate_row, B, T, S)
+    else:
+        want = x + y
+        xg = x.to(dev).clone()
+        got = K.gemm_bias_residual(a.to(dev), w.to(dev), bias.to(dev), xg)
+    assert got is not None and got.data_ptr() == xg.data_ptr(), "fused kernel must take this shape and update x in place"
+    _ulp_report(f"gemm+residual gate_row={gate_row} K={K_}", got, want, min_equal=0.98, max_ulps=2.0, row_floor=0.25)
+    # small M: the fused kernel declines (returns None) and nothing is written
+    tiny = K.gemm_bias_residual(a[:64].to(dev), w.to(dev), bias.to(dev), x.reshape(-1, N)[:64].to(dev).contiguous())
+    assert tiny is None
+
+
 def test_gemm_many_tiles_persistent():
     """More tiles than SMs so every CTA loops over several tiles (accumulator double-buffer phases)."""
     _gemm_check("gbig", 128 * 40, 192 * 8, 320, 0)

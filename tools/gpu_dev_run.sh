@@ -15,7 +15,7 @@ for g in "$@"; do
     elem)  run elem 300 tests/test_kernels_gpu.py -k "ln_modulate or gate_residual or qk_rmsnorm" ;;
     short) run short 300 tests/test_kernels_gpu.py -k "attn_short" ;;
     gemm)  run gemm 300 tests/test_kernels_gpu.py -k "gemm and not cta_pair" ;;
-    gemm2) run gemm2 300 tests/test_kernels_gpu.py -k "cta_pair or single_cta" ;;
+    gemm2) run gemm2 300 tests/test_kernels_gpu.py -k "cta_pair or single_cta or fused_residual" ;;
     pipe)  run pipe 300 tests/test_pipeline_gpu.py ;;
     bench2sm) timeout 900 python bench.py --opt gemm_2sm=1 $BENCH_ARGS > gpurun_out/bench2sm.json 2> gpurun_out/bench2sm.err
            echo "bench2sm exit $? : $(tail -c 300 gpurun_out/bench2sm.json)" | tee -a gpurun_out/summary.txt ;;

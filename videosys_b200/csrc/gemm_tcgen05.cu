@@ -226,8 +226,12 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tw, const CUten
   return check_launch("gemm_bf16_tn");
 }
 
+struct EpiArgs;
 int gemm2_dispatch(const void* A, const void* W, const void* bias, void* out, int M, int N, int K, int act,
-                   cudaStream_t st);  // gemm_tcgen05_2sm.cu
+                   cudaStream_t st, const EpiArgs* ep);  // gemm_tcgen05_2sm.cu
+int gemm2_residual(const void* A, const void* W, const void* bias, const void* resid, void* out, const void* mod,
+                   const unsigned char* x_mask, int gate_row, int M, int N, int K, int B, int T, int S,
+                   cudaStream_t st);
 int g_opt_gemm_2sm = 1;  // CTA-pair kernel for large problems (vsb_set_option("gemm_2sm", 0) selects 1-CTA tiles)
 
 }  // namespace vsb
@@ -241,7 +245,7 @@ extern "C" int vsb_gemm_bias_act(const vsb_bf16* A, const vsb_bf16* W, const vsb
     return fail(VSB_ERR_UNSUPPORTED, "gemm: need K %% 8 == 0, N %% 8 == 0, 16B-aligned pointers (M=%d N=%d K=%d)", M, N, K);
   if (act != 0 && act != 1) return fail(VSB_ERR_INVALID, "gemm: act=%d", act);
   if (g_opt_gemm_2sm && M >= 1024) {
-    const int rc2 = gemm2_dispatch(A, W, bias, out, M, N, K, act, (cudaStream_t)stream);
+    const int rc2 = gemm2_dispatch(A, W, bias, out, M, N, K, act, (cudaStream_t)stream, nullptr);
     if (rc2 <= 0) return rc2;  // 1 = not applicable -> single-CTA kernel below
   }
   // tile width: 192 divides every STDiT3 width (1152, 2304, 3456, 4608); narrow outputs use 64/128
@@ -274,4 +278,20 @@ extern "C" int vsb_gemm_bias_act(const vsb_bf16* A, const vsb_bf16* W, const vsb
   }
 #undef VSB_GEMM_CASE
   return fail(VSB_ERR_UNSUPPORTED, "gemm: no tile config");
+}
+
+// Fused epilogue: out = resid + [gate *] (A @ W^T + bias), see include/vsb200.h.  Returns 1 (nothing launched) when
+// the CTA-pair kernel does not take this shape; the caller then runs vsb_gemm_bias_act + vsb_gate_residual.
+extern "C" int vsb_gemm_bias_residual(const vsb_bf16* A, const vsb_bf16* W, const vsb_bf16* bias, const vsb_bf16* resid,
+                                      vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask, int gate_row, int M,
+                                      int N, int K, int B, int T, int S, void* stream) {
+  if (!A || !W || !resid || !out || M <= 0 || N <= 0 || K <= 0) return fail(VSB_ERR_INVALID, "gemm_residual: bad args");
+  if (K % 8 || N % 8 || !aligned16(A) || !aligned16(W) || !aligned16(out) || !aligned16(resid))
+    return fail(VSB_ERR_UNSUPPORTED, "gemm_residual: need K %% 8 == 0, N %% 8 == 0, 16B-aligned pointers");
+  if (gate_row >= 0) {
+    if (!mod || gate_row > 5 || B <= 0 || T <= 0 || S <= 0 || (long long)B * T * S != M || !aligned16(mod))
+      return fail(VSB_ERR_INVALID, "gemm_residual: gate needs mod[2,B,6,N] and B*T*S == M");
+  }
+  if (!g_opt_gemm_2sm || M < 1024) return 1;
+  return gemm2_residual(A, W, bias, resid, out, mod, x_mask, gate_row, M, N, K, B, T, S, (cudaStream_t)stream);
 }

@@ -40,10 +40,20 @@ __device__ __forceinline__ float gelu_tanh_f2(float x) {
   return 0.5f * x * (1.f + th);
 }
 
+// ACT == 2: out = resid + g, g = bf16(gate * y) (gate_row >= 0, per-frame t/t0 select) or g = y (plain residual add),
+// y = bf16(acc + bias): the eager chain of open_sora_transformer_3d.py:219-228 / :240 / :270-284 in the epilogue.
+struct EpiArgs {
+  const bf16* resid;       // [M, N], may alias the output
+  const bf16* mod;         // [2, B, 6, N] or null
+  const uint8_t* x_mask;   // [B, T] or null
+  int gate_row, B, T, S;
+};
+
 template <int BN, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(k2Threads, 1)
 gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
-                     const __grid_constant__ CUtensorMap tm_c, const bf16* __restrict__ bias, int M, int N, int K) {
+                     const __grid_constant__ CUtensorMap tm_c, const bf16* __restrict__ bias, int M, int N, int K,
+                     const EpiArgs ep) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ unsigned char smem_dyn[];
@@ -159,6 +169,18 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       if (threadIdx.x == 128) tma_store_wait_read0();
       named_bar_sync(1, 128);
       const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
+      const long long grow = (long long)m0 + row;
+      const bf16* res_row = nullptr;
+      const bf16* gate_vec = nullptr;
+      if (ACT == 2 && grow < M) {
+        res_row = ep.resid + (size_t)grow * N;
+        if (ep.gate_row >= 0) {
+          const long long bt = grow / ep.S;
+          const int bb = int(bt / ep.T);
+          const int sel = (ep.x_mask != nullptr && ep.x_mask[bt] == 0) ? 1 : 0;
+          gate_vec = ep.mod + ((size_t)(sel * ep.B + bb) * 6 + ep.gate_row) * N;
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < BN / 64; ++c) {
         uint32_t r0[32], r1[32];
@@ -175,6 +197,24 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float v[8];
+          float xr[8], gt[8];
+          if (ACT == 2) {
+            const int gc = ncol0 + j * 8;
+            uint4 ux = make_uint4(0, 0, 0, 0), ug = make_uint4(0, 0, 0, 0);
+            if (res_row != nullptr && gc < N) {
+              ux = *reinterpret_cast<const uint4*>(res_row + gc);
+              if (gate_vec != nullptr) ug = __ldg(reinterpret_cast<const uint4*>(gate_vec + gc));
+            }
+            const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float2 fx = unpack_bf16x2(wx[q]), fg = unpack_bf16x2(wg[q]);
+              xr[2 * q] = fx.x;
+              xr[2 * q + 1] = fx.y;
+              gt[2 * q] = fg.x;
+              gt[2 * q + 1] = fg.y;
+            }
+          }
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int col = j * 8 + e;
@@ -183,6 +223,11 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             const float b = (bias != nullptr && gcol < N) ? __bfloat162float(__ldg(bias + gcol)) : 0.f;
             float x = a + b;
             if (ACT == 1) x = gelu_tanh_f2(rbf(x));
+            if (ACT == 2) {
+              float y = rbf(x);                                  // the Linear's bf16 output
+              if (gate_vec != nullptr) y = rbf(gt[e] * y);       // bf16(gate * y)
+              x = xr[e] + y;                                     // residual add (rounded by the pack below)
+            }
             v[e] = x;
           }
           uint4 u;
@@ -218,7 +263,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
 template <int BN, int ACT>
 static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& tc, const bf16* bias, int M,
-                        int N, int K, cudaStream_t st) {
+                        int N, int K, cudaStream_t st, const EpiArgs& ep = EpiArgs{nullptr, nullptr, nullptr, -1, 1, 1, 1}) {
   using Cfg = Gemm2Cfg<BN>;
   static bool attr = false;
   if (!attr) {
@@ -230,13 +275,14 @@ static int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tw, const CUte
   const int tiles = ((M + 2 * k2BM - 1) / (2 * k2BM)) * ((N + BN - 1) / BN);
   int pairs = num_sms() / 2;
   if (pairs > tiles) pairs = tiles;
-  gemm2_bf16_tn_kernel<BN, ACT><<<pairs * 2, k2Threads, Cfg::kSmemBytes, st>>>(ta, tw, tc, bias, M, N, K);
+  gemm2_bf16_tn_kernel<BN, ACT><<<pairs * 2, k2Threads, Cfg::kSmemBytes, st>>>(ta, tw, tc, bias, M, N, K, ep);
   return check_launch("gemm2_bf16_tn");
 }
 
-// Called by vsb_gemm_bias_act (gemm_tcgen05.cu) for large problems.  Returns 1 if this variant does not apply.
+// Called by vsb_gemm_bias_act / vsb_gemm_bias_residual (gemm_tcgen05.cu).  Returns 1 if this variant does not apply.
+// act: 0 none, 1 gelu, 2 fused residual (ep != nullptr).
 int gemm2_dispatch(const void* A, const void* W, const void* bias, void* out, int M, int N, int K, int act,
-                   cudaStream_t st) {
+                   cudaStream_t st, const EpiArgs* ep) {
   int BN;
   if (N % 256 == 0)
     BN = 256;
@@ -260,9 +306,20 @@ int gemm2_dispatch(const void* A, const void* W, const void* bias, void* out, in
   rc = make_tmap_bf16(&tc, out, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const bf16* b = (const bf16*)bias;
+  if (act == 2) {
+    if (BN == 256) return launch_gemm2<256, 2>(ta, tw, tc, b, M, N, K, st, *ep);
+    return launch_gemm2<192, 2>(ta, tw, tc, b, M, N, K, st, *ep);
+  }
   if (BN == 256)
     return act ? launch_gemm2<256, 1>(ta, tw, tc, b, M, N, K, st) : launch_gemm2<256, 0>(ta, tw, tc, b, M, N, K, st);
   return act ? launch_gemm2<192, 1>(ta, tw, tc, b, M, N, K, st) : launch_gemm2<192, 0>(ta, tw, tc, b, M, N, K, st);
+}
+
+int gemm2_residual(const void* A, const void* W, const void* bias, const void* resid, void* out, const void* mod,
+                   const unsigned char* x_mask, int gate_row, int M, int N, int K, int B, int T, int S,
+                   cudaStream_t st) {
+  EpiArgs ep{(const bf16*)resid, (const bf16*)mod, x_mask, gate_row, B, T, S};
+  return gemm2_dispatch(A, W, bias, out, M, N, K, 2, st, &ep);
 }
 
 }  // namespace vsb

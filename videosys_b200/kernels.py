@@ -156,6 +156,25 @@ def gemm_bias_act(a, w, bias=None, act: int = 0, out=None):
     return out
 
 
+def gemm_bias_residual(a, w, bias, resid, mod=None, x_mask_u8=None, gate_row: int = -1, B=1, T=1, S=1, out=None):
+    """out = resid + [gate *] (a @ w^T + bias) with the branch fused into the GEMM epilogue.
+    Returns None (nothing launched) when the fused kernel does not take the shape: use the unfused pair then."""
+    lib, st = _prep(a, w, bias, resid, mod, x_mask_u8, out)
+    K = a.shape[-1]
+    M = a.numel() // K
+    N = w.shape[0]
+    out = resid if out is None else out
+    with _Timed("gemm", 2 * M * N * K):
+        rc = lib.vsb_gemm_bias_residual(_p(a), _p(w), _p(bias), _p(resid), _p(out), _p(mod), _p(x_mask_u8), gate_row, M,
+                                        N, K, B, T, S, st)
+    if rc == 1:
+        if PROFILE is not None:
+            PROFILE.pop()
+        return None
+    _lib.check(rc, "gemm_bias_residual")
+    return out
+
+
 def attn_flash(q, k, v, nb, nq, nk, H, D, q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, scale,
                kv_lens: Optional[Sequence[int]] = None, out=None):
     """q/k/v: tensors whose data_ptr() is the first element of the strided view (may be slices of one buffer)."""

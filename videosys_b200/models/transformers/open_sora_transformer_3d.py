@@ -325,15 +325,20 @@ class STDiT3(nn.Module):
                                      Sa * 3 * C, D**-0.5)
                 else:
                     o = K.attn_short(qkv.view(-1, 3, H, D), wq, wk, None, None, B * Ta, 1, Sa, 0, 1, Sa, H, D, D**-0.5)
-            y = K.gemm_bias_act(o.view(-1, C), a.proj.weight, a.proj.bias)
-            if not blk.temporal and sp > 1:
-                y = self._switch(y.view(B, Ta, Sa, C), Tg, Sg, to_spatial_shard=True)
-            cache = None
-            if pab_on:
-                if blk.last_attn is None or blk.last_attn.shape != x.shape:
-                    blk.last_attn = torch.empty_like(x)
-                cache = blk.last_attn
-            K.gate_residual(x, y.reshape(x.shape), mod, mask_u8, 2, B, T, S, out=x, cache_out=cache)
+            fused = None
+            if not pab_on and (blk.temporal or sp == 1):
+                # gate + select + residual in the proj GEMM's epilogue (no PAB cache to fill, no reshard in between)
+                fused = K.gemm_bias_residual(o.view(-1, C), a.proj.weight, a.proj.bias, x, mod, mask_u8, 2, B, T, S)
+            if fused is None:
+                y = K.gemm_bias_act(o.view(-1, C), a.proj.weight, a.proj.bias)
+                if not blk.temporal and sp > 1:
+                    y = self._switch(y.view(B, Ta, Sa, C), Tg, Sg, to_spatial_shard=True)
+                cache = None
+                if pab_on:
+                    if blk.last_attn is None or blk.last_attn.shape != x.shape:
+                        blk.last_attn = torch.empty_like(x)
+                    cache = blk.last_attn
+                K.gate_residual(x, y.reshape(x.shape), mod, mask_u8, 2, B, T, S, out=x, cache_out=cache)
 
         # ---- cross attention ----
         reuse = False
@@ -349,17 +354,22 @@ class STDiT3(nn.Module):
             kv2 = kv.view(-1, 2, C)
             o = K.attn_flash(q, kv2[:, 0], kv2[:, 1], B, T * S, Lv, H, D, C, T * S * C, 2 * C, Lv * 2 * C, D**-0.5,
                              kv_lens=kv_lens)
-            out = blk.last_cross if (pab_on and blk.last_cross is not None and blk.last_cross.shape == x.shape) else None
-            xc = K.gemm_bias_act(o, c.proj.weight, c.proj.bias, out=out)
-            if pab_on:
-                blk.last_cross = xc
-            K.residual_add(x, xc.view(x.shape), out=x)
+            fused = None
+            if not pab_on:
+                fused = K.gemm_bias_residual(o.view(-1, C), c.proj.weight, c.proj.bias, x)  # x += proj(o) in the epilogue
+            if fused is None:
+                out = blk.last_cross if (pab_on and blk.last_cross is not None and blk.last_cross.shape == x.shape) else None
+                xc = K.gemm_bias_act(o, c.proj.weight, c.proj.bias, out=out)
+                if pab_on:
+                    blk.last_cross = xc
+                K.residual_add(x, xc.view(x.shape), out=x)
 
         # ---- MLP ----
         xm = K.ln_modulate(x, mod, mask_u8, 3, 4, B, T, S)
         h = K.gemm_bias_act(xm, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=1)
-        y = K.gemm_bias_act(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias)
-        K.gate_residual(x, y, mod, mask_u8, 5, B, T, S, out=x)
+        if K.gemm_bias_residual(h.view(-1, h.shape[-1]), blk.mlp.fc2.weight, blk.mlp.fc2.bias, x, mod, mask_u8, 5, B, T, S) is None:
+            y = K.gemm_bias_act(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias)
+            K.gate_residual(x, y, mod, mask_u8, 5, B, T, S, out=x)
         return x
 
     # ---- STDiT3.forward --------------------------------------------------------------------------------------
