@@ -272,7 +272,7 @@ def test_gemm_fused_residual_epilogue(B, T, S, N, K_, gate_row):
         xg = x.to(dev).clone()
         got = K.gemm_bias_residual(a.to(dev), w.to(dev), bias.to(dev), xg)
     assert got is not None and got.data_ptr() == xg.data_ptr(), "fused kernel must take this shape and update x in place"
-    _ulp_report(f"gemm+residual gate_row={gate_row} K={K_}", got, want, min_equal=0.98, max_ulps=2.0, row_floor=0.25)
+    _ulp_report(f"gemm+residual gate_row={gate_row} K={K_}", got, want, min_equal=0.98, max_ulps=3.0, row_floor=0.25)
     # small M: the fused kernel declines (returns None) and nothing is written
     tiny = K.gemm_bias_residual(a[:64].to(dev), w.to(dev), bias.to(dev), x.reshape(-1, N)[:64].to(dev).contiguous())
     assert tiny is None

@@ -22,6 +22,17 @@ for g in "$@"; do
     flash) run flash 300 tests/test_kernels_gpu.py -k "attn_flash" ;;
     model) run model 600 tests/test_model_gpu.py ;;
     all)   run all 900 tests ;;
+    dsp)   run dsp 600 tests/test_dsp_gpu.py ;;
+    kbench) timeout 600 python tools/kernel_bench.py > gpurun_out/kernel_bench.log 2>&1; echo "kbench exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/kernel_bench.log | tail -12 ;;
+    mbenchnccl*) n=${g#mbenchnccl}; echo "=== bench N=$n (NCCL a2a) ===" | tee -a gpurun_out/summary.txt
+           VSB_DSP_P2P=0 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29534 \
+              bench.py --gpus $n $BENCH_ARGS > gpurun_out/bench_nccl_n$n.json 2> gpurun_out/bench_nccl_n$n.err
+           echo "exit $? : $(tail -c 1500 gpurun_out/bench_nccl_n$n.json | cut -c1-300)" | tee -a gpurun_out/summary.txt ;;
+    mbench*) n=${g#mbench}; echo "=== bench N=$n ===" | tee -a gpurun_out/summary.txt
+           timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 \
+              bench.py --gpus $n $BENCH_ARGS > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
+           echo "exit $? : $(tail -c 1500 gpurun_out/bench_n$n.json | cut -c1-400)" | tee -a gpurun_out/summary.txt
+           tail -n 8 gpurun_out/bench_n$n.err ;;
     smoke) echo "=== smoke ===" | tee -a gpurun_out/summary.txt
            timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
            echo "exit $? : $(tail -n 1 gpurun_out/smoke.log)" | tee -a gpurun_out/summary.txt ;;

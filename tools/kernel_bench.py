@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Per-shape microbenchmarks on the GPU box: our GEMM (1-CTA / CTA-pair) vs cuBLAS, our flash attention vs SDPA,
+elementwise kernels vs the HBM copy peak.  Library kernels are timed only as yardsticks (never on the product path)."""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from videosys_b200 import kernels as K  # noqa: E402
+
+dev = torch.device("cuda:0")
+bf = torch.bfloat16
+
+
+def timeit(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters * 1e-3
+
+
+out = {}
+M = 144000
+for name, (N, Kd, act) in {"qkv": (3456, 1152, 0), "proj": (1152, 1152, 0), "fc1": (4608, 1152, 1), "fc2": (1152, 4608, 0)}.items():
+    a = torch.randn(M, Kd, device=dev, dtype=bf)
+    w = torch.randn(N, Kd, device=dev, dtype=bf) * 0.02
+    b = torch.randn(N, device=dev, dtype=bf)
+    o = torch.empty(M, N, device=dev, dtype=bf)
+    fl = 2.0 * M * N * Kd
+    r = {}
+    for opt in (0, 1):
+        K.set_option("gemm_2sm", opt)
+        t = timeit(lambda: K.gemm_bias_act(a, w, b, act=act, out=o))
+        r["2sm" if opt else "1sm"] = round(fl / t / 1e12, 1)
+    t = timeit(lambda: torch.nn.functional.linear(a, w, b))
+    r["cublas_linear"] = round(fl / t / 1e12, 1)
+    out["gemm_" + name] = r
+    print("gemm", name, r, flush=True)
+    del a, w, o
+K.set_option("gemm_2sm", 1)
+
+# attention: spatial 720p (40 x 16 heads x 3600 x 72), cross (2 x 16 x 72000 x 300)
+C, H, D = 1152, 16, 72
+qkv = torch.randn(40, 3600, 3, H, D, device=dev, dtype=bf)
+fl = 4.0 * 40 * H * 3600 * 3600 * D
+t = timeit(lambda: K.attn_flash(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 40, 3600, 3600, H, D, 3 * C, 3600 * 3 * C, 3 * C, 3600 * 3 * C, D**-0.5), iters=5)
+r = {"ours": round(fl / t / 1e12, 1)}
+q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)
+for nm, be in (("sdpa_flash", "FLASH_ATTENTION"), ("sdpa_cudnn", "CUDNN_ATTENTION"), ("sdpa_efficient", "EFFICIENT_ATTENTION")):
+    try:
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+
+        with sdpa_kernel([getattr(SDPBackend, be)]):
+            t = timeit(lambda: torch.nn.functional.scaled_dot_product_attention(q, k, v), iters=5)
+        r[nm] = round(fl / t / 1e12, 1)
+    except Exception as e:
+        r[nm] = f"n/a ({type(e).__name__})"
+out["attn_spatial_720p"] = r
+print("attn spatial", r, flush=True)
+del qkv
+
+x = torch.randn(2, 72000, C, device=dev, dtype=bf)
+y = torch.randn(2, 72000, C, device=dev, dtype=bf)
+mod = torch.randn(2, 2, 6, C, device=dev, dtype=bf)
+m8 = torch.ones(2, 20, dtype=torch.uint8, device=dev)
+o = torch.empty_like(x)
+nb = x.numel() * 2
+r = {}
+t = timeit(lambda: K.ln_modulate(x, mod, m8, 0, 1, 2, 20, 3600, out=o)); r["ln_modulate_GBs"] = round(2 * nb / t / 1e9)
+t = timeit(lambda: K.gate_residual(x, y, mod, m8, 2, 2, 20, 3600, out=o)); r["gate_residual_GBs"] = round(3 * nb / t / 1e9)
+t = timeit(lambda: K.residual_add(x, y, out=o)); r["residual_add_GBs"] = round(3 * nb / t / 1e9)
+t = timeit(lambda: o.copy_(x)); r["torch_copy_GBs"] = round(2 * nb / t / 1e9)
+qkv = torch.randn(144000, 3, H, D, device=dev, dtype=bf)
+wq = torch.ones(D, device=dev, dtype=bf)
+t = timeit(lambda: K.qk_rmsnorm_(qkv, wq, wq, H, D)); r["qk_rmsnorm_GBs"] = round(4 * 144000 * C * 2 / t / 1e9)
+cos = torch.randn(20, D, device=dev); sin = torch.randn(20, D, device=dev)
+t = timeit(lambda: K.attn_short(qkv, wq, wq, cos, sin, 2, 3600, 20 * 3600, 1, 3600, 20, H, D, D**-0.5, out=o.view(-1, C)))
+r["attn_short_GBs"] = round(4 * 144000 * C * 2 / t / 1e9); r["attn_short_ms"] = round(t * 1e3, 3)
+out["elementwise"] = r
+print("elementwise", r, flush=True)
+os.makedirs("gpurun_out", exist_ok=True)
+json.dump(out, open("gpurun_out/kernel_bench.json", "w"), indent=1)

@@ -18,6 +18,11 @@ namespace vsb {
 constexpr int kMaxN = 32;
 constexpr int kWarpsPerBlock = 4;
 
+union Vec8s {
+  uint4 u;
+  __nv_bfloat162 h[4];
+};
+
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
@@ -106,40 +111,70 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
       continue;
     }
 
-    // ---- 2. RMSNorm (+RoPE) in place; lane = row, q then k ----
-    if (lane < n) {
-#pragma unroll 1
-      for (int which = 0; which < 2; ++which) {
-        __nv_bfloat162* r2 = reinterpret_cast<__nv_bfloat162*>((which ? sk : sq) + lane * D);
-        const __nv_bfloat162* w2 = reinterpret_cast<const __nv_bfloat162*>(which ? wk : wq);
+    // ---- 2. RMSNorm (+RoPE, q scale) in place.  LPR lanes share one row (CPL 16-byte chunks each); the 2n rows
+    //         (q rows then k rows) are walked 32/LPR at a time; the sum of squares crosses lanes by shuffle ----
+    {
+      constexpr int LPR = (D == 72) ? 3 : 2;  // lanes per row
+      constexpr int CPL = VPR / LPR;          // chunks per lane (3 or 4)
+      constexpr int RPP = 32 / LPR;           // rows per pass
+      const int gi = lane / LPR, part = lane - gi * LPR;
+      const int gbase = (gi < RPP ? gi : 0) * LPR;
+      for (int vr0 = 0; vr0 < 2 * n; vr0 += RPP) {
+        const int vr = vr0 + gi;
+        const bool act = (gi < RPP) && (vr < 2 * n);
+        const int which = (act && vr >= n) ? 1 : 0;
+        const int r = act ? (vr - which * n) : 0;
+        bf16* rowp = (which ? sk : sq) + r * D + part * CPL * 8;
+        Vec8s v[CPL];
         float ss = 0.f;
+        if (act) {
 #pragma unroll
-        for (int d = 0; d < D / 2; ++d) {
-          const float2 f = __bfloat1622float2(r2[d]);
-          ss += f.x * f.x + f.y * f.y;
+          for (int c = 0; c < CPL; ++c) {
+            v[c].u = *reinterpret_cast<const uint4*>(rowp + c * 8);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(v[c].h[j]);
+              ss = fmaf(f.x, f.x, ss);
+              ss = fmaf(f.y, f.y, ss);
+            }
+          }
         }
-        const float rs = rsqrtf(ss / (float)D + eps);
-#pragma unroll 4
-        for (int d = 0; d < D / 2; ++d) {
-          const float2 f = __bfloat1622float2(r2[d]);
-          const float2 w = __bfloat1622float2(__ldg(w2 + d));
-          // normalization.py:28-33: h = bf16(x*rstd); y = bf16(w*h)
-          float y0 = rbf(w.x * rbf(f.x * rs));
-          float y1 = rbf(w.y * rbf(f.y * rs));
-          if (has_rope) {
-            // rotate_queries_or_keys: t*cos + rotate_half(t)*sin in fp32, pairs (2i, 2i+1): rot = (-x2, x1)
-            const float2 cs = *reinterpret_cast<const float2*>(s_cos + lane * D + 2 * d);
-            const float2 sn = *reinterpret_cast<const float2*>(s_sin + lane * D + 2 * d);
-            const float o0 = __fadd_rn(__fmul_rn(y0, cs.x), __fmul_rn(-y1, sn.x));
-            const float o1 = __fadd_rn(__fmul_rn(y1, cs.y), __fmul_rn(y0, sn.y));
-            y0 = rbf(o0);
-            y1 = rbf(o1);
+        float tot = 0.f;
+#pragma unroll
+        for (int i = 0; i < LPR; ++i) tot += __shfl_sync(0xffffffffu, ss, gbase + i);
+        if (act) {
+          const float rs = rsqrtf(tot / (float)D + eps);
+          const bf16* wrow = (which ? wk : wq) + part * CPL * 8;
+#pragma unroll
+          for (int c = 0; c < CPL; ++c) {
+            Vec8s w, o;
+            w.u = __ldg(reinterpret_cast<const uint4*>(wrow + c * 8));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __bfloat1622float2(v[c].h[j]);
+              // normalization.py:28-33: h = bf16(x*rstd); y = bf16(w*h)
+              __nv_bfloat162 y2 = __hmul2(w.h[j], __floats2bfloat162_rn(f.x * rs, f.y * rs));
+              if (has_rope || which == 0) {
+                float2 y = __bfloat1622float2(y2);
+                if (has_rope) {
+                  // rotate_queries_or_keys: t*cos + rotate_half(t)*sin in fp32, pairs (2i, 2i+1): rot = (-x2, x1)
+                  const int d = (part * CPL + c) * 8 + 2 * j;
+                  const float2 cs = *reinterpret_cast<const float2*>(s_cos + r * D + d);
+                  const float2 sn = *reinterpret_cast<const float2*>(s_sin + r * D + d);
+                  const float o0 = __fadd_rn(__fmul_rn(y.x, cs.x), __fmul_rn(-y.y, sn.x));
+                  const float o1 = __fadd_rn(__fmul_rn(y.y, cs.y), __fmul_rn(y.x, sn.y));
+                  y = __bfloat1622float2(__floats2bfloat162_rn(o0, o1));
+                }
+                if (which == 0) {  // q = bf16(q * scale)  (attentions.py:113)
+                  y.x *= scale;
+                  y.y *= scale;
+                }
+                y2 = __floats2bfloat162_rn(y.x, y.y);
+              }
+              o.h[j] = y2;
+            }
+            *reinterpret_cast<uint4*>(rowp + c * 8) = o.u;
           }
-          if (which == 0) {  // q = bf16(q * scale)  (attentions.py:113)
-            y0 = y0 * scale;
-            y1 = y1 * scale;
-          }
-          r2[d] = __floats2bfloat162_rn(y0, y1);
         }
       }
     }

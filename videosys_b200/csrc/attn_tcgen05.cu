@@ -16,13 +16,13 @@
 
 namespace vsb {
 
-constexpr int kAttnThreads = 384;
+constexpr int kAttnThreads = 640;  // 4 control warps + 2 query tiles x 8 softmax warps (2 threads per row)
 constexpr int kKvStages = 3;
 constexpr int kTileA = 128 * 128;  // bytes: 128 rows x 64 bf16 (SWIZZLE_128B)
 constexpr int kTileB = 128 * 32;   // bytes: 128 rows x 16 bf16 (SWIZZLE_32B)
 constexpr int kQBytes = kTileA + kTileB;
 constexpr int kKvStageBytes = 2 * (kTileA + kTileB);
-constexpr int kAttnSmem = 2 * kQBytes + kKvStages * kKvStageBytes + 1024 + 256;
+constexpr int kAttnSmem = 2 * kQBytes + kKvStages * kKvStageBytes + 1024 + 256 + 4096;  // + max/sum exchange
 
 // TMEM columns
 __host__ __device__ constexpr uint32_t col_s(int x) { return uint32_t(x) * 128u; }        // S_A, S_B
@@ -57,6 +57,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   uint64_t* p_full = s_full + 2;           // [2]
   uint64_t* o_full = p_full + 2;           // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+  float* xch = reinterpret_cast<float*>(bars) + 64;  // [2 buffers][2 tiles][2 halves][128 rows] after the barriers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
@@ -82,7 +83,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);  // one arrival per softmax warp
+      mbar_init(&p_full[i], 8);  // one arrival per softmax warp (8 per query tile)
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
@@ -175,53 +176,53 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
   } else if (warp >= 4) {
     // =============================== softmax warpgroups ===============================
-    const int x = (warp - 4) >> 2;          // query tile 0/1
-    const int ew = warp & 3;                // TMEM lane quarter
+    // Two threads per query row: warp (ew, half) owns TMEM lanes 32*ew.. and key columns [64*half, 64*half+64).
+    // The row max crosses the two halves through shared memory (double-buffered, one named barrier per tile);
+    // 16 softmax warps (4 per scheduler) hide the TMEM-load / MUFU / barrier latencies that 8 could not.
+    const int sw = warp - 4;
+    const int x = sw >> 3;                  // query tile 0/1
+    const int ew = sw & 3;                  // TMEM lane quarter (== warp % 4)
+    const int half = (sw >> 2) & 1;         // key-column half
     const int row = ew * 32 + lane;
     const uint32_t lane_off = uint32_t(ew * 32) << 16;
     const uint32_t tS = tmem_base + lane_off + col_s(x);
     const uint32_t tO = tmem_base + lane_off + col_o(x);
+    constexpr int kOChunks = kHasB ? 10 : 8;                  // 8-column chunks of O (80 / 64 columns)
+    const int oc0 = half ? kOChunks / 2 : 0, oc1 = half ? kOChunks : kOChunks / 2;
     const float sl2 = p.scale_log2;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[x], j & 1);
       tc_fence_after();
-      const int valid = kv_len - j * 128;  // >= 128: full tile; columns >= valid are masked
-      // ---- all 128 scores of my row -> registers (4 loads in flight, one wait) ----
-      uint32_t a[4][32];
-      tmem_ld32(tS, a[0]);
-      tmem_ld32(tS + 32, a[1]);
-      tmem_ld32(tS + 64, a[2]);
-      tmem_ld32(tS + 96, a[3]);
+      const int valid = kv_len - j * 128 - half * 64;  // >= 64: my 64 columns are all real keys
+      uint32_t a[2][32];
+      tmem_ld32(tS + half * 64, a[0]);
+      tmem_ld32(tS + half * 64 + 32, a[1]);
       tmem_wait_ld();
       float mx;
-      if (valid >= 128) {
+      if (valid >= 64) {
         float m0 = fmax3(__uint_as_float(a[0][0]), __uint_as_float(a[0][1]), __uint_as_float(a[0][2]));
         float m1 = fmax3(__uint_as_float(a[1][0]), __uint_as_float(a[1][1]), __uint_as_float(a[1][2]));
-        float m2 = fmax3(__uint_as_float(a[2][0]), __uint_as_float(a[2][1]), __uint_as_float(a[2][2]));
-        float m3 = fmax3(__uint_as_float(a[3][0]), __uint_as_float(a[3][1]), __uint_as_float(a[3][2]));
 #pragma unroll
         for (int i = 3; i < 31; i += 2) {
           m0 = fmax3(m0, __uint_as_float(a[0][i]), __uint_as_float(a[0][i + 1]));
           m1 = fmax3(m1, __uint_as_float(a[1][i]), __uint_as_float(a[1][i + 1]));
-          m2 = fmax3(m2, __uint_as_float(a[2][i]), __uint_as_float(a[2][i + 1]));
-          m3 = fmax3(m3, __uint_as_float(a[3][i]), __uint_as_float(a[3][i + 1]));
         }
-        m0 = fmaxf(m0, __uint_as_float(a[0][31]));
-        m1 = fmaxf(m1, __uint_as_float(a[1][31]));
-        m2 = fmaxf(m2, __uint_as_float(a[2][31]));
-        m3 = fmaxf(m3, __uint_as_float(a[3][31]));
-        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        mx = fmax3(m0, m1, fmaxf(__uint_as_float(a[0][31]), __uint_as_float(a[1][31])));
       } else {  // ragged last tile: masked columns never win the max and get p = 0 below
         mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < 2; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (c * 32 + i >= valid) a[c][i] = 0xff800000u;  // -inf
             mx = fmaxf(mx, __uint_as_float(a[c][i]));
           }
       }
+      float* xb = xch + ((j & 1) * 2 + x) * 256;
+      xb[half * 128 + row] = mx;
+      named_bar_sync(2 + x, 256);  // also orders my S loads before the partner's P stores over the same columns
+      mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
       // ---- lazy rescale: keep the stale running max unless it grew by more than 2^8 (p stays <= 256) ----
       const float m_new = fmaxf(m_run, mx);
       const bool grow = (m_new - m_run) * sl2 > 8.f;  // first tile: m_run = -inf -> true
@@ -229,21 +230,21 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
         // O is quiescent here: S_x(j) complete implies PV_x(j-1) complete (in-order tensor pipe)
 #pragma unroll 1
-        for (int c = 0; c < (kHasB ? 5 : 4); ++c) {  // rare path: one 16-column chunk at a time (register budget)
-          uint32_t o[16];
-          tmem_ld16(tO + c * 16, o);
+        for (int c = oc0; c < oc1; ++c) {  // my half of the O columns
+          uint32_t o[8];
+          tmem_ld8(tO + c * 8, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st16(tO + c * 16, o);
+          for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st8(tO + c * 8, o);
         }
       }
       if (grow) m_run = m_new;
       const float mb = m_run * sl2;
-      // ---- p = exp2(s*sl2 - m*sl2); row sum (4 chains); bf16 P -> TMEM over the consumed S columns ----
+      // ---- p = exp2(s*sl2 - m*sl2); partial row sum; bf16 P -> TMEM over consumed S columns ----
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -258,7 +259,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
           pk[i >> 1] = pack_bf16x2(p0, p1);
           pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
         }
-        tmem_st16(tS + c * 16, pk);
+        tmem_st16(tS + half * 32 + c * 16, pk);
       }
       l_run = l_run * alpha + ((s0 + s1) + (s2 + s3));
       tmem_wait_st();
@@ -266,14 +267,21 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[x]);
     }
-    // ---- epilogue: O / l -> bf16 -> global ----
+    // ---- epilogue: combine the two partial row sums, O / l -> bf16 -> global (each half writes its columns) ----
+    {
+      float* xb = xch + ((n_tiles & 1) * 2 + x) * 256;
+      xb[half * 128 + row] = l_run;
+      named_bar_sync(2 + x, 256);
+      l_run += xb[(half ^ 1) * 128 + row];
+    }
     mbar_wait(&o_full[x], 0);
     tc_fence_after();
     const int qrow = q0 + x * 128 + row;
     const float inv = 1.f / l_run;
     bf16* dst = p.out + ((size_t)((size_t)b * p.nq + (qrow < p.nq ? qrow : 0)) * p.H + h) * D;
+    const int ec0 = half ? (D / 8 + 1) / 2 : 0, ec1 = half ? D / 8 : (D / 8 + 1) / 2;
 #pragma unroll 1
-    for (int c = 0; c < D / 8; ++c) {
+    for (int c = ec0; c < ec1; ++c) {
       uint32_t r[8];
       tmem_ld8(tO + c * 8, r);
       tmem_wait_ld();

@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
       }
     }
     const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+    const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.f, 1.f);
     bf16* orow = out + (size_t)row * C;
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
@@ -100,13 +101,11 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           float2 f = __bfloat1622float2(v[i].h[j]);
-          float2 fs = __bfloat1622float2(sc.h[j]);
-          float2 fh = __bfloat1622float2(sh.h[j]);
-          // eager chain: n = bf16(LN(x)); g = bf16(1 + scale); m = bf16(n * g); out = bf16(m + shift)
-          float n0 = rbf((f.x - mean) * rstd), n1 = rbf((f.y - mean) * rstd);
-          float g0 = rbf(1.f + fs.x), g1 = rbf(1.f + fs.y);
-          float m0 = rbf(n0 * g0), m1 = rbf(n1 * g1);
-          o.h[j] = __floats2bfloat162_rn(m0 + fh.x, m1 + fh.y);
+          // eager chain on packed bf16 (each op = exact result rounded once, like the eager bf16 kernels):
+          // n = bf16(LN(x)); g = bf16(1 + scale); m = bf16(n * g); out = bf16(m + shift)
+          const __nv_bfloat162 n2 = __floats2bfloat162_rn((f.x - mean) * rstd, (f.y - mean) * rstd);
+          const __nv_bfloat162 g2 = __hadd2(one2, sc.h[j]);
+          o.h[j] = __hadd2(__hmul2(n2, g2), sh.h[j]);
         }
         st_stream(orow + vi * 8, o.u);
       }
@@ -150,10 +149,8 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(const bf16* __restri
     vg.u = __ldg(reinterpret_cast<const uint4*>(gate + vi * 8));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      float2 fx = __bfloat1622float2(vx.h[j]), fy = __bfloat1622float2(vy.h[j]), fg = __bfloat1622float2(vg.h[j]);
-      g.h[j] = __floats2bfloat162_rn(fg.x * fy.x, fg.y * fy.y);
-      float2 gg = __bfloat1622float2(g.h[j]);
-      o.h[j] = __floats2bfloat162_rn(fx.x + gg.x, fx.y + gg.y);
+      g.h[j] = __hmul2(vg.h[j], vy.h[j]);  // bf16(gate * y)
+      o.h[j] = __hadd2(vx.h[j], g.h[j]);   // bf16(x + gated)
     }
     if (cache != nullptr) st_stream(cache + i * 8, g.u);
     st_stream(out + i * 8, o.u);
@@ -168,10 +165,7 @@ __global__ void __launch_bounds__(256) residual_add_kernel(const bf16* __restric
     vx.u = ld_stream(x + i * 8);
     vy.u = ld_stream(y + i * 8);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float2 fx = __bfloat1622float2(vx.h[j]), fy = __bfloat1622float2(vy.h[j]);
-      o.h[j] = __floats2bfloat162_rn(fx.x + fy.x, fx.y + fy.y);
-    }
+    for (int j = 0; j < 4; ++j) o.h[j] = __hadd2(vx.h[j], vy.h[j]);
     st_stream(out + i * 8, o.u);
   }
 }
@@ -232,9 +226,9 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv,
         Vec8 o;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float2 f = __bfloat1622float2(v[u].h[j]), fw = __bfloat1622float2(wv[which[u]].h[j]);
+          float2 f = __bfloat1622float2(v[u].h[j]);
           // eager: h = bf16(x * rstd); out = bf16(w * h)
-          o.h[j] = __floats2bfloat162_rn(fw.x * rbf(f.x * r), fw.y * rbf(f.y * r));
+          o.h[j] = __hmul2(wv[which[u]].h[j], __floats2bfloat162_rn(f.x * r, f.y * r));
         }
         *reinterpret_cast<uint4*>(p[u]) = o.u;
       }

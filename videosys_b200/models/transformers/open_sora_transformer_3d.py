@@ -191,6 +191,10 @@ class STDiT3(nn.Module):
         self._dsp: Optional[comm.DspP2P] = None
         self._pos_cache = {}
         self._rope_cache = {}
+        # gate/residual inside the proj / fc2 GEMM epilogue (vsb_gemm_bias_residual).  Measured on B200 (720p): the
+        # per-thread residual reads put the epilogue on the critical path (+41 ms GEMM vs -28 ms of elementwise
+        # passes), so the separate one-pass kernels stay the default until the residual tile is TMA-prefetched.
+        self._fuse_epilogue = os.environ.get("VSB_FUSE_EPILOGUE", "0") == "1"
 
     # ------------------------------------------------------------------------------------------------------
     def initialize_weights(self):
@@ -326,7 +330,7 @@ class STDiT3(nn.Module):
                 else:
                     o = K.attn_short(qkv.view(-1, 3, H, D), wq, wk, None, None, B * Ta, 1, Sa, 0, 1, Sa, H, D, D**-0.5)
             fused = None
-            if not pab_on and (blk.temporal or sp == 1):
+            if self._fuse_epilogue and not pab_on and (blk.temporal or sp == 1):
                 # gate + select + residual in the proj GEMM's epilogue (no PAB cache to fill, no reshard in between)
                 fused = K.gemm_bias_residual(o.view(-1, C), a.proj.weight, a.proj.bias, x, mod, mask_u8, 2, B, T, S)
             if fused is None:
@@ -355,7 +359,7 @@ class STDiT3(nn.Module):
             o = K.attn_flash(q, kv2[:, 0], kv2[:, 1], B, T * S, Lv, H, D, C, T * S * C, 2 * C, Lv * 2 * C, D**-0.5,
                              kv_lens=kv_lens)
             fused = None
-            if not pab_on:
+            if self._fuse_epilogue and not pab_on:
                 fused = K.gemm_bias_residual(o.view(-1, C), c.proj.weight, c.proj.bias, x)  # x += proj(o) in the epilogue
             if fused is None:
                 out = blk.last_cross if (pab_on and blk.last_cross is not None and blk.last_cross.shape == x.shape) else None
@@ -367,7 +371,10 @@ class STDiT3(nn.Module):
         # ---- MLP ----
         xm = K.ln_modulate(x, mod, mask_u8, 3, 4, B, T, S)
         h = K.gemm_bias_act(xm, blk.mlp.fc1.weight, blk.mlp.fc1.bias, act=1)
-        if K.gemm_bias_residual(h.view(-1, h.shape[-1]), blk.mlp.fc2.weight, blk.mlp.fc2.bias, x, mod, mask_u8, 5, B, T, S) is None:
+        fused = None
+        if self._fuse_epilogue:
+            fused = K.gemm_bias_residual(h.view(-1, h.shape[-1]), blk.mlp.fc2.weight, blk.mlp.fc2.bias, x, mod, mask_u8, 5, B, T, S)
+        if fused is None:
             y = K.gemm_bias_act(h, blk.mlp.fc2.weight, blk.mlp.fc2.bias)
             K.gate_residual(x, y, mod, mask_u8, 5, B, T, S, out=x)
         return x
