@@ -23,6 +23,8 @@ for g in "$@"; do
     model) run model 600 tests/test_model_gpu.py ;;
     all)   run all 900 tests ;;
     dsp)   run dsp 600 tests/test_dsp_gpu.py ;;
+    refgpu) timeout 600 python tests/bench_reference_gpu.py > gpurun_out/refgpu.log 2>&1; echo "refgpu exit $? $(tail -n 1 gpurun_out/refgpu.log | cut -c1-300)" | tee -a gpurun_out/summary.txt ;;
+    atrace) timeout 300 python tools/attn_trace.py > gpurun_out/attn_trace.log 2>&1; echo "atrace exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/attn_trace.log ;;
     kbench) timeout 600 python tools/kernel_bench.py > gpurun_out/kernel_bench.log 2>&1; echo "kbench exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/kernel_bench.log | tail -12 ;;
     mbenchnccl*) n=${g#mbenchnccl}; echo "=== bench N=$n (NCCL a2a) ===" | tee -a gpurun_out/summary.txt
            VSB_DSP_P2P=0 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29534 \
@@ -48,6 +50,9 @@ for g in "$@"; do
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 14 -c 4 -o gpurun_out/prof_gemm -f \
               python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
            echo "ncu_gemm exit $?" | tee -a gpurun_out/summary.txt ;;
+    ncu_short) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_short -c 1 -o gpurun_out/prof_short -f \
+              python tools/kernel_bench.py > gpurun_out/ncu_short.log 2>&1
+           echo "ncu_short exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_flash -s 2 -c 2 -o gpurun_out/prof_attn -f \
               python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline > gpurun_out/ncu_attn.log 2>&1
            echo "ncu_attn exit $?" | tee -a gpurun_out/summary.txt ;;

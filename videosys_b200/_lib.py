@@ -18,6 +18,7 @@ SIGNATURES = {
     "vsb_init": (_i, [_i]),
     "vsb_launch_count": (C.c_ulonglong, []),
     "vsb_set_option": (_i, [C.c_char_p, _i]),
+    "vsb_debug_attn_trace": (_i, [_vp]),
     "vsb_ln_modulate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "vsb_modulation_table": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "vsb_gate_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -79,11 +79,21 @@ extern "C" int vsb_init(int device) {
 
 namespace vsb {
 extern int g_opt_gemm_2sm;
+extern int g_opt_attn_variant;
+extern int g_opt_attn_pingpong;
 }
 extern "C" int vsb_set_option(const char* name, int value) {
   if (!name) return fail(VSB_ERR_INVALID, "set_option: null name");
   if (!strcmp(name, "gemm_2sm")) {
     g_opt_gemm_2sm = value;
+    return VSB_OK;
+  }
+  if (!strcmp(name, "attn_pingpong")) {
+    g_opt_attn_pingpong = value;
+    return VSB_OK;
+  }
+  if (!strcmp(name, "attn_variant")) {
+    g_opt_attn_variant = value;
     return VSB_OK;
   }
   return fail(VSB_ERR_INVALID, "set_option: unknown option '%s'", name);

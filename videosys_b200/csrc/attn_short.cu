@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
             for (int j = 0; j < 4; ++j) {
               const float2 f = __bfloat1622float2(v[c].h[j]);
               // normalization.py:28-33: h = bf16(x*rstd); y = bf16(w*h)
-              __nv_bfloat162 y2 = __hmul2(w.h[j], __floats2bfloat162_rn(f.x * rs, f.y * rs));
+              __nv_bfloat162 y2 = __hmul2_rn(w.h[j], __floats2bfloat162_rn(f.x * rs, f.y * rs));
               if (has_rope || which == 0) {
                 float2 y = __bfloat1622float2(y2);
                 if (has_rope) {

@@ -16,19 +16,30 @@
 
 namespace vsb {
 
-constexpr int kAttnThreads = 640;  // 4 control warps + 2 query tiles x 8 softmax warps (2 threads per row)
+constexpr int kAttnThreads = 384;
 constexpr int kKvStages = 3;
 constexpr int kTileA = 128 * 128;  // bytes: 128 rows x 64 bf16 (SWIZZLE_128B)
 constexpr int kTileB = 128 * 32;   // bytes: 128 rows x 16 bf16 (SWIZZLE_32B)
 constexpr int kQBytes = kTileA + kTileB;
 constexpr int kKvStageBytes = 2 * (kTileA + kTileB);
-constexpr int kAttnSmem = 2 * kQBytes + kKvStages * kKvStageBytes + 1024 + 256 + 4096;  // + max/sum exchange
+constexpr int kAttnSmem = 2 * kQBytes + kKvStages * kKvStageBytes + 1024 + 256;
 
 // TMEM columns
 __host__ __device__ constexpr uint32_t col_s(int x) { return uint32_t(x) * 128u; }        // S_A, S_B
 __host__ __device__ constexpr uint32_t col_o(int x) { return 256u + uint32_t(x) * 80u; }  // O_A, O_B: 64 + 16 columns
 
+// Debug timeline: when AttnParams::trace != nullptr, CTA (0,0,0) records clock64() at [actor][tile < 16][event < 4]
+// (actor 0 = MMA thread, 1/2 = softmax warpgroup A/B, lane 0 of its first warp).  Null in normal runs.
+#define VSB_TRACE(actor, tile, ev)                                                                   \
+  do {                                                                                               \
+    if (p.trace != nullptr && (tile) < 16 && lane == 0 && (warp == 1 || (warp & 3) == 0) &&         \
+        blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)                                       \
+      p.trace[((actor) * 16 + (tile)) * 4 + (ev)] = clock64();                                       \
+  } while (0)
+
 struct AttnParams {
+  int pingpong;  // 1: the two softmax warpgroups take turns on the exp2 (MUFU) phase through named barriers
+  long long* trace;
   bf16* out;
   int nb, nq, nk, H;
   float scale_log2;  // softmax scale * log2(e)
@@ -36,7 +47,7 @@ struct AttnParams {
   int lens[8];
 };
 
-template <int D>
+template <int D, bool kStale>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qb,
                   const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_kb,
@@ -57,7 +68,6 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   uint64_t* p_full = s_full + 2;           // [2]
   uint64_t* o_full = p_full + 2;           // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
-  float* xch = reinterpret_cast<float*>(bars) + 64;  // [2 buffers][2 tiles][2 halves][128 rows] after the barriers
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
@@ -83,7 +93,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 8);  // one arrival per softmax warp (8 per query tile)
+      mbar_init(&p_full[i], 4);  // one arrival per softmax warp
       mbar_init(&o_full[i], 1);
     }
     fence_barrier_init();
@@ -95,134 +105,243 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * kQTx);
-      for (int x = 0; x < 2; ++x) {
-        tma_load_4d(&tm_q, q_full, sQ + x * kQBytes, 0, h, q0 + x * 128, b);
-        if (kHasB) tma_load_4d(&tm_qb, q_full, sQ + x * kQBytes + kTileA, 64, h, q0 + x * 128, b);
-      }
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % kKvStages;
-        const uint32_t ph = (j / kKvStages) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        unsigned char* st = sKV + s * kKvStageBytes;
-        mbar_arrive_expect_tx(&k_full[s], kQTx);
-        tma_load_4d(&tm_k, &k_full[s], st, 0, h, j * 128, b);
-        if (kHasB) tma_load_4d(&tm_kb, &k_full[s], st + kTileA, 64, h, j * 128, b);
-        mbar_arrive_expect_tx(&v_full[s], kQTx);
-        tma_load_4d(&tm_v, &v_full[s], st + kQBytes, 0, h, j * 128, b);
-        if (kHasB) tma_load_4d(&tm_vb, &v_full[s], st + kQBytes + kTileA, 64, h, j * 128, b);
-      }
+    // =============================== TMA producer (whole warp converged, one elected lane issues) ==========
+    const uint32_t elected = elect_one();
+    mbar_arrive_expect_tx_w(elected, q_full, 2 * kQTx);
+    for (int x = 0; x < 2; ++x) {
+      tma_load_4d_w(elected, &tm_q, q_full, sQ + x * kQBytes, 0, h, q0 + x * 128, b);
+      if (kHasB) tma_load_4d_w(elected, &tm_qb, q_full, sQ + x * kQBytes + kTileA, 64, h, q0 + x * 128, b);
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j % kKvStages;
+      const uint32_t ph = (j / kKvStages) & 1;
+      mbar_wait(&kv_empty[s], ph ^ 1);
+      unsigned char* st = sKV + s * kKvStageBytes;
+      mbar_arrive_expect_tx_w(elected, &k_full[s], kQTx);
+      tma_load_4d_w(elected, &tm_k, &k_full[s], st, 0, h, j * 128, b);
+      if (kHasB) tma_load_4d_w(elected, &tm_kb, &k_full[s], st + kTileA, 64, h, j * 128, b);
+      mbar_arrive_expect_tx_w(elected, &v_full[s], kQTx);
+      tma_load_4d_w(elected, &tm_v, &v_full[s], st + kQBytes, 0, h, j * 128, b);
+      if (kHasB) tma_load_4d_w(elected, &tm_vb, &v_full[s], st + kQBytes + kTileA, 64, h, j * 128, b);
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T, both K-major
-      constexpr uint32_t idesc_o64 = umma_idesc_bf16(128, 64, 0, 1);  // O[:, 0:64]  += P V, V MN-major
-      constexpr uint32_t idesc_o16 = umma_idesc_bf16(128, 16, 0, 1);  // O[:, 64:80] += P V
-      auto issue_S = [&](int x, int stage) {
-        const uint32_t qa = smem_u32(sQ + x * kQBytes);
-        const uint32_t ka = smem_u32(sKV + stage * kKvStageBytes);
-        const uint32_t d = tmem_base + col_s(x);
+    // =============================== MMA issuer (whole warp converged, one elected lane issues) ============
+    // Operands are warp-uniform and the descriptors are (constant high word, low word + small immediate), so each
+    // tcgen05.mma costs a handful of instructions: with 21 small MMAs per key tile the issue rate, not the tensor
+    // pipe, was the bottleneck when they were built inside `if (lane == 0)` (measured 83 cycles per MMA).
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // S = Q K^T, both K-major
+    constexpr uint32_t idesc_o64 = umma_idesc_bf16(128, 64, 0, 1);  // O[:, 0:64]  += P V, V MN-major
+    constexpr uint32_t idesc_o16 = umma_idesc_bf16(128, 16, 0, 1);  // O[:, 64:80] += P V
+    constexpr uint32_t hi128 = umma_desc_hi(1024, 2);               // SWIZZLE_128B, 8-row / 8-key groups 1024 B apart
+    constexpr uint32_t hi32 = umma_desc_hi(256, 6);                 // SWIZZLE_32B, groups 256 B apart
+    const uint32_t elected = elect_one();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t q_lo = umma_desc_lo(smem_u32(sQ), 16);
+    const uint32_t kv_lo = umma_desc_lo(smem_u32(sKV), 16);
+    auto issue_S = [&](int x, int stage) {
+      const uint32_t qa = q_lo + x * (kQBytes >> 4);
+      const uint32_t ka = kv_lo + stage * (kKvStageBytes >> 4);
+      const uint32_t d = tb + col_s(x);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_ss(d, umma_smem_desc(qa + k * 32, 16, 1024, kSwz128), umma_smem_desc(ka + k * 32, 16, 1024, kSwz128),
-                  idesc_s, k > 0 ? 1u : 0u);
-        if (kHasB)
-          umma_ss(d, umma_smem_desc(qa + kTileA, 16, 256, kSwz32), umma_smem_desc(ka + kTileA, 16, 256, kSwz32),
-                  idesc_s, 1u);
-        umma_commit(&s_full[x]);
-      };
-      auto issue_PV = [&](int x, int stage, bool accumulate) {
-        const uint32_t va = smem_u32(sKV + stage * kKvStageBytes + kQBytes);
-        const uint32_t pt = tmem_base + col_s(x);  // bf16 P aliases the first 64 columns of S_x
-        const uint32_t d = tmem_base + col_o(x);
+      for (int k = 0; k < 4; ++k)
+        umma_ss_w(elected, d, desc_pack(qa + 2 * k, hi128), desc_pack(ka + 2 * k, hi128), idesc_s, k > 0 ? 1u : 0u);
+      if (kHasB)
+        umma_ss_w(elected, d, desc_pack(qa + (kTileA >> 4), hi32), desc_pack(ka + (kTileA >> 4), hi32), idesc_s, 1u);
+      umma_commit_w(elected, &s_full[x]);
+    };
+    auto issue_PV = [&](int x, int stage, bool accumulate) {
+      // V tiles are MN-major: LBO = stride between 64-wide (16-wide) d atoms, unused with a single atom
+      const uint32_t va = kv_lo + stage * (kKvStageBytes >> 4) + (kQBytes >> 4) - (1u << 16) + ((16384u >> 4) << 16);
+      const uint32_t vb = kv_lo + stage * (kKvStageBytes >> 4) + ((kQBytes + kTileA) >> 4) - (1u << 16) + ((4096u >> 4) << 16);
+      const uint32_t pt = tb + col_s(x);  // bf16 P aliases the first 64 columns of S_x
+      const uint32_t d = tb + col_o(x);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {  // 16 keys per step
-          const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
-          umma_ts(d, pt + ks * 8, umma_smem_desc(va + ks * 2048, 16384, 1024, kSwz128), idesc_o64, acc);
-          if (kHasB)
-            umma_ts(d + 64, pt + ks * 8, umma_smem_desc(va + kTileA + ks * 512, 4096, 256, kSwz32), idesc_o16, acc);
-        }
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
-      tc_fence_after();
-      issue_S(0, 0);
-      issue_S(1, 0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int s = j % kKvStages;
-        const uint32_t ph = (j / kKvStages) & 1;
-        const int s1 = (j + 1) % kKvStages;
-        const uint32_t ph1 = ((j + 1) / kKvStages) & 1;
-        for (int x = 0; x < 2; ++x) {
-          mbar_wait(&p_full[x], j & 1);
-          if (x == 0) mbar_wait(&v_full[s], ph);
-          tc_fence_after();
-          issue_PV(x, s, j > 0);
-          if (x == 1) umma_commit(&kv_empty[s]);  // K_j and V_j fully consumed by both query tiles
-          if (j + 1 < n_tiles) {
-            if (x == 0) {
-              mbar_wait(&k_full[s1], ph1);
-              tc_fence_after();
-            }
-            issue_S(x, s1);
-          } else {
-            umma_commit(&o_full[x]);
+      for (int ks = 0; ks < 8; ++ks) {  // 16 keys per step: +2048 B in the 128B-swizzled chunk, +512 B in the 32B one
+        const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
+        umma_ts_w(elected, d, pt + ks * 8, desc_pack(va + ks * 128, hi128), idesc_o64, acc);
+        if (kHasB) umma_ts_w(elected, d + 64, pt + ks * 8, desc_pack(vb + ks * 32, hi32), idesc_o16, acc);
+      }
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    issue_S(0, 0);
+    issue_S(1, 0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j % kKvStages;
+      const uint32_t ph = (j / kKvStages) & 1;
+      const int s1 = (j + 1) % kKvStages;
+      const uint32_t ph1 = ((j + 1) / kKvStages) & 1;
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait(&p_full[x], j & 1);
+        if (x == 0) mbar_wait(&v_full[s], ph);
+        tc_fence_after();
+        VSB_TRACE(0, j, x * 2);
+        issue_PV(x, s, j > 0);
+        if (x == 1) umma_commit_w(elected, &kv_empty[s]);  // K_j and V_j fully consumed by both query tiles
+        if (j + 1 < n_tiles) {
+          if (x == 0) {
+            mbar_wait(&k_full[s1], ph1);
+            tc_fence_after();
           }
+          issue_S(x, s1);
+          VSB_TRACE(0, j, x * 2 + 1);
+        } else {
+          umma_commit_w(elected, &o_full[x]);
         }
       }
     }
   } else if (warp >= 4) {
     // =============================== softmax warpgroups ===============================
-    // Two threads per query row: warp (ew, half) owns TMEM lanes 32*ew.. and key columns [64*half, 64*half+64).
-    // The row max crosses the two halves through shared memory (double-buffered, one named barrier per tile);
-    // 16 softmax warps (4 per scheduler) hide the TMEM-load / MUFU / barrier latencies that 8 could not.
-    const int sw = warp - 4;
-    const int x = sw >> 3;                  // query tile 0/1
-    const int ew = sw & 3;                  // TMEM lane quarter (== warp % 4)
-    const int half = (sw >> 2) & 1;         // key-column half
+    const int x = (warp - 4) >> 2;          // query tile 0/1
+    const int ew = warp & 3;                // TMEM lane quarter
     const int row = ew * 32 + lane;
     const uint32_t lane_off = uint32_t(ew * 32) << 16;
     const uint32_t tS = tmem_base + lane_off + col_s(x);
     const uint32_t tO = tmem_base + lane_off + col_o(x);
-    constexpr int kOChunks = kHasB ? 10 : 8;                  // 8-column chunks of O (80 / 64 columns)
-    const int oc0 = half ? kOChunks / 2 : 0, oc1 = half ? kOChunks : kOChunks / 2;
     const float sl2 = p.scale_log2;
-    float m_run = -INFINITY, l_run = 0.f;
+    float l_run = 0.f;
+    if (p.pingpong && x == 1) named_bar_arrive(2, 256);  // warpgroup A goes first
+    if constexpr (kStale) {
+    // Online softmax with a STALE reference max.  TMEM reads (tcgen05.ld) and exp2 (MUFU) are the two long poles of a
+    // tile; a thread can only overlap them if the exponentials of chunk c do not have to wait for the max of the
+    // whole tile.  So tile j uses m_run = the max known BEFORE the tile (tile 0: the true max of the tile); the true
+    // tile max is tracked on the side and folded in at the next tile boundary, where O and l are rescaled only if the
+    // reference moved by more than 2^8.  p = exp2((s - m_run) * sl2) may exceed 1 inside one tile (bounded by the score
+    // range: |s| <= D * max|w_q| * max|w_k| for RMS/LayerNormed q, k), which fp32 sums / bf16 P represent exactly as
+    // well; the final O / l is invariant to the reference.
+    float m_run = -INFINITY, m_seen = -INFINITY;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[x], j & 1);
       tc_fence_after();
-      const int valid = kv_len - j * 128 - half * 64;  // >= 64: my 64 columns are all real keys
+      VSB_TRACE(1 + x, j, 0);
+      const int valid = kv_len - j * 128;  // >= 128: full tile; columns >= valid are masked
       uint32_t a[2][32];
-      tmem_ld32(tS + half * 64, a[0]);
-      tmem_ld32(tS + half * 64 + 32, a[1]);
+      tmem_ld32(tS, a[0]);
+      if (j == 0) {
+        // first tile: the reference is the true max of the tile (one extra pass over TMEM, once per CTA)
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(a[0][i]));
+          if (c < 3) tmem_ld32(tS + (c + 1) * 32, a[0]);
+        }
+        m_run = m_seen = mx;
+        tmem_ld32(tS, a[0]);
+      } else {
+        // fold in what the previous tile saw; rescale O / l only when the reference moved by more than 2^8
+        const bool grow = (m_seen - m_run) * sl2 > 8.f;
+        if (__any_sync(0xffffffffu, grow)) {
+          const float alpha = grow ? fast_exp2((m_run - m_seen) * sl2) : 1.f;
+          // O is quiescent here: S_x(j) complete implies PV_x(j-1) complete (in-order tensor pipe)
+          tmem_wait_ld();
+#pragma unroll 1
+          for (int c = 0; c < (kHasB ? 5 : 4); ++c) {
+            uint32_t o[16];
+            tmem_ld16(tO + c * 16, o);
+            tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(tO + c * 16, o);
+          }
+          l_run *= alpha;
+          if (grow) m_run = m_seen;
+        }
+      }
+      const float mb = m_run * sl2;
+      if (p.pingpong) named_bar_sync(2 + x, 256);  // my turn on the MUFU pipe
+      VSB_TRACE(1 + x, j, 1);
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      float t0 = m_seen, t1 = m_seen;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        tmem_wait_ld();                                          // chunk c has landed
+        if (c < 3) tmem_ld32(tS + (c + 1) * 32, a[(c + 1) & 1]);  // next chunk flies while this one is exponentiated
+        uint32_t(&r)[32] = a[c & 1];
+        if (valid < 128) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i >= valid) r[i] = 0xff800000u;  // -inf -> p = 0, never wins the max
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          const float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
+          const float v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
+          t0 = fmax3(t0, v0, v1);
+          t1 = fmax3(t1, v2, v3);
+          const float p0 = fast_exp2(fmaf(v0, sl2, -mb));
+          const float p1 = fast_exp2(fmaf(v1, sl2, -mb));
+          const float p2 = fast_exp2(fmaf(v2, sl2, -mb));
+          const float p3 = fast_exp2(fmaf(v3, sl2, -mb));
+          s0 += p0;
+          s1 += p1;
+          s2 += p2;
+          s3 += p3;
+          pk[i >> 1] = pack_bf16x2(p0, p1);
+          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+        }
+        // P chunk c overwrites S columns [16c, 16c+16): already consumed (chunk c holds S columns [32c, 32c+32));
+        // the in-flight load of chunk c+1 reads columns >= 32(c+1), disjoint from the store
+        tmem_st16(tS + c * 16, pk);
+      }
+      m_seen = fmaxf(t0, t1);
+      l_run += (s0 + s1) + (s2 + s3);
+      if (p.pingpong) named_bar_arrive(2 + (x ^ 1), 256);  // hand the MUFU pipe to the other warpgroup
+      VSB_TRACE(1 + x, j, 2);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);
+      VSB_TRACE(1 + x, j, 3);
+    }
+    } else {
+    float m_run = -INFINITY;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&s_full[x], j & 1);
+      tc_fence_after();
+      VSB_TRACE(1 + x, j, 0);
+      const int valid = kv_len - j * 128;  // >= 128: full tile; columns >= valid are masked
+      // ---- all 128 scores of my row -> registers (4 loads in flight, one wait) ----
+      uint32_t a[4][32];
+      tmem_ld32(tS, a[0]);
+      tmem_ld32(tS + 32, a[1]);
+      tmem_ld32(tS + 64, a[2]);
+      tmem_ld32(tS + 96, a[3]);
       tmem_wait_ld();
+      VSB_TRACE(1 + x, j, 1);
       float mx;
-      if (valid >= 64) {
+      if (valid >= 128) {
         float m0 = fmax3(__uint_as_float(a[0][0]), __uint_as_float(a[0][1]), __uint_as_float(a[0][2]));
         float m1 = fmax3(__uint_as_float(a[1][0]), __uint_as_float(a[1][1]), __uint_as_float(a[1][2]));
+        float m2 = fmax3(__uint_as_float(a[2][0]), __uint_as_float(a[2][1]), __uint_as_float(a[2][2]));
+        float m3 = fmax3(__uint_as_float(a[3][0]), __uint_as_float(a[3][1]), __uint_as_float(a[3][2]));
 #pragma unroll
         for (int i = 3; i < 31; i += 2) {
           m0 = fmax3(m0, __uint_as_float(a[0][i]), __uint_as_float(a[0][i + 1]));
           m1 = fmax3(m1, __uint_as_float(a[1][i]), __uint_as_float(a[1][i + 1]));
+          m2 = fmax3(m2, __uint_as_float(a[2][i]), __uint_as_float(a[2][i + 1]));
+          m3 = fmax3(m3, __uint_as_float(a[3][i]), __uint_as_float(a[3][i + 1]));
         }
-        mx = fmax3(m0, m1, fmaxf(__uint_as_float(a[0][31]), __uint_as_float(a[1][31])));
+        m0 = fmaxf(m0, __uint_as_float(a[0][31]));
+        m1 = fmaxf(m1, __uint_as_float(a[1][31]));
+        m2 = fmaxf(m2, __uint_as_float(a[2][31]));
+        m3 = fmaxf(m3, __uint_as_float(a[3][31]));
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       } else {  // ragged last tile: masked columns never win the max and get p = 0 below
         mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < 2; ++c)
+        for (int c = 0; c < 4; ++c)
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             if (c * 32 + i >= valid) a[c][i] = 0xff800000u;  // -inf
             mx = fmaxf(mx, __uint_as_float(a[c][i]));
           }
       }
-      float* xb = xch + ((j & 1) * 2 + x) * 256;
-      xb[half * 128 + row] = mx;
-      named_bar_sync(2 + x, 256);  // also orders my S loads before the partner's P stores over the same columns
-      mx = fmaxf(mx, xb[(half ^ 1) * 128 + row]);
       // ---- lazy rescale: keep the stale running max unless it grew by more than 2^8 (p stays <= 256) ----
       const float m_new = fmaxf(m_run, mx);
       const bool grow = (m_new - m_run) * sl2 > 8.f;  // first tile: m_run = -inf -> true
@@ -230,21 +349,22 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       if (j > 0 && __any_sync(0xffffffffu, grow)) {
         // O is quiescent here: S_x(j) complete implies PV_x(j-1) complete (in-order tensor pipe)
 #pragma unroll 1
-        for (int c = oc0; c < oc1; ++c) {  // my half of the O columns
-          uint32_t o[8];
-          tmem_ld8(tO + c * 8, o);
+        for (int c = 0; c < (kHasB ? 5 : 4); ++c) {  // rare path: one 16-column chunk at a time (register budget)
+          uint32_t o[16];
+          tmem_ld16(tO + c * 16, o);
           tmem_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st8(tO + c * 8, o);
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tO + c * 16, o);
         }
       }
       if (grow) m_run = m_new;
       const float mb = m_run * sl2;
-      // ---- p = exp2(s*sl2 - m*sl2); partial row sum; bf16 P -> TMEM over consumed S columns ----
+      if (p.pingpong) named_bar_sync(2 + x, 256);  // my turn on the MUFU pipe (the other warpgroup arrived)
+      // ---- p = exp2(s*sl2 - m*sl2); row sum (4 chains); bf16 P -> TMEM over the consumed S columns ----
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
@@ -259,29 +379,26 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
           pk[i >> 1] = pack_bf16x2(p0, p1);
           pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
         }
-        tmem_st16(tS + half * 32 + c * 16, pk);
+        tmem_st16(tS + c * 16, pk);
       }
       l_run = l_run * alpha + ((s0 + s1) + (s2 + s3));
+      if (p.pingpong) named_bar_arrive(2 + (x ^ 1), 256);  // hand the MUFU pipe to the other warpgroup
+      VSB_TRACE(1 + x, j, 2);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[x]);
+      VSB_TRACE(1 + x, j, 3);
     }
-    // ---- epilogue: combine the two partial row sums, O / l -> bf16 -> global (each half writes its columns) ----
-    {
-      float* xb = xch + ((n_tiles & 1) * 2 + x) * 256;
-      xb[half * 128 + row] = l_run;
-      named_bar_sync(2 + x, 256);
-      l_run += xb[(half ^ 1) * 128 + row];
     }
+    // ---- epilogue: O / l -> bf16 -> global ----
     mbar_wait(&o_full[x], 0);
     tc_fence_after();
     const int qrow = q0 + x * 128 + row;
     const float inv = 1.f / l_run;
     bf16* dst = p.out + ((size_t)((size_t)b * p.nq + (qrow < p.nq ? qrow : 0)) * p.H + h) * D;
-    const int ec0 = half ? (D / 8 + 1) / 2 : 0, ec1 = half ? D / 8 : (D / 8 + 1) / 2;
 #pragma unroll 1
-    for (int c = ec0; c < ec1; ++c) {
+    for (int c = 0; c < D / 8; ++c) {
       uint32_t r[8];
       tmem_ld8(tO + c * 8, r);
       tmem_wait_ld();
@@ -301,9 +418,18 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
+long long* g_attn_trace = nullptr;  // vsb_set_option_ptr("attn_trace", device buffer of 3*16*4 int64)
+int g_opt_attn_pingpong = 1;        // softmax warpgroups alternate on the MUFU phase
+int g_opt_attn_variant = 0;         // 0 = max-first single pass (fastest measured), 1 = stale-reference max
+
 }  // namespace vsb
 
 using namespace vsb;
+
+extern "C" int vsb_debug_attn_trace(void* device_buffer) {
+  g_attn_trace = (long long*)device_buffer;
+  return VSB_OK;
+}
 
 extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb, int nq,
                               int nk, int H, int D, long long q_row_stride, long long q_batch_stride,
@@ -317,6 +443,8 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
   if (host_kv_lens && nb > 8) return fail(VSB_ERR_UNSUPPORTED, "attn_flash: per-batch key lengths need nb <= 8");
   if (nb > 65535 || H > 65535) return fail(VSB_ERR_UNSUPPORTED, "attn_flash: grid too large");
   AttnParams prm;
+  prm.trace = g_attn_trace;
+  prm.pingpong = g_opt_attn_pingpong;
   prm.out = (bf16*)out;
   prm.nb = nb;
   prm.nq = nq;
@@ -354,19 +482,27 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
   if (D == 72) {
     static bool attr = false;
     if (!attr) {
-      cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<72, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<72, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
       if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash: smem attr: %s", cudaGetErrorString(e));
       attr = true;
     }
-    attn_flash_kernel<72><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+    if (g_opt_attn_variant)
+      attn_flash_kernel<72, true><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+    else
+      attn_flash_kernel<72, false><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
   } else {
     static bool attr = false;
     if (!attr) {
-      cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
       if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash: smem attr: %s", cudaGetErrorString(e));
       attr = true;
     }
-    attn_flash_kernel<64><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+    if (g_opt_attn_variant)
+      attn_flash_kernel<64, true><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+    else
+      attn_flash_kernel<64, false><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
   }
   return check_launch("attn_flash");
 }

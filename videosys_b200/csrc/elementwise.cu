@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
           // eager chain on packed bf16 (each op = exact result rounded once, like the eager bf16 kernels):
           // n = bf16(LN(x)); g = bf16(1 + scale); m = bf16(n * g); out = bf16(m + shift)
           const __nv_bfloat162 n2 = __floats2bfloat162_rn((f.x - mean) * rstd, (f.y - mean) * rstd);
-          const __nv_bfloat162 g2 = __hadd2(one2, sc.h[j]);
-          o.h[j] = __hadd2(__hmul2(n2, g2), sh.h[j]);
+          const __nv_bfloat162 g2 = __hadd2_rn(one2, sc.h[j]);
+          o.h[j] = __hadd2_rn(__hmul2_rn(n2, g2), sh.h[j]);
         }
         st_stream(orow + vi * 8, o.u);
       }
@@ -149,8 +149,8 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(const bf16* __restri
     vg.u = __ldg(reinterpret_cast<const uint4*>(gate + vi * 8));
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      g.h[j] = __hmul2(vg.h[j], vy.h[j]);  // bf16(gate * y)
-      o.h[j] = __hadd2(vx.h[j], g.h[j]);   // bf16(x + gated)
+      g.h[j] = __hmul2_rn(vg.h[j], vy.h[j]);  // bf16(gate * y)
+      o.h[j] = __hadd2_rn(vx.h[j], g.h[j]);   // bf16(x + gated)
     }
     if (cache != nullptr) st_stream(cache + i * 8, g.u);
     st_stream(out + i * 8, o.u);
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) residual_add_kernel(const bf16* __restric
     vx.u = ld_stream(x + i * 8);
     vy.u = ld_stream(y + i * 8);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) o.h[j] = __hadd2(vx.h[j], vy.h[j]);
+    for (int j = 0; j < 4; ++j) o.h[j] = __hadd2_rn(vx.h[j], vy.h[j]);
     st_stream(out + i * 8, o.u);
   }
 }
@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv,
         for (int j = 0; j < 4; ++j) {
           float2 f = __bfloat1622float2(v[u].h[j]);
           // eager: h = bf16(x * rstd); out = bf16(w * h)
-          o.h[j] = __hmul2(wv[which[u]].h[j], __floats2bfloat162_rn(f.x * r, f.y * r));
+          o.h[j] = __hmul2_rn(wv[which[u]].h[j], __floats2bfloat162_rn(f.x * r, f.y * r));
         }
         *reinterpret_cast<uint4*>(p[u]) = o.u;
       }

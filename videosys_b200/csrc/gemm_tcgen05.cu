@@ -83,60 +83,58 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          unsigned char* sa = smem_ab + stage * Cfg::kStageBytes;
-          mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
-          tma_load_2d(&tm_a, &full[stage], sa, kb * kBK, m0);
-          tma_load_2d(&tm_w, &full[stage], sa + kBM * kBK * 2, kb * kBK, n0);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+    // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+    const uint32_t elected = elect_one();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * kBM, n0 = (tile % tiles_n) * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty[stage], phase ^ 1);
+        unsigned char* sa = smem_ab + stage * Cfg::kStageBytes;
+        mbar_arrive_expect_tx_w(elected, &full[stage], Cfg::kStageBytes);
+        tma_load_2d_w(elected, &tm_a, &full[stage], sa, kb * kBK, m0);
+        tma_load_2d_w(elected, &tm_w, &full[stage], sa + kBM * kBK * 2, kb * kBK, n0);
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+    // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+    constexpr uint32_t idesc = umma_idesc_bf16(kBM, BN, 0, 0);
+    constexpr uint32_t dhi = umma_desc_hi(1024, 2);  // K-major SWIZZLE_128B: 8-row groups 1024 B apart
+    const uint32_t elected = elect_one();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t lo0 = umma_desc_lo(smem_u32(smem_ab), 16);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      mbar_wait(&tempty[acc], acc_phase ^ 1);  // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tb + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem_ab + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + kBM * kBK * 2;
+        const uint32_t la = lo0 + stage * (Cfg::kStageBytes >> 4);
+        const uint32_t lb = la + ((kBM * kBK * 2) >> 4);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // K-major SWIZZLE_128B: 8-row groups 1024 B apart; advance 32 B per K=16 step inside the atom
-            const uint64_t da = umma_smem_desc(sa + k * 32, 16, 1024, kSwz128);
-            const uint64_t db = umma_smem_desc(sb + k * 32, 16, 1024, kSwz128);
-            umma_ss(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
-          }
+        for (int k = 0; k < kBK / 16; ++k)  // +32 B (2 x 16-byte units) per K=16 step inside the swizzle atom
+          umma_ss_w(elected, d_tmem, desc_pack(la + 2 * k, dhi), desc_pack(lb + 2 * k, dhi), idesc,
+                    (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit_w(elected, &empty[stage]);  // smem slot reusable once these MMAs retire
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
         }
-        umma_commit(&tfull[acc]);  // accumulator complete
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
+      }
+      umma_commit_w(elected, &tfull[acc]);  // accumulator complete
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
       }
     }
   } else if (warp >= 4) {

@@ -19,7 +19,7 @@ namespace vsb {
 
 constexpr int k2BM = 128;  // rows per CTA (256 per pair)
 constexpr int k2BK = 64;
-constexpr int k2Threads = 256;
+constexpr int k2Threads = 384;  // 4 control warps + 8 epilogue warps (2 per TMEM lane quarter, split by columns)
 
 template <int BN>
 struct Gemm2Cfg {
@@ -29,7 +29,7 @@ struct Gemm2Cfg {
   static constexpr int kCBytes = k2BM * BN * 2;
   static constexpr int kStages = (BN >= 256) ? 5 : 6;
   static constexpr int kTmemCols = 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kCBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kCBytes + 1024 + 256 + 512;  // + bias tile
 };
 
 __device__ __forceinline__ float gelu_tanh_f2(float x) {
@@ -66,6 +66,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   uint64_t* tfull = bars + 2 * kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty + 2);
+  bf16* sbias = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(bars) + 256);  // [BN] bias of the current tile
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t cta = cluster_ctarank();
@@ -87,7 +88,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 8);
+      mbar_init(&tempty[i], 16);  // 8 epilogue warps x 2 CTAs
     }
     fence_barrier_init();
   }
@@ -98,8 +99,9 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
+    // ===================== TMA producer (both CTAs; whole warp converged, one elected lane issues) ==============
+    {
+      const uint32_t elected = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -108,10 +110,10 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           unsigned char* sa = smem_ab + stage * Cfg::kStageBytes;
-          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+          if (leader) mbar_arrive_expect_tx_w(elected, &full[stage], 2 * Cfg::kStageBytes);
           const uint32_t fb = mapa_u32(&full[stage], 0);
-          tma_load_2d_2sm_to(&tm_a, fb, sa, kb * k2BK, m0);
-          tma_load_2d_2sm_to(&tm_w, fb, sa + Cfg::kABytes, kb * k2BK, n0);
+          tma_load_2d_2sm_to_w(elected, &tm_a, fb, sa, kb * k2BK, m0);
+          tma_load_2d_2sm_to_w(elected, &tm_w, fb, sa + Cfg::kABytes, kb * k2BK, n0);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
@@ -120,9 +122,13 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (leader CTA only) =====================
-    if (leader && lane == 0) {
+    // ===================== MMA issuer (leader CTA only; whole warp converged, one elected lane issues) ==========
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * k2BM, BN, 0, 0);
+      constexpr uint32_t dhi = umma_desc_hi(1024, 2);  // K-major SWIZZLE_128B: 8-row groups 1024 B apart
+      const uint32_t elected = elect_one();
+      const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t lo0 = umma_desc_lo(smem_u32(smem_ab), 16);  // stage 0, A tile; +2 per K=16 step (32 B)
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -130,25 +136,23 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&tempty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t d_tmem = tb + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem_ab + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t la = lo0 + stage * (Cfg::kStageBytes >> 4);
+          const uint32_t lb = la + (Cfg::kABytes >> 4);
 #pragma unroll
-          for (int k = 0; k < k2BK / 16; ++k) {
-            const uint64_t da = umma_smem_desc(sa + k * 32, 16, 1024, kSwz128);
-            const uint64_t db = umma_smem_desc(sb + k * 32, 16, 1024, kSwz128);
-            umma_ss_2sm(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit_2sm_mcast(&empty[stage], 0x3);  // frees the stage in both CTAs
+          for (int k = 0; k < k2BK / 16; ++k)
+            umma_ss_2sm_w(elected, d_tmem, desc_pack(la + 2 * k, dhi), desc_pack(lb + 2 * k, dhi), idesc,
+                          (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm_mcast_w(elected, &empty[stage], 0x3);  // frees the stage in both CTAs
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_2sm_mcast(&tfull[acc], 0x3);
+        umma_commit_2sm_mcast_w(elected, &tfull[acc], 0x3);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -156,9 +160,13 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (both CTAs, own 128 rows) =====================
-    const int ew = warp - 4;
+    // ===================== epilogue (both CTAs, own 128 rows; 8 warps: lane quarter x column half) ==========
+    const int ew = (warp - 4) & 3;
+    const int half = (warp - 4) >> 2;
+    constexpr int kChunks = BN / 64;
+    const int c_begin = half ? (kChunks + 1) / 2 : 0, c_end = half ? kChunks : (kChunks + 1) / 2;
     const int row = ew * 32 + lane;
+    const int et = threadIdx.x - 128;  // 0..255 among the epilogue threads
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
@@ -167,7 +175,12 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
       if (threadIdx.x == 128) tma_store_wait_read0();
-      named_bar_sync(1, 128);
+      if (et < BN / 8) {  // stage the tile's bias once (every thread needs all BN values)
+        uint4 bv = make_uint4(0, 0, 0, 0);
+        if (bias != nullptr && n0 + et * 8 < N) bv = __ldg(reinterpret_cast<const uint4*>(bias + n0 + et * 8));
+        *reinterpret_cast<uint4*>(sbias + et * 8) = bv;
+      }
+      named_bar_sync(1, 256);
       const uint32_t t_row = tmem_base + (uint32_t(ew * 32) << 16) + acc * BN;
       const long long grow = (long long)m0 + row;
       const bf16* res_row = nullptr;
@@ -182,12 +195,12 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         }
       }
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         uint32_t r0[32], r1[32];
         tmem_ld32(t_row + c * 64, r0);
         tmem_ld32(t_row + c * 64 + 32, r1);
         tmem_wait_ld();
-        if (c == BN / 64 - 1) {
+        if (c == c_end - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(mapa_u32(&tempty[acc], 0));
@@ -215,13 +228,14 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
               gt[2 * q + 1] = fg.y;
             }
           }
+          const uint4 bq = *reinterpret_cast<const uint4*>(sbias + c * 64 + j * 8);  // smem broadcast
+          const uint32_t bw[4] = {bq.x, bq.y, bq.z, bq.w};
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int col = j * 8 + e;
             const float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]);
-            const int gcol = ncol0 + col;
-            const float b = (bias != nullptr && gcol < N) ? __bfloat162float(__ldg(bias + gcol)) : 0.f;
-            float x = a + b;
+            const float2 b2 = unpack_bf16x2(bw[e >> 1]);
+            float x = a + ((e & 1) ? b2.y : b2.x);
             if (ACT == 1) x = gelu_tanh_f2(rbf(x));
             if (ACT == 2) {
               float y = rbf(x);                                  // the Linear's bf16 output
@@ -239,7 +253,7 @@ gemm2_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
         }
       }
       fence_proxy_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (threadIdx.x == 128) {
         if (m0 < M) {
 #pragma unroll 1

@@ -193,6 +193,104 @@ __device__ __forceinline__ void umma_commit_2sm_mcast(uint64_t* bar, uint16_t ct
       : "memory");
 }
 
+// ---- warp-converged issue helpers -------------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit / TMA take their operands from UNIFORM registers.  Issued from inside `if (lane == 0)`
+// (divergent control flow) ptxas has to build every operand in vector registers and move it over with an
+// ELECT + R2UR.BROADCAST loop: ~20 dependent instructions (~80 cycles) per MMA, which starves the tensor pipe
+// (measured: 83 cycles per issued MMA).  These variants are executed by the WHOLE converged warp on warp-uniform
+// operands; `elected` (from elect_one()) predicates the single issuing lane inside the asm block.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred;
+}
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+// high word of a shared-memory matrix descriptor: SBO (16-byte units) | version 1 | layout; low word = addr>>4 | LBO<<16
+__host__ __device__ constexpr uint32_t umma_desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ void umma_ss_w(uint32_t elected, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\tsetp.ne.b32 pe, %5, 0;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ts_w(uint32_t elected, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\tsetp.ne.b32 pe, %5, 0;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_ss_2sm_w(uint32_t elected, uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, pe;\n\tsetp.ne.b32 pe, %5, 0;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "@pe tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_w(uint32_t elected, uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %1, 0;\n\t"
+      "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm_mcast_w(uint32_t elected, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %2, 0;\n\t"
+      "@pe tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask), "r"(elected)
+      : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx_w(uint32_t elected, uint64_t* bar, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %2, 0;\n\t"
+      "@pe mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "r"(bytes), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_w(uint32_t elected, const CUtensorMap* m, uint64_t* bar, void* dst, int c0,
+                                              int c1) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %5, 0;\n\t"
+      "@pe cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n\t}" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm_to_w(uint32_t elected, const CUtensorMap* m, uint32_t bar_cluster_addr,
+                                                     void* dst, int c0, int c1) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %5, 0;\n\t"
+      "@pe cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+      "%4}], [%2];\n\t}" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(elected)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_w(uint32_t elected, const CUtensorMap* m, uint64_t* bar, void* dst, int c0,
+                                              int c1, int c2, int c3) {
+  asm volatile(
+      "{\n\t.reg .pred pe;\n\tsetp.ne.b32 pe, %7, 0;\n\t"
+      "@pe cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];\n\t}" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(elected)
+      : "memory");
+}
+
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32 (cute/arch/mma_sm100_desc.hpp InstrDescriptor bit layout).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                      // c_format = F32
@@ -282,6 +380,9 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ void named_bar_arrive(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ float fmax3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));

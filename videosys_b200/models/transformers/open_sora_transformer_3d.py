@@ -315,20 +315,29 @@ class STDiT3(nn.Module):
                     raise RuntimeError("temporal sequences >= 30 frames are not supported by vsb_attn_short")
                 o = K.attn_short(qkv.view(-1, 3, H, D), wq, wk, cos, sin, B, S, T * S, 1, S, T, H, D, D**-0.5)
             else:
+                Ba = B
                 if sp > 1:  # S-sharded -> T-sharded: attention needs every patch of a frame
-                    xm = self._switch(xm.view(B, T, S, C), Tg, Sg, to_spatial_shard=False)
+                    if self._dsp is not None:
+                        # P2P path: scatter the B*T (batch, frame) sequences, not the T frames of each sample.
+                        # Spatial attention is independent per (b, t), so the result is identical, and 2*20 = 40
+                        # sequences split 8 ways exactly (5 each) where T = 20 would pad to 24 and leave rank 7
+                        # computing only padding (SURVEY.md section 7 "T=20 on 8 GPUs").
+                        xm = self._switch(xm.view(1, B * T, S, C), B * Tg, Sg, to_spatial_shard=False)
+                        Ba = 1
+                    else:
+                        xm = self._switch(xm.view(B, T, S, C), Tg, Sg, to_spatial_shard=False)
                     Ta, Sa = xm.shape[1], xm.shape[2]
-                    xm = xm.reshape(B, Ta * Sa, C)
+                    xm = xm.reshape(Ba, Ta * Sa, C)
                 else:
                     Ta, Sa = T, S
                 qkv = K.gemm_bias_act(xm, a.qkv.weight, a.qkv.bias)
                 if Sa >= 30:
                     K.qk_rmsnorm_(qkv, wq, wk, H, D)
                     q3 = qkv.view(-1, 3, C)
-                    o = K.attn_flash(q3[:, 0], q3[:, 1], q3[:, 2], B * Ta, Sa, Sa, H, D, 3 * C, Sa * 3 * C, 3 * C,
+                    o = K.attn_flash(q3[:, 0], q3[:, 1], q3[:, 2], Ba * Ta, Sa, Sa, H, D, 3 * C, Sa * 3 * C, 3 * C,
                                      Sa * 3 * C, D**-0.5)
                 else:
-                    o = K.attn_short(qkv.view(-1, 3, H, D), wq, wk, None, None, B * Ta, 1, Sa, 0, 1, Sa, H, D, D**-0.5)
+                    o = K.attn_short(qkv.view(-1, 3, H, D), wq, wk, None, None, Ba * Ta, 1, Sa, 0, 1, Sa, H, D, D**-0.5)
             fused = None
             if self._fuse_epilogue and not pab_on and (blk.temporal or sp == 1):
                 # gate + select + residual in the proj GEMM's epilogue (no PAB cache to fill, no reshard in between)
@@ -336,7 +345,10 @@ class STDiT3(nn.Module):
             if fused is None:
                 y = K.gemm_bias_act(o.view(-1, C), a.proj.weight, a.proj.bias)
                 if not blk.temporal and sp > 1:
-                    y = self._switch(y.view(B, Ta, Sa, C), Tg, Sg, to_spatial_shard=True)
+                    if self._dsp is not None:
+                        y = self._switch(y.view(1, Ta, Sa, C), B * Tg, Sg, to_spatial_shard=True)
+                    else:
+                        y = self._switch(y.view(B, Ta, Sa, C), Tg, Sg, to_spatial_shard=True)
                 cache = None
                 if pab_on:
                     if blk.last_attn is None or blk.last_attn.shape != x.shape:
@@ -476,8 +488,8 @@ class STDiT3(nn.Module):
             return
         pm = self.parallel_manager
         w = pm.sp_size
-        Tl = -(-T // w)
-        elems = B * max(T * Sl, Tl * Sl * w) * C
+        Tl = -(-(B * T) // w)  # the P2P path scatters the B*T (batch, frame) sequences
+        elems = max(B * T * Sl, Tl * Sl * w) * C
         self._dsp = comm.DspP2P(pm.sp_group, elems, device)
 
     def _final_layer(self, x, t, x_mask, t0, B, T, S):
