@@ -277,8 +277,13 @@ def run_ours(args):
     peaks = _peaks()
     gm = by_kind.get("gemm", [1e-9, 0.0, 1])
     gemm_tflops = gm[1] / (gm[0] * 1e-3) / 1e12
-    roofline = {"kernel": "gemm_bf16_tn_kernel (all Linear layers)", "bound": "tensor", "achieved": gemm_tflops,
-                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": gemm_tflops / peaks["tflops"], "traffic": None,
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath) and args.workload == "opensora_720p_68f_50step":
+        traffic = json.load(open(tpath)).get("gemm_qkv_720p_n1")
+    roofline = {"kernel": "gemm2_bf16_tn_kernel / gemm_bf16_tn_kernel (all Linear layers, 392 launches per step)",
+                "bound": "tensor", "achieved": gemm_tflops,
+                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": gemm_tflops / peaks["tflops"], "traffic": traffic,
                 "peak_source": peaks["src"], "launches_timed": gm[2],
                 "share_of_step": gm[0] / (sec * 1e3)}
     shares = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,

@@ -171,12 +171,16 @@ class DspP2P:
         out_shape = (B, T, Sl, Cc) if to_spatial_shard else (B, Tl, S, Cc)
         self.epoch[d] += 1
         st = torch.cuda.current_stream().cuda_stream
-        self._libmod.check(
-            self.lib.vsb_dsp_scatter(x.data_ptr(), self._recv_arr[d], self._flag_arr[d], self.rank, w, d, B, T, S, Cc,
-                                     self.epoch[d], st),
-            "dsp_scatter",
-        )
-        self._libmod.check(self.lib.vsb_dsp_wait(self._own[d][1], w, self.epoch[d], st), "dsp_wait")
+        from ... import kernels
+
+        # algorithmic bytes = what leaves this rank (the (w-1)/w of the local tensor that other ranks own)
+        with kernels._Timed("dsp_switch", x.numel() * 2 * (w - 1) // w):
+            self._libmod.check(
+                self.lib.vsb_dsp_scatter(x.data_ptr(), self._recv_arr[d], self._flag_arr[d], self.rank, w, d, B, T, S,
+                                         Cc, self.epoch[d], st),
+                "dsp_scatter",
+            )
+            self._libmod.check(self.lib.vsb_dsp_wait(self._own[d][1], w, self.epoch[d], st), "dsp_wait")
         return self._window(d, out_shape)
 
     def close(self):

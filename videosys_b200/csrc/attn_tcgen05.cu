@@ -361,25 +361,32 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
       if (grow) m_run = m_new;
       const float mb = m_run * sl2;
       if (p.pingpong) named_bar_sync(2 + x, 256);  // my turn on the MUFU pipe (the other warpgroup arrived)
-      // ---- p = exp2(s*sl2 - m*sl2); row sum (4 chains); bf16 P -> TMEM over the consumed S columns ----
+      // ---- p = exp2(s*sl2 - m*sl2) in place; row sum and bf16 packing of chunk c-1 are interleaved with the
+      //      exponentials of chunk c, so the MUFU results are consumed ~32 instructions after they were issued and a
+      //      single warp can keep the MUFU pipe (8 cycles per warp instruction) busy back to back ----
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t pk[16];
+      for (int c = 0; c < 5; ++c) {
+        if (c < 4) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(a[c][i]), sl2, -mb));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(a[c][i + 1]), sl2, -mb));
-          const float p2 = fast_exp2(fmaf(__uint_as_float(a[c][i + 2]), sl2, -mb));
-          const float p3 = fast_exp2(fmaf(__uint_as_float(a[c][i + 3]), sl2, -mb));
-          s0 += p0;
-          s1 += p1;
-          s2 += p2;
-          s3 += p3;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          for (int i = 0; i < 32; ++i)
+            a[c][i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(a[c][i]), sl2, -mb)));
         }
-        tmem_st16(tS + c * 16, pk);
+        if (c > 0) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float p0 = __uint_as_float(a[c - 1][i]), p1 = __uint_as_float(a[c - 1][i + 1]);
+            const float p2 = __uint_as_float(a[c - 1][i + 2]), p3 = __uint_as_float(a[c - 1][i + 3]);
+            s0 += p0;
+            s1 += p1;
+            s2 += p2;
+            s3 += p3;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+            pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          }
+          tmem_st16(tS + (c - 1) * 16, pk);
+        }
       }
       l_run = l_run * alpha + ((s0 + s1) + (s2 + s3));
       if (p.pingpong) named_bar_arrive(2 + (x ^ 1), 256);  // hand the MUFU pipe to the other warpgroup

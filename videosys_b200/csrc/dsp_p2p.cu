@@ -36,38 +36,48 @@ __global__ void __launch_bounds__(256) dsp_scatter_kernel(const bf16* __restrict
   const int Tl = Tp / world, Sl = Sp / world;
   const int cv = C >> 3;
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  if (dir == 0) {
-    const long long total = (long long)B * Tp * Sl * cv;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+  // 4 independent 16-byte vectors per thread per trip: all loads are issued before the (posted) peer stores so
+  // that enough bytes are in flight to cover the NVLink round trip.
+  constexpr int U = 4;
+  const long long nthreads = (long long)gridDim.x * blockDim.x;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = dir == 0 ? (long long)B * Tp * Sl * cv : (long long)B * Tl * Sp * cv;
+  for (long long i0 = tid; i0 < total; i0 += nthreads * U) {
+    uint4 v[U];
+    uint4* dst[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + (long long)u * nthreads;
+      dst[u] = nullptr;
+      v[u] = zero;
+      if (i >= total) continue;
       const int c = int(i % cv);
       long long r = i / cv;
-      const int sl = int(r % Sl);
-      r /= Sl;
-      const int t = int(r % Tp);
-      const int b = int(r / Tp);
-      const int col = rank * Sl + sl;
-      if (col >= S) continue;  // gathered-axis padding is narrowed away at the receiver: never sent
-      const int d = t / Tl, tl = t - d * Tl;
-      uint4 v = zero;
-      if (t < T) v = *reinterpret_cast<const uint4*>(local + (((size_t)b * T + t) * Sl + sl) * C + c * 8);
-      *reinterpret_cast<uint4*>(peers.recv[d] + (((size_t)b * Tl + tl) * S + col) * C + c * 8) = v;
+      if (dir == 0) {
+        const int sl = int(r % Sl);
+        r /= Sl;
+        const int t = int(r % Tp);
+        const int b = int(r / Tp);
+        const int col = rank * Sl + sl;
+        if (col >= S) continue;  // gathered-axis padding is narrowed away at the receiver: never sent
+        const int d = t / Tl, tl = t - d * Tl;
+        if (t < T) v[u] = *reinterpret_cast<const uint4*>(local + (((size_t)b * T + t) * Sl + sl) * C + c * 8);
+        dst[u] = reinterpret_cast<uint4*>(peers.recv[d] + (((size_t)b * Tl + tl) * S + col) * C + c * 8);
+      } else {
+        const int col = int(r % Sp);
+        r /= Sp;
+        const int tl = int(r % Tl);
+        const int b = int(r / Tl);
+        const int tg = rank * Tl + tl;
+        if (tg >= T) continue;
+        const int d = col / Sl, sl = col - d * Sl;
+        if (col < S) v[u] = *reinterpret_cast<const uint4*>(local + (((size_t)b * Tl + tl) * S + col) * C + c * 8);
+        dst[u] = reinterpret_cast<uint4*>(peers.recv[d] + (((size_t)b * T + tg) * Sl + sl) * C + c * 8);
+      }
     }
-  } else {
-    const long long total = (long long)B * Tl * Sp * cv;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-      const int c = int(i % cv);
-      long long r = i / cv;
-      const int col = int(r % Sp);
-      r /= Sp;
-      const int tl = int(r % Tl);
-      const int b = int(r / Tl);
-      const int tg = rank * Tl + tl;
-      if (tg >= T) continue;
-      const int d = col / Sl, sl = col - d * Sl;
-      uint4 v = zero;
-      if (col < S) v = *reinterpret_cast<const uint4*>(local + (((size_t)b * Tl + tl) * S + col) * C + c * 8);
-      *reinterpret_cast<uint4*>(peers.recv[d] + (((size_t)b * T + tg) * Sl + sl) * C + c * 8) = v;
-    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (dst[u] != nullptr) *dst[u] = v[u];
   }
   __threadfence_system();
   __syncthreads();
@@ -111,7 +121,7 @@ extern "C" int vsb_dsp_scatter(const vsb_bf16* local, void* const* host_peer_rec
     peers.flags[i] = (unsigned*)host_peer_flags[i];
     if (!peers.recv[i] || !peers.flags[i] || !aligned16(peers.recv[i])) return fail(VSB_ERR_INVALID, "dsp_scatter: peer %d window", i);
   }
-  const int grid = num_sms() * 2;
+  const int grid = num_sms() * 4;
   dsp_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)local, peers, rank, world, to_spatial_shard,
                                                               B, T, S, C, epoch);
   return check_launch("dsp_scatter");

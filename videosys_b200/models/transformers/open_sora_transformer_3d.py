@@ -280,10 +280,12 @@ class STDiT3(nn.Module):
         if self._dsp is not None:
             return self._dsp.switch(x4.contiguous(), T, S, to_spatial_shard)
         if to_spatial_shard:
-            return comm.all_to_all_with_pad(x4, pm.sp_group, scatter_dim=2, gather_dim=1,
-                                            scatter_pad=comm.get_pad("spatial"), gather_pad=comm.get_pad("temporal"))
-        return comm.all_to_all_with_pad(x4, pm.sp_group, scatter_dim=1, gather_dim=2,
-                                        scatter_pad=comm.get_pad("temporal"), gather_pad=comm.get_pad("spatial"))
+            out = comm.all_to_all_with_pad(x4, pm.sp_group, scatter_dim=2, gather_dim=1,
+                                           scatter_pad=comm.get_pad("spatial"), gather_pad=comm.get_pad("temporal"))
+        else:
+            out = comm.all_to_all_with_pad(x4, pm.sp_group, scatter_dim=1, gather_dim=2,
+                                           scatter_pad=comm.get_pad("temporal"), gather_pad=comm.get_pad("spatial"))
+        return out.contiguous()  # the narrow() that drops the padding leaves a strided view
 
     def _run_block(self, blk: STDiT3Block, x, y_tok, kv_lens, t_mlp, t0_mlp, mask_u8, B, T, S, Tg, Sg, ts_int):
         """x: [B, T*S, C] resident layout (T full, S local); Tg/Sg are the global extents (== T, S when sp == 1)."""
