@@ -56,6 +56,13 @@ int vsb_debug_attn_trace(void* device_buffer);
 int vsb_ln_modulate(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask, int shift_row,
                     int scale_row, int B, int T, int S, int C, float eps, void* stream);
 
+/* Same with nn.LayerNorm(C, eps, elementwise_affine=True) in front (gamma, beta [C]): the video / text streams of
+ * CogVideoXLayerNormZero (models/modules/normalization.py:51-57): mod = the 6-way chunk of linear(silu(temb)) laid
+ * out as [1 or 2, B, 6, C]; rows (0,1) video, (3,4) text. */
+int vsb_ln_modulate_affine(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
+                           const vsb_bf16* gamma, const vsb_bf16* beta, int shift_row, int scale_row, int B, int T, int S,
+                           int C, float eps, void* stream);
+
 /* mod[0,b,r,:] = bf16(table[r,:] + t[b, r*C:(r+1)*C]); mod[1] likewise from t0 (t0 may be NULL -> mod[1]=mod[0]).
  * replaces open_sora_transformer_3d.py:177-184.  table [6,C], t/t0 [B,6C], mod [2,B,6,C]. */
 int vsb_modulation_table(const vsb_bf16* table, const vsb_bf16* t, const vsb_bf16* t0, vsb_bf16* mod, int B, int C,
@@ -77,14 +84,22 @@ int vsb_residual_add(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* out, size_t
 int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D, float eps,
                    void* stream);
 
+/* Per-head LayerNorm(D, eps, affine) of q and k in place (CogVideoX: diffusers Attention(qk_norm="layer_norm"),
+ * models/transformers/cogvideox_transformer_3d.py:241-242 -> processor :130-133).  wq,bq,wk,bk [D] bf16. */
+int vsb_qk_layernorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* bq, const vsb_bf16* wk, const vsb_bf16* bk,
+                     size_t rows, int H, int D, float eps, void* stream);
+
 /* ---- short-sequence attention (n < 30): RMSNorm(q,k) -> [RoPE] -> native_attention, one warp per (seq, head) --
  * replaces OpenSoraAttention.forward's N<30 path: attentions.py:59-78,95-97,111-120 with the reference's op order
  * (bf16(q*scale), bf16 scores, fp32 softmax, bf16 probs).  Reads the packed qkv of the token-major activation
  * without any rearrange: sequence (o,i) token j lives at row o*outer_stride + i*inner_stride + j*tok_stride.
- *   qkv [rows,3,H,D] bf16; out [rows,H*D] bf16; rope_cos/rope_sin [n, D] fp32 or NULL; n == 1 copies v (:65-66). */
+ *   qkv [rows,3,H,D] bf16; out [rows,H*D] bf16; rope_cos/rope_sin [n, D] fp32 or NULL; n == 1 copies v (:65-66).
+ *   flags: bit 0 = no q/k RMSNorm (wq, wk may be NULL): diffusers Attention as used by Latte
+ *          (models/transformers/latte_transformer_3d.py:259-268,611-619); bit 1 = SDPA rounding (fp32 scores, scale
+ *          inside the softmax) instead of native_attention's bf16 intermediate steps. */
 int vsb_attn_short(const vsb_bf16* qkv, vsb_bf16* out, const vsb_bf16* wq, const vsb_bf16* wk, const float* rope_cos,
                    const float* rope_sin, int n_outer, int n_inner, long long outer_stride, long long inner_stride,
-                   long long tok_stride, int n, int H, int D, float eps, float scale, void* stream);
+                   long long tok_stride, int n, int H, int D, float eps, float scale, int flags, void* stream);
 
 /* ---- GEMM on tcgen05: out[M,N] = act(A[M,K] @ W[N,K]^T + bias[N]) ---------------------------------------------
  * replaces every nn.Linear on the path (attentions.py:59,107,156-157; timm Mlp fc1/fc2) and the tanh-GELU between

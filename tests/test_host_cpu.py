@@ -185,3 +185,28 @@ def test_dsp_comm_gloo_world2(T, S):
         assert torch.equal(a.reshape(B, -1, C), sw[r]) and (a.shape[1], a.shape[2]) == (new_t, new_s)
         assert torch.equal(b, x)
         assert torch.equal(g, full)
+
+
+def test_rflow_timesteps_match_reference_known_answers(golden_dir):
+    """The scheduler mirror reproduces the reference's transformed timesteps: int(bf16(t)) == SURVEY Appendix A."""
+    from videosys_b200.schedulers.scheduling_rflow_open_sora import RFLOW
+
+    kat = json.load(open(os.path.join(golden_dir, "pab_schedules.json")))
+    for name, (hh, ww, nf, steps) in {"240p_51f_30": (240, 426, 51, 30), "720p_68f_50": (720, 1280, 68, 50)}.items():
+        bf = torch.bfloat16
+        margs = dict(height=torch.tensor([hh], dtype=bf), width=torch.tensor([ww], dtype=bf), num_frames=torch.tensor([nf], dtype=bf))
+        ts = RFLOW(num_sampling_steps=steps, use_timestep_transform=True).prepare_timesteps(1, "cpu", margs)
+        assert [int(t.to(bf).item()) for t in ts] == kat[name]["timesteps"]
+        # and bit-identical to the oracle's restatement (which is pinned against the reference)
+        ots, _ = O.rflow_timesteps(steps, hh, ww, nf)
+        assert all(torch.equal(a, b) for a, b in zip(ts, ots))
+
+
+def test_latent_and_image_size_tables():
+    from videosys_b200.pipelines.open_sora.pipeline_open_sora import get_image_size, get_latent_size, get_num_frames
+
+    assert get_image_size("720p", "9:16") == (720, 1280) and get_image_size("240p", "9:16") == (240, 426)
+    assert get_latent_size(68, 720, 1280) == (20, 90, 160) and get_latent_size(51, 240, 426) == (15, 30, 53)  # SURVEY App. B
+    assert get_num_frames("2s") == 51 and get_num_frames(68) == 68
+    with pytest.raises(ValueError):
+        get_image_size("720p", "3:8")

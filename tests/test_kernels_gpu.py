@@ -335,3 +335,20 @@ def test_attn_flash_self(nb, n, H, D):
 @pytest.mark.parametrize("nb,nq,nk,H,D,lens", [(2, 500, 300, 16, 72, None), (2, 257, 300, 4, 72, [300, 120]), (2, 180, 15, 4, 72, [15, 15])])
 def test_attn_flash_cross(nb, nq, nk, H, D, lens):
     _flash_check(f"cross{nq}x{nk}", nb, nq, nk, H, D, lens=lens, packed_qkv=False)
+
+
+@pytest.mark.parametrize("opts", [dict(attn_variant=1), dict(attn_poly_exp=1), dict(attn_pingpong=0), dict(attn_poly_exp=1, attn_pingpong=0)])
+def test_attn_flash_schedule_options(opts):
+    """Every softmax schedule of vsb_attn_flash (vsb_set_option knobs) gives the same attention within tolerance."""
+    from videosys_b200 import kernels as K
+
+    _dev()
+    defaults = dict(attn_variant=0, attn_poly_exp=0, attn_pingpong=1)
+    try:
+        for k, v in opts.items():
+            K.set_option(k, v)
+        _flash_check("opt" + "".join(f"{k[5]}{v}" for k, v in opts.items()), 2, 700, 700, 3, 72)
+        _flash_check("optx" + "".join(f"{k[5]}{v}" for k, v in opts.items()), 2, 300, 200, 2, 72, lens=[200, 77], packed_qkv=False)
+    finally:
+        for k, v in defaults.items():
+            K.set_option(k, v)

@@ -161,3 +161,23 @@ def test_dsp_reshard_matches_reference_comm(sp, T, S):
         assert torch.equal(a, padded_t[:, r * new_t:(r + 1) * new_t])  # Appendix E: a slice of the T-padded tensor
         assert torch.equal(b.reshape(B, -1, C), back[r]) and torch.equal(b, x)
     assert torch.equal(dsp_oracle.gather_sequence([o[2] for o in outs], 2, spd), full)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_cogvideox_layernorm_zero(dtype):
+    """The in-tree half of the CogVideoX block: CogVideoXLayerNormZero (models/modules/normalization.py:36-57)."""
+    from oracle import cogvideox_oracle as CO
+
+    N = ref_loader.load().normalization
+    mod = N.CogVideoXLayerNormZero(64, 128, True, 1e-5, bias=True).to(dtype)
+    sd = {"n." + k: v for k, v in synth.fill_state_dict(mod.state_dict(), "lnz.").items()}
+    sd["n.norm.weight"] = (1 + 0.2 * synth.uniform("lnz.w", (128,))).to(dtype)
+    mod.load_state_dict({k[2:]: v for k, v in sd.items()})
+    h = synth.normalish("lnz.h", (2, 9, 128)).to(dtype)
+    e = synth.normalish("lnz.e", (2, 4, 128)).to(dtype)
+    t = synth.normalish("lnz.t", (2, 64)).to(dtype)
+    with torch.no_grad():
+        ref = mod(h, e, t)
+        got = CO.layer_norm_zero(sd, "n.", h, e, t)
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)

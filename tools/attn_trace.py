@@ -15,9 +15,10 @@ nb, n = 40, 3600
 qkv = torch.randn(nb, n, 3, H, D, device=dev, dtype=bf)
 lib = _lib.load()
 trace = torch.zeros(3 * 16 * 4, dtype=torch.int64, device=dev)
-for variant, pp in ((0, 0), (0, 1), (1, 1)):
+for variant, pp, poly in ((0, 1, 0), (0, 1, 1), (0, 0, 1)):
     K.set_option("attn_variant", variant)
     K.set_option("attn_pingpong", pp)
+    K.set_option("attn_poly_exp", poly)
     K.attn_flash(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], nb, n, n, H, D, 3 * C, n * 3 * C, 3 * C, n * 3 * C, D**-0.5)
     torch.cuda.synchronize()
     trace.zero_()
@@ -30,7 +31,7 @@ for variant, pp in ((0, 0), (0, 1), (1, 1)):
     lib.vsb_debug_attn_trace(None)
     t = trace.cpu().view(3, 16, 4)
     base = int(t[t > 0].min())
-    print(f"\n=== variant {variant} pingpong {pp}: kernel {e0.elapsed_time(e1):.3f} ms; clock64 deltas (cycles), CTA 0 ===")
+    print(f"\n=== variant {variant} pingpong {pp} poly {poly}: kernel {e0.elapsed_time(e1):.3f} ms; clock64 deltas (cycles), CTA 0 ===")
     print("softmax WG A/B per tile: wait->loaded, loaded->exps done, exps->arrived, arrive->next s_full | period")
     for a in (1, 2):
         for j in range(1, 6):

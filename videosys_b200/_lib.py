@@ -20,11 +20,13 @@ SIGNATURES = {
     "vsb_set_option": (_i, [C.c_char_p, _i]),
     "vsb_debug_attn_trace": (_i, [_vp]),
     "vsb_ln_modulate": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "vsb_ln_modulate_affine": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "vsb_qk_layernorm": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _f, _vp]),
     "vsb_modulation_table": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "vsb_gate_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "vsb_residual_add": (_i, [_vp, _vp, _vp, _sz, _vp]),
     "vsb_qk_rmsnorm": (_i, [_vp, _vp, _vp, _sz, _i, _i, _f, _vp]),
-    "vsb_attn_short": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _i, _i, _i, _f, _f, _vp]),
+    "vsb_attn_short": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _ll, _ll, _ll, _i, _i, _i, _f, _f, _i, _vp]),
     "vsb_gemm_bias_act": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "vsb_gemm_bias_residual": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "vsb_attn_flash": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, C.POINTER(_i), _f, _vp]),

@@ -81,11 +81,16 @@ namespace vsb {
 extern int g_opt_gemm_2sm;
 extern int g_opt_attn_variant;
 extern int g_opt_attn_pingpong;
+extern int g_opt_attn_poly;
 }
 extern "C" int vsb_set_option(const char* name, int value) {
   if (!name) return fail(VSB_ERR_INVALID, "set_option: null name");
   if (!strcmp(name, "gemm_2sm")) {
     g_opt_gemm_2sm = value;
+    return VSB_OK;
+  }
+  if (!strcmp(name, "attn_poly_exp")) {
+    g_opt_attn_poly = value;
     return VSB_OK;
   }
   if (!strcmp(name, "attn_pingpong")) {

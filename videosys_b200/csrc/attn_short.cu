@@ -55,7 +55,8 @@ template <int D>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
     const bf16* __restrict__ qkv, bf16* __restrict__ out, const bf16* __restrict__ wq, const bf16* __restrict__ wk,
     const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int n_outer, int n_inner,
-    long long outer_stride, long long inner_stride, long long tok_stride, int n, int H, float eps, float scale) {
+    long long outer_stride, long long inner_stride, long long tok_stride, int n, int H, float eps, float scale,
+    int flags) {
   constexpr int VPR = D / 8;        // 16-byte vectors per head row
   constexpr int K16 = D / 16;       // full k16 steps of Q K^T
   constexpr bool K8 = (D % 16) != 0;  // one trailing k8 step (D = 72)
@@ -69,6 +70,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
   bf16* sk = sq + kMaxN * D;
   bf16* sv = sk + kMaxN * D;
   const bool has_rope = rope_cos != nullptr;
+  const bool do_norm = (flags & 1) == 0;   // flag bit 0: q/k arrive un-normalised and stay so (Latte / plain MHA)
+  const bool sdpa_math = (flags & 2) != 0; // flag bit 1: F.scaled_dot_product_attention rounding (fp32 scores,
+                                           // scale inside the softmax) instead of native_attention's bf16 steps
   if (has_rope) {
     for (int i = threadIdx.x; i < n * D; i += blockDim.x) {
       s_cos[i] = rope_cos[i];
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
 
     // ---- 2. RMSNorm (+RoPE, q scale) in place.  LPR lanes share one row (CPL 16-byte chunks each); the 2n rows
     //         (q rows then k rows) are walked 32/LPR at a time; the sum of squares crosses lanes by shuffle ----
-    {
+    if (do_norm || has_rope || !sdpa_math) {
       constexpr int LPR = (D == 72) ? 3 : 2;  // lanes per row
       constexpr int CPL = VPR / LPR;          // chunks per lane (3 or 4)
       constexpr int RPP = 32 / LPR;           // rows per pass
@@ -143,18 +147,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
 #pragma unroll
         for (int i = 0; i < LPR; ++i) tot += __shfl_sync(0xffffffffu, ss, gbase + i);
         if (act) {
-          const float rs = rsqrtf(tot / (float)D + eps);
+          const float rs = do_norm ? rsqrtf(tot / (float)D + eps) : 1.f;
           const bf16* wrow = (which ? wk : wq) + part * CPL * 8;
 #pragma unroll
           for (int c = 0; c < CPL; ++c) {
             Vec8s w, o;
-            w.u = __ldg(reinterpret_cast<const uint4*>(wrow + c * 8));
+            w.u = do_norm ? __ldg(reinterpret_cast<const uint4*>(wrow + c * 8)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float2 f = __bfloat1622float2(v[c].h[j]);
               // normalization.py:28-33: h = bf16(x*rstd); y = bf16(w*h)
-              __nv_bfloat162 y2 = __hmul2_rn(w.h[j], __floats2bfloat162_rn(f.x * rs, f.y * rs));
-              if (has_rope || which == 0) {
+              __nv_bfloat162 y2 = do_norm ? __hmul2_rn(w.h[j], __floats2bfloat162_rn(f.x * rs, f.y * rs)) : v[c].h[j];
+              if (has_rope || (which == 0 && !sdpa_math)) {
                 float2 y = __bfloat1622float2(y2);
                 if (has_rope) {
                   // rotate_queries_or_keys: t*cos + rotate_half(t)*sin in fp32, pairs (2i, 2i+1): rot = (-x2, x1)
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
                   const float o1 = __fadd_rn(__fmul_rn(y.y, cs.y), __fmul_rn(y.x, sn.y));
                   y = __bfloat1622float2(__floats2bfloat162_rn(o0, o1));
                 }
-                if (which == 0) {  // q = bf16(q * scale)  (attentions.py:113)
+                if (which == 0 && !sdpa_math) {  // q = bf16(q * scale)  (attentions.py:113)
                   y.x *= scale;
                   y.y *= scale;
                 }
@@ -220,7 +224,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = j * 8 + 2 * t + (e & 1);
-          const float v = (j < nt && col < n) ? rbf(sacc[j][e]) : -INFINITY;  // bf16 matmul output; mask pad keys
+          // native_attention: bf16 matmul output; SDPA: fp32 scores scaled inside the softmax; pad keys masked
+          const float v = (j < nt && col < n) ? (sdpa_math ? sacc[j][e] * scale : rbf(sacc[j][e])) : -INFINITY;
           sacc[j][e] = v;
           if (e < 2) mx0 = fmaxf(mx0, v); else mx1 = fmaxf(mx1, v);
         }
@@ -287,7 +292,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
 template <int D>
 static int launch_short(const bf16* qkv, bf16* out, const bf16* wq, const bf16* wk, const float* rc, const float* rs,
                         int n_outer, int n_inner, long long os, long long is, long long ts, int n, int H, float eps,
-                        float scale, cudaStream_t st) {
+                        float scale, int flags, cudaStream_t st) {
   const size_t smem = 2 * kMaxN * D * sizeof(float) + (size_t)kWarpsPerBlock * 3 * kMaxN * D * sizeof(bf16);
   static bool attr = false;
   if (!attr) {
@@ -300,7 +305,7 @@ static int launch_short(const bf16* qkv, bf16* out, const bf16* wq, const bf16* 
   const long long cap = (long long)num_sms() * 3 * 4;  // 3 resident blocks per SM, ~4 items per warp
   if (blocks > cap) blocks = cap;
   attn_short_kernel<D><<<(int)blocks, kWarpsPerBlock * 32, smem, st>>>(qkv, out, wq, wk, rc, rs, n_outer, n_inner, os,
-                                                                       is, ts, n, H, eps, scale);
+                                                                       is, ts, n, H, eps, scale, flags);
   return check_launch("attn_short");
 }
 
@@ -311,18 +316,19 @@ using namespace vsb;
 extern "C" int vsb_attn_short(const vsb_bf16* qkv, vsb_bf16* out, const vsb_bf16* wq, const vsb_bf16* wk,
                               const float* rope_cos, const float* rope_sin, int n_outer, int n_inner,
                               long long outer_stride, long long inner_stride, long long tok_stride, int n, int H,
-                              int D, float eps, float scale, void* stream) {
-  if (!qkv || !out || !wq || !wk || n_outer <= 0 || n_inner <= 0 || n <= 0 || H <= 0)
+                              int D, float eps, float scale, int flags, void* stream) {
+  if (!qkv || !out || n_outer <= 0 || n_inner <= 0 || n <= 0 || H <= 0)
     return fail(VSB_ERR_INVALID, "attn_short: bad args");
+  if ((flags & 1) == 0 && (!wq || !wk)) return fail(VSB_ERR_INVALID, "attn_short: q/k norm weights required (or flag 1)");
   if (n > kMaxN) return fail(VSB_ERR_UNSUPPORTED, "attn_short: n=%d > %d (use vsb_attn_flash)", n, kMaxN);
   if ((rope_cos == nullptr) != (rope_sin == nullptr)) return fail(VSB_ERR_INVALID, "attn_short: rope tables");
   if (!aligned16(qkv) || !aligned16(out)) return fail(VSB_ERR_UNSUPPORTED, "attn_short: alignment");
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 72)
     return launch_short<72>((const bf16*)qkv, (bf16*)out, (const bf16*)wq, (const bf16*)wk, rope_cos, rope_sin, n_outer,
-                            n_inner, outer_stride, inner_stride, tok_stride, n, H, eps, scale, st);
+                            n_inner, outer_stride, inner_stride, tok_stride, n, H, eps, scale, flags, st);
   if (D == 64)
     return launch_short<64>((const bf16*)qkv, (bf16*)out, (const bf16*)wq, (const bf16*)wk, rope_cos, rope_sin, n_outer,
-                            n_inner, outer_stride, inner_stride, tok_stride, n, H, eps, scale, st);
+                            n_inner, outer_stride, inner_stride, tok_stride, n, H, eps, scale, flags, st);
   return fail(VSB_ERR_UNSUPPORTED, "attn_short: head_dim %d (72 or 64 only)", D);
 }

@@ -38,6 +38,7 @@ __host__ __device__ constexpr uint32_t col_o(int x) { return 256u + uint32_t(x) 
   } while (0)
 
 struct AttnParams {
+  int poly_exp;  // 1: every other exp2 runs as a polynomial on the FMA pipe (halves the MUFU load)
   int pingpong;  // 1: the two softmax warpgroups take turns on the exp2 (MUFU) phase through named barriers
   long long* trace;
   bf16* out;
@@ -368,9 +369,17 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 5; ++c) {
         if (c < 4) {
+          if (p.poly_exp) {  // odd columns on the FMA pipe, even columns on the MUFU pipe
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            a[c][i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(a[c][i]), sl2, -mb)));
+            for (int i = 0; i < 32; i += 2) {
+              a[c][i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(a[c][i]), sl2, -mb)));
+              a[c][i + 1] = __float_as_uint(exp2_poly(fmaf(__uint_as_float(a[c][i + 1]), sl2, -mb)));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              a[c][i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(a[c][i]), sl2, -mb)));
+          }
         }
         if (c > 0) {
           uint32_t pk[16];
@@ -426,6 +435,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 }
 
 long long* g_attn_trace = nullptr;  // vsb_set_option_ptr("attn_trace", device buffer of 3*16*4 int64)
+int g_opt_attn_poly = 0;            // polynomial exp2 for odd columns (variant 0)
 int g_opt_attn_pingpong = 1;        // softmax warpgroups alternate on the MUFU phase
 int g_opt_attn_variant = 0;         // 0 = max-first single pass (fastest measured), 1 = stale-reference max
 
@@ -452,6 +462,7 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
   AttnParams prm;
   prm.trace = g_attn_trace;
   prm.pingpong = g_opt_attn_pingpong;
+  prm.poly_exp = g_opt_attn_poly;
   prm.out = (bf16*)out;
   prm.nb = nb;
   prm.nq = nq;

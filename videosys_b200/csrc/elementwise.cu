@@ -38,7 +38,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ mod,
                                                           const uint8_t* __restrict__ x_mask, int shift_row,
                                                           int scale_row, int B, int T, int S, int C, float eps,
-                                                          long long rows) {
+                                                          long long rows, const bf16* __restrict__ gamma,
+                                                          const bf16* __restrict__ beta) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
@@ -103,7 +104,14 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
           float2 f = __bfloat1622float2(v[i].h[j]);
           // eager chain on packed bf16 (each op = exact result rounded once, like the eager bf16 kernels):
           // n = bf16(LN(x)); g = bf16(1 + scale); m = bf16(n * g); out = bf16(m + shift)
-          const __nv_bfloat162 n2 = __floats2bfloat162_rn((f.x - mean) * rstd, (f.y - mean) * rstd);
+          float n0 = (f.x - mean) * rstd, n1 = (f.y - mean) * rstd;
+          if (gamma != nullptr) {  // nn.LayerNorm with affine: one rounding after weight and bias (CogVideoXLayerNormZero)
+            const float2 gw = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gamma + vi * 8 + 2 * j));
+            const float2 gb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(beta + vi * 8 + 2 * j));
+            n0 = n0 * gw.x + gb.x;
+            n1 = n1 * gw.y + gb.y;
+          }
+          const __nv_bfloat162 n2 = __floats2bfloat162_rn(n0, n1);
           const __nv_bfloat162 g2 = __hadd2_rn(one2, sc.h[j]);
           o.h[j] = __hadd2_rn(__hmul2_rn(n2, g2), sh.h[j]);
         }
@@ -236,6 +244,75 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv,
   }
 }
 
+// Per-head LayerNorm(D, eps, affine) of q and k inside a packed [rows, 3, H, D] buffer (CogVideoX: diffusers Attention
+// with qk_norm="layer_norm", cogvideox_transformer_3d.py:241-242).  Same lane grouping as qk_rmsnorm_kernel.
+template <int D>
+__global__ void __launch_bounds__(256) qk_layernorm_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ wq,
+                                                           const bf16* __restrict__ bq, const bf16* __restrict__ wk,
+                                                           const bf16* __restrict__ bk, long long rows, int H,
+                                                           float eps) {
+  constexpr int LPG = D / 8;
+  constexpr int GPW = 32 / LPG;
+  const int lane = threadIdx.x & 31;
+  const int g = lane / LPG, l = lane % LPG;
+  const int gs = (g < GPW ? g : 0) * LPG;
+  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long ngroups = rows * 2 * H;
+  Vec8 wv[2], bv[2];
+  wv[0].u = __ldg(reinterpret_cast<const uint4*>(wq + l * 8));
+  wv[1].u = __ldg(reinterpret_cast<const uint4*>(wk + l * 8));
+  bv[0].u = __ldg(reinterpret_cast<const uint4*>(bq + l * 8));
+  bv[1].u = __ldg(reinterpret_cast<const uint4*>(bk + l * 8));
+  for (long long base = warp * GPW; base < ngroups; base += nwarps * GPW) {
+    const long long gi = base + g;
+    const bool active = (g < GPW) && (gi < ngroups);
+    Vec8 v;
+    bf16* p = nullptr;
+    int which = 0;
+    float s1 = 0.f;
+    if (active) {
+      const long long row = gi / (2 * H);
+      const int rem = int(gi - row * 2 * H);
+      which = rem / H;
+      const int h = rem - which * H;
+      p = qkv + ((size_t)row * 3 + which) * H * D + (size_t)h * D + l * 8;
+      v.u = *reinterpret_cast<const uint4*>(p);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(v.h[j]);
+        s1 += f.x + f.y;
+      }
+    }
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < LPG; ++i) tot += __shfl_sync(0xffffffffu, s1, gs + i);
+    const float mean = tot / (float)D;
+    float s2 = 0.f;
+    if (active) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(v.h[j]);
+        s2 += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+      }
+    }
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < LPG; ++i) var += __shfl_sync(0xffffffffu, s2, gs + i);
+    if (active) {
+      const float r = rsqrtf(var / (float)D + eps);
+      Vec8 o;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float2 f = __bfloat1622float2(v.h[j]);
+        float2 w = __bfloat1622float2(wv[which].h[j]), b = __bfloat1622float2(bv[which].h[j]);
+        o.h[j] = __floats2bfloat162_rn((f.x - mean) * r * w.x + b.x, (f.y - mean) * r * w.y + b.y);
+      }
+      *reinterpret_cast<uint4*>(p) = o.u;
+    }
+  }
+}
+
 static int grid_for(long long work_items, int per_block) {
   long long blocks = (work_items + per_block - 1) / per_block;
   long long cap = (long long)num_sms() * 8;
@@ -248,8 +325,10 @@ static int grid_for(long long work_items, int per_block) {
 
 using namespace vsb;
 
-extern "C" int vsb_ln_modulate(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
-                               int shift_row, int scale_row, int B, int T, int S, int C, float eps, void* stream) {
+extern "C" int vsb_ln_modulate_affine(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
+                                      const vsb_bf16* gamma, const vsb_bf16* beta, int shift_row, int scale_row, int B,
+                                      int T, int S, int C, float eps, void* stream) {
+  if ((gamma == nullptr) != (beta == nullptr)) return fail(VSB_ERR_INVALID, "ln_modulate: gamma and beta go together");
   if (!x || !out || !mod || B <= 0 || T <= 0 || S <= 0 || C <= 0) return fail(VSB_ERR_INVALID, "ln_modulate: bad args");
   if (C % 8 || C > 2048 || !aligned16(x) || !aligned16(out) || !aligned16(mod))
     return fail(VSB_ERR_UNSUPPORTED, "ln_modulate: need C %% 8 == 0, C <= 2048, 16B-aligned pointers (C=%d)", C);
@@ -259,11 +338,16 @@ extern "C" int vsb_ln_modulate(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16*
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 1280)
     ln_modulate_kernel<5><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, (const bf16*)mod, x_mask, shift_row,
-                                                 scale_row, B, T, S, C, eps, rows);
+                                                 scale_row, B, T, S, C, eps, rows, (const bf16*)gamma, (const bf16*)beta);
   else
     ln_modulate_kernel<8><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, (const bf16*)mod, x_mask, shift_row,
-                                                 scale_row, B, T, S, C, eps, rows);
+                                                 scale_row, B, T, S, C, eps, rows, (const bf16*)gamma, (const bf16*)beta);
   return check_launch("ln_modulate");
+}
+
+extern "C" int vsb_ln_modulate(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
+                               int shift_row, int scale_row, int B, int T, int S, int C, float eps, void* stream) {
+  return vsb_ln_modulate_affine(x, out, mod, x_mask, nullptr, nullptr, shift_row, scale_row, B, T, S, C, eps, stream);
 }
 
 extern "C" int vsb_modulation_table(const vsb_bf16* table, const vsb_bf16* t, const vsb_bf16* t0, vsb_bf16* mod,
@@ -315,4 +399,24 @@ extern "C" int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16*
   else
     return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: head_dim %d (72 or 64 only)", D);
   return check_launch("qk_rmsnorm");
+}
+
+extern "C" int vsb_qk_layernorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* bq, const vsb_bf16* wk,
+                                const vsb_bf16* bk, size_t rows, int H, int D, float eps, void* stream) {
+  if (!qkv || !wq || !bq || !wk || !bk || rows == 0 || H <= 0) return fail(VSB_ERR_INVALID, "qk_layernorm: bad args");
+  if (!aligned16(qkv) || !aligned16(wq) || !aligned16(bq) || !aligned16(wk) || !aligned16(bk))
+    return fail(VSB_ERR_UNSUPPORTED, "qk_layernorm: alignment");
+  long long groups = (long long)rows * 2 * H;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (D == 64)
+    qk_layernorm_kernel<64><<<grid_for(groups, 8 * 4), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)bq,
+                                                                       (const bf16*)wk, (const bf16*)bk, (long long)rows,
+                                                                       H, eps);
+  else if (D == 72)
+    qk_layernorm_kernel<72><<<grid_for(groups, 8 * 3), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)bq,
+                                                                       (const bf16*)wk, (const bf16*)bk, (long long)rows,
+                                                                       H, eps);
+  else
+    return fail(VSB_ERR_UNSUPPORTED, "qk_layernorm: head_dim %d (64 or 72 only)", D);
+  return check_launch("qk_layernorm");
 }

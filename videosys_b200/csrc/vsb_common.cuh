@@ -388,6 +388,19 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) {
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
   return d;
 }
+// 2^x on the FMA/ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max relative error 7.5e-5, far below the bf16 rounding of P), exponent patched in with an
+// integer add.  Valid for x >= -126 (clamped); used for every other score so the MUFU pipe (the bound of the
+// attention kernel at head_dim 72) only sees half of the exponentials.
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -126.f);
+  const float t = x + 12582912.f;   // 1.5 * 2^23: rint(x) lands in the low mantissa bits
+  const float f = x - (t - 12582912.f);
+  float p = fmaf(f, 0.05517164245247841f, 0.2426111251115799f);
+  p = fmaf(f, p, 0.6932609677314758f);
+  p = fmaf(f, p, 0.9999280571937561f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
 __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

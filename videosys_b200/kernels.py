@@ -85,14 +85,16 @@ def modulation_table(table: torch.Tensor, t: torch.Tensor, t0: Optional[torch.Te
     return mod
 
 
-def ln_modulate(x, mod, x_mask_u8, shift_row, scale_row, B, T, S, out=None, eps=1e-6):
-    lib, st = _prep(x, mod, x_mask_u8, out)
+def ln_modulate(x, mod, x_mask_u8, shift_row, scale_row, B, T, S, out=None, eps=1e-6, gamma=None, beta=None):
+    """LayerNorm (optionally affine: gamma/beta) + modulate + per-frame select; x viewed as [B, T, S, C]."""
+    lib, st = _prep(x, mod, x_mask_u8, out, gamma, beta)
     _bf16(x, "x")
     Cc = x.shape[-1]
     out = torch.empty_like(x) if out is None else out
     with _Timed("ln_modulate", 2 * x.numel() * 2):
         _lib.check(
-            lib.vsb_ln_modulate(_p(x), _p(out), _p(mod), _p(x_mask_u8), shift_row, scale_row, B, T, S, Cc, eps, st),
+            lib.vsb_ln_modulate_affine(_p(x), _p(out), _p(mod), _p(x_mask_u8), _p(gamma), _p(beta), shift_row,
+                                       scale_row, B, T, S, Cc, eps, st),
             "ln_modulate",
         )
     return out
@@ -127,15 +129,23 @@ def qk_rmsnorm_(qkv, wq, wk, H, D, eps=1e-6):
     return qkv
 
 
+def qk_layernorm_(qkv, wq, bq, wk, bk, H, D, eps=1e-6):
+    lib, st = _prep(qkv, wq, bq, wk, bk)
+    rows = qkv.numel() // (3 * H * D)
+    with _Timed("qk_rmsnorm", 4 * rows * H * D * 2):
+        _lib.check(lib.vsb_qk_layernorm(_p(qkv), _p(wq), _p(bq), _p(wk), _p(bk), rows, H, D, eps, st), "qk_layernorm")
+    return qkv
+
+
 def attn_short(qkv, wq, wk, rope_cos, rope_sin, n_outer, n_inner, outer_stride, inner_stride, tok_stride, n, H, D,
-               scale, out=None, eps=1e-6):
+               scale, out=None, eps=1e-6, flags: int = 0):
     lib, st = _prep(qkv, wq, wk, rope_cos, rope_sin, out)
     rows = qkv.numel() // (3 * H * D)
     out = torch.empty(rows, H * D, dtype=torch.bfloat16, device=qkv.device) if out is None else out
     with _Timed("attn_short", 4 * rows * H * D * 2):
         _lib.check(
             lib.vsb_attn_short(_p(qkv), _p(out), _p(wq), _p(wk), _p(rope_cos), _p(rope_sin), n_outer, n_inner,
-                               outer_stride, inner_stride, tok_stride, n, H, D, eps, scale, st),
+                               outer_stride, inner_stride, tok_stride, n, H, D, eps, scale, flags, st),
             "attn_short",
         )
     return out
