@@ -1,0 +1,33 @@
+// vsb200 -- shared between the two flash-attention kernels (attn_tcgen05.cu: 128-key tiles with ping-pong;
+// attn_tcgen05_kt64.cu: 64-key tiles with double-buffered S).
+#pragma once
+#include "vsb_common.cuh"
+#include "vsb_host.h"
+
+namespace vsb {
+
+// Debug timeline: when AttnParams::trace != nullptr, CTA (0,0,0) records clock64() at [actor][tile < 16][event < 4]
+// (actor 0 = MMA thread, 1/2 = softmax warpgroup A/B, lane 0 of its first warp).  Null in normal runs.
+#define VSB_TRACE(actor, tile, ev)                                                                   \
+  do {                                                                                               \
+    if (p.trace != nullptr && (tile) < 16 && lane == 0 && (warp == 1 || (warp & 3) == 0) &&         \
+        blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)                                       \
+      p.trace[((actor) * 16 + (tile)) * 4 + (ev)] = clock64();                                       \
+  } while (0)
+
+struct AttnParams {
+  int poly_exp;  // 1: every other exp2 runs as a polynomial on the FMA pipe (halves the MUFU load)
+  int pingpong;  // 1: the two softmax warpgroups take turns on the exp2 (MUFU) phase through named barriers
+  long long* trace;
+  bf16* out;
+  int nb, nq, nk, H;
+  float scale_log2;  // softmax scale * log2(e)
+  int has_lens;
+  int lens[8];
+};
+
+
+// attn_tcgen05_kt64.cu.  tm = {q64, q16, k64, k16, v64, v16} with 64-row key boxes.
+int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st);
+
+}  // namespace vsb

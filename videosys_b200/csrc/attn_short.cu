@@ -1,13 +1,17 @@
-// vsb200 -- short-sequence attention (n < 30 tokens): the temporal self-attention of STDiT3 (n = T = 15..20).
+// vsb200 -- short-sequence attention (n <= 32 tokens): the temporal self-attention of STDiT3 (n = T = 15..20).
 //
-// FLOPs are negligible (3.7e11 per step at 720p); the kernel must be HBM-bound on one read of q,k,v and one write
-// of o.  One warp owns one (sequence, head):
-//   1. q,k,v rows (n x D each) -> per-warp shared memory (16-byte loads straight from the packed token-major qkv);
-//   2. lane = row: per-head RMSNorm (+ RoPE from a per-block smem table) in place on q and k, q scaled;
+// FLOPs are negligible (3.7e11 per step at 720p); the kernel should be HBM-bound on one read of q,k,v and one write
+// of o.  One warp owns one (sequence, head) at a time; a CTA is 8..16 such warps (one CTA per SM, persistent):
+//   1. q,k,v rows (n x D each) -> per-warp shared memory by THREE 5-D TMA box loads ({D, 1 head, 1 sequence, n tokens,
+//      1 batch} of the packed token-major qkv) on the warp's own mbarrier: no address arithmetic, no registers, and
+//      the load of the NEXT item is in flight as soon as the store of this one has released the Q rows;
+//   2. RMSNorm (+ RoPE from a per-block smem table, q scale) in place on q and k, three lanes per row;
 //   3. S = Q K^T and O = P V on the warp-level tensor path (mma.sync m16n8k16 / m16n8k8 bf16, fp32 accumulate,
 //      ldmatrix fragments; P is re-packed from the S accumulators, FA2 style) -- the sequences are far too short for
 //      a tcgen05 tile (20 keys against a 128-key MMA would waste 84 % of the work);
-//   4. O staged through smem, written with 16-byte stores.
+//   4. O staged over the dead Q rows and written by one TMA box store.
+// (The first version staged with per-lane 16-byte loads / stores: 4800 instructions per item, half of them index
+// arithmetic, 12 warps per SM: 1.08 ms for the 720p launch, 15 % of HBM peak -- profiles/r01_attn_short_ncu_full.txt.)
 // Rounding follows the reference's eager op order (attentions.py:111-120): bf16(q*scale), bf16(q@k^T),
 // fp32 softmax, bf16(probs), bf16(probs@v).
 #include "vsb_common.cuh"
@@ -16,7 +20,7 @@
 namespace vsb {
 
 constexpr int kMaxN = 32;
-constexpr int kWarpsPerBlock = 4;
+constexpr int kMaxWarps = 16;
 
 union Vec8s {
   uint4 u;
@@ -52,23 +56,29 @@ __device__ __forceinline__ void mma_k8(float (&c)[4], const uint32_t (&a)[2], ui
 }
 
 template <int D>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
-    const bf16* __restrict__ qkv, bf16* __restrict__ out, const bf16* __restrict__ wq, const bf16* __restrict__ wk,
-    const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int n_outer, int n_inner,
-    long long outer_stride, long long inner_stride, long long tok_stride, int n, int H, float eps, float scale,
-    int flags) {
+__global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
+    const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+    const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const bf16* __restrict__ wq,
+    const bf16* __restrict__ wk, const float* __restrict__ rope_cos, const float* __restrict__ rope_sin, int n_outer,
+    int n_inner, int n, int H, float eps, float scale, int flags) {
   constexpr int VPR = D / 8;        // 16-byte vectors per head row
   constexpr int K16 = D / 16;       // full k16 steps of Q K^T
   constexpr bool K8 = (D % 16) != 0;  // one trailing k8 step (D = 72)
   constexpr int ND = D / 8;         // n8 tiles of the output
-  extern __shared__ __align__(16) unsigned char smem_raw[];
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);  // keeps the shared address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // [rope cos | rope sin] (fp32, n x D each, shared by the block) then per warp q | k | v (bf16, 32 x D each)
-  float* s_cos = reinterpret_cast<float*>(smem_raw);
+  const int nwarps = blockDim.x >> 5;
+  const int rq = (n + 7) & ~7;  // q / k rows per warp (TMA destinations stay 128-byte aligned: 8 rows = 9 * 128 B)
+  // [mbarriers | rope cos | rope sin] (fp32, n x D each, shared by the block) then per warp q[rq] | k[rq] | v[32].
+  // ldmatrix of Q rows >= rq runs on into K / V (valid memory, results unused); V rows n..31 are zero.
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  float* s_cos = reinterpret_cast<float*>(smem_raw + 128);
   float* s_sin = s_cos + kMaxN * D;
-  bf16* sq = reinterpret_cast<bf16*>(s_sin + kMaxN * D) + (size_t)warp * 3 * kMaxN * D;
-  bf16* sk = sq + kMaxN * D;
-  bf16* sv = sk + kMaxN * D;
+  bf16* sq = reinterpret_cast<bf16*>(s_sin + kMaxN * D) + (size_t)warp * (2 * rq + kMaxN) * D;
+  bf16* sk = sq + (size_t)rq * D;
+  bf16* sv = sk + (size_t)rq * D;
+  uint64_t* bar = &bars[warp];
   const bool has_rope = rope_cos != nullptr;
   const bool do_norm = (flags & 1) == 0;   // flag bit 0: q/k arrive un-normalised and stay so (Latte / plain MHA)
   const bool sdpa_math = (flags & 2) != 0; // flag bit 1: F.scaled_dot_product_attention rounding (fp32 scores,
@@ -79,42 +89,43 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
       s_sin[i] = rope_sin[i];
     }
   }
-  // zero V's padding rows once (P is 0 there, but 0 * garbage could be NaN); loads below never touch them
+  // zero V's padding rows once (P is 0 there, but 0 * garbage could be NaN); the TMA boxes never touch them
   for (int i = lane; i < (kMaxN - n) * VPR; i += 32)
     *reinterpret_cast<uint4*>(sv + (size_t)n * D + i * 8) = make_uint4(0, 0, 0, 0);
+  if (lane == 0) {
+    mbar_init(bar, 1);
+    fence_barrier_init();
+  }
   __syncthreads();
 
-  const long long total = (long long)n_outer * n_inner * H;
-  const int C = H * D;
+  const unsigned total = (unsigned)n_outer * n_inner * H;  // < 2^31 (checked by the launcher)
+  const unsigned stride = gridDim.x * nwarps;
   const int nt = (n + 7) >> 3;   // key n8 tiles
   const int kk = (n + 15) >> 4;  // key k16 steps of P V
   const int g = lane >> 2, t = lane & 3;
+  const uint32_t tx_bytes = 3u * n * D * sizeof(bf16);
+  auto issue_loads = [&](unsigned item) {  // lane 0 only
+    const unsigned seq = item / (unsigned)H;
+    const int h = int(item - seq * H);
+    const int ou = int(seq / (unsigned)n_inner), in = int(seq - (unsigned)ou * n_inner);
+    mbar_arrive_expect_tx(bar, tx_bytes);
+    tma_load_5d(&tm_q, bar, sq, 0, h, in, 0, ou);
+    tma_load_5d(&tm_k, bar, sk, 0, h, in, 0, ou);
+    tma_load_5d(&tm_v, bar, sv, 0, h, in, 0, ou);
+  };
+  unsigned item = blockIdx.x * nwarps + warp;
+  if (item < total && lane == 0) issue_loads(item);
+  uint32_t phase = 0;
 
-  for (long long item = (long long)blockIdx.x * kWarpsPerBlock + warp; item < total;
-       item += (long long)gridDim.x * kWarpsPerBlock) {
-    const int h = int(item % H);
-    const long long seq = item / H;
-    const long long row0 = (seq / n_inner) * outer_stride + (seq % n_inner) * inner_stride;
-
-    // ---- 1. stage q,k,v rows ----
-    for (int idx = lane; idx < 3 * n * VPR; idx += 32) {
-      const int which = idx / (n * VPR);
-      const int rem = idx - which * n * VPR;
-      const int j = rem / VPR, c = rem - j * VPR;
-      const bf16* src = qkv + ((size_t)(row0 + (long long)j * tok_stride) * 3 + which) * C + (size_t)h * D + c * 8;
-      *reinterpret_cast<uint4*>(sq + (size_t)which * kMaxN * D + j * D + c * 8) =
-          __ldg(reinterpret_cast<const uint4*>(src));
-    }
-    __syncwarp();
+  for (; item < total; item += stride) {
+    // ---- 1. this item's q,k,v rows have landed (the loads were issued one iteration ago) ----
+    mbar_wait(bar, phase);
+    phase ^= 1;
 
     if (n == 1) {  // attentions.py:65-66: x = v
       for (int c = lane; c < VPR; c += 32)
-        *reinterpret_cast<uint4*>(out + (size_t)row0 * C + (size_t)h * D + c * 8) =
-            *reinterpret_cast<const uint4*>(sv + c * 8);
-      __syncwarp();
-      continue;
-    }
-
+        *reinterpret_cast<uint4*>(sq + c * 8) = *reinterpret_cast<const uint4*>(sv + c * 8);
+    } else {
     // ---- 2. RMSNorm (+RoPE, q scale) in place.  LPR lanes share one row (CPL 16-byte chunks each); the 2n rows
     //         (q rows then k rows) are walked 32/LPR at a time; the sum of squares crosses lanes by shuffle ----
     if (do_norm || has_rope || !sdpa_math) {
@@ -271,41 +282,74 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 3) attn_short_kernel(
           }
         }
       }
-      // ---- 4. O (bf16) -> smem over this m-tile's Q rows (Q is dead for these rows) ----
+      // ---- 4. O (bf16) -> smem over this m-tile's Q rows (Q is dead for these rows; rows >= n are not stored) ----
       __syncwarp();
+      const int r0 = mt * 16 + g, r1 = r0 + 8;
 #pragma unroll
       for (int jd = 0; jd < ND; ++jd) {
-        *reinterpret_cast<uint32_t*>(sq + (size_t)(mt * 16 + g) * D + jd * 8 + 2 * t) = pack_bf16x2(oacc[jd][0], oacc[jd][1]);
-        *reinterpret_cast<uint32_t*>(sq + (size_t)(mt * 16 + g + 8) * D + jd * 8 + 2 * t) = pack_bf16x2(oacc[jd][2], oacc[jd][3]);
+        if (r0 < n) *reinterpret_cast<uint32_t*>(sq + (size_t)r0 * D + jd * 8 + 2 * t) = pack_bf16x2(oacc[jd][0], oacc[jd][1]);
+        if (r1 < n) *reinterpret_cast<uint32_t*>(sq + (size_t)r1 * D + jd * 8 + 2 * t) = pack_bf16x2(oacc[jd][2], oacc[jd][3]);
       }
     }
+    }
+    // ---- 5. one TMA box store of the n x D output rows; then the next item's loads (K and V are dead after the last
+    //         ldmatrix above, Q's rows once the store has read them) ----
+    fence_proxy_async_smem();  // my generic-proxy writes of O -> visible to the async proxy
     __syncwarp();
-    for (int idx = lane; idx < n * VPR; idx += 32) {
-      const int j = idx / VPR, c = idx - j * VPR;
-      *reinterpret_cast<uint4*>(out + (size_t)(row0 + (long long)j * tok_stride) * C + (size_t)h * D + c * 8) =
-          *reinterpret_cast<const uint4*>(sq + (size_t)j * D + c * 8);
+    if (lane == 0) {
+      const unsigned seq = item / (unsigned)H;
+      const int ou = int(seq / (unsigned)n_inner);
+      tma_store_5d(&tm_o, sq, 0, int(item - seq * H), int(seq - (unsigned)ou * n_inner), 0, ou);
+      tma_store_commit();
+      tma_store_wait_read0();
+      if (item + stride < total) issue_loads(item + stride);
     }
     __syncwarp();
   }
+  if (lane == 0) tma_store_wait0();
 }
 
 template <int D>
 static int launch_short(const bf16* qkv, bf16* out, const bf16* wq, const bf16* wk, const float* rc, const float* rs,
                         int n_outer, int n_inner, long long os, long long is, long long ts, int n, int H, float eps,
                         float scale, int flags, cudaStream_t st) {
-  const size_t smem = 2 * kMaxN * D * sizeof(float) + (size_t)kWarpsPerBlock * 3 * kMaxN * D * sizeof(bf16);
+  const int C = H * D;
+  const int rq = (n + 7) & ~7;
+  const size_t fixed = 128 + 128 + 2 * kMaxN * D * sizeof(float);  // alignment slack, mbarriers, rope tables
+  const size_t per_warp = (size_t)(2 * rq + kMaxN) * D * sizeof(bf16);
+  int warps = int((227 * 1024 - fixed) / per_warp);
+  warps = warps >= kMaxWarps ? kMaxWarps : (warps & ~3);
+  if (warps < 4) return fail(VSB_ERR_UNSUPPORTED, "attn_short: shared memory");
+  const size_t smem = fixed + warps * per_warp;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_short_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_short_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_short: smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
+  // 5-D views {d, head, inner sequence index, token of the sequence, outer sequence index}; box = one head of one
+  // sequence: {D, 1, 1, n, 1}.  q / k / v are the three column blocks of the packed qkv rows.
+  CUtensorMap tm[4];
+  const unsigned long long dims[5] = {(unsigned long long)D, (unsigned long long)H, (unsigned long long)n_inner,
+                                      (unsigned long long)n, (unsigned long long)n_outer};
+  const unsigned box[5] = {(unsigned)D, 1, 1, (unsigned)n, 1};
+  for (int i = 0; i < 4; ++i) {
+    const unsigned long long row = (unsigned long long)(i < 3 ? 3 * C : C) * sizeof(bf16);
+    // a dimension of extent 1 is never stepped: give it a valid (non-zero, 16-byte multiple) stride
+    const unsigned long long str[4] = {(unsigned long long)D * sizeof(bf16),
+                                       (unsigned long long)(n_inner > 1 ? is : 1) * row,
+                                       (unsigned long long)(n > 1 ? ts : 1) * row,
+                                       (unsigned long long)(n_outer > 1 ? os : 1) * row};
+    const void* base = i < 3 ? (const void*)(qkv + (size_t)i * C) : (const void*)out;
+    int rc2 = make_tmap_bf16(&tm[i], base, 5, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE);
+    if (rc2) return rc2;
+  }
   const long long total = (long long)n_outer * n_inner * H;
-  long long blocks = (total + kWarpsPerBlock - 1) / kWarpsPerBlock;
-  const long long cap = (long long)num_sms() * 3 * 4;  // 3 resident blocks per SM, ~4 items per warp
-  if (blocks > cap) blocks = cap;
-  attn_short_kernel<D><<<(int)blocks, kWarpsPerBlock * 32, smem, st>>>(qkv, out, wq, wk, rc, rs, n_outer, n_inner, os,
-                                                                       is, ts, n, H, eps, scale, flags);
+  if (total >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "attn_short: %lld (sequence, head) items", total);
+  long long blocks = (total + warps - 1) / warps;
+  if (blocks > num_sms()) blocks = num_sms();  // persistent: one CTA per SM, each warp walks its share of the items
+  attn_short_kernel<D><<<(int)blocks, warps * 32, smem, st>>>(tm[0], tm[1], tm[2], tm[3], wq, wk, rc, rs, n_outer, n_inner,
+                                                               n, H, eps, scale, flags);
   return check_launch("attn_short");
 }
 

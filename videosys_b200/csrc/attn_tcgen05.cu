@@ -11,8 +11,7 @@
 // head_dim 72 is not a multiple of the 128-byte swizzle span: every operand tile is staged as a 64-wide
 // SWIZZLE_128B chunk plus a 16-wide SWIZZLE_32B chunk (columns 64..79; the tensor map's inner extent is 72, so
 // TMA zero-fills 72..79).  QK^T runs 4+1 K-steps, PV runs two N-slices (64 and 16) per K-step.
-#include "vsb_common.cuh"
-#include "vsb_host.h"
+#include "attn_params.cuh"
 
 namespace vsb {
 
@@ -28,27 +27,7 @@ constexpr int kAttnSmem = 2 * kQBytes + kKvStages * kKvStageBytes + 1024 + 256;
 __host__ __device__ constexpr uint32_t col_s(int x) { return uint32_t(x) * 128u; }        // S_A, S_B
 __host__ __device__ constexpr uint32_t col_o(int x) { return 256u + uint32_t(x) * 80u; }  // O_A, O_B: 64 + 16 columns
 
-// Debug timeline: when AttnParams::trace != nullptr, CTA (0,0,0) records clock64() at [actor][tile < 16][event < 4]
-// (actor 0 = MMA thread, 1/2 = softmax warpgroup A/B, lane 0 of its first warp).  Null in normal runs.
-#define VSB_TRACE(actor, tile, ev)                                                                   \
-  do {                                                                                               \
-    if (p.trace != nullptr && (tile) < 16 && lane == 0 && (warp == 1 || (warp & 3) == 0) &&         \
-        blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)                                       \
-      p.trace[((actor) * 16 + (tile)) * 4 + (ev)] = clock64();                                       \
-  } while (0)
-
-struct AttnParams {
-  int poly_exp;  // 1: every other exp2 runs as a polynomial on the FMA pipe (halves the MUFU load)
-  int pingpong;  // 1: the two softmax warpgroups take turns on the exp2 (MUFU) phase through named barriers
-  long long* trace;
-  bf16* out;
-  int nb, nq, nk, H;
-  float scale_log2;  // softmax scale * log2(e)
-  int has_lens;
-  int lens[8];
-};
-
-template <int D, bool kStale>
+template <int D>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qb,
                   const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_kb,
@@ -204,103 +183,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     const float sl2 = p.scale_log2;
     float l_run = 0.f;
     if (p.pingpong && x == 1) named_bar_arrive(2, 256);  // warpgroup A goes first
-    if constexpr (kStale) {
-    // Online softmax with a STALE reference max.  TMEM reads (tcgen05.ld) and exp2 (MUFU) are the two long poles of a
-    // tile; a thread can only overlap them if the exponentials of chunk c do not have to wait for the max of the
-    // whole tile.  So tile j uses m_run = the max known BEFORE the tile (tile 0: the true max of the tile); the true
-    // tile max is tracked on the side and folded in at the next tile boundary, where O and l are rescaled only if the
-    // reference moved by more than 2^8.  p = exp2((s - m_run) * sl2) may exceed 1 inside one tile (bounded by the score
-    // range: |s| <= D * max|w_q| * max|w_k| for RMS/LayerNormed q, k), which fp32 sums / bf16 P represent exactly as
-    // well; the final O / l is invariant to the reference.
-    float m_run = -INFINITY, m_seen = -INFINITY;
-    for (int j = 0; j < n_tiles; ++j) {
-      mbar_wait(&s_full[x], j & 1);
-      tc_fence_after();
-      VSB_TRACE(1 + x, j, 0);
-      const int valid = kv_len - j * 128;  // >= 128: full tile; columns >= valid are masked
-      uint32_t a[2][32];
-      tmem_ld32(tS, a[0]);
-      if (j == 0) {
-        // first tile: the reference is the true max of the tile (one extra pass over TMEM, once per CTA)
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(a[0][i]));
-          if (c < 3) tmem_ld32(tS + (c + 1) * 32, a[0]);
-        }
-        m_run = m_seen = mx;
-        tmem_ld32(tS, a[0]);
-      } else {
-        // fold in what the previous tile saw; rescale O / l only when the reference moved by more than 2^8
-        const bool grow = (m_seen - m_run) * sl2 > 8.f;
-        if (__any_sync(0xffffffffu, grow)) {
-          const float alpha = grow ? fast_exp2((m_run - m_seen) * sl2) : 1.f;
-          // O is quiescent here: S_x(j) complete implies PV_x(j-1) complete (in-order tensor pipe)
-          tmem_wait_ld();
-#pragma unroll 1
-          for (int c = 0; c < (kHasB ? 5 : 4); ++c) {
-            uint32_t o[16];
-            tmem_ld16(tO + c * 16, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st16(tO + c * 16, o);
-          }
-          l_run *= alpha;
-          if (grow) m_run = m_seen;
-        }
-      }
-      const float mb = m_run * sl2;
-      if (p.pingpong) named_bar_sync(2 + x, 256);  // my turn on the MUFU pipe
-      VSB_TRACE(1 + x, j, 1);
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      float t0 = m_seen, t1 = m_seen;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        tmem_wait_ld();                                          // chunk c has landed
-        if (c < 3) tmem_ld32(tS + (c + 1) * 32, a[(c + 1) & 1]);  // next chunk flies while this one is exponentiated
-        uint32_t(&r)[32] = a[c & 1];
-        if (valid < 128) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i >= valid) r[i] = 0xff800000u;  // -inf -> p = 0, never wins the max
-        }
-        uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-          const float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]);
-          const float v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
-          t0 = fmax3(t0, v0, v1);
-          t1 = fmax3(t1, v2, v3);
-          const float p0 = fast_exp2(fmaf(v0, sl2, -mb));
-          const float p1 = fast_exp2(fmaf(v1, sl2, -mb));
-          const float p2 = fast_exp2(fmaf(v2, sl2, -mb));
-          const float p3 = fast_exp2(fmaf(v3, sl2, -mb));
-          s0 += p0;
-          s1 += p1;
-          s2 += p2;
-          s3 += p3;
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-          pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
-        }
-        // P chunk c overwrites S columns [16c, 16c+16): already consumed (chunk c holds S columns [32c, 32c+32));
-        // the in-flight load of chunk c+1 reads columns >= 32(c+1), disjoint from the store
-        tmem_st16(tS + c * 16, pk);
-      }
-      m_seen = fmaxf(t0, t1);
-      l_run += (s0 + s1) + (s2 + s3);
-      if (p.pingpong) named_bar_arrive(2 + (x ^ 1), 256);  // hand the MUFU pipe to the other warpgroup
-      VSB_TRACE(1 + x, j, 2);
-      tmem_wait_st();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[x]);
-      VSB_TRACE(1 + x, j, 3);
-    }
-    } else {
+    {
     float m_run = -INFINITY;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(&s_full[x], j & 1);
@@ -369,17 +252,9 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 #pragma unroll
       for (int c = 0; c < 5; ++c) {
         if (c < 4) {
-          if (p.poly_exp) {  // odd columns on the FMA pipe, even columns on the MUFU pipe
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              a[c][i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(a[c][i]), sl2, -mb)));
-              a[c][i + 1] = __float_as_uint(exp2_poly(fmaf(__uint_as_float(a[c][i + 1]), sl2, -mb)));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              a[c][i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(a[c][i]), sl2, -mb)));
-          }
+          for (int i = 0; i < 32; ++i)
+            a[c][i] = __float_as_uint(fast_exp2(fmaf(__uint_as_float(a[c][i]), sl2, -mb)));
         }
         if (c > 0) {
           uint32_t pk[16];
@@ -434,10 +309,10 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-long long* g_attn_trace = nullptr;  // vsb_set_option_ptr("attn_trace", device buffer of 3*16*4 int64)
-int g_opt_attn_poly = 0;            // polynomial exp2 for odd columns (variant 0)
-int g_opt_attn_pingpong = 1;        // softmax warpgroups alternate on the MUFU phase
-int g_opt_attn_variant = 0;         // 0 = max-first single pass (fastest measured), 1 = stale-reference max
+long long* g_attn_trace = nullptr;  // vsb_debug_attn_trace(device buffer of 3*16*4 int64)
+int g_opt_attn_poly = 0;            // variant 2 only: every fourth exp2 as a polynomial on the FMA pipe
+int g_opt_attn_pingpong = 1;        // variant 0 only: softmax warpgroups alternate on the MUFU phase
+int g_opt_attn_variant = 2;         // 0 = 128-key tiles, ping-pong; 2 = 64-key tiles, double-buffered S
 
 }  // namespace vsb
 
@@ -485,7 +360,8 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
     unsigned long long dims[4] = {(unsigned long long)D, (unsigned long long)H, (unsigned long long)(i == 0 ? nq : nk),
                                   (unsigned long long)nb};
     unsigned long long str[3] = {(unsigned long long)D * 2, (unsigned long long)rs * 2, (unsigned long long)bs * 2};
-    unsigned boxA[4] = {64, 1, 128, 1}, boxB[4] = {16, 1, 128, 1};
+    const unsigned rows = (i > 0 && g_opt_attn_variant == 2) ? 64u : 128u;  // key tile of the selected schedule
+    unsigned boxA[4] = {64, 1, rows, 1}, boxB[4] = {16, 1, rows, 1};
     int rc = make_tmap_bf16(&tm[2 * i], base[i], 4, dims, str, boxA, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
     if (D == 72) {
@@ -495,32 +371,19 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
       tm[2 * i + 1] = tm[2 * i];  // unused by the head_dim-64 instantiation
     }
   }
-  dim3 grid((nq + 255) / 256, H, nb);
   cudaStream_t st = (cudaStream_t)stream;
-  if (D == 72) {
-    static bool attr = false;
-    if (!attr) {
-      cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<72, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<72, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-      if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash: smem attr: %s", cudaGetErrorString(e));
-      attr = true;
-    }
-    if (g_opt_attn_variant)
-      attn_flash_kernel<72, true><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
-    else
-      attn_flash_kernel<72, false><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
-  } else {
-    static bool attr = false;
-    if (!attr) {
-      cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-      if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
-      if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash: smem attr: %s", cudaGetErrorString(e));
-      attr = true;
-    }
-    if (g_opt_attn_variant)
-      attn_flash_kernel<64, true><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
-    else
-      attn_flash_kernel<64, false><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+  if (g_opt_attn_variant == 2) return attn_flash_kt64_launch(tm, prm, D, g_opt_attn_poly, st);
+  dim3 grid((nq + 255) / 256, H, nb);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_flash_kernel<72>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_flash_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem);
+    if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash: smem attr: %s", cudaGetErrorString(e));
+    attr = true;
   }
+  if (D == 72)
+    attn_flash_kernel<72><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+  else
+    attn_flash_kernel<64><<<grid, kAttnThreads, kAttnSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
   return check_launch("attn_flash");
 }

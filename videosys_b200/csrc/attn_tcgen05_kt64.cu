@@ -1,0 +1,344 @@
+// vsb200 -- flash attention forward on tcgen05, 64-key tiles with a double-buffered S (attn_variant = 2).
+//
+// Why a second schedule.  At head_dim 72 the kernel is bound by the exp2 (MUFU, 16 lanes/clk/SM) of the softmax, not by
+// the tensor pipe: a pair of 128x128 score tiles costs 2048 MUFU cycles against 1280 tensor cycles.  The 128-key kernel
+// (attn_tcgen05.cu) keeps P aliased on the only S buffer of a query tile, so S(j+1) cannot start before PV(j) and each
+// softmax warpgroup sits idle for a full PV + S round trip per key tile (measured: 1250 idle cycles of a 3750-cycle
+// period).  Here every query tile owns TWO 64-column S buffers in TMEM:
+//
+//     softmax WG x, tile t   : wait S_x(t) in buf t&1 -> max / exp2 / bf16 P_x(t) back into the head of buf t&1
+//     MMA warp, iteration t  : wait P_x(t) -> O_x += P_x(t) V(t) -> S_x(t+2) = Q_x K(t+2)^T into buf t&1
+//
+// so while warpgroup x exponentiates tile t+1 (buf (t+1)&1, filled one iteration earlier) the tensor pipe retires
+// PV_x(t) and S_x(t+2): the softmax warps never wait on the tensor core as long as it keeps up (640 tensor cycles per
+// 64-key step of both query tiles against >= 1024 MUFU cycles).  Both warpgroups exponentiate concurrently (two warps
+// per SM sub-partition keep the MUFU pipe busier than one: 9.5 vs 11.7 cycles per warp instruction measured).
+//
+//   warp 0        TMA producer: Q tiles once, K/V 64-key tiles through a 6-deep mbarrier ring (K leads V by 2 tiles)
+//   warp 1        MMA issuer (whole warp converged, elected lane issues)
+//   warp 2        TMEM allocator: S buffers at columns x*128 + buf*64, O_x at 256 + x*80
+//   warps 4..7    softmax warpgroup A (thread = query row), warps 8..11 warpgroup B
+//
+// Lazy rescale of O needs O quiescent: PV_x(t-1) may still be in flight when tile t finds a much larger max, so that
+// (rare) path first waits for the commit the MMA warp posts after PV_x(t-1) [+ S_x(t+1)] on s_full[x][(t+1)&1].
+// A CTA whose second query tile starts past nq (the ragged tail of a sequence) runs warpgroup A only.
+#include "attn_params.cuh"
+
+namespace vsb {
+
+constexpr int kT64Threads = 384;
+constexpr int kT64Stages = 6;
+constexpr int kQA = 128 * 128;  // Q: 128 rows x 64 bf16, SWIZZLE_128B
+constexpr int kQB = 128 * 32;   // Q: 128 rows x 16 bf16, SWIZZLE_32B
+constexpr int kQT = kQA + kQB;
+constexpr int kKA = 64 * 128;   // K / V: 64 keys x 64 bf16, SWIZZLE_128B
+constexpr int kKB = 64 * 32;    // K / V: 64 keys x 16 bf16, SWIZZLE_32B
+constexpr int kKT = kKA + kKB;
+constexpr int kStage = 2 * kKT;  // K_A | K_B | V_A | V_B
+constexpr int kT64Smem = 2 * kQT + kT64Stages * kStage + 1024 + 512;
+
+__host__ __device__ constexpr uint32_t c_s(int x, int buf) { return uint32_t(x) * 128u + uint32_t(buf) * 64u; }
+__host__ __device__ constexpr uint32_t c_o(int x) { return 256u + uint32_t(x) * 80u; }
+
+template <int D, bool kPoly>
+__global__ void __launch_bounds__(kT64Threads, 1)
+attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qb,
+                       const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_kb,
+                       const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_vb,
+                       const __grid_constant__ AttnParams p) {
+  constexpr bool kHasB = (D > 64);
+  constexpr int kQTx = kHasB ? kQT : kQA;
+  constexpr int kKTx = kHasB ? kKT : kKA;
+  constexpr int ST = kT64Stages;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sQ = smem;               // [2][Q_A | Q_B]
+  unsigned char* sKV = smem + 2 * kQT;    // [stages][K_A | K_B | V_A | V_B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + ST * kStage);
+  uint64_t* q_full = bars;              // [1]
+  uint64_t* k_full = bars + 1;          // [ST]
+  uint64_t* v_full = k_full + ST;       // [ST]
+  uint64_t* kv_empty = v_full + ST;     // [ST]
+  uint64_t* s_full = kv_empty + ST;     // [x][buf]
+  uint64_t* p_full = s_full + 4;        // [x][buf]
+  uint64_t* o_full = p_full + 4;        // [x]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 256, h = blockIdx.y, b = blockIdx.z;
+  const int kv_len = p.has_lens ? p.lens[b] : p.nk;
+  const int n_tiles = (kv_len + 63) / 64;
+  const int nx = (q0 + 128 < p.nq) ? 2 : 1;  // query tiles of this CTA that hold real rows
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    if (kHasB) {
+      tma_prefetch_desc(&tm_qb);
+      tma_prefetch_desc(&tm_kb);
+      tma_prefetch_desc(&tm_vb);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ST; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);  // one arrival per softmax warp
+    }
+    mbar_init(&o_full[0], 1);
+    mbar_init(&o_full[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    const uint32_t elected = elect_one();
+    mbar_arrive_expect_tx_w(elected, q_full, nx * kQTx);
+    for (int x = 0; x < nx; ++x) {
+      tma_load_4d_w(elected, &tm_q, q_full, sQ + x * kQT, 0, h, q0 + x * 128, b);
+      if (kHasB) tma_load_4d_w(elected, &tm_qb, q_full, sQ + x * kQT + kQA, 64, h, q0 + x * 128, b);
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      const int s = j % ST;
+      const uint32_t ph = (j / ST) & 1;
+      mbar_wait(&kv_empty[s], ph ^ 1);
+      unsigned char* st = sKV + s * kStage;
+      mbar_arrive_expect_tx_w(elected, &k_full[s], kKTx);
+      tma_load_4d_w(elected, &tm_k, &k_full[s], st, 0, h, j * 64, b);
+      if (kHasB) tma_load_4d_w(elected, &tm_kb, &k_full[s], st + kKA, 64, h, j * 64, b);
+      mbar_arrive_expect_tx_w(elected, &v_full[s], kKTx);
+      tma_load_4d_w(elected, &tm_v, &v_full[s], st + kKT, 0, h, j * 64, b);
+      if (kHasB) tma_load_4d_w(elected, &tm_vb, &v_full[s], st + kKT + kKA, 64, h, j * 64, b);
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);    // S = Q K^T (128 x 64), both K-major
+    constexpr uint32_t idesc_o64 = umma_idesc_bf16(128, 64, 0, 1);  // O[:, 0:64]  += P V, V MN-major
+    constexpr uint32_t idesc_o16 = umma_idesc_bf16(128, 16, 0, 1);  // O[:, 64:80] += P V
+    constexpr uint32_t hi128 = umma_desc_hi(1024, 2);               // SWIZZLE_128B, 8-row / 8-key groups 1024 B apart
+    constexpr uint32_t hi32 = umma_desc_hi(256, 6);                 // SWIZZLE_32B, groups 256 B apart
+    const uint32_t elected = elect_one();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t q_lo = umma_desc_lo(smem_u32(sQ), 16);
+    const uint32_t kv_lo = umma_desc_lo(smem_u32(sKV), 16);
+    auto issue_S = [&](int x, int buf, int stage) {
+      const uint32_t qa = q_lo + x * (kQT >> 4);
+      const uint32_t ka = kv_lo + stage * (kStage >> 4);
+      const uint32_t d = tb + c_s(x, buf);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss_w(elected, d, desc_pack(qa + 2 * k, hi128), desc_pack(ka + 2 * k, hi128), idesc_s, k > 0 ? 1u : 0u);
+      if (kHasB)
+        umma_ss_w(elected, d, desc_pack(qa + (kQA >> 4), hi32), desc_pack(ka + (kKA >> 4), hi32), idesc_s, 1u);
+    };
+    auto issue_PV = [&](int x, int buf, int stage, bool accumulate) {
+      // V tiles are MN-major (d contiguous): the LBO field is the stride between d atoms, unused with a single atom
+      const uint32_t va = kv_lo + stage * (kStage >> 4) + (kKT >> 4) - (1u << 16) + ((uint32_t(kKA) >> 4) << 16);
+      const uint32_t vb = kv_lo + stage * (kStage >> 4) + ((kKT + kKA) >> 4) - (1u << 16) + ((uint32_t(kKB) >> 4) << 16);
+      const uint32_t pt = tb + c_s(x, buf);  // bf16 P: 32 columns at the head of the S buffer
+      const uint32_t d = tb + c_o(x);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {  // 16 keys per step: +2048 B in the 128B-swizzled chunk, +512 B in the 32B one
+        const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
+        umma_ts_w(elected, d, pt + ks * 8, desc_pack(va + ks * 128, hi128), idesc_o64, acc);
+        if (kHasB) umma_ts_w(elected, d + 64, pt + ks * 8, desc_pack(vb + ks * 32, hi32), idesc_o16, acc);
+      }
+    };
+    mbar_wait(q_full, 0);
+    for (int t = 0; t < 2 && t < n_tiles; ++t) {  // prologue: S(0) -> buf 0, S(1) -> buf 1
+      mbar_wait(&k_full[t], 0);
+      tc_fence_after();
+      for (int x = 0; x < nx; ++x) {
+        issue_S(x, t, t);
+        umma_commit_w(elected, &s_full[x * 2 + t]);
+      }
+    }
+    for (int t = 0; t < n_tiles; ++t) {
+      const int s = t % ST;
+      const uint32_t ph = (t / ST) & 1;
+      const int buf = t & 1;
+      const uint32_t pph = (t >> 1) & 1;
+      const int s2 = (t + 2) % ST;
+      const uint32_t ph2 = ((t + 2) / ST) & 1;
+      for (int x = 0; x < nx; ++x) {
+        mbar_wait(&p_full[x * 2 + buf], pph);
+        if (x == 0) mbar_wait(&v_full[s], ph);
+        tc_fence_after();
+        VSB_TRACE(0, t, x * 2);
+        issue_PV(x, buf, s, t > 0);
+        if (x == nx - 1) umma_commit_w(elected, &kv_empty[s]);  // K(t) (used by S(t) earlier) and V(t) are consumed
+        if (t + 2 < n_tiles) {
+          if (x == 0) {
+            mbar_wait(&k_full[s2], ph2);
+            tc_fence_after();
+          }
+          issue_S(x, buf, s2);
+        }
+        // also posted without a new S: the softmax warps use it as "PV_x(t) has completed" on their rare rescale path
+        umma_commit_w(elected, &s_full[x * 2 + buf]);
+        if (t + 1 == n_tiles) umma_commit_w(elected, &o_full[x]);
+        VSB_TRACE(0, t, x * 2 + 1);
+      }
+    }
+  } else if (warp >= 4 && ((warp - 4) >> 2) < nx) {
+    // =============================== softmax warpgroups ===============================
+    const int x = (warp - 4) >> 2;  // query tile 0/1
+    const int ew = warp & 3;        // TMEM lane quarter
+    const int row = ew * 32 + lane;
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const uint32_t tO = tmem_base + lane_off + c_o(x);
+    const float sl2 = p.scale_log2;
+    float l_run = 0.f, m_run = -INFINITY;
+    for (int t = 0; t < n_tiles; ++t) {
+      const int buf = t & 1;
+      const uint32_t tS = tmem_base + lane_off + c_s(x, buf);
+      mbar_wait(&s_full[x * 2 + buf], (t >> 1) & 1);
+      tc_fence_after();
+      VSB_TRACE(1 + x, t, 0);
+      const int valid = kv_len - t * 64;  // >= 64: full tile; columns >= valid are masked
+      uint32_t a[2][32];
+      tmem_ld32(tS, a[0]);
+      tmem_ld32(tS + 32, a[1]);
+      tmem_wait_ld();
+      VSB_TRACE(1 + x, t, 1);
+      float mx;
+      if (valid >= 64) {
+        float m0 = fmax3(__uint_as_float(a[0][0]), __uint_as_float(a[0][1]), __uint_as_float(a[0][2]));
+        float m1 = fmax3(__uint_as_float(a[1][0]), __uint_as_float(a[1][1]), __uint_as_float(a[1][2]));
+        float m2 = fmax3(__uint_as_float(a[0][3]), __uint_as_float(a[0][4]), __uint_as_float(a[0][5]));
+        float m3 = fmax3(__uint_as_float(a[1][3]), __uint_as_float(a[1][4]), __uint_as_float(a[1][5]));
+#pragma unroll
+        for (int i = 6; i < 30; i += 4) {
+          m0 = fmax3(m0, __uint_as_float(a[0][i]), __uint_as_float(a[0][i + 1]));
+          m1 = fmax3(m1, __uint_as_float(a[1][i]), __uint_as_float(a[1][i + 1]));
+          m2 = fmax3(m2, __uint_as_float(a[0][i + 2]), __uint_as_float(a[0][i + 3]));
+          m3 = fmax3(m3, __uint_as_float(a[1][i + 2]), __uint_as_float(a[1][i + 3]));
+        }
+        m0 = fmax3(m0, __uint_as_float(a[0][30]), __uint_as_float(a[0][31]));
+        m1 = fmax3(m1, __uint_as_float(a[1][30]), __uint_as_float(a[1][31]));
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+      } else {  // ragged last tile: masked columns never win the max and get p = 0 below
+        mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            if (c * 32 + i >= valid) a[c][i] = 0xff800000u;  // -inf
+            mx = fmaxf(mx, __uint_as_float(a[c][i]));
+          }
+      }
+      // ---- lazy rescale: keep the stale running max unless it grew by more than 2^8 (p stays <= 256) ----
+      const float m_new = fmaxf(m_run, mx);
+      const bool grow = (m_new - m_run) * sl2 > 8.f;  // first tile: m_run = -inf -> true
+      const float alpha = grow ? fast_exp2((m_run - m_new) * sl2) : 1.f;
+      if (t > 0 && __any_sync(0xffffffffu, grow)) {
+        // PV_x(t-1) may still be running: the MMA warp's iteration t-1 ends with a commit on s_full[x][(t+1)&1]
+        mbar_wait(&s_full[x * 2 + (buf ^ 1)], ((t + 1) >> 1) & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < (kHasB ? 5 : 4); ++c) {  // one 16-column chunk at a time (register budget)
+          uint32_t o[16];
+          tmem_ld16(tO + c * 16, o);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+          tmem_st16(tO + c * 16, o);
+        }
+      }
+      if (grow) m_run = m_new;
+      const float mb = m_run * sl2;
+      // ---- p = exp2(s*sl2 - m*sl2); row sum; bf16 P into the head of this S buffer ----
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (c < 2) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = fmaf(__uint_as_float(a[c][i]), sl2, -mb);
+            // kPoly: every fourth exponential runs as a polynomial on the FMA pipe (relieves the MUFU pipe by 25 %)
+            a[c][i] = __float_as_uint((kPoly && (i & 3) == 3) ? exp2_poly(e) : fast_exp2(e));
+          }
+        }
+        if (c > 0) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float p0 = __uint_as_float(a[c - 1][i]), p1 = __uint_as_float(a[c - 1][i + 1]);
+            const float p2 = __uint_as_float(a[c - 1][i + 2]), p3 = __uint_as_float(a[c - 1][i + 3]);
+            s0 += p0;
+            s1 += p1;
+            s2 += p2;
+            s3 += p3;
+            pk[i >> 1] = pack_bf16x2(p0, p1);
+            pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
+          }
+          // P chunk c-1 overwrites S columns [16(c-1), 16c): all 64 score columns already sit in registers
+          tmem_st16(tS + (c - 1) * 16, pk);
+        }
+      }
+      l_run = l_run * alpha + ((s0 + s1) + (s2 + s3));
+      VSB_TRACE(1 + x, t, 2);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x * 2 + buf]);
+      VSB_TRACE(1 + x, t, 3);
+    }
+    // ---- epilogue: O / l -> bf16 -> global ----
+    mbar_wait(&o_full[x], 0);
+    tc_fence_after();
+    const int qrow = q0 + x * 128 + row;
+    const float inv = 1.f / l_run;
+    bf16* dst = p.out + ((size_t)((size_t)b * p.nq + (qrow < p.nq ? qrow : 0)) * p.H + h) * D;
+#pragma unroll 1
+    for (int c = 0; c < D / 8; ++c) {
+      uint32_t r[8];
+      tmem_ld8(tO + c * 8, r);
+      tmem_wait_ld();
+      if (qrow < p.nq) {
+        uint4 u;
+        u.x = pack_bf16x2(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+        u.y = pack_bf16x2(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+        u.z = pack_bf16x2(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+        u.w = pack_bf16x2(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+        *reinterpret_cast<uint4*>(dst + c * 8) = u;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+template <int D, bool kPoly>
+static int launch_kt64(const CUtensorMap* tm, const AttnParams& prm, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_flash_kt64_kernel<D, kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kT64Smem);
+    if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash(kt64): smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  dim3 grid((prm.nq + 255) / 256, prm.H, prm.nb);
+  attn_flash_kt64_kernel<D, kPoly><<<grid, kT64Threads, kT64Smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+  return check_launch("attn_flash(kt64)");
+}
+
+int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st) {
+  if (D == 72) return poly ? launch_kt64<72, true>(tm, prm, st) : launch_kt64<72, false>(tm, prm, st);
+  return poly ? launch_kt64<64, true>(tm, prm, st) : launch_kt64<64, false>(tm, prm, st);
+}
+
+}  // namespace vsb

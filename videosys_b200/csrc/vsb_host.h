@@ -34,7 +34,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled();
 
-// bf16 tensor map, rank <= 4; dims/strides innermost first; strides in BYTES for dims 1..rank-1.
+// bf16 tensor map, rank <= 5; dims/strides innermost first; strides in BYTES for dims 1..rank-1.
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
                    const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz);
 int num_sms();
