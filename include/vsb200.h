@@ -44,7 +44,7 @@ int vsb_set_option(const char* name, int value);
  *   "attn_poly_exp" (default 0, variant 2): every fourth exp2 as a polynomial on the FMA pipe.
  *   "attn_pingpong" (default 1, variant 0): the warpgroups alternate on the MUFU phase.
  *   Same results up to fp32 rounding.
- * vsb_debug_attn_trace: device buffer of 3*16*4 int64 that CTA (0,0,0) of vsb_attn_flash fills with clock64()
+ * vsb_debug_attn_trace: device buffer of 9*16*4 int64 that CTA (0,0,0) of vsb_attn_flash fills with clock64()
  * timestamps (profiling aid, NULL disables). */
 int vsb_debug_attn_trace(void* device_buffer);
 

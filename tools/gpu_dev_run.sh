@@ -24,6 +24,7 @@ for g in "$@"; do
     all)   run all 900 tests ;;
     dsp)   run dsp 600 tests/test_dsp_gpu.py ;;
     refgpu) timeout 600 python tests/bench_reference_gpu.py > gpurun_out/refgpu.log 2>&1; echo "refgpu exit $? $(tail -n 1 gpurun_out/refgpu.log | cut -c1-300)" | tee -a gpurun_out/summary.txt ;;
+    mmab) timeout 120 tools/_bin/mma_microbench > gpurun_out/mma_microbench.txt 2>&1; echo "mmab exit $?" | tee -a gpurun_out/summary.txt ;;
     atrace) timeout 300 python tools/attn_trace.py > gpurun_out/attn_trace.log 2>&1; echo "atrace exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/attn_trace.log ;;
     kbench) timeout 600 python tools/kernel_bench.py > gpurun_out/kernel_bench.log 2>&1; echo "kbench exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/kernel_bench.log | tail -12 ;;
     mbenchnccl*) n=${g#mbenchnccl}; echo "=== bench N=$n (NCCL a2a) ===" | tee -a gpurun_out/summary.txt

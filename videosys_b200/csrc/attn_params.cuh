@@ -15,6 +15,13 @@ namespace vsb {
       p.trace[((actor) * 16 + (tile)) * 4 + (ev)] = clock64();                                       \
   } while (0)
 
+// per-warp variant (attn_tcgen05_kt64.cu): actor 0 = MMA issuer warps 0..3, 1..8 = softmax warps 4..11; 9*16*4 int64
+#define VSB_TRACE_W(tile, ev)                                                                            \
+  do {                                                                                                   \
+    if (p.trace != nullptr && (tile) < 16 && lane == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) \
+      p.trace[((warp < 4 ? 0 : warp - 3) * 16 + (tile)) * 4 + (ev)] = clock64();                        \
+  } while (0)
+
 struct AttnParams {
   int poly_exp;  // 1: every other exp2 runs as a polynomial on the FMA pipe (halves the MUFU load)
   int pingpong;  // 1: the two softmax warpgroups take turns on the exp2 (MUFU) phase through named barriers

@@ -14,10 +14,17 @@
 // 64-key step of both query tiles against >= 1024 MUFU cycles).  Both warpgroups exponentiate concurrently (two warps
 // per SM sub-partition keep the MUFU pipe busier than one: 9.5 vs 11.7 cycles per warp instruction measured).
 //
-//   warp 0        TMA producer: Q tiles once, K/V 64-key tiles through a 6-deep mbarrier ring (K leads V by 2 tiles)
-//   warp 1        MMA issuer (whole warp converged, elected lane issues)
-//   warp 2        TMEM allocator: S buffers at columns x*128 + buf*64, O_x at 256 + x*80
+//   warps 0..3    MMA issuers, one per SM sub-partition: warp (x, parity) owns S buffer `parity` of query tile x, i.e.
+//                 PV_x(t) and S_x(t+2) for t = parity (mod 2).  Four issuers instead of one because (per-warp clock64
+//                 trace + tools/mma_microbench.cu): (1) a tcgen05.mma that finds the tensor queue full (4-5 MMAs deep)
+//                 stalls in the issue stage and slows the OTHER warps of its sub-partition -- next to a single issuer
+//                 two softmax warps ran 1.65x slower than the other six and set the pace; (2) every mbarrier wait costs
+//                 >= 90 cycles even when already complete, and one warp doing 5 of them per key tile between blocked
+//                 issue bursts left the tensor pipe idle half of the time.  The four issuers need no ordering among
+//                 themselves: S buffers are private, O_x is only ever accumulated into (the softmax warps zero it).
+//                 Warp 0 also owns the TMEM allocation: S buffers at columns x*128 + buf*64, O_x at 256 + x*80.
 //   warps 4..7    softmax warpgroup A (thread = query row), warps 8..11 warpgroup B
+//   warp 12       TMA producer: Q tiles once, K/V 64-key tiles through a 6-deep mbarrier ring (K leads V by 2 tiles)
 //
 // Lazy rescale of O needs O quiescent: PV_x(t-1) may still be in flight when tile t finds a much larger max, so that
 // (rare) path first waits for the commit the MMA warp posts after PV_x(t-1) [+ S_x(t+1)] on s_full[x][(t+1)&1].
@@ -26,7 +33,7 @@
 
 namespace vsb {
 
-constexpr int kT64Threads = 384;
+constexpr int kT64Threads = 416;  // 4 MMA issuer warps, 8 softmax warps, 1 TMA producer warp
 constexpr int kT64Stages = 6;
 constexpr int kQA = 128 * 128;  // Q: 128 rows x 64 bf16, SWIZZLE_128B
 constexpr int kQB = 128 * 32;   // Q: 128 rows x 16 bf16, SWIZZLE_32B
@@ -40,7 +47,7 @@ constexpr int kT64Smem = 2 * kQT + kT64Stages * kStage + 1024 + 512;
 __host__ __device__ constexpr uint32_t c_s(int x, int buf) { return uint32_t(x) * 128u + uint32_t(buf) * 64u; }
 __host__ __device__ constexpr uint32_t c_o(int x) { return 256u + uint32_t(x) * 80u; }
 
-template <int D, bool kPoly>
+template <int D, int kPoly>
 __global__ void __launch_bounds__(kT64Threads, 1)
 attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qb,
                        const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_kb,
@@ -70,7 +77,7 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const int n_tiles = (kv_len + 63) / 64;
   const int nx = (q0 + 128 < p.nq) ? 2 : 1;  // query tiles of this CTA that hold real rows
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 12 && lane == 0) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
@@ -85,23 +92,23 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     for (int i = 0; i < ST; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&kv_empty[i], nx);  // one commit per active query tile (after its P V of the tile)
     }
     for (int i = 0; i < 4; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);  // one arrival per softmax warp
     }
-    mbar_init(&o_full[0], 1);
-    mbar_init(&o_full[1], 1);
+    mbar_init(&o_full[0], 2);  // both issuers of the query tile
+    mbar_init(&o_full[1], 2);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_ptr);
+  if (warp == 0) tmem_alloc<512>(tmem_ptr);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == 12) {
     // =============================== TMA producer ===============================
     const uint32_t elected = elect_one();
     mbar_arrive_expect_tx_w(elected, q_full, nx * kQTx);
@@ -121,8 +128,8 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       tma_load_4d_w(elected, &tm_v, &v_full[s], st + kKT, 0, h, j * 64, b);
       if (kHasB) tma_load_4d_w(elected, &tm_vb, &v_full[s], st + kKT + kKA, 64, h, j * 64, b);
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
+  } else if (warp < 4 && (warp >> 1) < nx) {
+    // =============================== MMA issuers: warp = (query tile x, S buffer / key-tile parity) ===============
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);    // S = Q K^T (128 x 64), both K-major
     constexpr uint32_t idesc_o64 = umma_idesc_bf16(128, 64, 0, 1);  // O[:, 0:64]  += P V, V MN-major
     constexpr uint32_t idesc_o16 = umma_idesc_bf16(128, 16, 0, 1);  // O[:, 64:80] += P V
@@ -142,7 +149,7 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       if (kHasB)
         umma_ss_w(elected, d, desc_pack(qa + (kQA >> 4), hi32), desc_pack(ka + (kKA >> 4), hi32), idesc_s, 1u);
     };
-    auto issue_PV = [&](int x, int buf, int stage, bool accumulate) {
+    auto issue_PV = [&](int x, int buf, int stage) {
       // V tiles are MN-major (d contiguous): the LBO field is the stride between d atoms, unused with a single atom
       const uint32_t va = kv_lo + stage * (kStage >> 4) + (kKT >> 4) - (1u << 16) + ((uint32_t(kKA) >> 4) << 16);
       const uint32_t vb = kv_lo + stage * (kStage >> 4) + ((kKT + kKA) >> 4) - (1u << 16) + ((uint32_t(kKB) >> 4) << 16);
@@ -150,47 +157,37 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const uint32_t d = tb + c_o(x);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {  // 16 keys per step: +2048 B in the 128B-swizzled chunk, +512 B in the 32B one
-        const uint32_t acc = (accumulate || ks > 0) ? 1u : 0u;
-        umma_ts_w(elected, d, pt + ks * 8, desc_pack(va + ks * 128, hi128), idesc_o64, acc);
-        if (kHasB) umma_ts_w(elected, d + 64, pt + ks * 8, desc_pack(vb + ks * 32, hi32), idesc_o16, acc);
+        umma_ts_w(elected, d, pt + ks * 8, desc_pack(va + ks * 128, hi128), idesc_o64, 1u);
+        if (kHasB) umma_ts_w(elected, d + 64, pt + ks * 8, desc_pack(vb + ks * 32, hi32), idesc_o16, 1u);
       }
     };
+    const int x = warp >> 1, par = warp & 1;
     mbar_wait(q_full, 0);
-    for (int t = 0; t < 2 && t < n_tiles; ++t) {  // prologue: S(0) -> buf 0, S(1) -> buf 1
-      mbar_wait(&k_full[t], 0);
+    if (par < n_tiles) {  // prologue: S_x(par) -> my buffer
+      mbar_wait(&k_full[par], 0);
       tc_fence_after();
-      for (int x = 0; x < nx; ++x) {
-        issue_S(x, t, t);
-        umma_commit_w(elected, &s_full[x * 2 + t]);
-      }
+      issue_S(x, par, par);
+      umma_commit_w(elected, &s_full[x * 2 + par]);
     }
-    for (int t = 0; t < n_tiles; ++t) {
+    for (int t = par; t < n_tiles; t += 2) {
       const int s = t % ST;
-      const uint32_t ph = (t / ST) & 1;
-      const int buf = t & 1;
-      const uint32_t pph = (t >> 1) & 1;
       const int s2 = (t + 2) % ST;
-      const uint32_t ph2 = ((t + 2) / ST) & 1;
-      for (int x = 0; x < nx; ++x) {
-        mbar_wait(&p_full[x * 2 + buf], pph);
-        if (x == 0) mbar_wait(&v_full[s], ph);
-        tc_fence_after();
-        VSB_TRACE(0, t, x * 2);
-        issue_PV(x, buf, s, t > 0);
-        if (x == nx - 1) umma_commit_w(elected, &kv_empty[s]);  // K(t) (used by S(t) earlier) and V(t) are consumed
-        if (t + 2 < n_tiles) {
-          if (x == 0) {
-            mbar_wait(&k_full[s2], ph2);
-            tc_fence_after();
-          }
-          issue_S(x, buf, s2);
-        }
-        // also posted without a new S: the softmax warps use it as "PV_x(t) has completed" on their rare rescale path
-        umma_commit_w(elected, &s_full[x * 2 + buf]);
-        if (t + 1 == n_tiles) umma_commit_w(elected, &o_full[x]);
-        VSB_TRACE(0, t, x * 2 + 1);
-      }
+      // operands first (they land long before P is ready: these waits are off the critical path) ...
+      mbar_wait(&v_full[s], (t / ST) & 1);
+      if (t + 2 < n_tiles) mbar_wait(&k_full[s2], ((t + 2) / ST) & 1);
+      // ... then the softmax warps' P_x(t)
+      mbar_wait(&p_full[x * 2 + par], (t >> 1) & 1);
+      tc_fence_after();
+      VSB_TRACE_W(t, x * 2);
+      issue_PV(x, par, s);
+      // K(t) (read by my S_x(t) two tiles ago, retired before this P V) and V(t) are consumed by query tile x
+      umma_commit_w(elected, &kv_empty[s]);
+      if (t + 2 < n_tiles) issue_S(x, par, s2);
+      // also posted without a new S: the softmax warps use it as "PV_x(t) has completed" on their rare rescale path
+      umma_commit_w(elected, &s_full[x * 2 + par]);
+      VSB_TRACE_W(t, x * 2 + 1);
     }
+    umma_commit_w(elected, &o_full[x]);  // all my P V MMAs (immediate if I had no key tile)
   } else if (warp >= 4 && ((warp - 4) >> 2) < nx) {
     // =============================== softmax warpgroups ===============================
     const int x = (warp - 4) >> 2;  // query tile 0/1
@@ -200,18 +197,25 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const uint32_t tO = tmem_base + lane_off + c_o(x);
     const float sl2 = p.scale_log2;
     float l_run = 0.f, m_run = -INFINITY;
+    {  // O_x starts at zero: both issuers of this query tile only ever accumulate into it
+      uint32_t z[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) z[i] = 0u;
+#pragma unroll
+      for (int c = 0; c < (kHasB ? 5 : 4); ++c) tmem_st16(tO + c * 16, z);
+    }
     for (int t = 0; t < n_tiles; ++t) {
       const int buf = t & 1;
       const uint32_t tS = tmem_base + lane_off + c_s(x, buf);
       mbar_wait(&s_full[x * 2 + buf], (t >> 1) & 1);
       tc_fence_after();
-      VSB_TRACE(1 + x, t, 0);
+      VSB_TRACE_W(t, 0);
       const int valid = kv_len - t * 64;  // >= 64: full tile; columns >= valid are masked
       uint32_t a[2][32];
       tmem_ld32(tS, a[0]);
       tmem_ld32(tS + 32, a[1]);
       tmem_wait_ld();
-      VSB_TRACE(1 + x, t, 1);
+      VSB_TRACE_W(t, 1);
       float mx;
       if (valid >= 64) {
         float m0 = fmax3(__uint_as_float(a[0][0]), __uint_as_float(a[0][1]), __uint_as_float(a[0][2]));
@@ -266,8 +270,9 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             const float e = fmaf(__uint_as_float(a[c][i]), sl2, -mb);
-            // kPoly: every fourth exponential runs as a polynomial on the FMA pipe (relieves the MUFU pipe by 25 %)
-            a[c][i] = __float_as_uint((kPoly && (i & 3) == 3) ? exp2_poly(e) : fast_exp2(e));
+            // kPoly: 2 / 3 / 4 of every 8 exponentials run as a polynomial on the FMA pipe (relieves the MUFU pipe)
+            constexpr uint32_t kMask = kPoly == 1 ? 0x88u : kPoly == 2 ? 0xA8u : kPoly == 3 ? 0xAAu : 0u;
+            a[c][i] = __float_as_uint(((kMask >> (i & 7)) & 1u) ? exp2_poly(e) : fast_exp2(e));
           }
         }
         if (c > 0) {
@@ -288,12 +293,12 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
       }
       l_run = l_run * alpha + ((s0 + s1) + (s2 + s3));
-      VSB_TRACE(1 + x, t, 2);
+      VSB_TRACE_W(t, 2);
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[x * 2 + buf]);
-      VSB_TRACE(1 + x, t, 3);
+      VSB_TRACE_W(t, 3);
     }
     // ---- epilogue: O / l -> bf16 -> global ----
     mbar_wait(&o_full[x], 0);
@@ -319,10 +324,10 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
-template <int D, bool kPoly>
+template <int D, int kPoly>
 static int launch_kt64(const CUtensorMap* tm, const AttnParams& prm, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
@@ -337,8 +342,15 @@ static int launch_kt64(const CUtensorMap* tm, const AttnParams& prm, cudaStream_
 }
 
 int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st) {
-  if (D == 72) return poly ? launch_kt64<72, true>(tm, prm, st) : launch_kt64<72, false>(tm, prm, st);
-  return poly ? launch_kt64<64, true>(tm, prm, st) : launch_kt64<64, false>(tm, prm, st);
+  if (D == 72) {
+    switch (poly) {
+      case 1: return launch_kt64<72, 1>(tm, prm, st);
+      case 2: return launch_kt64<72, 2>(tm, prm, st);
+      case 3: return launch_kt64<72, 3>(tm, prm, st);
+      default: return launch_kt64<72, 0>(tm, prm, st);
+    }
+  }
+  return poly ? launch_kt64<64, 1>(tm, prm, st) : launch_kt64<64, 0>(tm, prm, st);
 }
 
 }  // namespace vsb
