@@ -342,7 +342,8 @@ def test_attn_flash_cross(nb, nq, nk, H, D, lens):
     _flash_check(f"cross{nq}x{nk}", nb, nq, nk, H, D, lens=lens, packed_qkv=False)
 
 
-@pytest.mark.parametrize("opts", [dict(attn_variant=0), dict(attn_variant=0, attn_pingpong=0), dict(attn_variant=2, attn_poly_exp=1)])
+@pytest.mark.parametrize("opts", [dict(attn_variant=0), dict(attn_variant=0, attn_pingpong=0), dict(attn_variant=2, attn_poly_exp=1),
+                                  dict(attn_variant=2, attn_poly_exp=3), dict(attn_variant=3), dict(attn_variant=3, attn_poly_exp=2)])
 def test_attn_flash_schedule_options(opts):
     """Every schedule of vsb_attn_flash (vsb_set_option knobs) gives the same attention within tolerance."""
     from videosys_b200 import kernels as K
@@ -389,3 +390,25 @@ def test_attn_flash_large_max_growth():
     err = (got.double() - exact).abs()
     print(f"[parity] attn_flash max-growth: max|err| {err.max().item():.3e} mean {err.mean().item():.3e}")
     assert (err <= 2.0**-7 * exact.abs().clamp_min(0.02) + 4e-3).all()
+
+
+@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("case", ["self_ragged", "cross_lens", "tails"])
+def test_attn_flash_many_items(variant, case):
+    """More (batch, head, query-pair) items than SMs, so a persistent CTA (variant 3) walks several items: pairs whose
+    second query tile is empty, per-batch key lengths (different tile counts inside one CTA's range), lone key tiles."""
+    from videosys_b200 import kernels as K
+
+    _dev()
+    try:
+        K.set_option("attn_variant", variant)
+        if case == "self_ragged":
+            _flash_check(f"many{variant}", 4, 600, 600, 16, 72)  # 192 items, every third pair has one live query tile
+        elif case == "cross_lens":
+            _flash_check(f"manyx{variant}", 2, 2500, 300, 16, 72, lens=[300, 120], packed_qkv=False)  # 320 items
+        else:
+            for n in (16, 65, 129, 272):
+                _flash_check(f"tailv{variant}_{n}", 1, n, n, 2, 72)
+            _flash_check(f"tailx{variant}", 2, 100, 40, 24, 72, lens=[40, 1], packed_qkv=False)  # one key, 1 tile
+    finally:
+        K.set_option("attn_variant", 2)

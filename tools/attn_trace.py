@@ -15,7 +15,7 @@ nb, n = 40, 3600
 qkv = torch.randn(nb, n, 3, H, D, device=dev, dtype=bf)
 lib = _lib.load()
 trace = torch.zeros(9 * 16 * 4, dtype=torch.int64, device=dev)
-for variant, pp, poly in ((2, 1, 0), (2, 1, 1)):
+for variant, pp, poly in ((2, 1, 0), (3, 1, 0)):
     K.set_option("attn_variant", variant)
     K.set_option("attn_pingpong", pp)
     K.set_option("attn_poly_exp", poly)

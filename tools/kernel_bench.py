@@ -52,7 +52,7 @@ C, H, D = 1152, 16, 72
 qkv = torch.randn(40, 3600, 3, H, D, device=dev, dtype=bf)
 fl = 4.0 * 40 * H * 3600 * 3600 * D
 r = {}
-for nm, (var, poly) in (("ours_kt128_pingpong", (0, 0)), ("ours_kt64", (2, 0)), ("ours_kt64_poly25", (2, 1)), ("ours_kt64_poly37", (2, 2)), ("ours_kt64_poly50", (2, 3))):
+for nm, (var, poly) in (("ours_kt128_pingpong", (0, 0)), ("ours_kt64", (2, 0)), ("ours_kt64_poly25", (2, 1)), ("ours_kt64_poly37", (2, 2)), ("ours_kt64p", (3, 0)), ("ours_kt64p_poly37", (3, 2))):
     K.set_option("attn_variant", var)
     K.set_option("attn_poly_exp", poly)
     t = timeit(lambda: K.attn_flash(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 40, 3600, 3600, H, D, 3 * C, 3600 * 3 * C, 3 * C, 3600 * 3 * C, D**-0.5), iters=5)
@@ -63,7 +63,7 @@ K.set_option("attn_poly_exp", 0)
 qx = torch.randn(2, 72000, H, D, device=dev, dtype=bf)
 kvx = torch.randn(2, 300, 2, H, D, device=dev, dtype=bf)
 flx = 4.0 * 2 * H * 72000 * 300 * D
-for nm, var in (("cross_kt128", 0), ("cross_kt64", 2)):
+for nm, var in (("cross_kt128", 0), ("cross_kt64", 2), ("cross_kt64p", 3)):
     K.set_option("attn_variant", var)
     t = timeit(lambda: K.attn_flash(qx, kvx[:, :, 0], kvx[:, :, 1], 2, 72000, 300, H, D, C, 72000 * C, 2 * C, 300 * 2 * C, D**-0.5), iters=5)
     r[nm] = round(flx / t / 1e12, 1)

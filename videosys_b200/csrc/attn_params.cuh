@@ -36,5 +36,7 @@ struct AttnParams {
 
 // attn_tcgen05_kt64.cu.  tm = {q64, q16, k64, k16, v64, v16} with 64-row key boxes.
 int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st);
+// attn_tcgen05_kt64p.cu: the same tiles under persistent CTAs.
+int attn_flash_kt64p_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st);
 
 }  // namespace vsb

@@ -360,7 +360,7 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
     unsigned long long dims[4] = {(unsigned long long)D, (unsigned long long)H, (unsigned long long)(i == 0 ? nq : nk),
                                   (unsigned long long)nb};
     unsigned long long str[3] = {(unsigned long long)D * 2, (unsigned long long)rs * 2, (unsigned long long)bs * 2};
-    const unsigned rows = (i > 0 && g_opt_attn_variant == 2) ? 64u : 128u;  // key tile of the selected schedule
+    const unsigned rows = (i > 0 && g_opt_attn_variant >= 2) ? 64u : 128u;  // key tile of the selected schedule
     unsigned boxA[4] = {64, 1, rows, 1}, boxB[4] = {16, 1, rows, 1};
     int rc = make_tmap_bf16(&tm[2 * i], base[i], 4, dims, str, boxA, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -372,6 +372,7 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_opt_attn_variant == 3) return attn_flash_kt64p_launch(tm, prm, D, g_opt_attn_poly, st);
   if (g_opt_attn_variant == 2) return attn_flash_kt64_launch(tm, prm, D, g_opt_attn_poly, st);
   dim3 grid((nq + 255) / 256, H, nb);
   static bool attr = false;
