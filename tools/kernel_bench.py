@@ -29,7 +29,9 @@ def timeit(fn, iters=20, warm=3):
 
 out = {}
 M = 144000
-for name, (N, Kd, act) in {"qkv": (3456, 1152, 0), "proj": (1152, 1152, 0), "fc1": (4608, 1152, 1), "fc2": (1152, 4608, 0)}.items():
+ONLY = os.environ.get("KB_ONLY", "")  # "attn": skip the GEMM and elementwise sections
+SHAPES = {} if ONLY == "attn" else {"qkv": (3456, 1152, 0), "proj": (1152, 1152, 0), "fc1": (4608, 1152, 1), "fc2": (1152, 4608, 0)}
+for name, (N, Kd, act) in SHAPES.items():
     a = torch.randn(M, Kd, device=dev, dtype=bf)
     w = torch.randn(N, Kd, device=dev, dtype=bf) * 0.02
     b = torch.randn(N, device=dev, dtype=bf)
@@ -71,7 +73,7 @@ for nm, var in (("cross_kt128", 0), ("cross_kt64", 2), ("cross_kt64p", 3)):
 K.set_option("attn_variant", 2)
 del qx, kvx
 q, k, v = qkv.permute(2, 0, 3, 1, 4).unbind(0)
-for nm, be in (("sdpa_flash", "FLASH_ATTENTION"), ("sdpa_cudnn", "CUDNN_ATTENTION"), ("sdpa_efficient", "EFFICIENT_ATTENTION")):
+for nm, be in (() if ONLY == "attn" else (("sdpa_flash", "FLASH_ATTENTION"), ("sdpa_cudnn", "CUDNN_ATTENTION"), ("sdpa_efficient", "EFFICIENT_ATTENTION"))):
     try:
         from torch.nn.attention import SDPBackend, sdpa_kernel
 
@@ -84,6 +86,9 @@ out["attn_spatial_720p"] = r
 print("attn spatial", r, flush=True)
 del qkv
 
+if ONLY == "attn":
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "kernel_bench_attn.json"), "w"), indent=1)
+    sys.exit(0)
 x = torch.randn(2, 72000, C, device=dev, dtype=bf)
 y = torch.randn(2, 72000, C, device=dev, dtype=bf)
 mod = torch.randn(2, 2, 6, C, device=dev, dtype=bf)

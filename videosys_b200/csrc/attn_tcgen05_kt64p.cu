@@ -63,14 +63,15 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   unsigned char* sKV = smem + 4 * kQT;    // [stages][K_A | K_B | V_A | V_B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + ST * kStage);
   uint64_t* q_full = bars;              // [2]
-  uint64_t* q_empty = bars + 2;         // [2]  4 commits: every S MMA that reads the buffer has retired
+  uint64_t* q_empty = bars + 2;         // [2]  8 arrivals (softmax warps, after the item's last MMA has retired)
   uint64_t* k_full = bars + 4;          // [ST]
   uint64_t* v_full = k_full + ST;       // [ST]
   uint64_t* kv_empty = v_full + ST;     // [ST] 2 commits: P V of both query tiles (one issuer commits twice if nx = 1)
   uint64_t* s_full = kv_empty + ST;     // [x][buf]
   uint64_t* p_full = s_full + 4;        // [x][buf]
-  uint64_t* o_full = p_full + 4;        // [x][issuer parity]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_full + 4);
+  uint64_t* o_full = p_full + 4;        // [x][issuer parity]: that issuer's last P V of the item has retired
+  uint64_t* pv_done = o_full + 4;       // [x][issuer parity]: its latest P V has retired (rare O-rescale path)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_pairs = (p.nq + 255) / 256;
@@ -91,7 +92,7 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < 2; ++i) {
       mbar_init(&q_full[i], 1);
-      mbar_init(&q_empty[i], 4);
+      mbar_init(&q_empty[i], 8);
     }
     for (int i = 0; i < ST; ++i) {
       mbar_init(&k_full[i], 1);
@@ -102,6 +103,7 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 4);  // one arrival per softmax warp
       mbar_init(&o_full[i], 1);
+      mbar_init(&pv_done[i], 1);
     }
     fence_barrier_init();
   }
@@ -187,30 +189,12 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     auto seek = [&](Cur& c) {  // ... that is mine: my parity, and my query tile is live in its item
       while (c.item < i1 && !(((c.g & 1) == par) && c.it.nx > x)) step(c);
     };
-    auto commit_item_done = [&](int item, int nx_item) {  // my share of "item finished": O partial sums, Q buffer
-      const int qb = (item - i0) & 1;
-      umma_commit_w(elected, &o_full[x * 2 + par]);
-      umma_commit_w(elected, &q_empty[qb]);
-      if (nx_item == 1) umma_commit_w(elected, &q_empty[qb]);  // standing in for the idle issuers of query tile 1
-    };
-    int book = i0;  // items before `book` have had their commit_item_done from me
-    auto settle = [&](int upto) {  // live items in [book, upto) hold no key tile of mine: nothing to wait for but Q
-      for (; book < upto; ++book) {
-        const Item it = item_of(p, book, n_pairs);
-        if (it.nx > x) {
-          const int li = book - i0;
-          mbar_wait(&q_full[li & 1], (li >> 1) & 1);  // keeps my q_empty arrivals in item order
-          commit_item_done(book, it.nx);
-        }
-      }
-    };
     Cur cur;
     cur.item = i0;
     cur.t = 0;
     cur.g = 0;
     if (i0 < i1) cur.it = item_of(p, i0, n_pairs);
     seek(cur);
-    settle(cur.item < i1 ? cur.item : i1);
     uint32_t cnt = 0;  // P tiles consumed from my buffer
     if (cur.item < i1) {  // prologue: S for my first tile
       const int li = cur.item - i0;
@@ -226,15 +210,18 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       seek(nxt);
       const bool has_next = nxt.item < i1;
       const bool last_in_item = nxt.item != cur.item;
+      // The operands of my next tile can be awaited BEFORE P(cur) only if they cannot depend on work I still owe:
+      // the next item's Q sits in the other Q buffer and a K tile at most two ahead has had its ring slot free for
+      // a while.  Anything further (I skip an item whose query tile 1 is empty) needs this item's Q buffer or ring
+      // slots released -- by retiring, among others, the very P V below.
+      const bool near = has_next && nxt.item <= cur.item + 1 && nxt.g <= cur.g + 2;
       const int s = cur.g % ST;
-      // operands first (they land long before P is ready: these waits are off the critical path) ...
       mbar_wait(&v_full[s], (cur.g / ST) & 1);
-      if (has_next) {
+      if (near) {
         const int li = nxt.item - i0;
         mbar_wait(&q_full[li & 1], (li >> 1) & 1);
         mbar_wait(&k_full[nxt.g % ST], (nxt.g / ST) & 1);
       }
-      // ... then the softmax warps' P
       mbar_wait(&p_full[x * 2 + par], cnt & 1);
       ++cnt;
       tc_fence_after();
@@ -242,15 +229,19 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       issue_PV(x, par, s);
       umma_commit_w(elected, &kv_empty[s]);
       if (cur.it.nx == 1) umma_commit_w(elected, &kv_empty[s]);  // no second query tile to wait for
-      if (last_in_item) {
-        commit_item_done(cur.item, cur.it.nx);
-        book = cur.item + 1;
+      umma_commit_w(elected, &pv_done[x * 2 + par]);
+      if (last_in_item) umma_commit_w(elected, &o_full[x * 2 + par]);
+      if (has_next) {
+        if (!near) {
+          const int li = nxt.item - i0;
+          mbar_wait(&q_full[li & 1], (li >> 1) & 1);
+          mbar_wait(&k_full[nxt.g % ST], (nxt.g / ST) & 1);
+          tc_fence_after();
+        }
+        issue_S(x, par, nxt.g % ST, (nxt.item - i0) & 1);
+        umma_commit_w(elected, &s_full[x * 2 + par]);
       }
-      if (has_next) issue_S(x, par, nxt.g % ST, (nxt.item - i0) & 1);
-      // also posted without a new S: the softmax warps use it as "my P V has completed" on their rare rescale path
-      umma_commit_w(elected, &s_full[x * 2 + par]);
       VSB_TRACE_W(cur.g, x * 2 + 1);
-      if (last_in_item) settle(has_next ? nxt.item : i1);
       cur = nxt;
     }
   } else if (warp >= 4 && warp < 12) {
@@ -261,8 +252,8 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const uint32_t lane_off = uint32_t(ew * 32) << 16;
     const uint32_t tO = tmem_base + lane_off + c_o(x);
     const float sl2 = p.scale_log2;
-    uint32_t cnt[2] = {0u, 0u};  // S tiles consumed per buffer
-    uint32_t items_done = 0;
+    uint32_t cnt[2] = {0u, 0u};    // S tiles consumed per buffer
+    uint32_t odone[2] = {0u, 0u};  // o_full phases consumed per issuer
     int g = 0;
     for (int item = i0; item < i1; ++item) {
       const Item it = item_of(p, item, n_pairs);
@@ -322,8 +313,8 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const bool grow = (m_new - m_run) * sl2 > 8.f;  // first tile: m_run = -inf -> true
       const float alpha = grow ? fast_exp2((m_run - m_new) * sl2) : 1.f;
       if (t > 0 && __any_sync(0xffffffffu, grow)) {
-        // PV_x(t-1) may still be running: its issuer ends that tile with a post on the other S buffer's barrier
-        mbar_wait(&s_full[x * 2 + (buf ^ 1)], cnt[buf ^ 1] & 1);
+        // PV_x(t-1) may still be running: wait for the other buffer's issuer to report its latest P V retired
+        mbar_wait(&pv_done[x * 2 + (buf ^ 1)], (cnt[buf ^ 1] - 1) & 1);
         tc_fence_after();
 #pragma unroll 1
         for (int c = 0; c < (kHasB ? 5 : 4); ++c) {  // one 16-column chunk at a time (register budget)
@@ -375,10 +366,17 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       if (lane == 0) mbar_arrive(&p_full[x * 2 + buf]);
       VSB_TRACE_W(g, 3);
       }
-      // ---- epilogue: both issuers' P V of this item have retired; O / l -> bf16 -> global ----
-      mbar_wait(&o_full[x * 2], items_done & 1);
-      mbar_wait(&o_full[x * 2 + 1], items_done & 1);
-      ++items_done;
+      // ---- epilogue: the last P V of each issuer that had a tile in this item has retired; O / l -> bf16 -> global ----
+      {
+        const int g0 = g - it.n_tiles;  // global index of the item's first key tile
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+          if (it.n_tiles >= 2 || (g0 & 1) == par) {
+            mbar_wait(&o_full[x * 2 + par], odone[par] & 1);
+            ++odone[par];
+          }
+        }
+      }
       tc_fence_after();
       const int qrow = it.q0 + x * 128 + row;
       const float inv = 1.f / l_run;
@@ -398,6 +396,13 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         }
       }
       tc_fence_before();  // the zeroing of O for the next item is ordered after these reads
+      // every MMA of this item that reads the Q buffer retired before the o_full waits above returned (the S MMAs
+      // precede the P V in the tensor pipe): release it.  Eight arrivals per item; warpgroup A stands in for B when
+      // the pair has one live query tile.
+      if (lane == 0) {
+        mbar_arrive(&q_empty[(item - i0) & 1]);
+        if (it.nx == 1) mbar_arrive(&q_empty[(item - i0) & 1]);
+      }
     }
   }
 

@@ -69,15 +69,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Spin with a watchdog: a protocol bug traps (kernel error) instead of hanging the GPU box.
 #ifndef VSB_WATCHDOG_CYCLES
-#define VSB_WATCHDOG_CYCLES 4000000000ll  // ~2 s at 2 GHz
+#define VSB_WATCHDOG_CYCLES 400000000ll  // ~0.2 s at 2 GHz: far beyond any legitimate wait inside one kernel
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > VSB_WATCHDOG_CYCLES) {
-      printf("vsb200: mbarrier watchdog block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
-             blockIdx.z, threadIdx.x, smem_u32(bar), parity);
+      if ((threadIdx.x & 31) == 0)
+        printf("vsb200: mbarrier watchdog block=(%d,%d,%d) warp=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y,
+               blockIdx.z, threadIdx.x >> 5, smem_u32(bar), parity);
       __trap();
     }
   }
