@@ -39,9 +39,12 @@ unsigned long long vsb_launch_count(void);
  *   "gemm_2sm" (default 1): CTA-pair (tcgen05 cta_group::2, M = 256) GEMM for M >= 1024 when N % 192 == 0 or
  *   N % 256 == 0; 0 forces the single-CTA (M = 128) kernel everywhere. */
 int vsb_set_option(const char* name, int value);
-/*   "attn_variant" (default 2): schedule of vsb_attn_flash: 2 = 64-key tiles with a double-buffered S in TMEM (the
- *   softmax warps never wait for the tensor pipe), 0 = 128-key tiles with the two softmax warpgroups ping-ponging.
- *   "attn_poly_exp" (default 0, variant 2): every fourth exp2 as a polynomial on the FMA pipe.
+/*   "attn_variant" (default -1 = auto): schedule of vsb_attn_flash.  2 = 64-key tiles with a double-buffered S in TMEM
+ *   and four MMA issuer warps, one CTA per pair of query tiles; 3 = the same tiles under persistent CTAs (one per SM,
+ *   running ahead across query pairs; auto picks it for nk <= 1024, where per-CTA fixed costs dominate); 0 = 128-key
+ *   tiles with the two softmax warpgroups ping-ponging (first version, kept for comparison).
+ *   "attn_poly_exp" (default 0; variants 2, 3): 1 / 2 / 3 = 25 / 37.5 / 50 % of the exp2 as a polynomial on the FMA
+ *   pipe (no gain measured at sustained clocks; kept as a knob).
  *   "attn_pingpong" (default 1, variant 0): the warpgroups alternate on the MUFU phase.
  *   Same results up to fp32 rounding.
  * vsb_debug_attn_trace: device buffer of 9*16*4 int64 that CTA (0,0,0) of vsb_attn_flash fills with clock64()

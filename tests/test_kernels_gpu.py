@@ -349,7 +349,7 @@ def test_attn_flash_schedule_options(opts):
     from videosys_b200 import kernels as K
 
     _dev()
-    defaults = dict(attn_variant=2, attn_poly_exp=0, attn_pingpong=1)
+    defaults = dict(attn_variant=-1, attn_poly_exp=0, attn_pingpong=1)
     tag = "".join(f"{k[5]}{v}" for k, v in opts.items())
     try:
         for k, v in opts.items():
@@ -411,4 +411,4 @@ def test_attn_flash_many_items(variant, case):
                 _flash_check(f"tailv{variant}_{n}", 1, n, n, 2, 72)
             _flash_check(f"tailx{variant}", 2, 100, 40, 24, 72, lens=[40, 1], packed_qkv=False)  # one key, 1 tile
     finally:
-        K.set_option("attn_variant", 2)
+        K.set_option("attn_variant", -1)

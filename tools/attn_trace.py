@@ -43,4 +43,4 @@ for variant, pp, poly in ((2, 1, 0), (3, 1, 0)):
     for j in range(1, 10):
         r = t[0, j]
         print(f"  tile {j}: pA@{int(r[0])-base:7d} issueA {int(r[1]-r[0]):4d}  pB@{int(r[2])-base:7d} issueB {int(r[3]-r[2]):4d}")
-K.set_option('attn_variant', 2); K.set_option('attn_poly_exp', 0)
+K.set_option('attn_variant', -1); K.set_option('attn_poly_exp', 0)

@@ -312,7 +312,8 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 long long* g_attn_trace = nullptr;  // vsb_debug_attn_trace(device buffer of 3*16*4 int64)
 int g_opt_attn_poly = 0;            // variant 2 only: every fourth exp2 as a polynomial on the FMA pipe
 int g_opt_attn_pingpong = 1;        // variant 0 only: softmax warpgroups alternate on the MUFU phase
-int g_opt_attn_variant = 2;         // 0 = 128-key tiles, ping-pong; 2 = 64-key tiles, double-buffered S
+int g_opt_attn_variant = -1;        // -1 = auto (3 for short key sequences, else 2); 0 = 128-key tiles, ping-pong;
+                                    // 2 = 64-key tiles, double-buffered S, one CTA per query pair; 3 = 2 + persistent CTAs
 
 }  // namespace vsb
 
@@ -353,6 +354,8 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
     }
   // Two tensor maps per operand: the 64-wide SWIZZLE_128B chunk and (head_dim 72 only) the 16-wide SWIZZLE_32B
   // chunk at d = 64..79.  The inner extent is D, so TMA zero-fills 72..79 and rows past nq / nk.
+  // auto: text cross-attention (a handful of key tiles per query pair) is dominated by per-CTA fixed costs
+  const int variant = g_opt_attn_variant >= 0 ? g_opt_attn_variant : (nk <= 1024 ? 3 : 2);
   CUtensorMap tm[6];
   const vsb_bf16* base[3] = {q, k, v};
   for (int i = 0; i < 3; ++i) {
@@ -360,7 +363,7 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
     unsigned long long dims[4] = {(unsigned long long)D, (unsigned long long)H, (unsigned long long)(i == 0 ? nq : nk),
                                   (unsigned long long)nb};
     unsigned long long str[3] = {(unsigned long long)D * 2, (unsigned long long)rs * 2, (unsigned long long)bs * 2};
-    const unsigned rows = (i > 0 && g_opt_attn_variant >= 2) ? 64u : 128u;  // key tile of the selected schedule
+    const unsigned rows = (i > 0 && variant >= 2) ? 64u : 128u;  // key tile of the selected schedule
     unsigned boxA[4] = {64, 1, rows, 1}, boxB[4] = {16, 1, rows, 1};
     int rc = make_tmap_bf16(&tm[2 * i], base[i], 4, dims, str, boxA, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -372,8 +375,8 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_opt_attn_variant == 3) return attn_flash_kt64p_launch(tm, prm, D, g_opt_attn_poly, st);
-  if (g_opt_attn_variant == 2) return attn_flash_kt64_launch(tm, prm, D, g_opt_attn_poly, st);
+  if (variant == 3) return attn_flash_kt64p_launch(tm, prm, D, g_opt_attn_poly, st);
+  if (variant == 2) return attn_flash_kt64_launch(tm, prm, D, g_opt_attn_poly, st);
   dim3 grid((nq + 255) / 256, H, nb);
   static bool attr = false;
   if (!attr) {
