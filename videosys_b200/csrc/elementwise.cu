@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) v[i].u = nxt[i].u;
     if (row + stride < rows) load_row(row + stride);  // keep the next row's 128-bit loads in flight
-    const long long bt = row / S;
-    const int b = int(bt / T);
+    const unsigned bt = (unsigned)row / (unsigned)S;  // rows < 2^31 (checked by the launcher)
+    const int b = int(bt / (unsigned)T);
     const int sel = (x_mask != nullptr && x_mask[bt] == 0) ? 1 : 0;
     const bf16* shift = mod + ((size_t)(sel * B + b) * 6 + shift_row) * C;
     const bf16* scale = mod + ((size_t)(sel * B + b) * 6 + scale_row) * C;
@@ -147,8 +147,8 @@ __global__ void __launch_bounds__(256) gate_residual_kernel(const bf16* __restri
        i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / nvec;
     const int vi = int(i - row * nvec);
-    const long long bt = row / S;
-    const int b = int(bt / T);
+    const unsigned bt = (unsigned)row / (unsigned)S;  // rows < 2^31 (checked by the launcher)
+    const int b = int(bt / (unsigned)T);
     const int sel = (x_mask != nullptr && x_mask[bt] == 0) ? 1 : 0;
     const bf16* gate = mod + ((size_t)(sel * B + b) * 6 + gate_row) * C;
     Vec8 vx, vy, vg, o, g;
@@ -190,27 +190,30 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv,
   const int lane = threadIdx.x & 31;
   const int g = lane / LPG, l = lane % LPG;
   const int gs = (g < GPW ? g : 0) * LPG;  // first lane of my group (idle tail lanes shadow group 0)
-  const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long nwarps = (long long)gridDim.x * (blockDim.x >> 5);
-  const long long ngroups = rows * 2 * H;  // (row, which in {q,k}, head)
+  // 32-bit index arithmetic (the launcher checks rows * 2 * H < 2^31): the 64-bit divisions of the first version cost
+  // more issue slots than the normalisation itself
+  const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+  const unsigned ngroups = (unsigned)rows * 2u * H;  // (row, which in {q,k}, head)
+  const unsigned H2 = 2u * H;
   Vec8 wv[2];
   wv[0].u = __ldg(reinterpret_cast<const uint4*>(wq + l * 8));
   wv[1].u = __ldg(reinterpret_cast<const uint4*>(wk + l * 8));
-  for (long long base = warp * (GPW * U); base < ngroups; base += nwarps * (GPW * U)) {
+  for (unsigned base = warp * (GPW * U); base < ngroups; base += nwarps * (GPW * U)) {
     Vec8 v[U];
     bf16* p[U];
     int which[U];
     bool active[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const long long gi = base + (long long)u * GPW + g;
+      const unsigned gi = base + u * GPW + g;
       active[u] = (g < GPW) && (gi < ngroups);
       p[u] = nullptr;
       which[u] = 0;
       if (active[u]) {
-        const long long row = gi / (2 * H);
-        const int rem = int(gi - row * 2 * H);
-        which[u] = rem / H;
+        const unsigned row = gi / H2;
+        const int rem = int(gi - row * H2);
+        which[u] = rem >= H ? 1 : 0;
         const int h = rem - which[u] * H;
         p[u] = qkv + ((size_t)row * 3 + which[u]) * H * D + (size_t)h * D + l * 8;
         v[u].u = *reinterpret_cast<const uint4*>(p[u]);
@@ -334,6 +337,7 @@ extern "C" int vsb_ln_modulate_affine(const vsb_bf16* x, vsb_bf16* out, const vs
     return fail(VSB_ERR_UNSUPPORTED, "ln_modulate: need C %% 8 == 0, C <= 2048, 16B-aligned pointers (C=%d)", C);
   if (shift_row < 0 || shift_row > 5 || scale_row < 0 || scale_row > 5) return fail(VSB_ERR_INVALID, "ln_modulate: row");
   long long rows = (long long)B * T * S;
+  if (rows >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "ln_modulate: %lld rows", rows);
   int grid = grid_for(rows, 8);
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 1280)
@@ -367,6 +371,7 @@ extern "C" int vsb_gate_residual(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16*
     return fail(VSB_ERR_INVALID, "gate_residual: bad args");
   if (C % 8 || !aligned16(x) || !aligned16(y) || !aligned16(out) || !aligned16(mod) || (cache_out && !aligned16(cache_out)))
     return fail(VSB_ERR_UNSUPPORTED, "gate_residual: need C %% 8 == 0 and 16B-aligned pointers");
+  if ((long long)B * T * S >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "gate_residual: too many rows");
   long long nvec = (long long)B * T * S * (C / 8);
   gate_residual_kernel<<<grid_for(nvec, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
       (const bf16*)x, (const bf16*)y, (bf16*)out, (bf16*)cache_out, (const bf16*)mod, x_mask, gate_row, B, T, S, C,
@@ -389,6 +394,7 @@ extern "C" int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16*
   if (!qkv || !wq || !wk || rows == 0 || H <= 0) return fail(VSB_ERR_INVALID, "qk_rmsnorm: bad args");
   if (!aligned16(qkv) || !aligned16(wq) || !aligned16(wk)) return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: alignment");
   long long groups = (long long)rows * 2 * H;
+  if (groups >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: %lld head vectors", groups);
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 72)
     qk_rmsnorm_kernel<72><<<grid_for(groups, 8 * 3 * 4), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)wk,
