@@ -43,12 +43,16 @@ for g in "$@"; do
            timeout 900 python bench.py $BENCH_ARGS > gpurun_out/bench.json 2> gpurun_out/bench.err
            echo "exit $? : $(tail -c 600 gpurun_out/bench.json)" | tee -a gpurun_out/summary.txt
            tail -n 5 gpurun_out/bench.err ;;
-    bench240) timeout 600 python bench.py --workload opensora_240p_51f_30step $BENCH_ARGS > gpurun_out/bench240.json 2> gpurun_out/bench240.err
-           echo "exit $? : $(tail -c 400 gpurun_out/bench240.json)" | tee -a gpurun_out/summary.txt ;;
+    bench240) timeout 600 python bench.py --workload opensora_240p_51f_30step --no-cpu-baseline $BENCH_ARGS > gpurun_out/bench240.json 2> gpurun_out/bench240.err
+           echo "bench240 exit $? : $(tail -c 400 gpurun_out/bench240.json)" | tee -a gpurun_out/summary.txt ;;
+    benchpab) timeout 600 python bench.py --pab --no-cpu-baseline $BENCH_ARGS > gpurun_out/benchpab.json 2> gpurun_out/benchpab.err
+           echo "benchpab exit $? : $(tail -c 400 gpurun_out/benchpab.json)" | tee -a gpurun_out/summary.txt ;;
+    benchref) timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/benchref.json 2> gpurun_out/benchref.err
+           echo "benchref exit $? : $(tail -c 400 gpurun_out/benchref.json)" | tee -a gpurun_out/summary.txt ;;
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
               python bench.py --steps 1 --warmup 1 --depth 2 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
            echo "ncu_list exit $?" | tee -a gpurun_out/summary.txt ;;
-    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 14 -c 4 -o gpurun_out/prof_gemm -f \
+    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm2_bf16 -s 14 -c 4 -o gpurun_out/prof_gemm -f \
               python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
            echo "ncu_gemm exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_short) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_short -c 1 -o gpurun_out/prof_short -f \
