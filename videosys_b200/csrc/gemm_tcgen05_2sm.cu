@@ -33,11 +33,17 @@ struct Gemm2Cfg {
 };
 
 __device__ __forceinline__ float gelu_tanh_f2(float x) {
-  const float kBeta = 0.7978845608028654f, kKappa = 0.044715f;
-  const float inner = kBeta * (x + kKappa * x * x * x);
-  const float e = __expf(2.f * inner);
-  const float th = 1.f - __fdividef(2.f, e + 1.f);
-  return 0.5f * x * (1.f + th);
+  // torch GELU(approximate='tanh') = 0.5 x (1 + tanh(u)), u = sqrt(2/pi) (x + 0.044715 x^3), rewritten as
+  //   x * sigmoid(2u) = x / (1 + 2^(-2 u log2 e)):
+  // 5 ALU + 2 MUFU per element instead of ~14 + 2 (the fc1 epilogue, not its mainloop, set the pace of that GEMM:
+  // tensor pipe 66 % active against 82-94 % for the other shapes, profiles/r01_gemm2_ncu_full_final.txt), and no
+  // cancellation in the negative tail.  |difference| to the tanh form <= 5e-7; 99.6 % of all bf16 inputs in [-12, 12]
+  // round to the same bf16 output as torch's fp32 evaluation, the rest differ below 1e-6 absolute (x < -3).
+  const float kC0 = -2.f * 0.7978845608028654f * 1.4426950408889634f, kC1 = kC0 * 0.044715f;
+  const float w = x * fmaf(x * x, kC1, kC0);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fast_exp2(w) + 1.f));
+  return x * r;
 }
 
 // ACT == 2: out = resid + g, g = bf16(gate * y) (gate_row >= 0, per-frame t/t0 select) or g = y (plain residual add),
