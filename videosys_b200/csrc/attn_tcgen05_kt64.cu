@@ -1,7 +1,7 @@
 // vsb200 -- flash attention forward on tcgen05, 64-key tiles with a double-buffered S (attn_variant = 2).
 //
-// Why a second schedule.  At head_dim 72 the kernel is bound by the exp2 (MUFU, 16 lanes/clk/SM) of the softmax, not by
-// the tensor pipe: a pair of 128x128 score tiles costs 2048 MUFU cycles against 1280 tensor cycles.  The 128-key kernel
+// Why a second schedule.  At head_dim 72 the kernel is bound by the exp2 (MUFU, 16 lanes/clk/SM) of the softmax more
+// than by the tensor pipe: a pair of 128x128 score tiles costs >= 2048 MUFU cycles against ~1430 tensor cycles.  The 128-key kernel
 // (attn_tcgen05.cu) keeps P aliased on the only S buffer of a query tile, so S(j+1) cannot start before PV(j) and each
 // softmax warpgroup sits idle for a full PV + S round trip per key tile (measured: 1250 idle cycles of a 3750-cycle
 // period).  Here every query tile owns TWO 64-column S buffers in TMEM:
@@ -10,9 +10,11 @@
 //     MMA warp, iteration t  : wait P_x(t) -> O_x += P_x(t) V(t) -> S_x(t+2) = Q_x K(t+2)^T into buf t&1
 //
 // so while warpgroup x exponentiates tile t+1 (buf (t+1)&1, filled one iteration earlier) the tensor pipe retires
-// PV_x(t) and S_x(t+2): the softmax warps never wait on the tensor core as long as it keeps up (640 tensor cycles per
-// 64-key step of both query tiles against >= 1024 MUFU cycles).  Both warpgroups exponentiate concurrently (two warps
-// per SM sub-partition keep the MUFU pipe busier than one: 9.5 vs 11.7 cycles per warp instruction measured).
+// PV_x(t) and S_x(t+2): the softmax warps do not wait on the tensor core as long as it keeps up.  Measured costs per
+// 64-key step of both query tiles (tools/mma_microbench.cu, per-warp clock64 trace): 868 tensor cycles (the SS MMAs of
+// S are shared-memory-bound at N = 64: 50.7 cycles each, not 32; the TS 64+16 pair of P V 47.5) against ~1150 MUFU
+// cycles (two softmax warps per SM sub-partition: ~9 cycles per MUFU.EX2 warp instruction, F2FP packs included).
+// Both warpgroups exponentiate concurrently.
 //
 //   warps 0..3    MMA issuers, one per SM sub-partition: warp (x, parity) owns S buffer `parity` of query tile x, i.e.
 //                 PV_x(t) and S_x(t+2) for t = parity (mod 2).  Four issuers instead of one because (per-warp clock64
