@@ -43,6 +43,23 @@ def _peaks():
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
+def kernel_fractions(shares, peaks, nvlink_gbs=770.0):
+    """Adds `frac_of_peak` to every per-kernel entry: achieved / the measured peak that bounds it (tensor
+    pipe for GEMM and attention, HBM copy bandwidth for the elementwise passes and the short attention, NVLink peer copy
+    for the DSP reshard -- 770 GB/s is what a bulk peer copy reached on this pool's boxes)."""
+    out = {}
+    for k, v in shares.items():
+        v = dict(v)
+        if v.get("unit") == "TFLOP/s":
+            v["frac_of_peak"], v["peak"] = v["achieved"] / peaks["tflops"], f"{peaks['tflops']:.0f} TFLOP/s sustained bf16 GEMM"
+        elif k == "dsp_switch":
+            v["frac_of_peak"], v["peak"] = v["achieved"] / nvlink_gbs, f"{nvlink_gbs:.0f} GB/s peer copy"
+        else:
+            v["frac_of_peak"], v["peak"] = v["achieved"] / peaks["hbm"], f"{peaks['hbm']:.0f} GB/s HBM copy"
+        out[k] = v
+    return out
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock + throttle reasons through NVML while the timed region runs."""
 
@@ -295,6 +312,7 @@ def run_ours(args):
     shares = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
                   "achieved": (v[1] / (v[0] * 1e-3) / 1e12) if k in ("gemm", "attn_flash") else (v[1] / (v[0] * 1e-3) / 1e9),
                   "unit": "TFLOP/s" if k in ("gemm", "attn_flash") else "GB/s"} for k, v in by_kind.items()}
+    shares = kernel_fractions(shares, peaks)
 
     # ---- e2e arm: host (pinned) latents in, host velocity/latents out, every step ----
     out_host = torch.empty(1, 4, T, Hl, Wl, dtype=torch.float32).pin_memory()

@@ -210,3 +210,18 @@ def test_latent_and_image_size_tables():
     assert get_num_frames("2s") == 51 and get_num_frames(68) == 68
     with pytest.raises(ValueError):
         get_image_size("720p", "3:8")
+
+
+def test_bench_kernel_fractions():
+    """bench.py's per-kernel roofline fractions: pure arithmetic on the measured peaks."""
+    import bench
+
+    peaks = dict(tflops=1386.7, tflops_burst=1674.1, hbm=6572.9, src="t")
+    shares = {"gemm": {"ms_per_step": 206.4, "launches_per_step": 392.0, "achieved": 1453.0, "unit": "TFLOP/s"},
+              "gate_residual": {"ms_per_step": 17.8, "launches_per_step": 112.0, "achieved": 6246.0, "unit": "GB/s"},
+              "dsp_switch": {"ms_per_step": 5.5, "launches_per_step": 56.0, "achieved": 367.0, "unit": "GB/s"}}
+    out = bench.kernel_fractions(shares, peaks)
+    assert abs(out["gemm"]["frac_of_peak"] - 1453.0 / 1386.7) < 1e-9
+    assert abs(out["gate_residual"]["frac_of_peak"] - 6246.0 / 6572.9) < 1e-9
+    assert abs(out["dsp_switch"]["frac_of_peak"] - 367.0 / 770.0) < 1e-9
+    assert shares["gemm"].get("frac_of_peak") is None  # input left untouched
