@@ -23,8 +23,8 @@ namespace vsb {
   } while (0)
 
 struct AttnParams {
-  int poly_exp;  // 1: every other exp2 runs as a polynomial on the FMA pipe (halves the MUFU load)
-  int pingpong;  // 1: the two softmax warpgroups take turns on the exp2 (MUFU) phase through named barriers
+  int poly_exp;  // host-side selector of the kt64 kernels' kPoly template (0 / 1 / 2 / 3 = 0 / 25 / 37.5 / 50 % of exp2 on the FMA pipe)
+  int pingpong;  // 128-key kernel only: 1 = the two softmax warpgroups take turns on the exp2 (MUFU) phase through named barriers
   long long* trace;
   bf16* out;
   int nb, nq, nk, H;
