@@ -43,6 +43,30 @@ def _peaks():
     return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
 
 
+def step_flops(W, depth=28, C=1152, B=2):
+    """Algorithmic FLOPs of one denoising step: returns (attention QK^T + PV only, everything dense)."""
+    T, Hl, Wl = W["lat"]
+    S = ((Hl + 1) // 2) * ((Wl + 1) // 2)  # 2x2 spatial patches, odd sizes padded
+    N, L = B * T * S, W["L"]
+    spatial = depth * 4.0 * (B * T) * S * S * C
+    temporal = depth * 4.0 * (B * S) * T * T * C
+    cross = 2 * depth * 4.0 * N * L * C
+    linear = 2 * depth * (2.0 * N * C * 3 * C + 2.0 * N * C * C + 2.0 * N * C * C + 2.0 * (B * L) * C * 2 * C + 2.0 * N * C * C
+                          + 16.0 * N * C * C)
+    attn = spatial + temporal + cross
+    return attn, attn + linear
+
+
+def attention_roofline(W, sec_per_step, peaks, depth=28):
+    """north_star: frames/s 'as achieved fraction of the attention-FLOP roofline' = the time the attention FLOPs alone
+    need at the measured tensor peak, over the measured step time (and the same for all dense FLOPs of the step)."""
+    attn, total = step_flops(W, depth)
+    return {"attention_flops_per_step": attn, "dense_flops_per_step": total, "peak_tflops": peaks["tflops"],
+            "frac_attention_only": attn / (peaks["tflops"] * 1e12) / sec_per_step,
+            "frac_all_dense_flops": total / (peaks["tflops"] * 1e12) / sec_per_step,
+            "note": "fraction of the step time that the listed FLOPs would take at the measured sustained bf16 peak"}
+
+
 def kernel_fractions(shares, peaks, nvlink_gbs=770.0):
     """Adds `frac_of_peak` to every per-kernel entry: achieved / the measured peak that bounds it (tensor
     pipe for GEMM and attention, HBM copy bandwidth for the elementwise passes and the short attention, NVLink peer copy
@@ -344,7 +368,9 @@ def run_ours(args):
             "config": _config(args, W),
             "e2e": {"value": val_e2e, "unit": "frames/s", "h2d_bytes_per_step": z_host.numel() * 4,
                     "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": sec_e2e / args.steps * 1e3},
-            "gpu_launches": int(launches), "roofline": roofline, "kernels": shares,
+            "gpu_launches": int(launches), "roofline": roofline,
+            "attention_flop_roofline": attention_roofline(W, sec / args.steps * world, peaks, cfg["depth"]),
+            "kernels": shares,
             "kernels_note": "gemm: events inside the timed region; the other kinds: a second pass of the same steps with "
                             f"events around every launch ({sec_profiled / args.steps * 1e3:.1f} ms/step with that overhead)",
             "cpu_baseline": cpu_base,

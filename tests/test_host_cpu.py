@@ -225,3 +225,15 @@ def test_bench_kernel_fractions():
     assert abs(out["gate_residual"]["frac_of_peak"] - 6246.0 / 6572.9) < 1e-9
     assert abs(out["dsp_switch"]["frac_of_peak"] - 367.0 / 770.0) < 1e-9
     assert shares["gemm"].get("frac_of_peak") is None  # input left untouched
+
+
+def test_bench_step_flops_match_survey():
+    """720p/68f step = 3.782e14 dense FLOPs, 7.841e13 of them attention; 240p/51f = 2.706e13 / 1.60e12."""
+    import bench
+
+    attn, total = bench.step_flops(bench.WORKLOADS["opensora_720p_68f_50step"])
+    assert abs(attn / 7.841e13 - 1) < 2e-3 and abs(total / 3.782e14 - 1) < 2e-3
+    attn, total = bench.step_flops(bench.WORKLOADS["opensora_240p_51f_30step"])
+    assert abs(attn / 1.60e12 - 1) < 1e-2 and abs(total / 2.706e13 - 1) < 1e-2
+    r = bench.attention_roofline(bench.WORKLOADS["opensora_720p_68f_50step"], 0.437, dict(tflops=1386.7))
+    assert 0.12 < r["frac_attention_only"] < 0.14 and 0.60 < r["frac_all_dense_flops"] < 0.65
