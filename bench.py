@@ -207,6 +207,35 @@ def _config(args, W):
             "l2": "per-step working set (activations 332 MB/tensor at 720p) exceeds the 126 MB L2; no flush needed"}
 
 
+def make_line(args, W, world, sec, sec_e2e, sec_profiled, launches, roofline, shares, cpu_base, clocks, peaks, depth,
+              h2d_bytes, d2h_bytes):
+    """The one JSON line of the ours arm (pure: unit-tested on CPU).  sec / sec_e2e / sec_profiled: seconds for
+    args.steps steps of the resident arm, the host-buffer arm and the all-kernels-profiled pass."""
+    frames, nsteps = W["frames"], W["steps"]
+    per = sec / args.steps
+    line = {
+        "metric": "frames/sec", "value": frames / (nsteps * per), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": _config(args, W),
+        "e2e": {"value": frames / (nsteps * sec_e2e / args.steps), "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": sec_e2e / args.steps * 1e3},
+        "gpu_launches": launches, "roofline": roofline,
+        "attention_flop_roofline": attention_roofline(W, per * world, peaks, depth),
+        "kernels": shares,
+        "kernels_note": "gemm: events inside the timed region; the other kinds: a second pass of the same steps with "
+                        f"events around every launch ({sec_profiled / args.steps * 1e3:.1f} ms/step with that overhead)",
+        "cpu_baseline": cpu_base,
+        "clocks": clocks,
+    }
+    if args.opt:
+        line["config"]["options"] = args.opt
+    if args.depth:
+        line["config"]["depth_override"] = args.depth
+        line["invalid"] = "reduced depth (debug run): not a bench value"
+    return line
+
+
 # ------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch.distributed as dist
@@ -352,8 +381,6 @@ def run_ours(args):
     step_e2e(0)
     sec_e2e = timed(step_e2e, args.steps)
     frames, nsteps = W["frames"], W["steps"]
-    val = frames / (nsteps * sec / args.steps)
-    val_e2e = frames / (nsteps * sec_e2e / args.steps)
 
     if rank == 0:
         cpu_base = None
@@ -361,26 +388,8 @@ def run_ours(args):
             ts, desc, cores, _ = cpu_reference(args.workload, budget_s=10.0)
             v = frames / (nsteps * statistics.mean(ts))
             cpu_base = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
-        line = {
-            "metric": "frames/sec", "value": val, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": _config(args, W),
-            "e2e": {"value": val_e2e, "unit": "frames/s", "h2d_bytes_per_step": z_host.numel() * 4,
-                    "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": sec_e2e / args.steps * 1e3},
-            "gpu_launches": int(launches), "roofline": roofline,
-            "attention_flop_roofline": attention_roofline(W, sec / args.steps * world, peaks, cfg["depth"]),
-            "kernels": shares,
-            "kernels_note": "gemm: events inside the timed region; the other kinds: a second pass of the same steps with "
-                            f"events around every launch ({sec_profiled / args.steps * 1e3:.1f} ms/step with that overhead)",
-            "cpu_baseline": cpu_base,
-            "clocks": clocks,
-        }
-        if args.opt:
-            line["config"]["options"] = args.opt
-        if args.depth:
-            line["config"]["depth_override"] = args.depth
-            line["invalid"] = "reduced depth (debug run): not a bench value"
+        line = make_line(args, W, world, sec, sec_e2e, sec_profiled, int(launches), roofline, shares, cpu_base, clocks,
+                         peaks, cfg["depth"], z_host.numel() * 4, out_host.numel() * 4)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

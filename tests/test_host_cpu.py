@@ -237,3 +237,26 @@ def test_bench_step_flops_match_survey():
     assert abs(attn / 1.60e12 - 1) < 1e-2 and abs(total / 2.706e13 - 1) < 1e-2
     r = bench.attention_roofline(bench.WORKLOADS["opensora_720p_68f_50step"], 0.437, dict(tflops=1386.7))
     assert 0.12 < r["frac_attention_only"] < 0.14 and 0.60 < r["frac_all_dense_flops"] < 0.65
+
+
+def test_bench_line_contract():
+    """The ours-arm JSON line carries every key the bench contract names (built from fake timings, no GPU)."""
+    import argparse
+    import json
+
+    import bench
+
+    args = argparse.Namespace(steps=4, warmup=3, workload="opensora_720p_68f_50step", pab=False, gpus=1, opt=[], depth=0)
+    W = bench.WORKLOADS[args.workload]
+    peaks = dict(tflops=1386.7, tflops_burst=1674.1, hbm=6572.9, src="t")
+    shares = bench.kernel_fractions({"gemm": {"ms_per_step": 206.4, "launches_per_step": 392.0, "achieved": 1453.0, "unit": "TFLOP/s"}}, peaks)
+    roofline = {"bound": "tensor", "achieved": 1453.0, "peak": 1386.7, "unit": "TFLOP/s", "frac": 1453.0 / 1386.7, "traffic": None}
+    clocks = {"sm_mhz": 1700, "sm_max_mhz": 1965, "reasons": ["sw_power_cap"]}
+    line = bench.make_line(args, W, 1, 4 * 0.437, 4 * 0.435, 4 * 0.44, 3472, roofline, shares, None, clocks, peaks, 28, 4608000, 4608000)
+    json.dumps(line)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in line, key
+    assert abs(line["value"] - 68 / (50 * 0.437)) < 1e-9 and abs(line["ms_per_step"] - 437.0) < 1e-6
+    assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
+    assert line["config"]["workload"] == args.workload and "model" not in line["config"]
