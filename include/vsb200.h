@@ -35,6 +35,9 @@ const char* vsb_last_error(void);
 int vsb_init(int device);
 /* Number of kernels this library has launched since load (all entries); bench.py reports the delta. */
 unsigned long long vsb_launch_count(void);
+/* Encoded TMA tensor maps are cached by (base, shape, strides, box, swizzle): which = 0 -> hits, 1 -> misses (host
+ * cuTensorMapEncodeTiled calls actually made).  Option "tmap_cache" (default 1) turns the cache off. */
+unsigned long long vsb_tmap_cache_stats(int which);
 /* Run-time kernel selection knobs (not a backend switch: every choice is an sm_100a kernel of this library).
  *   "gemm_2sm" (default 1): CTA-pair (tcgen05 cta_group::2, M = 256) GEMM for M >= 1024 when N % 192 == 0 or
  *   N % 256 == 0; 0 forces the single-CTA (M = 128) kernel everywhere. */
@@ -50,6 +53,9 @@ int vsb_set_option(const char* name, int value);
  * vsb_debug_attn_trace: device buffer of 9*16*4 int64 that CTA (0,0,0) of vsb_attn_flash fills with clock64()
  * timestamps (profiling aid, NULL disables). */
 int vsb_debug_attn_trace(void* device_buffer);
+/*   "attn_variant" 4 = variant 2 with the query rows resident in TMEM (S = Q K^T issued as TS MMAs: the A operand no
+ *   longer re-read from shared memory on every K step) and 8 instead of 6 K/V stages.
+ *   "dsp_rowwise" (default 1): vsb_dsp_scatter decodes indices once per token row; 0 = the first version (per vector). */
 
 /* ---- AdaLN: LayerNorm(eps, no affine) -> x*(1+scale)+shift with per-frame t / t0 select --------------------
  * replaces norm1/norm2 + t2i_modulate + t_mask_select: models/transformers/open_sora_transformer_3d.py:47-48,
@@ -89,6 +95,13 @@ int vsb_residual_add(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* out, size_t
  *   qkv [rows, 3, H, D] bf16, normalised in place for the q and k thirds; wq, wk [D] bf16. */
 int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D, float eps,
                    void* stream);
+/* Same, followed by RoPE on q and k (attentions.py:76-78 -> rotary_embedding_torch rotate_queries_or_keys: interleaved
+ * pairs, fp32 math, cast back): the pre-pass of TEMPORAL attention over >= 30 frames, where the reference leaves
+ * native_attention for F.scaled_dot_product_attention (attentions.py:95-100) and vsb_attn_short's 32-token limit is
+ * exceeded.  rope_cos / rope_sin [pos_mod, D] fp32; token row r sits at position (r / pos_div) % pos_mod
+ * (token-major [B, T, S] activation: pos_div = S, pos_mod = T). */
+int vsb_qk_rmsnorm_rope(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D, float eps,
+                        const float* rope_cos, const float* rope_sin, int pos_div, int pos_mod, void* stream);
 
 /* Per-head LayerNorm(D, eps, affine) of q and k in place (CogVideoX: diffusers Attention(qk_norm="layer_norm"),
  * models/transformers/cogvideox_transformer_3d.py:241-242 -> processor :130-133).  wq,bq,wk,bk [D] bf16. */
@@ -129,10 +142,17 @@ int vsb_gemm_bias_residual(const vsb_bf16* A, const vsb_bf16* W, const vsb_bf16*
  * replaces F.scaled_dot_product_attention at attentions.py:100 and :268 (bool key mask = per-batch key count).
  * q/k/v are strided views: element (b, n, h, d) at base + b*batch_stride + n*row_stride + h*D + d (strides in
  * elements, multiples of 8).  out [nb, nq, H*D] contiguous.  kv_lens (host int array, nullable) = valid keys per
- * batch (<= nk).  D must be 72 or 64. */
+ * batch (<= nk, nb <= 64 when given).  D must be 72 or 64. */
 int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb, int nq, int nk,
                    int H, int D, long long q_row_stride, long long q_batch_stride, long long kv_row_stride,
                    long long kv_batch_stride, const int* host_kv_lens, float scale, void* stream);
+/* Same with a strided OUTPUT view: element (b, n, h, d) at out + b*out_batch_stride + n*out_row_stride + h*D + d.
+ * Temporal attention over >= 30 frames runs on the token-major activation with batch = patch s, row = frame t:
+ * q/k/v row stride S*3C, batch stride 3C; out row stride S*C, batch stride C (one call per CFG sample). */
+int vsb_attn_flash_strided(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb, int nq, int nk,
+                           int H, int D, long long q_row_stride, long long q_batch_stride, long long kv_row_stride,
+                           long long kv_batch_stride, long long out_row_stride, long long out_batch_stride,
+                           const int* host_kv_lens, float scale, void* stream);
 
 /* ---- Pyramid Attention Broadcast gate (host integer logic, bit-exact) -------------------------------------------
  * replaces PABManager.if_broadcast_{spatial,temporal,cross}: core/pab/pab_mgr.py:54-91.
@@ -152,7 +172,29 @@ int vsb_pab_gate(int broadcast_on, int has_timestep, int timestep, int* count, i
  * vsb_dsp_wait blocks the stream until all `world` peers have delivered epoch `epoch`. */
 int vsb_dsp_scatter(const vsb_bf16* local, void* const* host_peer_recv, void* const* host_peer_flags, int rank,
                     int world, int to_spatial_shard, int B, int T, int S, int C, unsigned epoch, void* stream);
-int vsb_dsp_wait(const void* my_flags, int world, unsigned epoch, void* stream);
+int vsb_dsp_wait(void* my_flags, int world, unsigned epoch, void* stream);
+/* epoch == 0 (both calls above and below): take the next value of a DEVICE-side counter kept in the flag array
+ * (slots 32 = sent, 33 = waited), so a captured CUDA graph of a whole denoising step advances the epochs on every
+ * replay without host involvement.  Do not mix explicit and device-side epochs on one flag array.
+ *
+ * Producer- / consumer-fused forms of the same switch (north_star: "in-kernel sequence-dim all-to-all issuing P2P stores
+ * fused with the preceding [producer]"; in STDiT3 the producer of the S-shard -> T-shard switch is the AdaLN modulate,
+ * open_sora_transformer_3d.py:196-216, and the consumer of the switch back is the gate + residual, :213-228):
+ *
+ * vsb_ln_modulate_dsp = vsb_ln_modulate whose store path IS the reshard: row (b, t, sl) goes to peer (b*T+t) / Tl,
+ *   window viewed as [Tl, Sg, C], row ((b*T+t) % Tl, rank*Sl + sl), Tl = ceil(B*T / world) ((batch, frame) sequences
+ *   are scattered, not frames: 2*20 = 40 split 8 ways exactly); zero rows for padded sequences, padded columns never
+ *   sent; publishes the epoch like vsb_dsp_scatter.  Follow with vsb_dsp_wait on the same flag array.
+ * vsb_dsp_signal publishes the next epoch without moving data (the proj GEMM wrote into this rank's OWN window).
+ * vsb_gate_residual_dsp = vsb_gate_residual whose y operand is PULLED with 128-bit peer loads from the producers'
+ *   windows host_peer_y[r] (each viewed as [Tl, Sg, C]); call after vsb_dsp_wait on the signalled flag array. */
+int vsb_ln_modulate_dsp(const vsb_bf16* x, const vsb_bf16* mod, const uint8_t* x_mask, int shift_row, int scale_row,
+                        int B, int T, int Sl, int C, float eps, void* const* host_peer_recv, void* const* host_peer_flags,
+                        int rank, int world, int Sg, unsigned epoch, void* stream);
+int vsb_dsp_signal(void* const* host_peer_flags, int rank, int world, unsigned epoch, void* stream);
+int vsb_gate_residual_dsp(const vsb_bf16* x, void* const* host_peer_y, vsb_bf16* out, vsb_bf16* cache_out,
+                          const vsb_bf16* mod, const uint8_t* x_mask, int gate_row, int B, int T, int Sl, int C, int rank,
+                          int world, int Sg, void* stream);
 
 /* Symmetric receive windows for the reshard: cudaMalloc'ed (zeroed) here so that a CUDA IPC handle maps the exact
  * base address; handles (64 bytes) are exchanged once at initialize() over the process group's store.

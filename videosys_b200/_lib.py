@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libvsb200.so")
 
 _vp, _i, _ll, _f, _sz, _u = C.c_void_p, C.c_int, C.c_longlong, C.c_float, C.c_size_t, C.c_uint
 
-# name -> (restype, argtypes); must list every symbol include/vsb200.h declares (tests/test_abi.py checks)
+# name -> (restype, argtypes); must list every symbol include/vsb200.h declares (tests/test_host_cpu.py::test_library_exports_every_declared_symbol checks)
 SIGNATURES = {
     "vsb_version": (_i, []),
     "vsb_last_error": (C.c_char_p, []),
@@ -33,6 +33,14 @@ SIGNATURES = {
     "vsb_pab_gate": (_i, [_i, _i, _i, C.POINTER(_i), _i, _i, _i, _i]),
     "vsb_dsp_scatter": (_i, [_vp, C.POINTER(_vp), C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i, _u, _vp]),
     "vsb_dsp_wait": (_i, [_vp, _i, _u, _vp]),
+    "vsb_dsp_signal": (_i, [C.POINTER(_vp), _i, _i, _u, _vp]),
+    "vsb_ln_modulate_dsp": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, C.POINTER(_vp), C.POINTER(_vp), _i, _i, _i, _u,
+                                _vp]),
+    "vsb_gate_residual_dsp": (_i, [_vp, C.POINTER(_vp), _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "vsb_qk_rmsnorm_rope": (_i, [_vp, _vp, _vp, _sz, _i, _i, _f, _vp, _vp, _i, _i, _vp]),
+    "vsb_attn_flash_strided": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, C.POINTER(_i), _f,
+                                   _vp]),
+    "vsb_tmap_cache_stats": (C.c_ulonglong, [_i]),
     "vsb_dsp_alloc": (_i, [C.POINTER(_vp), _sz]),
     "vsb_dsp_free": (_i, [_vp]),
     "vsb_ipc_get_handle": (_i, [_vp, _vp]),

@@ -119,7 +119,8 @@ class DspP2P:
         self.rank = dist.get_rank(process_group)
         self.device = device
         self.max_elems = int(max_elems)
-        self.epoch = [0, 0]
+        # epochs live on the DEVICE (flag slots 32 / 33, csrc/dsp_common.cuh): every call passes epoch = 0, so a
+        # captured CUDA graph of a denoising step advances them on replay without the host
         self._own = []
         self._peer_recv: List[List[int]] = [[], []]
         self._peer_flag: List[List[int]] = [[], []]
@@ -169,7 +170,6 @@ class DspP2P:
         w = self.world
         Tl, Sl = -(-T // w), -(-S // w)
         out_shape = (B, T, Sl, Cc) if to_spatial_shard else (B, Tl, S, Cc)
-        self.epoch[d] += 1
         st = torch.cuda.current_stream().cuda_stream
         from ... import kernels
 
@@ -177,11 +177,58 @@ class DspP2P:
         with kernels._Timed("dsp_switch", x.numel() * 2 * (w - 1) // w):
             self._libmod.check(
                 self.lib.vsb_dsp_scatter(x.data_ptr(), self._recv_arr[d], self._flag_arr[d], self.rank, w, d, B, T, S,
-                                         Cc, self.epoch[d], st),
+                                         Cc, 0, st),
                 "dsp_scatter",
             )
-            self._libmod.check(self.lib.vsb_dsp_wait(self._own[d][1], w, self.epoch[d], st), "dsp_wait")
+            self._libmod.check(self.lib.vsb_dsp_wait(self._own[d][1], w, 0, st), "dsp_wait")
         return self._window(d, out_shape)
+
+    # ---- producer- / consumer-fused switch (csrc/elementwise.cu: ln_modulate_kernel<.., true>, gate_residual_dsp_kernel)
+    def ln_modulate_push(self, x, mod, mask_u8, shift_row: int, scale_row: int, B: int, T: int, Sl: int, Sg: int,
+                         eps: float = 1e-6) -> torch.Tensor:
+        """AdaLN modulate of the local S-shard x [B, T*Sl, C] whose stores ARE the S-shard -> T-shard switch: returns
+        this rank's receive window as [1, Tl, Sg, C] (the (batch, frame) sequences it owns, every patch of each)."""
+        from ... import kernels
+
+        w, Cc = self.world, x.shape[-1]
+        Tl = -(-(B * T) // w)
+        st = torch.cuda.current_stream().cuda_stream
+        with kernels._Timed("dsp_push", x.numel() * 2 * (w - 1) // w):
+            self._libmod.check(
+                self.lib.vsb_ln_modulate_dsp(x.data_ptr(), mod.data_ptr(), None if mask_u8 is None else mask_u8.data_ptr(),
+                                             shift_row, scale_row, B, T, Sl, Cc, eps, self._recv_arr[0], self._flag_arr[0],
+                                             self.rank, w, Sg, 0, st),
+                "ln_modulate_dsp",
+            )
+            self._libmod.check(self.lib.vsb_dsp_wait(self._own[0][1], w, 0, st), "dsp_wait")
+        return self._window(0, (1, Tl, Sg, Cc))
+
+    def branch_window(self, B: int, T: int, Sg: int, Cc: int) -> torch.Tensor:
+        """This rank's OWN direction-1 window as [Tl * Sg, C]: the proj GEMM writes the attention branch here and the
+        peers pull their columns from it (gate_residual_pull)."""
+        Tl = -(-(B * T) // self.world)
+        return self._window(1, (Tl * Sg, Cc))
+
+    def gate_residual_pull(self, x, mod, mask_u8, gate_row: int, B: int, T: int, Sl: int, Sg: int, out=None,
+                           cache_out=None) -> torch.Tensor:
+        """Publishes 'my branch window is written', waits for every peer's, then x + gate * y with y PULLED over
+        NVLink from the owners' windows (the T-shard -> S-shard switch fused into the consumer's loads)."""
+        from ... import kernels
+
+        w, Cc = self.world, x.shape[-1]
+        st = torch.cuda.current_stream().cuda_stream
+        out = torch.empty_like(x) if out is None else out
+        with kernels._Timed("dsp_pull", x.numel() * 2 * (w - 1) // w):
+            self._libmod.check(self.lib.vsb_dsp_signal(self._flag_arr[1], self.rank, w, 0, st), "dsp_signal")
+            self._libmod.check(self.lib.vsb_dsp_wait(self._own[1][1], w, 0, st), "dsp_wait")
+            self._libmod.check(
+                self.lib.vsb_gate_residual_dsp(x.data_ptr(), self._recv_arr[1], out.data_ptr(),
+                                               None if cache_out is None else cache_out.data_ptr(), mod.data_ptr(),
+                                               None if mask_u8 is None else mask_u8.data_ptr(), gate_row, B, T, Sl, Cc,
+                                               self.rank, w, Sg, st),
+                "gate_residual_dsp",
+            )
+        return out
 
     def close(self):
         for p in self._opened:

@@ -1,6 +1,9 @@
 // vsb200 -- C-ABI plumbing: error text, device check, tensor-map encoding, PAB integer gate.
 #include <string.h>
 
+#include <mutex>
+#include <unordered_map>
+
 #include "vsb_host.h"
 
 namespace vsb {
@@ -32,8 +35,70 @@ static int load_encode() {
   return VSB_OK;
 }
 
+// ---- tensor-map cache ------------------------------------------------------------------------------------------
+// cuTensorMapEncodeTiled costs ~1-2 us of host time; a denoising step made ~1800 such calls (3 per GEMM, 6 per
+// attention launch).  torch's caching allocator hands the same addresses back every step, so (base, shape, strides,
+// box, swizzle) repeats: an encoded map is a pure function of that key.  Bounded: cleared when it reaches kTmapCacheMax.
+struct TmapKey {
+  const void* base;
+  unsigned long long dims[5], strides[4];
+  unsigned box[5];
+  int rank, swz;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    const unsigned long long* w = reinterpret_cast<const unsigned long long*>(&k);
+    unsigned long long h = 0x9E3779B97F4A7C15ull;
+    for (size_t i = 0; i < sizeof(TmapKey) / 8; ++i) {
+      h ^= w[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    }
+    return (size_t)h;
+  }
+};
+static_assert(sizeof(TmapKey) % 8 == 0, "TmapKey is hashed as 64-bit words");
+constexpr size_t kTmapCacheMax = 8192;
+static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> g_tmap_cache;
+static std::mutex g_tmap_mu;
+static std::atomic<unsigned long long> g_tmap_hits{0}, g_tmap_misses{0};
+static int g_opt_tmap_cache = 1;
+
+static int make_tmap_bf16_uncached(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+                                   const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz);
+
 int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
                    const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz) {
+  if (!g_opt_tmap_cache || rank < 1 || rank > 5) return make_tmap_bf16_uncached(m, base, rank, dims, strides_bytes, box, swz);
+  TmapKey key;
+  memset(&key, 0, sizeof(key));
+  key.base = base;
+  key.rank = rank;
+  key.swz = (int)swz;
+  for (int i = 0; i < rank; ++i) {
+    key.dims[i] = dims[i];
+    key.box[i] = box[i];
+    if (i > 0) key.strides[i - 1] = strides_bytes[i - 1];
+  }
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    auto it = g_tmap_cache.find(key);
+    if (it != g_tmap_cache.end()) {
+      *m = it->second;
+      g_tmap_hits.fetch_add(1, std::memory_order_relaxed);
+      return VSB_OK;
+    }
+  }
+  int rc = make_tmap_bf16_uncached(m, base, rank, dims, strides_bytes, box, swz);
+  if (rc) return rc;
+  g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
+  std::lock_guard<std::mutex> g(g_tmap_mu);
+  if (g_tmap_cache.size() >= kTmapCacheMax) g_tmap_cache.clear();
+  g_tmap_cache.emplace(key, *m);
+  return VSB_OK;
+}
+
+static int make_tmap_bf16_uncached(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+                                   const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz) {
   int rc = load_encode();
   if (rc) return rc;
   cuuint64_t gdim[5];
@@ -61,6 +126,7 @@ using namespace vsb;
 extern "C" int vsb_version(void) { return 100; }
 extern "C" const char* vsb_last_error(void) { return g_err; }
 extern "C" unsigned long long vsb_launch_count(void) { return g_launches.load(); }
+extern "C" unsigned long long vsb_tmap_cache_stats(int which) { return which ? g_tmap_misses.load() : g_tmap_hits.load(); }
 
 extern "C" int vsb_init(int device) {
   int n = 0;
@@ -72,7 +138,8 @@ extern "C" int vsb_init(int device) {
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(VSB_ERR_CUDA, "cudaGetDeviceProperties failed");
   if (prop.major != 10) return fail(VSB_ERR_NO_DEVICE, "device %d is sm_%d%d; vsb200 kernels are sm_100a only", device, prop.major, prop.minor);
-  if (cudaSetDevice(device) != cudaSuccess) return fail(VSB_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  // cuTensorMapEncodeTiled needs a current context on some device, not on `device`: the caller's current device is
+  // left untouched (the first version called cudaSetDevice(device) and silently changed it)
   g_sms = prop.multiProcessorCount;
   return load_encode();
 }
@@ -82,6 +149,7 @@ extern int g_opt_gemm_2sm;
 extern int g_opt_attn_variant;
 extern int g_opt_attn_pingpong;
 extern int g_opt_attn_poly;
+extern int g_opt_dsp_rowwise;
 }
 extern "C" int vsb_set_option(const char* name, int value) {
   if (!name) return fail(VSB_ERR_INVALID, "set_option: null name");
@@ -99,6 +167,14 @@ extern "C" int vsb_set_option(const char* name, int value) {
   }
   if (!strcmp(name, "attn_variant")) {
     g_opt_attn_variant = value;
+    return VSB_OK;
+  }
+  if (!strcmp(name, "tmap_cache")) {
+    g_opt_tmap_cache = value;
+    return VSB_OK;
+  }
+  if (!strcmp(name, "dsp_rowwise")) {
+    g_opt_dsp_rowwise = value;
     return VSB_OK;
   }
   return fail(VSB_ERR_INVALID, "set_option: unknown option '%s'", name);

@@ -22,20 +22,27 @@ namespace vsb {
       p.trace[((warp < 4 ? 0 : warp - 3) * 16 + (tile)) * 4 + (ev)] = clock64();                        \
   } while (0)
 
+constexpr int kAttnMaxLens = 64;  // per-batch key counts travel by value in the kernel parameters
 struct AttnParams {
   int poly_exp;  // host-side selector of the kt64 kernels' kPoly template (0 / 1 / 2 / 3 = 0 / 25 / 37.5 / 50 % of exp2 on the FMA pipe)
   int pingpong;  // 128-key kernel only: 1 = the two softmax warpgroups take turns on the exp2 (MUFU) phase through named barriers
   long long* trace;
   bf16* out;
+  // out element (b, n, h, d) at out + b*out_batch_stride + n*out_row_stride + h*D + d (elements): the temporal
+  // (T >= 30) path writes straight back into the token-major activation
+  long long out_row_stride, out_batch_stride;
+  const bf16* q;  // raw query pointer + strides (elements): the Q-in-TMEM schedule moves its rows itself
+  long long q_row_stride, q_batch_stride;
   int nb, nq, nk, H;
   float scale_log2;  // softmax scale * log2(e)
   int has_lens;
-  int lens[8];
+  int lens[kAttnMaxLens];
 };
 
 
 // attn_tcgen05_kt64.cu.  tm = {q64, q16, k64, k16, v64, v16} with 64-row key boxes.
-int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st);
+// q_tmem: Q rows resident in TMEM, S = Q K^T issued as TS MMAs (attn_variant 4)
+int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, int q_tmem, cudaStream_t st);
 // attn_tcgen05_kt64p.cu: the same tiles under persistent CTAs.
 int attn_flash_kt64p_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st);
 

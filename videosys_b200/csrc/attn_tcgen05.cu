@@ -287,7 +287,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
     tc_fence_after();
     const int qrow = q0 + x * 128 + row;
     const float inv = 1.f / l_run;
-    bf16* dst = p.out + ((size_t)((size_t)b * p.nq + (qrow < p.nq ? qrow : 0)) * p.H + h) * D;
+    bf16* dst = p.out + (size_t)b * p.out_batch_stride + (size_t)(qrow < p.nq ? qrow : 0) * p.out_row_stride + (size_t)h * D;
 #pragma unroll 1
     for (int c = 0; c < D / 8; ++c) {
       uint32_t r[8];
@@ -328,25 +328,41 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
                               int nk, int H, int D, long long q_row_stride, long long q_batch_stride,
                               long long kv_row_stride, long long kv_batch_stride, const int* host_kv_lens, float scale,
                               void* stream) {
+  return vsb_attn_flash_strided(q, k, v, out, nb, nq, nk, H, D, q_row_stride, q_batch_stride, kv_row_stride,
+                                kv_batch_stride, (long long)H * D, (long long)nq * H * D, host_kv_lens, scale, stream);
+}
+
+extern "C" int vsb_attn_flash_strided(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb,
+                                      int nq, int nk, int H, int D, long long q_row_stride, long long q_batch_stride,
+                                      long long kv_row_stride, long long kv_batch_stride, long long out_row_stride,
+                                      long long out_batch_stride, const int* host_kv_lens, float scale, void* stream) {
   if (!q || !k || !v || !out || nb <= 0 || nq <= 0 || nk <= 0 || H <= 0) return fail(VSB_ERR_INVALID, "attn_flash: bad args");
+  if ((out_row_stride % 8) || (out_batch_stride % 8) || out_row_stride < (long long)H * D)
+    return fail(VSB_ERR_UNSUPPORTED, "attn_flash: output strides must be multiples of 8 elements, rows >= H*D apart");
   if (D != 72 && D != 64) return fail(VSB_ERR_UNSUPPORTED, "attn_flash: head_dim %d (72 or 64 only)", D);
   if ((q_row_stride % 8) || (q_batch_stride % 8) || (kv_row_stride % 8) || (kv_batch_stride % 8) || !aligned16(q) ||
       !aligned16(k) || !aligned16(v) || !aligned16(out))
     return fail(VSB_ERR_UNSUPPORTED, "attn_flash: strides must be multiples of 8 elements and pointers 16B-aligned");
-  if (host_kv_lens && nb > 8) return fail(VSB_ERR_UNSUPPORTED, "attn_flash: per-batch key lengths need nb <= 8");
+  if (host_kv_lens && nb > kAttnMaxLens)
+    return fail(VSB_ERR_UNSUPPORTED, "attn_flash: per-batch key lengths need nb <= %d", kAttnMaxLens);
   if (nb > 65535 || H > 65535) return fail(VSB_ERR_UNSUPPORTED, "attn_flash: grid too large");
   AttnParams prm;
   prm.trace = g_attn_trace;
   prm.pingpong = g_opt_attn_pingpong;
   prm.poly_exp = g_opt_attn_poly;
   prm.out = (bf16*)out;
+  prm.out_row_stride = out_row_stride;
+  prm.out_batch_stride = out_batch_stride;
+  prm.q = (const bf16*)q;
+  prm.q_row_stride = q_row_stride;
+  prm.q_batch_stride = q_batch_stride;
   prm.nb = nb;
   prm.nq = nq;
   prm.nk = nk;
   prm.H = H;
   prm.scale_log2 = scale * 1.4426950408889634f;
   prm.has_lens = host_kv_lens ? 1 : 0;
-  for (int i = 0; i < 8; ++i) prm.lens[i] = 0;
+  for (int i = 0; i < kAttnMaxLens; ++i) prm.lens[i] = 0;
   if (host_kv_lens)
     for (int i = 0; i < nb; ++i) {
       if (host_kv_lens[i] < 1 || host_kv_lens[i] > nk) return fail(VSB_ERR_INVALID, "attn_flash: kv_lens[%d]=%d", i, host_kv_lens[i]);
@@ -376,7 +392,7 @@ extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (variant == 3) return attn_flash_kt64p_launch(tm, prm, D, g_opt_attn_poly, st);
-  if (variant == 2) return attn_flash_kt64_launch(tm, prm, D, g_opt_attn_poly, st);
+  if (variant == 2 || variant == 4) return attn_flash_kt64_launch(tm, prm, D, g_opt_attn_poly, variant == 4, st);
   dim3 grid((nq + 255) / 256, H, nb);
   static bool attr = false;
   if (!attr) {

@@ -36,7 +36,8 @@
 namespace vsb {
 
 constexpr int kT64Threads = 416;  // 4 MMA issuer warps, 8 softmax warps, 1 TMA producer warp
-constexpr int kT64Stages = 6;
+constexpr int kT64Stages = 6;      // Q tiles staged in shared memory (SS-mode S)
+constexpr int kT64StagesQT = 8;    // Q resident in TMEM (TS-mode S): its 40 KB of smem become two more K/V stages
 constexpr int kQA = 128 * 128;  // Q: 128 rows x 64 bf16, SWIZZLE_128B
 constexpr int kQB = 128 * 32;   // Q: 128 rows x 16 bf16, SWIZZLE_32B
 constexpr int kQT = kQA + kQB;
@@ -45,11 +46,13 @@ constexpr int kKB = 64 * 32;    // K / V: 64 keys x 16 bf16, SWIZZLE_32B
 constexpr int kKT = kKA + kKB;
 constexpr int kStage = 2 * kKT;  // K_A | K_B | V_A | V_B
 constexpr int kT64Smem = 2 * kQT + kT64Stages * kStage + 1024 + 512;
+constexpr int kT64SmemQT = kT64StagesQT * kStage + 1024 + 512;
 
 __host__ __device__ constexpr uint32_t c_s(int x, int buf) { return uint32_t(x) * 128u + uint32_t(buf) * 64u; }
 __host__ __device__ constexpr uint32_t c_o(int x) { return 256u + uint32_t(x) * 80u; }
+__host__ __device__ constexpr uint32_t c_q(int x) { return 416u + uint32_t(x) * 40u; }  // Q_x as bf16 pairs: 80 / 2 columns
 
-template <int D, int kPoly>
+template <int D, int kPoly, bool kQTm>
 __global__ void __launch_bounds__(kT64Threads, 1)
 attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qb,
                        const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_kb,
@@ -58,14 +61,14 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   constexpr bool kHasB = (D > 64);
   constexpr int kQTx = kHasB ? kQT : kQA;
   constexpr int kKTx = kHasB ? kKT : kKA;
-  constexpr int ST = kT64Stages;
+  constexpr int ST = kQTm ? kT64StagesQT : kT64Stages;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char* sQ = smem;               // [2][Q_A | Q_B]
-  unsigned char* sKV = smem + 2 * kQT;    // [stages][K_A | K_B | V_A | V_B]
+  unsigned char* sQ = smem;                            // [2][Q_A | Q_B] (absent when Q lives in TMEM)
+  unsigned char* sKV = smem + (kQTm ? 0 : 2 * kQT);    // [stages][K_A | K_B | V_A | V_B]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sKV + ST * kStage);
-  uint64_t* q_full = bars;              // [1]
-  uint64_t* k_full = bars + 1;          // [ST]
+  uint64_t* q_full = bars;              // [2]: smem Q: [0] armed by the TMA; TMEM Q: [x] gets 4 softmax-warp arrivals
+  uint64_t* k_full = bars + 2;          // [ST]
   uint64_t* v_full = k_full + ST;       // [ST]
   uint64_t* kv_empty = v_full + ST;     // [ST]
   uint64_t* s_full = kv_empty + ST;     // [x][buf]
@@ -90,7 +93,8 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     }
   }
   if (warp == 1 && lane == 0) {
-    mbar_init(q_full, 1);
+    mbar_init(&q_full[0], kQTm ? 4 : 1);
+    mbar_init(&q_full[1], 4);
     for (int i = 0; i < ST; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
@@ -113,10 +117,12 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   if (warp == 12) {
     // =============================== TMA producer ===============================
     const uint32_t elected = elect_one();
-    mbar_arrive_expect_tx_w(elected, q_full, nx * kQTx);
-    for (int x = 0; x < nx; ++x) {
-      tma_load_4d_w(elected, &tm_q, q_full, sQ + x * kQT, 0, h, q0 + x * 128, b);
-      if (kHasB) tma_load_4d_w(elected, &tm_qb, q_full, sQ + x * kQT + kQA, 64, h, q0 + x * 128, b);
+    if (!kQTm) {
+      mbar_arrive_expect_tx_w(elected, q_full, nx * kQTx);
+      for (int x = 0; x < nx; ++x) {
+        tma_load_4d_w(elected, &tm_q, q_full, sQ + x * kQT, 0, h, q0 + x * 128, b);
+        if (kHasB) tma_load_4d_w(elected, &tm_qb, q_full, sQ + x * kQT + kQA, 64, h, q0 + x * 128, b);
+      }
     }
     for (int j = 0; j < n_tiles; ++j) {
       const int s = j % ST;
@@ -142,14 +148,24 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const uint32_t q_lo = umma_desc_lo(smem_u32(sQ), 16);
     const uint32_t kv_lo = umma_desc_lo(smem_u32(sKV), 16);
     auto issue_S = [&](int x, int buf, int stage) {
-      const uint32_t qa = q_lo + x * (kQT >> 4);
       const uint32_t ka = kv_lo + stage * (kStage >> 4);
       const uint32_t d = tb + c_s(x, buf);
+      if (kQTm) {
+        // A = Q_x from TMEM (bf16 pairs, 8 columns per 16-wide K step): an SS MMA re-reads its 4 KB Q slice from shared
+        // memory every K step and is smem-bound at N = 64 (50.7 cycles against 34 in TS mode, tools/mma_microbench.cu)
+        const uint32_t qt = tb + c_q(x);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_ss_w(elected, d, desc_pack(qa + 2 * k, hi128), desc_pack(ka + 2 * k, hi128), idesc_s, k > 0 ? 1u : 0u);
-      if (kHasB)
-        umma_ss_w(elected, d, desc_pack(qa + (kQA >> 4), hi32), desc_pack(ka + (kKA >> 4), hi32), idesc_s, 1u);
+        for (int k = 0; k < 4; ++k)
+          umma_ts_w(elected, d, qt + 8 * k, desc_pack(ka + 2 * k, hi128), idesc_s, k > 0 ? 1u : 0u);
+        if (kHasB) umma_ts_w(elected, d, qt + 32, desc_pack(ka + (kKA >> 4), hi32), idesc_s, 1u);
+      } else {
+        const uint32_t qa = q_lo + x * (kQT >> 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_ss_w(elected, d, desc_pack(qa + 2 * k, hi128), desc_pack(ka + 2 * k, hi128), idesc_s, k > 0 ? 1u : 0u);
+        if (kHasB)
+          umma_ss_w(elected, d, desc_pack(qa + (kQA >> 4), hi32), desc_pack(ka + (kKA >> 4), hi32), idesc_s, 1u);
+      }
     };
     auto issue_PV = [&](int x, int buf, int stage) {
       // V tiles are MN-major (d contiguous): the LBO field is the stride between d atoms, unused with a single atom
@@ -164,7 +180,8 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       }
     };
     const int x = warp >> 1, par = warp & 1;
-    mbar_wait(q_full, 0);
+    mbar_wait(&q_full[kQTm ? x : 0], 0);
+    if (kQTm) tc_fence_after();
     if (par < n_tiles) {  // prologue: S_x(par) -> my buffer
       mbar_wait(&k_full[par], 0);
       tc_fence_after();
@@ -199,6 +216,32 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     const uint32_t tO = tmem_base + lane_off + c_o(x);
     const float sl2 = p.scale_log2;
     float l_run = 0.f, m_run = -INFINITY;
+    if (kQTm) {  // my query row -> TMEM (A operand of S = Q K^T): D bf16 = D/2 columns, zero-padded to the next K step
+      const int qr = q0 + x * 128 + row;
+      const uint4* src = reinterpret_cast<const uint4*>(p.q + (size_t)b * p.q_batch_stride + (size_t)qr * p.q_row_stride +
+                                                         (size_t)h * D);
+      const uint32_t tQ = tmem_base + lane_off + c_q(x);
+      constexpr int NV = D / 8;  // 16-byte vectors per row
+#pragma unroll
+      for (int c = 0; c < (kHasB ? 5 : 4); ++c) {
+        uint32_t w[8];
+#pragma unroll
+        for (int v2 = 0; v2 < 2; ++v2) {
+          const int vi = c * 2 + v2;
+          uint4 u = make_uint4(0, 0, 0, 0);
+          if (vi < NV && qr < p.nq) u = __ldg(src + vi);
+          w[4 * v2] = u.x;
+          w[4 * v2 + 1] = u.y;
+          w[4 * v2 + 2] = u.z;
+          w[4 * v2 + 3] = u.w;
+        }
+        tmem_st8(tQ + c * 8, w);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_full[x]);
+    }
     {  // O_x starts at zero: both issuers of this query tile only ever accumulate into it
       uint32_t z[16];
 #pragma unroll
@@ -307,7 +350,7 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     tc_fence_after();
     const int qrow = q0 + x * 128 + row;
     const float inv = 1.f / l_run;
-    bf16* dst = p.out + ((size_t)((size_t)b * p.nq + (qrow < p.nq ? qrow : 0)) * p.H + h) * D;
+    bf16* dst = p.out + (size_t)b * p.out_batch_stride + (size_t)(qrow < p.nq ? qrow : 0) * p.out_row_stride + (size_t)h * D;
 #pragma unroll 1
     for (int c = 0; c < D / 8; ++c) {
       uint32_t r[8];
@@ -329,30 +372,36 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
-template <int D, int kPoly>
+template <int D, int kPoly, bool kQTm>
 static int launch_kt64(const CUtensorMap* tm, const AttnParams& prm, cudaStream_t st) {
+  constexpr int smem = kQTm ? kT64SmemQT : kT64Smem;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_flash_kt64_kernel<D, kPoly>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kT64Smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_flash_kt64_kernel<D, kPoly, kQTm>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash(kt64): smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
   dim3 grid((prm.nq + 255) / 256, prm.H, prm.nb);
-  attn_flash_kt64_kernel<D, kPoly><<<grid, kT64Threads, kT64Smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+  attn_flash_kt64_kernel<D, kPoly, kQTm><<<grid, kT64Threads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
   return check_launch("attn_flash(kt64)");
 }
 
-int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st) {
+template <bool kQTm>
+static int dispatch_kt64(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st) {
   if (D == 72) {
     switch (poly) {
-      case 1: return launch_kt64<72, 1>(tm, prm, st);
-      case 2: return launch_kt64<72, 2>(tm, prm, st);
-      case 3: return launch_kt64<72, 3>(tm, prm, st);
-      default: return launch_kt64<72, 0>(tm, prm, st);
+      case 1: return launch_kt64<72, 1, kQTm>(tm, prm, st);
+      case 2: return launch_kt64<72, 2, kQTm>(tm, prm, st);
+      case 3: return launch_kt64<72, 3, kQTm>(tm, prm, st);
+      default: return launch_kt64<72, 0, kQTm>(tm, prm, st);
     }
   }
-  return poly ? launch_kt64<64, 1>(tm, prm, st) : launch_kt64<64, 0>(tm, prm, st);
+  return poly ? launch_kt64<64, 1, kQTm>(tm, prm, st) : launch_kt64<64, 0, kQTm>(tm, prm, st);
+}
+
+int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, int q_tmem, cudaStream_t st) {
+  return q_tmem ? dispatch_kt64<true>(tm, prm, D, poly, st) : dispatch_kt64<false>(tm, prm, D, poly, st);
 }
 
 }  // namespace vsb

@@ -386,7 +386,7 @@ attn_flash_kt64p_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       tc_fence_after();
       const int qrow = it.q0 + x * 128 + row;
       const float inv = 1.f / l_run;
-      bf16* dst = p.out + ((size_t)((size_t)it.b * p.nq + (qrow < p.nq ? qrow : 0)) * p.H + it.h) * D;
+      bf16* dst = p.out + (size_t)it.b * p.out_batch_stride + (size_t)(qrow < p.nq ? qrow : 0) * p.out_row_stride + (size_t)it.h * D;
 #pragma unroll 1
       for (int c = 0; c < D / 8; ++c) {
         uint32_t r[8];

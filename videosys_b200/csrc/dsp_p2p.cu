@@ -5,39 +5,76 @@
 // destination rank's output tensor (zero padding of the scattered axis is synthesised, padding of the gathered
 // axis is never sent).  Completion: every CTA fences (system scope); the last CTA to finish publishes the epoch
 // into each peer's flag slot; vsb_dsp_wait spins (acquire, system scope) on the receiver's stream.
-#include "vsb_common.cuh"
+#include "dsp_common.cuh"
 #include "vsb_host.h"
 
 namespace vsb {
 
-constexpr int kMaxWorld = 16;
-struct DspPeers {
-  bf16* recv[kMaxWorld];
-  unsigned* flags[kMaxWorld];
-};
-
-__device__ unsigned g_dsp_done_ctas = 0;
-
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
+int g_opt_dsp_rowwise = 1;  // 1: one warp per token row (default); 0: the first version (decode per 16-byte vector)
 
 // dir 0: local [B, T, Sl, C] -> rank d receives frames [d*Tl, (d+1)*Tl) into [B, Tl, S, C] at columns rank*Sl + sl
 // dir 1: local [B, Tl, S, C] -> rank d receives columns [d*Sl, (d+1)*Sl) into [B, T, Sl, C] at frames rank*Tl + tl
+//
+// One warp per token row (C contiguous bf16 = C/8 vectors that all go to ONE contiguous row of ONE peer): the
+// (b, t, s) decode and the destination lookup cost a few 32-bit divisions per ROW.  The first version (below, kept as
+// dsp_rowwise=0) decoded every 16-byte vector with seven 64-bit divisions (~700 instructions per vector): it was
+// instruction-bound at 370-440 GB/s, not NVLink-bound.
 __global__ void __launch_bounds__(256) dsp_scatter_kernel(const bf16* __restrict__ local, DspPeers peers, int rank,
                                                           int world, int dir, int B, int T, int S, int C,
                                                           unsigned epoch) {
+  const unsigned Tp = ((T + world - 1) / world) * world, Sp = ((S + world - 1) / world) * world;
+  const unsigned Tl = Tp / world, Sl = Sp / world;
+  const int cv = C >> 3;
+  const int lane = threadIdx.x & 31;
+  const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+  const unsigned gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const unsigned nrows = dir == 0 ? (unsigned)B * Tp * Sl : (unsigned)B * Tl * Sp;  // < 2^31 (checked by the launcher)
+  constexpr int U = 5;  // 16-byte vectors per lane per trip: loads first, then the (posted) peer stores
+  for (unsigned r = gw; r < nrows; r += nwarps) {
+    const uint4* src = nullptr;  // nullptr: synthesise the zero padding of the scattered axis
+    uint4* dst;
+    if (dir == 0) {
+      const unsigned sl = r % Sl, bt = r / Sl;
+      const unsigned t = bt % Tp, b = bt / Tp;
+      const unsigned col = rank * Sl + sl;
+      if (col >= (unsigned)S) continue;  // gathered-axis padding is narrowed away at the receiver: never sent
+      const unsigned d = t / Tl, tl = t - d * Tl;
+      if (t < (unsigned)T) src = reinterpret_cast<const uint4*>(local + (((size_t)b * T + t) * Sl + sl) * C);
+      dst = reinterpret_cast<uint4*>(peers.recv[d] + (((size_t)b * Tl + tl) * S + col) * C);
+    } else {
+      const unsigned col = r % Sp, btl = r / Sp;
+      const unsigned tl = btl % Tl, b = btl / Tl;
+      const unsigned tg = rank * Tl + tl;
+      if (tg >= (unsigned)T) continue;
+      const unsigned d = col / Sl, sl = col - d * Sl;
+      if (col < (unsigned)S) src = reinterpret_cast<const uint4*>(local + (((size_t)b * Tl + tl) * S + col) * C);
+      dst = reinterpret_cast<uint4*>(peers.recv[d] + (((size_t)b * T + tg) * Sl + sl) * C);
+    }
+    for (int v0 = lane; v0 < cv; v0 += 32 * U) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int vi = v0 + 32 * u;
+        v[u] = (src != nullptr && vi < cv) ? src[vi] : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int vi = v0 + 32 * u;
+        if (vi < cv) dst[vi] = v[u];
+      }
+    }
+  }
+  dsp_publish(peers, rank, world, epoch);
+}
+
+// First version: every 16-byte vector decoded on its own.
+__global__ void __launch_bounds__(256) dsp_scatter_vec_kernel(const bf16* __restrict__ local, DspPeers peers, int rank,
+                                                              int world, int dir, int B, int T, int S, int C,
+                                                              unsigned epoch) {
   const int Tp = ((T + world - 1) / world) * world, Sp = ((S + world - 1) / world) * world;
   const int Tl = Tp / world, Sl = Sp / world;
   const int cv = C >> 3;
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  // 4 independent 16-byte vectors per thread per trip: all loads are issued before the (posted) peer stores so
-  // that enough bytes are in flight to cover the NVLink round trip.
   constexpr int U = 4;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,7 +96,7 @@ __global__ void __launch_bounds__(256) dsp_scatter_kernel(const bf16* __restrict
         const int t = int(r % Tp);
         const int b = int(r / Tp);
         const int col = rank * Sl + sl;
-        if (col >= S) continue;  // gathered-axis padding is narrowed away at the receiver: never sent
+        if (col >= S) continue;
         const int d = t / Tl, tl = t - d * Tl;
         if (t < T) v[u] = *reinterpret_cast<const uint4*>(local + (((size_t)b * T + t) * Sl + sl) * C + c * 8);
         dst[u] = reinterpret_cast<uint4*>(peers.recv[d] + (((size_t)b * Tl + tl) * S + col) * C + c * 8);
@@ -79,19 +116,27 @@ __global__ void __launch_bounds__(256) dsp_scatter_kernel(const bf16* __restrict
     for (int u = 0; u < U; ++u)
       if (dst[u] != nullptr) *dst[u] = v[u];
   }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned done = atomicAdd(&g_dsp_done_ctas, 1u) + 1u;
-    if (done == gridDim.x) {
-      g_dsp_done_ctas = 0;
-      __threadfence_system();
-      for (int d = 0; d < world; ++d) st_release_sys(peers.flags[d] + rank, epoch);
-    }
-  }
+  dsp_publish(peers, rank, world, epoch);
 }
 
-__global__ void dsp_wait_kernel(const unsigned* flags, int world, unsigned epoch) {
+// Publishes the next epoch without moving data: the producer (the proj GEMM) wrote its output into this rank's own
+// window and the consumers PULL their rows (vsb_gate_residual_dsp).
+__global__ void dsp_signal_kernel(DspPeers peers, int rank, int world, unsigned epoch) {
+  dsp_publish(peers, rank, world, epoch);
+}
+
+// epoch == 0: wait for the next value of the device-side wait counter (flags[kDspWaitCtr])
+__global__ void dsp_wait_kernel(unsigned* flags, int world, unsigned epoch) {
+  __shared__ unsigned s_epoch;
+  if (threadIdx.x == 0) {
+    if (epoch == 0) {
+      epoch = flags[kDspWaitCtr] + 1u;
+      flags[kDspWaitCtr] = epoch;
+    }
+    s_epoch = epoch;
+  }
+  __syncthreads();
+  epoch = s_epoch;
   const int src = threadIdx.x;
   if (src < world) {
     long long t0 = clock64();
@@ -102,6 +147,16 @@ __global__ void dsp_wait_kernel(const unsigned* flags, int world, unsigned epoch
       }
     }
   }
+}
+
+int dsp_fill_peers(DspPeers* peers, void* const* host_peer_recv, void* const* host_peer_flags, int world, const char* what) {
+  for (int i = 0; i < world; ++i) {
+    peers->recv[i] = host_peer_recv ? (bf16*)host_peer_recv[i] : nullptr;
+    peers->flags[i] = host_peer_flags ? (unsigned*)host_peer_flags[i] : nullptr;
+    if ((host_peer_recv && (!peers->recv[i] || !aligned16(peers->recv[i]))) || (host_peer_flags && !peers->flags[i]))
+      return fail(VSB_ERR_INVALID, "%s: peer %d window", what, i);
+  }
+  return VSB_OK;
 }
 
 }  // namespace vsb
@@ -115,21 +170,36 @@ extern "C" int vsb_dsp_scatter(const vsb_bf16* local, void* const* host_peer_rec
       S <= 0 || C <= 0)
     return fail(VSB_ERR_INVALID, "dsp_scatter: bad args");
   if (world > kMaxWorld || C % 8 || !aligned16(local)) return fail(VSB_ERR_UNSUPPORTED, "dsp_scatter: world <= 16, C %% 8 == 0");
-  DspPeers peers;
-  for (int i = 0; i < world; ++i) {
-    peers.recv[i] = (bf16*)host_peer_recv[i];
-    peers.flags[i] = (unsigned*)host_peer_flags[i];
-    if (!peers.recv[i] || !peers.flags[i] || !aligned16(peers.recv[i])) return fail(VSB_ERR_INVALID, "dsp_scatter: peer %d window", i);
+  {
+    const long long Tp = ((T + world - 1) / world) * (long long)world, Sp = ((S + world - 1) / world) * (long long)world;
+    if ((long long)B * Tp * Sp >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "dsp_scatter: too many rows");
   }
+  DspPeers peers;
+  int rc = dsp_fill_peers(&peers, host_peer_recv, host_peer_flags, world, "dsp_scatter");
+  if (rc) return rc;
   const int grid = num_sms() * 4;
-  dsp_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)local, peers, rank, world, to_spatial_shard,
-                                                              B, T, S, C, epoch);
+  if (g_opt_dsp_rowwise)
+    dsp_scatter_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)local, peers, rank, world, to_spatial_shard,
+                                                                B, T, S, C, epoch);
+  else
+    dsp_scatter_vec_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)local, peers, rank, world,
+                                                                    to_spatial_shard, B, T, S, C, epoch);
   return check_launch("dsp_scatter");
 }
 
-extern "C" int vsb_dsp_wait(const void* my_flags, int world, unsigned epoch, void* stream) {
+extern "C" int vsb_dsp_signal(void* const* host_peer_flags, int rank, int world, unsigned epoch, void* stream) {
+  if (!host_peer_flags || world < 1 || world > kMaxWorld || rank < 0 || rank >= world)
+    return fail(VSB_ERR_INVALID, "dsp_signal: bad args");
+  DspPeers peers;
+  int rc = dsp_fill_peers(&peers, nullptr, host_peer_flags, world, "dsp_signal");
+  if (rc) return rc;
+  dsp_signal_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(peers, rank, world, epoch);
+  return check_launch("dsp_signal");
+}
+
+extern "C" int vsb_dsp_wait(void* my_flags, int world, unsigned epoch, void* stream) {
   if (!my_flags || world < 1 || world > kMaxWorld) return fail(VSB_ERR_INVALID, "dsp_wait: bad args");
-  dsp_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned*)my_flags, world, epoch);
+  dsp_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned*)my_flags, world, epoch);
   return check_launch("dsp_wait");
 }
 

@@ -1,7 +1,9 @@
 // vsb200 -- HBM-bound kernels of the STDiT3 block: AdaLN modulate, gate+residual, residual add, q/k RMSNorm.
 // One pass over the activation each (128-bit coalesced loads/stores, fp32 math, bf16 rounding at the eager
 // op boundaries so results track the reference's eager chain bit-for-bit wherever the reduction order allows).
-#include "vsb_common.cuh"
+#include <string.h>
+
+#include "dsp_common.cuh"
 #include "vsb_host.h"
 
 namespace vsb {
@@ -33,13 +35,25 @@ __device__ __forceinline__ float warp_sum(float v) {
 // LayerNorm (no affine) + modulate + per-frame select.  One warp per token row; the row lives in registers.
 // kMaxVec: max 16-byte vectors per lane (C <= kMaxVec*32*8).
 // ---------------------------------------------------------------------------------------------------------
-template <int kMaxVec>
+// kDsp: the DSP dimension switch fused into the store path (north_star: the reshard issued by its producer).  The
+// modulated row (b, t, sl) of this rank's S-shard is stored straight into the receive window of the rank that owns
+// (batch, frame) sequence tf = b*T + t after the switch -- peers.recv[tf / Tl] viewed as [Tl, Sg, C], row
+// (tf % Tl, rank*S + sl) -- with 128-bit peer stores over NVLink; rows of padded frames (tf >= B*T) are written as
+// zeros, padded columns (rank*S + sl >= Sg) are never sent; the last CTA publishes the epoch (dsp_publish).
+struct LnDspArgs {
+  DspPeers peers;
+  int rank, world, Sg;
+  unsigned epoch;
+};
+
+template <int kMaxVec, bool kDsp>
 __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
                                                           const bf16* __restrict__ mod,
                                                           const uint8_t* __restrict__ x_mask, int shift_row,
                                                           int scale_row, int B, int T, int S, int C, float eps,
                                                           long long rows, const bf16* __restrict__ gamma,
-                                                          const bf16* __restrict__ beta) {
+                                                          const bf16* __restrict__ beta,
+                                                          const __grid_constant__ LnDspArgs dsp) {
   const int warps_per_block = blockDim.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
@@ -92,6 +106,15 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
     const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
     const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.f, 1.f);
     bf16* orow = out + (size_t)row * C;
+    bool send = true;
+    if (kDsp) {
+      const unsigned Tl = ((unsigned)(B * T) + dsp.world - 1) / dsp.world;
+      const unsigned sl = (unsigned)row - bt * (unsigned)S;
+      const unsigned col = (unsigned)dsp.rank * (unsigned)S + sl;
+      const unsigned d = bt / Tl, tl = bt - d * Tl;
+      send = col < (unsigned)dsp.Sg;
+      orow = dsp.peers.recv[d] + ((size_t)tl * dsp.Sg + col) * C;
+    }
 #pragma unroll
     for (int i = 0; i < kMaxVec; ++i) {
       const int vi = lane + i * 32;
@@ -115,9 +138,23 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
           const __nv_bfloat162 g2 = __hadd2_rn(one2, sc.h[j]);
           o.h[j] = __hadd2_rn(__hmul2_rn(n2, g2), sh.h[j]);
         }
-        st_stream(orow + vi * 8, o.u);
+        if (!kDsp || send) st_stream(orow + vi * 8, o.u);
       }
     }
+  }
+  if (kDsp) {
+    // zero rows of the padded frames [B*T, Tl*world): the receiver's attention reads them (the reference pads zeros)
+    const unsigned Tf = (unsigned)(B * T), Tl = (Tf + dsp.world - 1) / dsp.world;
+    const unsigned npad = (Tl * dsp.world - Tf) * (unsigned)S;
+    for (unsigned pr = blockIdx.x * warps_per_block + (threadIdx.x >> 5); pr < npad; pr += (unsigned)stride) {
+      const unsigned tf = Tf + pr / (unsigned)S, sl = pr % (unsigned)S;
+      const unsigned col = (unsigned)dsp.rank * (unsigned)S + sl;
+      if (col >= (unsigned)dsp.Sg) continue;
+      const unsigned d = tf / Tl, tl = tf - d * Tl;
+      bf16* orow = dsp.peers.recv[d] + ((size_t)tl * dsp.Sg + col) * C;
+      for (int vi = lane; vi < nvec; vi += 32) st_stream(orow + vi * 8, make_uint4(0, 0, 0, 0));
+    }
+    dsp_publish(dsp.peers, dsp.rank, dsp.world, dsp.epoch);
   }
 }
 
@@ -178,12 +215,68 @@ __global__ void __launch_bounds__(256) residual_add_kernel(const bf16* __restric
   }
 }
 
+// gate + residual with the DSP switch-back fused into the LOAD path: the branch output y lives T-sharded in the
+// producers' own windows (the proj GEMM wrote it there); this rank PULLS the rows of its S-shard over NVLink with
+// 128-bit peer loads -- row (b, t, sl) from peers.recv[tf / Tl] viewed as [Tl, Sg, C], row (tf % Tl, rank*S + sl),
+// tf = b*T + t -- so the reshard costs no kernel, no staging window and no extra HBM pass.  One warp per token row
+// (decode once per row), 5 x 16-byte loads of x and of y in flight per lane (NVLink round trip ~2 us).
+// Padded columns (rank*S + sl >= Sg) take y = 0, as the reference's zero padding does.
+template <int kMaxVec>
+__global__ void __launch_bounds__(256) gate_residual_dsp_kernel(const bf16* __restrict__ x, DspPeers peers,
+                                                                bf16* __restrict__ out, bf16* __restrict__ cache,
+                                                                const bf16* __restrict__ mod,
+                                                                const uint8_t* __restrict__ x_mask, int gate_row, int B,
+                                                                int T, int S, int C, int rank, int world, int Sg,
+                                                                unsigned rows) {
+  const int lane = threadIdx.x & 31;
+  const int nvec = C >> 3;
+  const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+  const unsigned Tl = ((unsigned)(B * T) + world - 1) / world;
+  for (unsigned row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += nwarps) {
+    const unsigned bt = row / (unsigned)S, sl = row - bt * (unsigned)S;
+    const int b = int(bt / (unsigned)T);
+    const int sel = (x_mask != nullptr && x_mask[bt] == 0) ? 1 : 0;
+    const bf16* gate = mod + ((size_t)(sel * B + b) * 6 + gate_row) * C;
+    const unsigned col = (unsigned)rank * (unsigned)S + sl;
+    const unsigned d = bt / Tl, tl = bt - d * Tl;
+    const bf16* yrow = col < (unsigned)Sg ? peers.recv[d] + ((size_t)tl * Sg + col) * C : nullptr;
+    const bf16* xrow = x + (size_t)row * C;
+    Vec8 vx[kMaxVec], vy[kMaxVec];
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int vi = lane + i * 32;
+      vy[i].u = make_uint4(0, 0, 0, 0);
+      if (vi < nvec) {
+        vx[i].u = ld_stream(xrow + vi * 8);
+        if (yrow != nullptr) vy[i].u = ld_stream(yrow + vi * 8);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kMaxVec; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        Vec8 vg, o, g;
+        vg.u = __ldg(reinterpret_cast<const uint4*>(gate + vi * 8));
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          g.h[j] = __hmul2_rn(vg.h[j], vy[i].h[j]);  // bf16(gate * y)
+          o.h[j] = __hadd2_rn(vx[i].h[j], g.h[j]);   // bf16(x + gated)
+        }
+        if (cache != nullptr) st_stream(cache + (size_t)row * C + vi * 8, g.u);
+        st_stream(out + (size_t)row * C + vi * 8, o.u);
+      }
+    }
+  }
+}
+
 // In-place RMSNorm of the q and k heads of a packed [rows, 3, H, D] buffer.  A group of D/8 lanes owns one
 // (row, q|k, head) vector of D elements (D=72 -> 9 lanes, D=64 -> 8 lanes); groups are packed 3 per warp.
 template <int D>
 __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ wq,
-                                                         const bf16* __restrict__ wk, long long rows, int H,
-                                                         float eps) {
+                                                         const bf16* __restrict__ wk, long long rows, int H, float eps,
+                                                         const float* __restrict__ rope_cos,
+                                                         const float* __restrict__ rope_sin, unsigned pos_div,
+                                                         unsigned pos_mod) {
   constexpr int LPG = D / 8;     // lanes per group
   constexpr int GPW = 32 / LPG;  // groups per warp (3 for D=72, 4 for D=64)
   constexpr int U = 4;           // independent head vectors in flight per lane
@@ -203,10 +296,12 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv,
     Vec8 v[U];
     bf16* p[U];
     int which[U];
+    unsigned pos[U];
     bool active[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const unsigned gi = base + u * GPW + g;
+      pos[u] = 0u;
       active[u] = (g < GPW) && (gi < ngroups);
       p[u] = nullptr;
       which[u] = 0;
@@ -217,6 +312,7 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv,
         const int h = rem - which[u] * H;
         p[u] = qkv + ((size_t)row * 3 + which[u]) * H * D + (size_t)h * D + l * 8;
         v[u].u = *reinterpret_cast<const uint4*>(p[u]);
+        pos[u] = rope_cos != nullptr ? (row / pos_div) % pos_mod : 0u;
       }
     }
 #pragma unroll
@@ -240,6 +336,17 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv,
           float2 f = __bfloat1622float2(v[u].h[j]);
           // eager: h = bf16(x * rstd); out = bf16(w * h)
           o.h[j] = __hmul2_rn(wv[which[u]].h[j], __floats2bfloat162_rn(f.x * r, f.y * r));
+          if (rope_cos != nullptr) {
+            // rotate_queries_or_keys (attentions.py:76-78): t*cos + rotate_half(t)*sin in fp32 on interleaved pairs
+            // (2i, 2i+1), rot = (-x2, x1), cast back to bf16; position = the token's frame index
+            const float2 y = __bfloat1622float2(o.h[j]);
+            const int d = l * 8 + 2 * j;
+            const float2 cs = *reinterpret_cast<const float2*>(rope_cos + (size_t)pos[u] * D + d);
+            const float2 sn = *reinterpret_cast<const float2*>(rope_sin + (size_t)pos[u] * D + d);
+            const float o0 = __fadd_rn(__fmul_rn(y.x, cs.x), __fmul_rn(-y.y, sn.x));
+            const float o1 = __fadd_rn(__fmul_rn(y.y, cs.y), __fmul_rn(y.x, sn.y));
+            o.h[j] = __floats2bfloat162_rn(o0, o1);
+          }
         }
         *reinterpret_cast<uint4*>(p[u]) = o.u;
       }
@@ -328,11 +435,11 @@ static int grid_for(long long work_items, int per_block) {
 
 using namespace vsb;
 
-extern "C" int vsb_ln_modulate_affine(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
-                                      const vsb_bf16* gamma, const vsb_bf16* beta, int shift_row, int scale_row, int B,
-                                      int T, int S, int C, float eps, void* stream) {
+static int ln_modulate_launch(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
+                              const vsb_bf16* gamma, const vsb_bf16* beta, int shift_row, int scale_row, int B, int T,
+                              int S, int C, float eps, const LnDspArgs* dsp, void* stream) {
   if ((gamma == nullptr) != (beta == nullptr)) return fail(VSB_ERR_INVALID, "ln_modulate: gamma and beta go together");
-  if (!x || !out || !mod || B <= 0 || T <= 0 || S <= 0 || C <= 0) return fail(VSB_ERR_INVALID, "ln_modulate: bad args");
+  if (!x || (!out && !dsp) || !mod || B <= 0 || T <= 0 || S <= 0 || C <= 0) return fail(VSB_ERR_INVALID, "ln_modulate: bad args");
   if (C % 8 || C > 2048 || !aligned16(x) || !aligned16(out) || !aligned16(mod))
     return fail(VSB_ERR_UNSUPPORTED, "ln_modulate: need C %% 8 == 0, C <= 2048, 16B-aligned pointers (C=%d)", C);
   if (shift_row < 0 || shift_row > 5 || scale_row < 0 || scale_row > 5) return fail(VSB_ERR_INVALID, "ln_modulate: row");
@@ -340,13 +447,73 @@ extern "C" int vsb_ln_modulate_affine(const vsb_bf16* x, vsb_bf16* out, const vs
   if (rows >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "ln_modulate: %lld rows", rows);
   int grid = grid_for(rows, 8);
   cudaStream_t st = (cudaStream_t)stream;
-  if (C <= 1280)
-    ln_modulate_kernel<5><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, (const bf16*)mod, x_mask, shift_row,
-                                                 scale_row, B, T, S, C, eps, rows, (const bf16*)gamma, (const bf16*)beta);
-  else
-    ln_modulate_kernel<8><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, (const bf16*)mod, x_mask, shift_row,
-                                                 scale_row, B, T, S, C, eps, rows, (const bf16*)gamma, (const bf16*)beta);
+  LnDspArgs none;
+  memset(&none, 0, sizeof(none));
+#define VSB_LN_LAUNCH(MV, DSP, ARGS)                                                                                   \
+  ln_modulate_kernel<MV, DSP><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, (const bf16*)mod, x_mask, shift_row,   \
+                                                     scale_row, B, T, S, C, eps, rows, (const bf16*)gamma,              \
+                                                     (const bf16*)beta, ARGS)
+  if (dsp) {
+    if (C <= 1280) VSB_LN_LAUNCH(5, true, *dsp); else VSB_LN_LAUNCH(8, true, *dsp);
+  } else {
+    if (C <= 1280) VSB_LN_LAUNCH(5, false, none); else VSB_LN_LAUNCH(8, false, none);
+  }
+#undef VSB_LN_LAUNCH
   return check_launch("ln_modulate");
+}
+
+extern "C" int vsb_ln_modulate_affine(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
+                                      const vsb_bf16* gamma, const vsb_bf16* beta, int shift_row, int scale_row, int B,
+                                      int T, int S, int C, float eps, void* stream) {
+  return ln_modulate_launch(x, out, mod, x_mask, gamma, beta, shift_row, scale_row, B, T, S, C, eps, nullptr, stream);
+}
+
+namespace vsb {
+int dsp_fill_peers(DspPeers* peers, void* const* host_peer_recv, void* const* host_peer_flags, int world, const char* what);
+}
+
+extern "C" int vsb_ln_modulate_dsp(const vsb_bf16* x, const vsb_bf16* mod, const uint8_t* x_mask, int shift_row,
+                                   int scale_row, int B, int T, int Sl, int C, float eps, void* const* host_peer_recv,
+                                   void* const* host_peer_flags, int rank, int world, int Sg, unsigned epoch,
+                                   void* stream) {
+  if (!host_peer_recv || !host_peer_flags || world < 1 || world > kMaxWorld || rank < 0 || rank >= world || Sg <= 0)
+    return fail(VSB_ERR_INVALID, "ln_modulate_dsp: bad args");
+  if ((long long)Sl * world < Sg) return fail(VSB_ERR_INVALID, "ln_modulate_dsp: Sl * world < Sg");
+  LnDspArgs a;
+  memset(&a, 0, sizeof(a));
+  int rc = dsp_fill_peers(&a.peers, host_peer_recv, host_peer_flags, world, "ln_modulate_dsp");
+  if (rc) return rc;
+  a.rank = rank;
+  a.world = world;
+  a.Sg = Sg;
+  a.epoch = epoch;
+  return ln_modulate_launch(x, nullptr, mod, x_mask, nullptr, nullptr, shift_row, scale_row, B, T, Sl, C, eps, &a, stream);
+}
+
+extern "C" int vsb_gate_residual_dsp(const vsb_bf16* x, void* const* host_peer_y, vsb_bf16* out, vsb_bf16* cache_out,
+                                     const vsb_bf16* mod, const uint8_t* x_mask, int gate_row, int B, int T, int Sl, int C,
+                                     int rank, int world, int Sg, void* stream) {
+  if (!x || !host_peer_y || !out || !mod || B <= 0 || T <= 0 || Sl <= 0 || C <= 0 || world < 1 || world > kMaxWorld ||
+      rank < 0 || rank >= world || Sg <= 0)
+    return fail(VSB_ERR_INVALID, "gate_residual_dsp: bad args");
+  if (C % 8 || C > 2048 || !aligned16(x) || !aligned16(out) || !aligned16(mod) || (cache_out && !aligned16(cache_out)))
+    return fail(VSB_ERR_UNSUPPORTED, "gate_residual_dsp: need C %% 8 == 0, C <= 2048 and 16B-aligned pointers");
+  long long rows = (long long)B * T * Sl;
+  if (rows >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "gate_residual_dsp: too many rows");
+  DspPeers peers;
+  int rc = dsp_fill_peers(&peers, host_peer_y, nullptr, world, "gate_residual_dsp");
+  if (rc) return rc;
+  const int grid = grid_for(rows, 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 1280)
+    gate_residual_dsp_kernel<5><<<grid, 256, 0, st>>>((const bf16*)x, peers, (bf16*)out, (bf16*)cache_out,
+                                                       (const bf16*)mod, x_mask, gate_row, B, T, Sl, C, rank, world, Sg,
+                                                       (unsigned)rows);
+  else
+    gate_residual_dsp_kernel<8><<<grid, 256, 0, st>>>((const bf16*)x, peers, (bf16*)out, (bf16*)cache_out,
+                                                       (const bf16*)mod, x_mask, gate_row, B, T, Sl, C, rank, world, Sg,
+                                                       (unsigned)rows);
+  return check_launch("gate_residual_dsp");
 }
 
 extern "C" int vsb_ln_modulate(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
@@ -391,17 +558,27 @@ extern "C" int vsb_residual_add(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* 
 
 extern "C" int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D,
                               float eps, void* stream) {
+  return vsb_qk_rmsnorm_rope(qkv, wq, wk, rows, H, D, eps, nullptr, nullptr, 1, 1, stream);
+}
+
+extern "C" int vsb_qk_rmsnorm_rope(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D,
+                                   float eps, const float* rope_cos, const float* rope_sin, int pos_div, int pos_mod,
+                                   void* stream) {
   if (!qkv || !wq || !wk || rows == 0 || H <= 0) return fail(VSB_ERR_INVALID, "qk_rmsnorm: bad args");
+  if ((rope_cos == nullptr) != (rope_sin == nullptr) || pos_div <= 0 || pos_mod <= 0)
+    return fail(VSB_ERR_INVALID, "qk_rmsnorm: rope tables / position map");
   if (!aligned16(qkv) || !aligned16(wq) || !aligned16(wk)) return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: alignment");
   long long groups = (long long)rows * 2 * H;
   if (groups >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: %lld head vectors", groups);
   cudaStream_t st = (cudaStream_t)stream;
   if (D == 72)
     qk_rmsnorm_kernel<72><<<grid_for(groups, 8 * 3 * 4), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)wk,
-                                                                     (long long)rows, H, eps);
+                                                                     (long long)rows, H, eps, rope_cos, rope_sin,
+                                                                     (unsigned)pos_div, (unsigned)pos_mod);
   else if (D == 64)
     qk_rmsnorm_kernel<64><<<grid_for(groups, 8 * 4 * 4), 256, 0, st>>>((bf16*)qkv, (const bf16*)wq, (const bf16*)wk,
-                                                                     (long long)rows, H, eps);
+                                                                     (long long)rows, H, eps, rope_cos, rope_sin,
+                                                                     (unsigned)pos_div, (unsigned)pos_mod);
   else
     return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: head_dim %d (72 or 64 only)", D);
   return check_launch("qk_rmsnorm");

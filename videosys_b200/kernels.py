@@ -1,6 +1,6 @@
 """Thin torch-tensor front end of the C-ABI (videosys_b200/_lib.py): pointer + shape marshalling only.
 
-Every function enqueues exactly one sm_100a kernel on the current CUDA stream.  CPU tensors are rejected:
+Every function enqueues exactly one sm_100a kernel on the current CUDA stream (capturable in a CUDA graph).  CPU tensors are rejected:
 there is no fallback path.
 """
 import ctypes as C
@@ -21,10 +21,11 @@ PROFILE_KINDS = None
 
 
 class _Timed:
-    __slots__ = ("kind", "work", "e0")
+    __slots__ = ("kind", "work", "e0", "cancelled")
 
     def __init__(self, kind, work):
         self.kind, self.work = kind, work
+        self.cancelled = False
 
     def __enter__(self):
         self.e0 = None
@@ -33,8 +34,12 @@ class _Timed:
             self.e0.record()
         return self
 
+    def cancel(self):
+        """Nothing was launched inside this block: record no entry."""
+        self.cancelled = True
+
     def __exit__(self, *exc):
-        if self.e0 is not None:
+        if self.e0 is not None and not self.cancelled:
             e1 = torch.cuda.Event(enable_timing=True)
             e1.record()
             PROFILE.append((self.kind, self.e0, e1, self.work))
@@ -77,6 +82,12 @@ def set_option(name: str, value: int) -> None:
 
 def launch_count() -> int:
     return int(_lib.load().vsb_launch_count())
+
+
+def tmap_cache_stats():
+    """(hits, misses) of the encoded-tensor-map cache; misses = host cuTensorMapEncodeTiled calls made."""
+    lib = _lib.load()
+    return int(lib.vsb_tmap_cache_stats(0)), int(lib.vsb_tmap_cache_stats(1))
 
 
 def modulation_table(table: torch.Tensor, t: torch.Tensor, t0: Optional[torch.Tensor]) -> torch.Tensor:
@@ -125,11 +136,13 @@ def residual_add(x, y, out=None):
     return out
 
 
-def qk_rmsnorm_(qkv, wq, wk, H, D, eps=1e-6):
-    lib, st = _prep(qkv, wq, wk)
+def qk_rmsnorm_(qkv, wq, wk, H, D, eps=1e-6, rope_cos=None, rope_sin=None, pos_div=1, pos_mod=1):
+    """In-place per-head RMSNorm of q and k; with rope tables also RoPE at position (row // pos_div) % pos_mod."""
+    lib, st = _prep(qkv, wq, wk, rope_cos, rope_sin)
     rows = qkv.numel() // (3 * H * D)
     with _Timed("qk_rmsnorm", 4 * rows * H * D * 2):
-        _lib.check(lib.vsb_qk_rmsnorm(_p(qkv), _p(wq), _p(wk), rows, H, D, eps, st), "qk_rmsnorm")
+        _lib.check(lib.vsb_qk_rmsnorm_rope(_p(qkv), _p(wq), _p(wk), rows, H, D, eps, _p(rope_cos), _p(rope_sin),
+                                           int(pos_div), int(pos_mod), st), "qk_rmsnorm")
     return qkv
 
 
@@ -178,20 +191,22 @@ def gemm_bias_residual(a, w, bias, resid, mod=None, x_mask_u8=None, gate_row: in
     M = a.numel() // K
     N = w.shape[0]
     out = resid if out is None else out
-    with _Timed("gemm", 2 * M * N * K):
+    with _Timed("gemm", 2 * M * N * K) as tm:
         rc = lib.vsb_gemm_bias_residual(_p(a), _p(w), _p(bias), _p(resid), _p(out), _p(mod), _p(x_mask_u8), gate_row, M,
                                         N, K, B, T, S, st)
+        if rc == 1:
+            tm.cancel()
     if rc == 1:
-        if PROFILE is not None:
-            PROFILE.pop()
         return None
     _lib.check(rc, "gemm_bias_residual")
     return out
 
 
 def attn_flash(q, k, v, nb, nq, nk, H, D, q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, scale,
-               kv_lens: Optional[Sequence[int]] = None, out=None):
-    """q/k/v: tensors whose data_ptr() is the first element of the strided view (may be slices of one buffer)."""
+               kv_lens: Optional[Sequence[int]] = None, out=None, out_row_stride=None, out_batch_stride=None):
+    """q/k/v: tensors whose data_ptr() is the first element of the strided view (may be slices of one buffer).
+    out_row_stride / out_batch_stride (elements): strided output view starting at out.data_ptr() (default: contiguous
+    [nb, nq, H*D])."""
     lib = _lib.load()
     if not q.is_cuda:
         raise _lib.VsbError("vsb200 kernels need CUDA tensors (no CPU fallback)")
@@ -203,8 +218,10 @@ def attn_flash(q, k, v, nb, nq, nk, H, D, q_row_stride, q_batch_stride, kv_row_s
         lens = (C.c_int * len(kv_lens))(*[int(v_) for v_ in kv_lens])
     with _Timed("attn_flash", 4 * nb * H * nq * nk * D):
         _lib.check(
-            lib.vsb_attn_flash(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), nb, nq, nk, H, D,
-                               q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride, lens, scale, st),
+            lib.vsb_attn_flash_strided(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), nb, nq, nk, H, D,
+                                       q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride,
+                                       H * D if out_row_stride is None else out_row_stride,
+                                       nq * H * D if out_batch_stride is None else out_batch_stride, lens, scale, st),
             "attn_flash",
         )
     return out

@@ -191,6 +191,12 @@ class STDiT3(nn.Module):
         self._dsp: Optional[comm.DspP2P] = None
         self._pos_cache = {}
         self._rope_cache = {}
+        self._text_cache = None  # per (y, mask): caption MLP output, key layout, per-block kv_linear outputs
+        self._hw_cache = None
+        self._final_pad = None
+        # DSP switch fused into its producer / consumer (ln_modulate stores to the peers, gate+residual pulls from
+        # them); VSB_DSP_FUSED=0 selects the standalone scatter kernel (vsb_dsp_scatter)
+        self._fuse_dsp = os.environ.get("VSB_DSP_FUSED", "1") == "1"
         # gate/residual inside the proj / fc2 GEMM epilogue (vsb_gemm_bias_residual).  Measured on B200 (720p): the
         # per-thread residual reads put the epilogue on the critical path (+41 ms GEMM vs -28 ms of elementwise
         # passes), so the separate one-pass kernels stay the default until the residual tile is TMA-prefetched.
@@ -260,8 +266,10 @@ class STDiT3(nn.Module):
         return emb.mlp(_sinusoid(v).to(dtype))
 
     def encode_text(self, y, mask=None):
+        """Reference STDiT3.encode_text (:526-537): caption MLP, then the mask-compacted [1, sum(lens), C] layout."""
         p = self.y_embedder.y_proj
-        y = F.linear(F.gelu(F.linear(y, p.fc1.weight, p.fc1.bias), approximate="tanh"), p.fc2.weight, p.fc2.bias)
+        y = kernels.gemm_bias_act(kernels.gemm_bias_act(y.contiguous(), p.fc1.weight, p.fc1.bias, act=1), p.fc2.weight,
+                                  p.fc2.bias)
         if mask is not None:
             if mask.shape[0] != y.shape[0]:
                 mask = mask.repeat(y.shape[0] // mask.shape[0], 1)
@@ -272,6 +280,69 @@ class STDiT3(nn.Module):
             y_lens = [y.shape[2]] * y.shape[0]
             y = y.squeeze(1).view(1, -1, self.hidden_size)
         return y, y_lens
+
+    def _text_state(self, y, mask, B):
+        """Timestep-independent text side of the step, computed once per (y, mask) and reused by every denoising step:
+        the caption MLP (the reference recomputes it every step, :590), the key layout of the cross-attention and each
+        block's kv_linear output.  Returns a dict with y_tok [B*Lv, C], Lv, kv_lens (None = all keys), kv cache.
+
+        Key addressing follows the reference's two implementations:
+          * enable_flash_attn=False (default; torch_impl, attentions.py:259-270): the compacted tokens are VIEWED as
+            [B, sum(lens)/B] and sample i attends the first min(len_i, sum/B) rows of its slice -- also when the lengths
+            differ (the view then crosses sample boundaries; kept bit-for-bit, it is what the reference computes);
+          * enable_flash_attn=True (flash_attn_varlen_func with cu_seqlens = cumsum(lens), :240-257): sample i attends
+            exactly its own len_i tokens -- here the padded [B, L] layout with per-sample key counts.
+        """
+        st = self._text_cache
+        key = (y._version, None if mask is None or not torch.is_tensor(mask) else mask._version, B)
+        if st is not None and st["y"] is y and st["mask"] is mask and st["key"] == key:
+            return st
+        C = self.hidden_size
+        if self.config.skip_y_embedder:
+            y_lens = mask.long().tolist() if isinstance(mask, torch.Tensor) else list(mask)
+            y_tok = y.reshape(-1, C).contiguous()
+            Lv = y_tok.shape[0] // B
+            kv_lens = [min(int(m), Lv) for m in y_lens]
+        elif getattr(self.config, "enable_flash_attn", False) and mask is not None:
+            p = self.y_embedder.y_proj
+            ye = kernels.gemm_bias_act(kernels.gemm_bias_act(y.contiguous(), p.fc1.weight, p.fc1.bias, act=1),
+                                       p.fc2.weight, p.fc2.bias).squeeze(1)  # [B, L, C]
+            m = mask
+            if m.shape[0] != ye.shape[0]:
+                m = m.repeat(ye.shape[0] // m.shape[0], 1)
+            m = m.reshape(ye.shape[0], -1) != 0
+            order = torch.argsort((~m).to(torch.uint8), dim=1, stable=True)  # attendable tokens first, order kept
+            y_tok = torch.gather(ye, 1, order[:, :, None].expand(-1, -1, C)).reshape(-1, C).contiguous()
+            Lv = ye.shape[1]
+            kv_lens = [int(v) for v in m.sum(dim=1).tolist()]
+        else:
+            y_c, y_lens = self.encode_text(y, mask)
+            y_tok = y_c.reshape(-1, C).contiguous()
+            Lv = y_tok.shape[0] // B
+            kv_lens = [min(int(m), Lv) for m in y_lens]
+        if Lv < 1 or min(kv_lens) < 1:
+            raise RuntimeError("cross attention needs at least one text token per sample")
+        if all(m == Lv for m in kv_lens):
+            kv_lens = None
+        self._text_cache = dict(y=y, mask=mask, key=key, y_tok=y_tok, Lv=Lv, kv_lens=kv_lens, kv={})
+        return self._text_cache
+
+    # ---- PAB plan: the per-step skip decisions, taken on the host before anything is launched ------------------------
+    def pab_plan(self, ts_int):
+        """Evaluates every block's broadcast gate for this step (reference :188-190,232 -> pab_mgr.py:54-91) in
+        execution order and ADVANCES the counters.  Returns a tuple of (reuse_attn, reuse_cross) per block, or None when
+        PAB is off.  Separating the integer decisions from the launches is what lets a whole step replay as a CUDA
+        graph: the plan is the graph's key (core/graph_step.py)."""
+        if not pab_mgr.enable_pab():
+            return None
+        plan = []
+        for d in range(self.depth):
+            for blk in (self.spatial_blocks[d], self.temporal_blocks[d]):
+                gate = pab_mgr.if_broadcast_temporal if blk.temporal else pab_mgr.if_broadcast_spatial
+                ra, blk.attn_count = gate(ts_int, blk.attn_count)
+                rc, blk.cross_count = pab_mgr.if_broadcast_cross(ts_int, blk.cross_count)
+                plan.append((bool(ra), bool(rc)))
+        return tuple(plan)
 
     # ---- one block on the kernels ----------------------------------------------------------------------------
     def _switch(self, x4: torch.Tensor, T: int, S: int, to_spatial_shard: bool) -> torch.Tensor:
@@ -287,38 +358,60 @@ class STDiT3(nn.Module):
                                            scatter_pad=comm.get_pad("temporal"), gather_pad=comm.get_pad("spatial"))
         return out.contiguous()  # the narrow() that drops the padding leaves a strided view
 
-    def _run_block(self, blk: STDiT3Block, x, y_tok, kv_lens, t_mlp, t0_mlp, mask_u8, B, T, S, Tg, Sg, ts_int):
-        """x: [B, T*S, C] resident layout (T full, S local); Tg/Sg are the global extents (== T, S when sp == 1)."""
+    def _temporal_attention(self, qkv, wq, wk, B, T, S, H, D, device):
+        """Temporal self-attention on the token-major [B, T, S] activation (no rearrange): sequences of T frames per
+        (sample, patch).  T < 30: native_attention semantics in one kernel (attentions.py:95-97,111-120).  T >= 30: the
+        reference takes F.scaled_dot_product_attention (attentions.py:98-100) -> RMSNorm + RoPE pre-pass, then the flash
+        kernel over strided views (batch = patch, row = frame), one launch per sample."""
+        K = kernels
+        C = H * D
+        cos, sin = self._rope_tables(T, device)
+        if T < 30:
+            return K.attn_short(qkv.view(-1, 3, H, D), wq, wk, cos, sin, B, S, T * S, 1, S, T, H, D, D**-0.5)
+        if S > 65535:
+            raise RuntimeError("temporal flash attention: more than 65535 patches per frame")
+        K.qk_rmsnorm_(qkv, wq, wk, H, D, rope_cos=cos, rope_sin=sin, pos_div=S, pos_mod=T)
+        o = torch.empty(B * T * S, C, dtype=qkv.dtype, device=device)
+        q3 = qkv.view(B, T * S, 3, C)
+        for b in range(B):
+            K.attn_flash(q3[b, :, 0], q3[b, :, 1], q3[b, :, 2], S, T, T, H, D, S * 3 * C, 3 * C, S * 3 * C, 3 * C, D**-0.5,
+                         out=o[b * T * S:], out_row_stride=S * C, out_batch_stride=C)
+        return o
+
+    def _run_block(self, blk: STDiT3Block, x, text, t_mlp, t0_mlp, mask_u8, B, T, S, Tg, Sg, plan=(False, False)):
+        """x: [B, T*S, C] resident layout (T full, S local); Tg/Sg are the global extents (== T, S when sp == 1).
+        text: the dict of _text_state; plan: (reuse_attn, reuse_cross) of this block for this step."""
         K = kernels
         C, H = self.hidden_size, self.num_heads
         D = C // H
         sp = self.parallel_manager.sp_size if self.parallel_manager is not None else 1
         mod = K.modulation_table(blk.scale_shift_table, t_mlp, t0_mlp)
         pab_on = pab_mgr.enable_pab()
+        reuse_attn, reuse_cross = plan
+        fused_dsp = self._dsp is not None and self._fuse_dsp and not blk.temporal and sp > 1
 
         # ---- self attention ----
-        reuse = False
-        if pab_on:
-            gate = pab_mgr.if_broadcast_temporal if blk.temporal else pab_mgr.if_broadcast_spatial
-            reuse, blk.attn_count = gate(ts_int, blk.attn_count)
-        if reuse:
+        if reuse_attn:
             K.residual_add(x, blk.last_attn, out=x)
         else:
-            xm = K.ln_modulate(x, mod, mask_u8, 0, 1, B, T, S)
             a = blk.attn
             wq = a.q_norm.weight if hasattr(a.q_norm, "weight") else None
             wk = a.k_norm.weight if hasattr(a.k_norm, "weight") else None
             if wq is None:
                 raise RuntimeError("vsb200 STDiT3 kernels implement qk_norm=True (the OpenSora v1.2 configuration)")
             if blk.temporal:
+                xm = K.ln_modulate(x, mod, mask_u8, 0, 1, B, T, S)
                 qkv = K.gemm_bias_act(xm, a.qkv.weight, a.qkv.bias)
-                cos, sin = self._rope_tables(T, x.device)
-                if T >= 30:
-                    raise RuntimeError("temporal sequences >= 30 frames are not supported by vsb_attn_short")
-                o = K.attn_short(qkv.view(-1, 3, H, D), wq, wk, cos, sin, B, S, T * S, 1, S, T, H, D, D**-0.5)
+                o = self._temporal_attention(qkv, wq, wk, B, T, S, H, D, x.device)
             else:
                 Ba = B
-                if sp > 1:  # S-sharded -> T-sharded: attention needs every patch of a frame
+                if fused_dsp:
+                    # the modulate kernel's stores ARE the S-shard -> T-shard switch (peer stores over NVLink)
+                    xm = self._dsp.ln_modulate_push(x, mod, mask_u8, 0, 1, B, T, S, Sg)
+                    Ba, Ta, Sa = 1, xm.shape[1], xm.shape[2]
+                    xm = xm.reshape(1, Ta * Sa, C)
+                elif sp > 1:  # S-sharded -> T-sharded: attention needs every patch of a frame
+                    xm = K.ln_modulate(x, mod, mask_u8, 0, 1, B, T, S)
                     if self._dsp is not None:
                         # P2P path: scatter the B*T (batch, frame) sequences, not the T frames of each sample.
                         # Spatial attention is independent per (b, t), so the result is identical, and 2*20 = 40
@@ -331,6 +424,7 @@ class STDiT3(nn.Module):
                     Ta, Sa = xm.shape[1], xm.shape[2]
                     xm = xm.reshape(Ba, Ta * Sa, C)
                 else:
+                    xm = K.ln_modulate(x, mod, mask_u8, 0, 1, B, T, S)
                     Ta, Sa = T, S
                 qkv = K.gemm_bias_act(xm, a.qkv.weight, a.qkv.bias)
                 if Sa >= 30:
@@ -340,38 +434,45 @@ class STDiT3(nn.Module):
                                      Sa * 3 * C, D**-0.5)
                 else:
                     o = K.attn_short(qkv.view(-1, 3, H, D), wq, wk, None, None, Ba * Ta, 1, Sa, 0, 1, Sa, H, D, D**-0.5)
+            cache = None
+            if pab_on:
+                if blk.last_attn is None or blk.last_attn.shape != x.shape:
+                    blk.last_attn = torch.empty_like(x)
+                cache = blk.last_attn
             fused = None
             if self._fuse_epilogue and not pab_on and (blk.temporal or sp == 1):
                 # gate + select + residual in the proj GEMM's epilogue (no PAB cache to fill, no reshard in between)
                 fused = K.gemm_bias_residual(o.view(-1, C), a.proj.weight, a.proj.bias, x, mod, mask_u8, 2, B, T, S)
-            if fused is None:
+            if fused is not None:
+                pass
+            elif fused_dsp:
+                # the branch stays T-sharded in this rank's own window; every rank PULLS the rows of its S-shard in the
+                # gate + residual kernel (peer loads over NVLink): the switch back costs no kernel of its own
+                K.gemm_bias_act(o.view(-1, C), a.proj.weight, a.proj.bias, out=self._dsp.branch_window(B, T, Sg, C))
+                self._dsp.gate_residual_pull(x, mod, mask_u8, 2, B, T, S, Sg, out=x, cache_out=cache)
+            else:
                 y = K.gemm_bias_act(o.view(-1, C), a.proj.weight, a.proj.bias)
                 if not blk.temporal and sp > 1:
                     if self._dsp is not None:
                         y = self._switch(y.view(1, Ta, Sa, C), B * Tg, Sg, to_spatial_shard=True)
                     else:
                         y = self._switch(y.view(B, Ta, Sa, C), Tg, Sg, to_spatial_shard=True)
-                cache = None
-                if pab_on:
-                    if blk.last_attn is None or blk.last_attn.shape != x.shape:
-                        blk.last_attn = torch.empty_like(x)
-                    cache = blk.last_attn
                 K.gate_residual(x, y.reshape(x.shape), mod, mask_u8, 2, B, T, S, out=x, cache_out=cache)
 
         # ---- cross attention ----
-        reuse = False
-        if pab_on:
-            reuse, blk.cross_count = pab_mgr.if_broadcast_cross(ts_int, blk.cross_count)
-        if reuse:
+        if reuse_cross:
             K.residual_add(x, blk.last_cross, out=x)
         else:
             c = blk.cross_attn
             q = K.gemm_bias_act(x, c.q_linear.weight, c.q_linear.bias)
-            kv = K.gemm_bias_act(y_tok, c.kv_linear.weight, c.kv_linear.bias)
-            Lv = kv.shape[-2] // B
+            kv = text["kv"].get(id(blk))
+            if kv is None:  # timestep-independent: one kv_linear per block per prompt, not per step
+                kv = K.gemm_bias_act(text["y_tok"], c.kv_linear.weight, c.kv_linear.bias)
+                text["kv"][id(blk)] = kv
+            Lv = text["Lv"]
             kv2 = kv.view(-1, 2, C)
             o = K.attn_flash(q, kv2[:, 0], kv2[:, 1], B, T * S, Lv, H, D, C, T * S * C, 2 * C, Lv * 2 * C, D**-0.5,
-                             kv_lens=kv_lens)
+                             kv_lens=text["kv_lens"])
             fused = None
             if self._fuse_epilogue and not pab_on:
                 fused = K.gemm_bias_residual(o.view(-1, C), c.proj.weight, c.proj.bias, x)  # x += proj(o) in the epilogue
@@ -394,6 +495,16 @@ class STDiT3(nn.Module):
         return x
 
     # ---- STDiT3.forward --------------------------------------------------------------------------------------
+    def _resolution_sq(self, height, width) -> float:
+        """sqrt(height * width) of the first sample as a host float (reference :574: a .item() sync per forward);
+        cached per (height, width) tensor pair -- the pipelines pass the same two tensors at every step."""
+        c = self._hw_cache
+        if c is not None and c[0] is height and c[1] is width and c[2] == (height._version, width._version):
+            return c[3]
+        v = (height[0].item() * width[0].item()) ** 0.5
+        self._hw_cache = (height, width, (height._version, width._version), v)
+        return v
+
     @torch.no_grad()
     def forward(self, x, timestep, y, all_timesteps=None, mask=None, x_mask=None, fps=None, height=None, width=None,
                 **kwargs):
@@ -410,14 +521,21 @@ class STDiT3(nn.Module):
         T, Hn, Wn = self.get_dynamic_size(x)
         B = x.size(0)
         C = self.hidden_size
+        if sp > 1 and Tx == 1:
+            raise NotImplementedError("image mode (one frame) under sequence parallelism: the reference scatters the "
+                                      "batch instead (:292-296); run images on one GPU")
         x = x.to(dtype)
         timestep = timestep.to(dtype)
-        y = y.to(dtype)
+        y = y if y.dtype == dtype else y.to(dtype)
+
+        # PAB decisions first (host integers); a caller that replays CUDA graphs passes the plan it keyed the graph on
+        plan = kwargs.get("pab_plan")
+        if plan is None and pab_mgr.enable_pab():
+            plan = self.pab_plan(int(timestep[0]))  # the reference's D2H sync, once per step instead of per block
 
         S = Hn * Wn
         base_size = round(S**0.5)
-        resolution_sq = (height[0].item() * width[0].item()) ** 0.5
-        pos = self._pos_embed(Hn, Wn, resolution_sq / self.input_sq_size, base_size, dtype, x.device)
+        pos = self._pos_embed(Hn, Wn, self._resolution_sq(height, width) / self.input_sq_size, base_size, dtype, x.device)
 
         t = self._embed(self.t_embedder, timestep, dtype)
         f = fps.unsqueeze(1)
@@ -425,26 +543,16 @@ class STDiT3(nn.Module):
             f = f.repeat(B // f.shape[0], 1)
         fps_e = self._embed(self.fps_embedder, f.reshape(-1), dtype).reshape(B, -1)
         t = t + fps_e
-        t_mlp = self.t_block(t)
+        tb = self.t_block[1]
+        t_mlp = kernels.gemm_bias_act(F.silu(t), tb.weight, tb.bias)
         t0 = t0_mlp = None
         mask_u8 = None
         if x_mask is not None:
             t0 = self._embed(self.t_embedder, torch.zeros_like(timestep), dtype) + fps_e
-            t0_mlp = self.t_block(t0)
+            t0_mlp = kernels.gemm_bias_act(F.silu(t0), tb.weight, tb.bias)
             mask_u8 = x_mask.to(torch.uint8).contiguous()
 
-        if self.config.skip_y_embedder:
-            y_lens = mask.long().tolist() if isinstance(mask, torch.Tensor) else mask
-            y_tok = y
-        else:
-            y_tok, y_lens = self.encode_text(y, mask)
-        y_tok = y_tok.reshape(-1, C).contiguous()
-        Lv = y_tok.shape[0] // B
-        kv_lens = [min(int(m), Lv) for m in y_lens]
-        if min(kv_lens) < 1:
-            raise RuntimeError("cross attention needs at least one text token per sample")
-        if all(m == Lv for m in kv_lens):
-            kv_lens = None
+        text = self._text_state(y, mask, B)
 
         # patch embed (right/bottom zero pad to the patch grid, then a strided conv)
         p = self.patch_size
@@ -467,20 +575,23 @@ class STDiT3(nn.Module):
             self._ensure_dsp(B, T, S, C, x.device)
         h = h.reshape(B, T * S, C).contiguous()
 
-        ts_int = int(timestep[0]) if pab_mgr.enable_pab() else None
         depth = kwargs.get("valid_depth", self.depth)
+        none = (False, False)
         for d in range(depth):
-            h = self._run_block(self.spatial_blocks[d], h, y_tok, kv_lens, t_mlp, t0_mlp, mask_u8, B, T, S, Tg, Sg, ts_int)
-            h = self._run_block(self.temporal_blocks[d], h, y_tok, kv_lens, t_mlp, t0_mlp, mask_u8, B, T, S, Tg, Sg, ts_int)
+            ps, pt = (plan[2 * d], plan[2 * d + 1]) if plan is not None else (none, none)
+            h = self._run_block(self.spatial_blocks[d], h, text, t_mlp, t0_mlp, mask_u8, B, T, S, Tg, Sg, ps)
+            h = self._run_block(self.temporal_blocks[d], h, text, t_mlp, t0_mlp, mask_u8, B, T, S, Tg, Sg, pt)
         if kwargs.get("return_tokens", False):
             return h
 
+        # final layer on the LOCAL S-shard (row-wise ops), then gather its 36x narrower output (reference gathers the
+        # C-wide activation first, :615-621: same values, 1/36 of the bytes, and no rank repeats the full-size tail)
+        out = self._final_layer(h, t, mask_u8, t0, B, T, S)
         if sp > 1:
-            h = comm.gather_sequence(h.reshape(B, T, S, C), pm.sp_group, dim=2, grad_scale="up", pad=comm.get_pad("spatial"))
-            S = h.shape[2]
-            h = h.reshape(B, T * S, C)
-
-        out = self._final_layer(h, t, x_mask, t0, B, T, S)
+            out = comm.gather_sequence(out.reshape(B, T, S, -1), pm.sp_group, dim=2, grad_scale="up",
+                                       pad=comm.get_pad("spatial"))
+            S = out.shape[2]
+            out = out.reshape(B, T * S, -1)
         out = self.unpatchify(out, T, Hn, Wn, Tx, Hx, Wx)
         return out.to(torch.float32)
 
@@ -494,19 +605,34 @@ class STDiT3(nn.Module):
         elems = max(B * T * Sl, Tl * Sl * w) * C
         self._dsp = comm.DspP2P(pm.sp_group, elems, device)
 
-    def _final_layer(self, x, t, x_mask, t0, B, T, S):
+    def _final_layer(self, x, t, mask_u8, t0, B, T, S):
         """T2IFinalLayer (reference :75-87), including its quirk: the t0 branch normalises the already
-        t-modulated tensor because line :81 rebinds x."""
+        t-modulated tensor because line :81 rebinds x.  LN + modulate run on vsb_ln_modulate (table rows 0 = shift,
+        1 = scale), the 1152 -> 32 projection on the tcgen05 GEMM."""
         fl = self.final_layer
         C = self.hidden_size
-        ln = lambda v: F.layer_norm(v, (C,), None, None, 1e-6)  # noqa: E731
-        shift, scale = (fl.scale_shift_table[None] + t[:, None]).chunk(2, dim=1)
-        out = ln(x) * (1 + scale) + shift
-        if x_mask is not None:
-            shift0, scale0 = (fl.scale_shift_table[None] + t0[:, None]).chunk(2, dim=1)
-            out0 = ln(out) * (1 + scale0) + shift0
-            out = torch.where(x_mask[:, :, None, None], out.view(B, T, S, C), out0.view(B, T, S, C)).view(B, T * S, C)
-        return fl.linear(out)
+        K = kernels
+        tab = fl.scale_shift_table
+        tab6 = torch.cat([tab, tab.new_zeros(4, C)], 0)  # the modulate kernel addresses [2, B, 6, C] tables
+        z4 = t.new_zeros(B, 4 * C)
+        mod = K.modulation_table(tab6, torch.cat([t, t, z4], 1).contiguous(),
+                                 None if t0 is None else torch.cat([t0, t0, z4], 1).contiguous())
+        out = K.ln_modulate(x, mod[:1].contiguous(), None, 0, 1, B, T, S)  # every frame with the t rows
+        if mask_u8 is not None:
+            out0 = K.ln_modulate(out, mod[1:].contiguous(), None, 0, 1, B, T, S)
+            out = torch.where(mask_u8.bool()[:, :, None, None], out.view(B, T, S, C), out0.view(B, T, S, C)).view(B, T * S, C)
+        # 32 output features: run the GEMM's narrowest (64-wide) tile on zero-padded weights, keep the first 32 columns
+        w, bias = fl.linear.weight, fl.linear.bias
+        n_out = w.shape[0]
+        if n_out % 64:
+            c = self._final_pad
+            if c is None or c[0] != (w._version, bias._version, w.data_ptr()):
+                n_pad = -(-n_out // 64) * 64
+                wp, bp = w.new_zeros(n_pad, C), bias.new_zeros(n_pad)
+                wp[:n_out], bp[:n_out] = w, bias
+                c = self._final_pad = ((w._version, bias._version, w.data_ptr()), wp, bp)
+            return K.gemm_bias_act(out.contiguous(), c[1], c[2])[..., :n_out]
+        return K.gemm_bias_act(out.contiguous(), w, bias)
 
     def unpatchify(self, x, N_t, N_h, N_w, R_t, R_h, R_w):
         B = x.shape[0]

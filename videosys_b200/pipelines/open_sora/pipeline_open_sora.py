@@ -122,6 +122,29 @@ class OpenSoraPipeline:
             dp_size = world // sp_size
         self.transformer.enable_parallel(dp_size, sp_size, enable_cp)
 
+    def _set_seed(self, seed: int):
+        """Reference set_seed (utils/utils.py:19-34): seed == -1 draws one, rank 0's value is BROADCAST so that every rank
+        of a sequence-parallel group denoises the same latent (each rank draws z and the per-step noise itself), the dp
+        rank is added, then python / numpy / torch generators are seeded."""
+        import random
+
+        import numpy as np
+        import torch.distributed as dist
+
+        if seed is None or seed == -1:
+            seed = random.randint(0, 1000000)
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            t = torch.tensor([seed], dtype=torch.int64, device=self._device)
+            dist.broadcast(t, src=0)
+            seed = int(t.item())
+        pm = self.transformer.parallel_manager
+        seed = int(seed) + (pm.dp_rank if pm is not None else 0)
+        random.seed(seed)
+        np.random.seed(seed)
+        torch.manual_seed(seed)
+        torch.cuda.manual_seed(seed)
+        return seed
+
     def _encode_text(self, prompt: str, negative: str = ""):
         cfg = self.transformer.config
         if self._config.text_encoder_fn is not None:
@@ -141,13 +164,16 @@ class OpenSoraPipeline:
         if loop != 1 or refs or ms:
             raise NotImplementedError("reference conditioning / looping are outside the hot-path scope")
         dev, dtype = self._device, torch.bfloat16
-        fps = 24
         image_size = get_image_size(resolution, aspect_ratio)
         nf = get_num_frames(num_frames)
+        fps = 24 if nf > 1 else 120  # IMG_FPS for single images (reference prepare_multi_resolution_info)
+        Tl_chk = get_latent_size(nf, *image_size)[0]
+        if Tl_chk == 1 and self.transformer.parallel_manager is not None and self.transformer.parallel_manager.sp_size > 1:
+            raise NotImplementedError("single-image generation under sequence parallelism (the reference scatters the "
+                                      "batch for images, open_sora_transformer_3d.py:292-296): use num_gpus=1")
         update_steps(self._config.num_sampling_steps)
         self.transformer.reset_pab_state()
-        if seed >= 0:
-            torch.manual_seed(seed)
+        self._set_seed(seed)
         y, mask, y_null = self._encode_text(prompt, negative_prompt)
         Tl, Hl, Wl = get_latent_size(nf, *image_size)
         z = torch.randn(1, self.transformer.in_channels, Tl, Hl, Wl, device=dev, dtype=dtype)

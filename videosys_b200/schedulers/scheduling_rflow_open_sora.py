@@ -2,7 +2,9 @@
 videosys/schedulers/scheduling_rflow_open_sora.py: timestep_transform :47-70, RFLOW.sample :188-257).
 
 Inference only (no training losses).  The loop body is what bench.py times as one "step": CFG batch of 2 through
-STDiT3.forward, guidance combine, Euler update.
+STDiT3.forward, guidance combine, Euler update.  With ``use_cuda_graph`` (default on CUDA) the step runs as a replayed
+CUDA graph keyed by the PAB skip pattern (core/graph_step.py): the per-step bookkeeping that stays on the host is the
+integer timestep list, the mask update and the graph lookup.
 """
 from typing import Callable, List, Optional
 
@@ -54,8 +56,16 @@ class RFLOW:
         v = uncond + guidance_scale * (cond - uncond)
         return z + v * dt[:, None, None, None, None]
 
-    def sample(self, model, z, model_args, y_null, device, mask=None, guidance_scale=None, progress=True, verbose=False):
+    def sample(self, model, z, model_args, y_null, device, mask=None, guidance_scale=None, progress=True, verbose=False,
+               use_cuda_graph=None):
         guidance_scale = self.cfg_scale if guidance_scale is None else guidance_scale
+        if use_cuda_graph is None:
+            use_cuda_graph = z.is_cuda
+        stepper = None
+        if use_cuda_graph:
+            from ..core.graph_step import StepGraph
+
+            stepper = StepGraph(model, guidance_scale)
         model_args = dict(model_args)
         model_args["y"] = torch.cat([model_args["y"], y_null], 0)
         timesteps = self.prepare_timesteps(z.shape[0], device, model_args)
@@ -76,7 +86,10 @@ class RFLOW:
                 z = torch.where((mask_t_upper & ~noise_added)[:, None, :, None, None], x_noise, x0)
                 noise_added = mask_t_upper
             dt = (timesteps[i] - timesteps[i + 1] if i < len(timesteps) - 1 else timesteps[i]) / self.num_timesteps
-            z = self.step(model, z, t, dt, fwd_args, guidance_scale)
+            if stepper is not None:
+                z = stepper.step(z, t, dt, fwd_args, ts_int=model_args["all_timesteps"][i])
+            else:
+                z = self.step(model, z, t, dt, fwd_args, guidance_scale)
             if mask is not None:
                 z = torch.where(mask_t_upper[:, None, :, None, None], z, x0)
         return z
