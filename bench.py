@@ -9,9 +9,15 @@ reference): CFG batch of 2 through STDiT3.forward (28 spatial + 28 temporal bloc
 on synthetic latents and random-init weights of the named architecture.  metric = output frames / (sampling steps x
 seconds per step).  N > 1 shards the sequence with DSP (strong scaling: the same video, split over N GPUs).
 
-JSON line: value (inputs resident in HBM), e2e (host buffers, H2D/D2H inside the timed region), roofline (the GEMM
-kernel, timed live with CUDA events on the launching stream during the timed region), cpu_baseline (the oracle port on
-the host cores, bounded sample), clocks, gpu_launches.  --impl reference times the reference's CPU path (oracle port).
+A step runs as a replayed CUDA graph (videosys_b200/core/graph_step.py; --no-graph launches every kernel from the host).
+
+JSON line: value (inputs resident in HBM), e2e (host buffers, H2D/D2H inside the timed region; timed interleaved with
+the resident arm), roofline (the GEMM kernel: CUDA-event pairs around every GEMM launch of an eager pass of the same
+steps, on the launching stream -- events cannot be read back from inside a replayed graph), kernels (the same for the
+other kernels), cpu_baseline (the oracle port on the host cores, bounded sample, 3 repetitions), gpu_baseline (N = 1:
+the reference's eager path = the oracle restatement on torch/cuBLAS/SDPA library kernels on the same GPU), dsp_parity
+(N > 1: sharded == unsharded, bit for bit, before anything is timed), clocks, gpu_launches.
+--impl reference times the reference's CPU path (oracle port).
 """
 import argparse
 import json
@@ -76,7 +82,7 @@ def kernel_fractions(shares, peaks, nvlink_gbs=770.0):
         v = dict(v)
         if v.get("unit") == "TFLOP/s":
             v["frac_of_peak"], v["peak"] = v["achieved"] / peaks["tflops"], f"{peaks['tflops']:.0f} TFLOP/s sustained bf16 GEMM"
-        elif k == "dsp_switch":
+        elif k.startswith("dsp_"):
             v["frac_of_peak"], v["peak"] = v["achieved"] / nvlink_gbs, f"{nvlink_gbs:.0f} GB/s peer copy"
         else:
             v["frac_of_peak"], v["peak"] = v["achieved"] / peaks["hbm"], f"{peaks['hbm']:.0f} GB/s HBM copy"
@@ -120,10 +126,15 @@ class ClockSampler(threading.Thread):
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / cpu_baseline: the oracle port (CPU restatement of the reference's eager path) on the host cores
 # ------------------------------------------------------------------------------------------------------------
-def cpu_reference(workload, budget_s=8.0, reps=1):
-    """Times a bounded sample: ONE (spatial + temporal) block pair of the 28, on T_s of the T latent frames
-    (CFG batch 2, full S patches, full text length), bf16 eager, all host threads.  Returns seconds per FULL step
-    extrapolated x28 x T/T_s, and a description of the sample."""
+def cpu_reference(workload):
+    """The bounded CPU sample of one denoising step: ONE of the 28 (spatial, temporal) block pairs of the oracle port, bf16
+    eager, all host threads, each block on the sequences it really sees --
+      spatial block : CFG batch 2 x ONE latent frame x all S patches (spatial attention over S keys; every frame costs
+                      the same, so x T),
+      temporal block: CFG batch 2 x all T frames x S_t of the S patches (temporal attention over the real T-frame
+                      sequences with RoPE, i.e. native_attention for T < 30; every patch costs the same, so x S / S_t),
+    with the full text length in both.  Returns (sample(), describe, cores): sample() runs the pair once and returns
+    the seconds of a FULL step extrapolated as 28 x (t_spatial x T + t_temporal x S / S_t)."""
     from oracle import stdit3_oracle as O
 
     torch.set_num_threads(os.cpu_count())
@@ -149,28 +160,26 @@ def cpu_reference(workload, budget_s=8.0, reps=1):
         sd[p + "attn.q_norm.weight"] = torch.ones(C // H, dtype=bf)
         sd[p + "attn.k_norm.weight"] = torch.ones(C // H, dtype=bf)
     freqs = O.rope_freqs(C // H).to(bf)
-    L = W["L"]
+    L, B = W["L"], 2
+    St = max(1, S // T)  # patches of the temporal sample: as many tokens as the spatial sample has
+    y = rnd(1, B * L, C, std=1.0)
+    t, t0 = rnd(B, 6 * C, std=0.5), rnd(B, 6 * C, std=0.5)
+    xs, xt = rnd(B, 1 * S, C, std=1.0), rnd(B, T * St, C, std=1.0)
 
-    def run(Ts):
-        B = 2
-        x = rnd(B, Ts * S, C, std=1.0)
-        y = rnd(1, B * L, C, std=1.0)
-        t, t0 = rnd(B, 6 * C, std=0.5), rnd(B, 6 * C, std=0.5)
-        xm = torch.ones(B, Ts, dtype=torch.bool)
-        t_a = time.perf_counter()
+    def sample():
         with torch.no_grad():
-            h = O.stdit3_block(sd, "spatial_blocks.0.", x, y, t, [L] * B, xm, t0, Ts, S, H, False)
-            h = O.stdit3_block(sd, "temporal_blocks.0.", h, y, t, [L] * B, xm, t0, Ts, S, H, True, freqs)
-        return time.perf_counter() - t_a
+            a = time.perf_counter()
+            O.stdit3_block(sd, "spatial_blocks.0.", xs, y, t, [L] * B, torch.ones(B, 1, dtype=torch.bool), t0, 1, S, H, False)
+            b = time.perf_counter()
+            O.stdit3_block(sd, "temporal_blocks.0.", xt, y, t, [L] * B, torch.ones(B, T, dtype=torch.bool), t0, T, St, H, True, freqs)
+            c = time.perf_counter()
+        return 28.0 * ((b - a) * T + (c - b) * S / St)
 
-    run(1)  # warm the thread pool / allocator
-    t1 = run(1)
-    Ts = max(1, min(T, int(budget_s / max(t1, 1e-3))))
-    scale = 28.0 * T / Ts
-    desc = (f"{workload}: 1 of 28 (spatial+temporal) block pairs of the oracle port, CFG batch 2 x {Ts} of {T} latent "
-            f"frames x {S} patches, {L} text tokens, bf16 eager, extrapolated x28 x {T}/{Ts}")
-    times = [t1 * scale] if (Ts == 1 and reps == 1) else [run(Ts) * scale for _ in range(reps)]
-    return times, desc, os.cpu_count(), (lambda: run(Ts) * scale)
+    desc = (f"{workload}: 1 of 28 (spatial, temporal) block pairs of the oracle port (CPU restatement of the reference's eager "
+            f"path), bf16, all host threads; spatial block on CFG batch 2 x 1 of {T} latent frames x {S} patches, temporal "
+            f"block on CFG batch 2 x {T} frames x {St} of {S} patches (real {T}-frame sequences), {L} text tokens; "
+            f"step = 28 x (t_spatial x {T} + t_temporal x {S}/{St})")
+    return sample, desc, os.cpu_count()
 
 
 def run_reference(args):
@@ -178,22 +187,25 @@ def run_reference(args):
     if rank != 0:
         return
     W = WORKLOADS[args.workload]
+    sample, desc, cores = cpu_reference(args.workload)
     per_step = []
-    desc = cores = None
-    budget = max(2.0, min(12.0, 150.0 / (args.steps + args.warmup)))
-    _, desc, cores, again = cpu_reference(args.workload, budget_s=budget)
     for i in range(args.warmup + args.steps):
-        t = again()
+        t = sample()
         if i >= args.warmup:
             per_step.append(t)
     sec = statistics.mean(per_step)
     val = W["frames"] / (W["steps"] * sec)
+    spread = {"min_s": min(per_step), "max_s": max(per_step), "n": len(per_step)}
     line = {
         "impl": "reference", "metric": "frames/sec", "value": val, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": _config(args, W),
-        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
+                         "step_seconds_extrapolated": spread,
+                         "note": "ms_per_step is EXTRAPOLATED from the bounded sample (the full step would take hours on the "
+                                 "host cores); /root/reference itself cannot travel to the GPU box, the port is pinned "
+                                 "bit-exact to it by tests/test_oracle_vs_reference.py"},
         "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -208,9 +220,9 @@ def _config(args, W):
 
 
 def make_line(args, W, world, sec, sec_e2e, sec_profiled, launches, roofline, shares, cpu_base, clocks, peaks, depth,
-              h2d_bytes, d2h_bytes):
+              h2d_bytes, d2h_bytes, extra=None):
     """The one JSON line of the ours arm (pure: unit-tested on CPU).  sec / sec_e2e / sec_profiled: seconds for
-    args.steps steps of the resident arm, the host-buffer arm and the all-kernels-profiled pass."""
+    args.steps steps of the resident arm, the host-buffer arm and the all-kernels-profiled (eager) pass."""
     frames, nsteps = W["frames"], W["steps"]
     per = sec / args.steps
     line = {
@@ -223,17 +235,82 @@ def make_line(args, W, world, sec, sec_e2e, sec_profiled, launches, roofline, sh
         "gpu_launches": launches, "roofline": roofline,
         "attention_flop_roofline": attention_roofline(W, per * world, peaks, depth),
         "kernels": shares,
-        "kernels_note": "gemm: events inside the timed region; the other kinds: a second pass of the same steps with "
-                        f"events around every launch ({sec_profiled / args.steps * 1e3:.1f} ms/step with that overhead)",
+        "kernels_note": "per-kernel CUDA-event pairs come from an eager pass of the same steps with events around every "
+                        f"launch ({sec_profiled / args.steps * 1e3:.1f} ms/step with that overhead); value / e2e are "
+                        "timed without any per-kernel event",
         "cpu_baseline": cpu_base,
         "clocks": clocks,
     }
+    if extra:
+        line.update(extra)
     if args.opt:
         line["config"]["options"] = args.opt
     if args.depth:
         line["config"]["depth_override"] = args.depth
         line["invalid"] = "reduced depth (debug run): not a bench value"
     return line
+
+
+def gpu_eager_baseline(W, dev, steps=5):
+    """The reference's own 1-GPU PyTorch path: the oracle's op-for-op restatement of STDiT3.forward executed by torch
+    library kernels (cuBLAS GEMMs, F.scaled_dot_product_attention, eager elementwise) on this GPU -- the denominator of
+    north_star's ">= 6x the reference's own 1-GPU PyTorch path".  Two SDPA settings: torch's default backend choice
+    and cuDNN attention forced.  A reported baseline; none of its kernels is ours."""
+    from oracle import stdit3_oracle as O
+    from tests.helpers import stdit3_state_dict_template
+
+    bf = torch.bfloat16
+    g = torch.Generator(device="cpu").manual_seed(0)
+    sd = {}
+    for k, v in stdit3_state_dict_template(dict(MODEL), bf).items():
+        if k.endswith("rope.freqs"):
+            sd[k] = O.rope_freqs(MODEL["hidden_size"] // MODEL["num_heads"]).to(bf).to(dev)
+        elif v.ndim >= 2:
+            sd[k] = (torch.randn(v.shape, generator=g) * 0.02).to(bf).to(dev)
+        else:
+            sd[k] = (torch.randn(v.shape, generator=g) * 0.02 + (1.0 if "norm" in k else 0.0)).to(bf).to(dev)
+    T, Hl, Wl = W["lat"]
+    inp = dict(
+        x=torch.randn(2, 4, T, Hl, Wl, generator=g).to(dev, bf), timestep=torch.tensor([900.0, 900.0], device=dev),
+        y=torch.randn(2, 1, W["L"], MODEL["caption_channels"], generator=g).to(dev, bf),
+        mask=torch.ones(1, W["L"], dtype=torch.long, device=dev), x_mask=torch.ones(2, T, dtype=torch.bool, device=dev),
+        fps=torch.tensor([24.0, 24.0], device=dev, dtype=bf), height=torch.tensor([float(W["h"])] * 2, device=dev, dtype=bf),
+        width=torch.tensor([float(W["w"])] * 2, device=dev, dtype=bf),
+    )
+    ocfg = dict(hidden_size=MODEL["hidden_size"], num_heads=MODEL["num_heads"], depth=MODEL["depth"])
+
+    def run(n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            O.stdit3_forward(sd, ocfg, **inp)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    out = {"what": "reference eager path (oracle restatement of STDiT3.forward on torch/cuBLAS/SDPA library kernels), same "
+                   "GPU, one forward of the CFG pair per step (no guidance / Euler update)", "steps_timed": steps}
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    with torch.no_grad():
+        run(1)
+        ms = run(steps)
+        out["default_sdpa"] = {"ms_per_step": ms, "frames_per_s": W["frames"] / (W["steps"] * ms / 1e3),
+                               "backends_enabled": {"flash": torch.backends.cuda.flash_sdp_enabled(),
+                                                    "mem_efficient": torch.backends.cuda.mem_efficient_sdp_enabled(),
+                                                    "cudnn": torch.backends.cuda.cudnn_sdp_enabled(),
+                                                    "math": torch.backends.cuda.math_sdp_enabled()}}
+        try:
+            with sdpa_kernel([SDPBackend.CUDNN_ATTENTION]):
+                run(1)
+                ms2 = run(steps)
+            out["cudnn_sdpa"] = {"ms_per_step": ms2, "frames_per_s": W["frames"] / (W["steps"] * ms2 / 1e3)}
+        except Exception as e:  # cuDNN may reject the masked cross-attention: report, do not fail the bench
+            out["cudnn_sdpa"] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+    del sd, inp
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -243,6 +320,7 @@ def run_ours(args):
     import videosys_b200  # noqa: F401
     from videosys_b200 import kernels
     from videosys_b200.core.distributed.parallel_mgr import initialize
+    from videosys_b200.core.graph_step import StepGraph
     from videosys_b200.core.pab import pab_mgr
     from videosys_b200.models.transformers.open_sora_transformer_3d import STDiT3, STDiT3Config
     from videosys_b200.pipelines.open_sora.pipeline_open_sora import OpenSoraPABConfig
@@ -270,9 +348,12 @@ def run_ours(args):
     net = STDiT3(STDiT3Config(**cfg)).to(bf).to(dev).eval()
     net.enable_parallel(dp_size=1, sp_size=world)
     sched = RFLOW(num_sampling_steps=W["steps"], cfg_scale=7.0, use_timestep_transform=True)
-    if args.pab:
-        pab_mgr.set_pab_manager(OpenSoraPABConfig())
-        pab_mgr.update_steps(W["steps"])
+
+    def pab_on(on):
+        pab_mgr.set_pab_manager(OpenSoraPABConfig() if on else None)
+        if on:
+            pab_mgr.update_steps(W["steps"])
+        net.reset_pab_state()
 
     T, Hl, Wl = W["lat"]
     g = torch.Generator(device="cpu").manual_seed(1)
@@ -286,26 +367,28 @@ def run_ours(args):
     )
     # the timestep schedule is host arithmetic (50 tiny transforms): keep it off the GPU launch list
     margs_cpu = {k: v.cpu() for k, v in margs.items() if k in ("height", "width", "num_frames")}
-    timesteps = [t.to(dev) for t in sched.prepare_timesteps(1, "cpu", margs_cpu)]
+    ts_cpu = sched.prepare_timesteps(1, "cpu", margs_cpu)
+    timesteps = [t.to(dev) for t in ts_cpu]
+    ts_int = [int(t.to(bf).item()) for t in ts_cpu]  # what the reference's int(timestep[0]) sees (bf16 timestep)
     fwd_args = {k: v for k, v in margs.items() if k != "num_frames"}
     fwd_args["x_mask"] = torch.ones(2, T, dtype=torch.bool, device=dev)  # generate() always passes an all-true mask
     n_ts = len(timesteps)
-
-    def dt_of(i):
-        return (timesteps[i] - timesteps[i + 1] if i < n_ts - 1 else timesteps[i]) / 1000.0
+    # PAB only broadcasts inside (450, 930): a short bench that started at schedule index 0 would time no PAB step
+    first = args.first_step if args.first_step >= 0 else (10 if (args.pab and args.steps + args.warmup < n_ts) else 0)
+    dts = [((timesteps[i] - timesteps[i + 1] if i < n_ts - 1 else timesteps[i]) / 1000.0) for i in range(n_ts)]
 
     def sync_all():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, n):
+    def timed(fn, n, i0=0):
         """n calls of fn(i) between events; returns seconds (max over ranks)."""
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n):
-            fn(i)
+            fn(i0 + i)
         e1.record()
         sync_all()
         sec = e0.elapsed_time(e1) / 1e3
@@ -315,34 +398,74 @@ def run_ours(args):
             sec = t.item()
         return sec
 
-    # ---- resident arm: latents stay in HBM ----
-    z = z_host.to(dev, bf)
-    state = {"z": z}
+    # ---- N > 1: parity before anything is timed ----
+    dsp_parity = None
+    if world > 1:
+        dsp_parity = _dsp_parity(net, sched, z_host.to(dev, bf), timesteps, dts, fwd_args, dev, dist, args)
+
+    pab_on(args.pab)
+    stepper = StepGraph(net, 7.0, enabled=not args.no_graph)
+    state = {"z": z_host.to(dev, bf)}
 
     def step_resident(i):
-        k = i % n_ts
-        state["z"] = sched.step(net, state["z"], timesteps[k], dt_of(k), fwd_args, 7.0)
+        k = (first + i) % n_ts
+        state["z"] = stepper.step(state["z"], timesteps[k], dts[k], fwd_args, ts_int=ts_int[k])
 
-    for i in range(args.warmup):
+    # ---- e2e arm: host (pinned) latents in, host latents out, every step ----
+    out_host = torch.empty(1, 4, T, Hl, Wl, dtype=torch.float32).pin_memory()
+    zdev = torch.empty(1, 4, T, Hl, Wl, device=dev, dtype=torch.float32)
+
+    def step_e2e(i):
+        k = (first + i) % n_ts
+        zdev.copy_(z_host, non_blocking=True)
+        znew = stepper.step(zdev.to(bf), timesteps[k], dts[k], fwd_args, ts_int=ts_int[k])
+        out_host.copy_(znew.float(), non_blocking=True)
+
+    # warm-up: at least 3 steps; with graphs the first step of a pattern is eager, the second captures
+    for i in range(max(args.warmup, 3)):
         step_resident(i)
-    net.reset_pab_state()
+    step_e2e(0)
+    if args.pab:  # warm (capture) every PAB pattern the timed steps will meet, then rewind the counters
+        net.reset_pab_state()
+        for rep_ in range(2):
+            for i in range(args.steps):
+                step_resident(i)
+            net.reset_pab_state()
     sampler = ClockSampler(local)
     sampler.start()
-    # timed region: CUDA-event pairs only around the dominant kernel (every Linear layer's GEMM, 392 launches per step)
-    kernels.PROFILE, kernels.PROFILE_KINDS = [], {"gemm"}
+    # timed region: resident and e2e arms INTERLEAVED in blocks (run-order / clock-ramp noise hits both alike)
+    nblk = 2 if args.steps >= 4 and not args.pab else 1
+    per_blk = [args.steps // nblk + (1 if b < args.steps % nblk else 0) for b in range(nblk)]
+    sec = sec_e2e = 0.0
     l0 = kernels.launch_count()
-    sec = timed(step_resident, args.steps)
-    launches = kernels.launch_count() - l0
-    prof_gemm = kernels.PROFILE
+    r0 = stepper.replayed_launches
+    done = 0
+    for b in range(nblk):
+        net.reset_pab_state() if args.pab else None
+        sec += timed(step_resident, per_blk[b], done)
+        net.reset_pab_state() if args.pab else None
+        sec_e2e += timed(step_e2e, per_blk[b], done)
+        done += per_blk[b]
+    # our launches inside the two timed regions: host launches + the launches baked into every replayed graph
+    launches = ((kernels.launch_count() - l0) + (stepper.replayed_launches - r0)) // 2
     clocks = sampler.stop()
-    # a second pass of the same steps with events around EVERY launch: the per-kernel breakdown ("kernels"), not timed
-    kernels.PROFILE, kernels.PROFILE_KINDS = [], None
+
+    # ---- per-kernel pass: EAGER steps with CUDA-event pairs around every launch of ours (not part of value) ----
+    eager = StepGraph(net, 7.0, enabled=False)
+    state["z"] = z_host.to(dev, bf)
+
+    def step_eager(i):
+        k = (first + i) % n_ts
+        state["z"] = eager.step(state["z"], timesteps[k], dts[k], fwd_args, ts_int=ts_int[k])
+
     net.reset_pab_state()
-    sec_profiled = timed(step_resident, args.steps)
-    prof = [p_ for p_ in kernels.PROFILE if p_[0] != "gemm"] + prof_gemm
+    step_eager(0)
+    net.reset_pab_state()
+    kernels.PROFILE, kernels.PROFILE_KINDS = [], None
+    sec_profiled = timed(step_eager, args.steps)
+    prof = kernels.PROFILE
     kernels.PROFILE = None
 
-    # ---- per-kernel shares from the live CUDA-event pairs ----
     by_kind = {}
     for kind, a, b, work in prof:
         ms = a.elapsed_time(b)
@@ -356,44 +479,89 @@ def run_ours(args):
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath) and args.workload == "opensora_720p_68f_50step":
-        traffic = json.load(open(tpath)).get("gemm_qkv_720p_n1")
-    roofline = {"kernel": "gemm2_bf16_tn_kernel / gemm_bf16_tn_kernel (all Linear layers, 392 launches per step)",
+        traffic = json.load(open(tpath)).get("gemm_720p_n1")
+    roofline = {"kernel": "gemm2_bf16_tn_kernel / gemm_bf16_tn_kernel (every Linear layer of the step)",
                 "bound": "tensor", "achieved": gemm_tflops,
                 "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": gemm_tflops / peaks["tflops"], "traffic": traffic,
-                "peak_source": peaks["src"], "launches_timed": gm[2], "timed_in": "the timed region (CUDA-event pairs)",
-                "share_of_step": gm[0] / (sec * 1e3)}
+                "peak_source": peaks["src"], "launches_timed": gm[2],
+                "timed_in": "an eager pass of the same steps, CUDA-event pair around every GEMM launch on the launching "
+                            "stream (the value / e2e regions replay CUDA graphs, whose launches carry no events)",
+                "share_of_step": gm[0] / (sec_profiled * 1e3)}
+    tflop_kinds = ("gemm", "attn_flash")
     shares = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
-                  "achieved": (v[1] / (v[0] * 1e-3) / 1e12) if k in ("gemm", "attn_flash") else (v[1] / (v[0] * 1e-3) / 1e9),
-                  "unit": "TFLOP/s" if k in ("gemm", "attn_flash") else "GB/s"} for k, v in by_kind.items()}
+                  "achieved": (v[1] / (v[0] * 1e-3) / 1e12) if k in tflop_kinds else (v[1] / (v[0] * 1e-3) / 1e9),
+                  "unit": "TFLOP/s" if k in tflop_kinds else "GB/s"} for k, v in by_kind.items()}
     shares = kernel_fractions(shares, peaks)
-
-    # ---- e2e arm: host (pinned) latents in, host velocity/latents out, every step ----
-    out_host = torch.empty(1, 4, T, Hl, Wl, dtype=torch.float32).pin_memory()
-    zdev = torch.empty(1, 4, T, Hl, Wl, device=dev, dtype=torch.float32)
-
-    def step_e2e(i):
-        k = i % n_ts
-        zdev.copy_(z_host, non_blocking=True)
-        znew = sched.step(net, zdev.to(bf), timesteps[k], dt_of(k), fwd_args, 7.0)
-        out_host.copy_(znew.float(), non_blocking=True)
-
-    net.reset_pab_state()
-    step_e2e(0)
-    sec_e2e = timed(step_e2e, args.steps)
-    frames, nsteps = W["frames"], W["steps"]
 
     if rank == 0:
         cpu_base = None
+        extra = {"cuda_graph": not args.no_graph, "first_schedule_index": first,
+                 "tensor_map_cache": dict(zip(("hits", "host_encodes"), kernels.tmap_cache_stats()))}
+        if dsp_parity is not None:
+            extra["dsp_parity"] = dsp_parity
         if world == 1 and not args.no_cpu_baseline:
-            ts, desc, cores, _ = cpu_reference(args.workload, budget_s=10.0)
-            v = frames / (nsteps * statistics.mean(ts))
-            cpu_base = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc}
+            sample, desc, cores = cpu_reference(args.workload)
+            sample()  # warm the thread pool / allocator
+            ts = [sample() for _ in range(3)]
+            v = W["frames"] / (W["steps"] * statistics.mean(ts))
+            cpu_base = {"value": v, "unit": "frames/s", "cores": cores, "kind": "port", "sample": desc,
+                        "step_seconds_extrapolated": {"mean": statistics.mean(ts), "min": min(ts), "max": max(ts), "n": 3}}
+        if world == 1 and not args.no_gpu_baseline and not args.depth:
+            state.clear()
+            torch.cuda.empty_cache()
+            extra["gpu_baseline"] = gpu_eager_baseline(W, dev)
         line = make_line(args, W, world, sec, sec_e2e, sec_profiled, int(launches), roofline, shares, cpu_base, clocks,
-                         peaks, cfg["depth"], z_host.numel() * 4, out_host.numel() * 4)
+                         peaks, cfg["depth"], z_host.numel() * 4, out_host.numel() * 4, extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _dsp_parity(net, sched, z0, timesteps, dts, fwd_args, dev, dist, args):
+    """Sharded == unsharded, bit for bit, on THIS workload's shapes: (1) one forward of the first 2 block pairs;
+    (2) 4 full-depth denoising steps through the replayed step graph (28 spatial blocks x 4 steps = 112 uses of each DSP
+    window and flag array: the window-reuse argument of DESIGN.md section 5 under load).  The unsharded run is the same
+    network with its parallel manager taken away, on every rank; the reshard is a permutation and every kernel is
+    row-independent, so ANY difference is a bug."""
+    from videosys_b200.core.graph_step import StepGraph
+
+    res = {"transport": ("p2p-fused" if net._fuse_dsp else "p2p-scatter") if os.environ.get("VSB_DSP_P2P", "1") == "1" else "nccl"}
+    z_in, tt = torch.cat([z0, z0], 0), torch.cat([timesteps[0], timesteps[0]], 0)
+    pm = net.parallel_manager
+
+    def unsharded(fn):
+        net.parallel_manager = None
+        try:
+            return fn()
+        finally:
+            net.parallel_manager = pm
+
+    a = net(z_in, tt, valid_depth=2, **fwd_args)
+    b = unsharded(lambda: net(z_in, tt, valid_depth=2, **fwd_args))
+    ok1 = torch.equal(a, b)
+    d1 = (a.float() - b.float()).abs().max().item()
+
+    def run4(graph):
+        st = StepGraph(net, 7.0, enabled=graph)
+        z = z0.clone()
+        for i in range(4):
+            z = st.step(z, timesteps[i], dts[i], fwd_args)
+        return z
+
+    zs = run4(not args.no_graph)
+    zu = unsharded(lambda: run4(False))
+    ok2 = torch.equal(zs, zu)
+    d2 = (zs.float() - zu.float()).abs().max().item()
+    flags = torch.tensor([int(ok1), int(ok2)], device=dev)
+    dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    res["depth2_forward"] = "bit_equal" if flags[0].item() else f"DIFFERS (max abs {d1:.3e} on rank {dist.get_rank()})"
+    res["steps4_depth28_graph_replay" if not args.no_graph else "steps4_depth28"] = (
+        "bit_equal" if flags[1].item() else f"DIFFERS (max abs {d2:.3e} on rank {dist.get_rank()})")
+    res["ranks"] = dist.get_world_size()
+    if args.depth:
+        res["note"] = f"depth override {args.depth}"
+    return res
 
 
 def main():
@@ -406,6 +574,9 @@ def main():
     ap.add_argument("--pab", action="store_true", help="enable Pyramid Attention Broadcast (config 5)")
     ap.add_argument("--depth", type=int, default=0, help="debug only: fewer block pairs (marks the line invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager torch/cuBLAS/SDPA baseline (N = 1)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from the host instead of replaying CUDA graphs")
+    ap.add_argument("--first-step", type=int, default=-1, help="schedule index of the first timed step (default 0; 10 with --pab)")
     ap.add_argument("--opt", action="append", default=[], help="kernel selection knob name=value (vsb_set_option)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -144,6 +144,25 @@ def cross_attention(sd, p: str, x: Tensor, cond: Tensor, y_lens: List[int], num_
     return F.linear(o, sd[p + "proj.weight"], sd[p + "proj.bias"])
 
 
+def cross_attention_varlen(sd, p: str, x: Tensor, cond: Tensor, y_lens: List[int], num_heads: int) -> Tensor:
+    """OpenSoraMultiHeadCrossAttention.forward with enable_flash_attn=True: attentions.py:152-185 -> flash_attn_impl
+    :240-257.  flash_attn_varlen_func (third party, flash-attn) is called with cu_seqlens_q = [0, N, 2N, ..] and
+    cu_seqlens_k = cumsum(y_lens): sample i's queries attend exactly the y_lens[i] packed keys of sample i --
+    restated as one softmax(q k^T / sqrt(d)) v per sample (the library's published semantics)."""
+    B, N, C = x.shape
+    D = C // num_heads
+    q = F.linear(x, sd[p + "q_linear.weight"], sd[p + "q_linear.bias"]).view(B, N, num_heads, D)
+    kv = F.linear(cond, sd[p + "kv_linear.weight"], sd[p + "kv_linear.bias"]).view(-1, 2, num_heads, D)
+    outs, start = [], 0
+    for i, m in enumerate(y_lens):
+        k, v = kv[start:start + m, 0], kv[start:start + m, 1]  # [m, H, D]
+        start += m
+        o = F.scaled_dot_product_attention(q[i].transpose(0, 1)[None], k.transpose(0, 1)[None], v.transpose(0, 1)[None])
+        outs.append(o[0].transpose(0, 1).reshape(N, C))
+    o = torch.stack(outs, 0)
+    return F.linear(o, sd[p + "proj.weight"], sd[p + "proj.bias"])
+
+
 # ----------------------------------------------------------------------------------------------
 # PAB per-block state (the reference keeps these as attributes on the block: :141-147)
 # ----------------------------------------------------------------------------------------------
@@ -176,6 +195,7 @@ def stdit3_block(
     pab_state: Optional[BlockPABState] = None,
     timestep_int: Optional[int] = None,
     spatial_attn_fn=None,
+    cross_varlen: bool = False,
 ) -> Tensor:
     """STDiT3Block.forward: open_sora_transformer_3d.py:162-286 (mlp_broadcast unreachable for OpenSora,
     SURVEY fact 7).  ``pab`` is an oracle.pab_oracle.PABGate or None; ``spatial_attn_fn`` lets the DSP
@@ -222,7 +242,7 @@ def stdit3_block(
     if pab_on and reuse_cross:
         x = x + pab_state.last_cross
     else:
-        x_cross = cross_attention(sd, p + "cross_attn.", x, y, y_lens, num_heads)
+        x_cross = (cross_attention_varlen if cross_varlen else cross_attention)(sd, p + "cross_attn.", x, y, y_lens, num_heads)
         if pab_on:
             pab_state.last_cross = x_cross
         x = x + x_cross
@@ -360,6 +380,7 @@ def stdit3_forward(
     pab_states=None,
     valid_depth: Optional[int] = None,
     return_tokens: bool = False,
+    cross_varlen: bool = False,
 ) -> Tensor:
     """STDiT3.forward on one rank (sp=cp=1): open_sora_transformer_3d.py:539-632.
 
@@ -421,6 +442,7 @@ def stdit3_forward(
                 pab,
                 pab_states[kind][d] if pab_states is not None else None,
                 ts_int,
+                cross_varlen=cross_varlen,
             )
     if return_tokens:
         return h

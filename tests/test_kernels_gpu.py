@@ -213,6 +213,9 @@ def _gemm_check(name, M, N, K_, act):
     (515, 1152, 4608, 0),   # fc2
     (260, 256, 512, 0),     # BN=256 path
     (130, 128, 96, 1),      # BN=128 path, K tail
+    (2, 6912, 1152, 0),     # t_block: a CFG pair of rows (M far below one tile)
+    (1500, 64, 1152, 0),    # final layer (32 features zero-padded to the narrowest tile), M >= 1024 on the 1-CTA kernel
+    (600, 1152, 4096, 1),   # caption y_proj.fc1 + GELU (K = 4096)
 ])
 def test_gemm(M, N, K_, act):
     _gemm_check(f"g{M}x{N}x{K_}", M, N, K_, act)
@@ -343,7 +346,8 @@ def test_attn_flash_cross(nb, nq, nk, H, D, lens):
 
 
 @pytest.mark.parametrize("opts", [dict(attn_variant=0), dict(attn_variant=0, attn_pingpong=0), dict(attn_variant=2, attn_poly_exp=1),
-                                  dict(attn_variant=2, attn_poly_exp=3), dict(attn_variant=3), dict(attn_variant=3, attn_poly_exp=2)])
+                                  dict(attn_variant=2, attn_poly_exp=3), dict(attn_variant=3), dict(attn_variant=3, attn_poly_exp=2),
+                                  dict(attn_variant=4), dict(attn_variant=4, attn_poly_exp=1)])
 def test_attn_flash_schedule_options(opts):
     """Every schedule of vsb_attn_flash (vsb_set_option knobs) gives the same attention within tolerance."""
     from videosys_b200 import kernels as K
@@ -392,7 +396,7 @@ def test_attn_flash_large_max_growth():
     assert (err <= 2.0**-7 * exact.abs().clamp_min(0.02) + 4e-3).all()
 
 
-@pytest.mark.parametrize("variant", [2, 3])
+@pytest.mark.parametrize("variant", [2, 3, 4])
 @pytest.mark.parametrize("case", ["self_ragged", "cross_lens", "tails"])
 def test_attn_flash_many_items(variant, case):
     """More (batch, head, query-pair) items than SMs, so a persistent CTA (variant 3) walks several items: pairs whose
@@ -412,3 +416,98 @@ def test_attn_flash_many_items(variant, case):
             _flash_check(f"tailx{variant}", 2, 100, 40, 24, 72, lens=[40, 1], packed_qkv=False)  # one key, 1 tile
     finally:
         K.set_option("attn_variant", -1)
+
+
+def test_attn_flash_q_in_tmem_720p_sequence():
+    """attn_variant 4 (Q rows resident in TMEM, S = Q K^T as TS MMAs) on the 720p spatial sequence length (3600 keys =
+    56 full key tiles + a 16-key tail, 14 query pairs + a lone 16-row tile) and with head_dim 64."""
+    from videosys_b200 import kernels as K
+
+    _dev()
+    try:
+        K.set_option("attn_variant", 4)
+        _flash_check("qt3600", 1, 3600, 3600, 2, 72)
+        _flash_check("qt64", 2, 700, 700, 2, 64)
+    finally:
+        K.set_option("attn_variant", -1)
+
+
+def test_attn_flash_many_key_lengths():
+    """Per-batch key counts beyond the first version's limit of 8 batches (kv_lens travel by value, up to 64)."""
+    lens = [40, 1, 17, 64, 65, 100, 3, 99, 128, 127, 50, 77]
+    _flash_check("lens12", len(lens), 130, 128, 2, 72, lens=lens, packed_qkv=False)
+
+
+@pytest.mark.parametrize("B,T,S,H,D", [(2, 5, 7, 4, 72), (1, 33, 10, 16, 72), (2, 3, 4, 2, 64)])
+def test_qk_rmsnorm_rope(B, T, S, H, D):
+    """RMSNorm + RoPE pre-pass of the long temporal path: position of token row r = (r // S) % T."""
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    qkv = (synth.normalish(f"rr.qkv{T}{S}", (B, T, S, 3, H, D)) * 1.3).to(BF)
+    wq = (1 + 0.2 * synth.uniform("rr.wq", (D,))).to(BF)
+    wk = (1 + 0.2 * synth.uniform("rr.wk", (D,))).to(BF)
+    freqs = O.rope_freqs(D).to(BF)
+    seq = qkv.permute(0, 2, 1, 3, 4, 5).reshape(B * S, T, 3, H, D)  # sequences over T per (b, s)
+    q, k, v = seq.permute(2, 0, 3, 1, 4).unbind(0)                   # [B*S, H, T, D]
+    qn = O.rotate_queries_or_keys(O.llama_rms_norm(q, wq), freqs)
+    kn = O.rotate_queries_or_keys(O.llama_rms_norm(k, wk), freqs)
+    want = torch.stack([qn, kn, v], 0).permute(1, 3, 0, 2, 4).reshape(B, S, T, 3, H, D).permute(0, 2, 1, 3, 4, 5)
+    cos, sin = _rope_tables(T, D)
+    got = K.qk_rmsnorm_(qkv.clone().to(dev).reshape(-1, 3, H, D), wq.to(dev), wk.to(dev), H, D, rope_cos=cos.to(dev),
+                        rope_sin=sin.to(dev), pos_div=S, pos_mod=T)
+    _ulp_report(f"qk_rmsnorm_rope T={T} S={S} D={D}", got.reshape(B, T, S, 3, H, D), want)
+
+
+@pytest.mark.parametrize("B,T,S,H,D", [(2, 30, 5, 4, 72), (1, 34, 130, 16, 72), (2, 64, 3, 2, 72)])
+def test_temporal_attention_long(B, T, S, H, D):
+    """Temporal attention over >= 30 frames (the reference's SDPA branch, attentions.py:98-100): RMSNorm + RoPE pre-pass,
+    then the flash kernel over strided views of the token-major activation (batch = patch, row = frame), strided output."""
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    C = H * D
+    qkv = synth.normalish(f"tl.qkv{T}{S}", (B, T, S, 3, H, D)).to(BF)
+    wq = (1 + 0.2 * synth.uniform("tl.wq", (D,))).to(BF)
+    wk = (1 + 0.2 * synth.uniform("tl.wk", (D,))).to(BF)
+    freqs = O.rope_freqs(D).to(BF)
+    seq = qkv.permute(0, 2, 1, 3, 4, 5).reshape(B * S, T, 3, H, D)
+    q, k, v = seq.permute(2, 0, 3, 1, 4).unbind(0)
+    qn = O.rotate_queries_or_keys(O.llama_rms_norm(q, wq), freqs)
+    kn = O.rotate_queries_or_keys(O.llama_rms_norm(k, wk), freqs)
+    want = torch.nn.functional.scaled_dot_product_attention(qn, kn, v)            # oracle op (attentions.py:100)
+    exact = torch.nn.functional.scaled_dot_product_attention(qn.double(), kn.double(), v.double())
+    to_tok = lambda o: o.transpose(1, 2).reshape(B, S, T, C).permute(0, 2, 1, 3).reshape(B * T * S, C)  # noqa: E731
+    want, exact = to_tok(want), to_tok(exact)
+    cos, sin = _rope_tables(T, D)
+    g = qkv.clone().to(dev).reshape(B * T * S, 3 * C)
+    K.qk_rmsnorm_(g, wq.to(dev), wk.to(dev), H, D, rope_cos=cos.to(dev), rope_sin=sin.to(dev), pos_div=S, pos_mod=T)
+    out = torch.full((B * T * S, C), float("nan"), dtype=BF, device=dev)
+    q3 = g.view(B, T * S, 3, C)
+    for b in range(B):
+        K.attn_flash(q3[b, :, 0], q3[b, :, 1], q3[b, :, 2], S, T, T, H, D, S * 3 * C, 3 * C, S * 3 * C, 3 * C, D**-0.5,
+                     out=out[b * T * S:], out_row_stride=S * C, out_batch_stride=C)
+    got = out.cpu()
+    assert not torch.isnan(got.float()).any(), "strided output left rows unwritten"
+    err, err_or = (got.double() - exact).abs(), (want.double() - exact).abs()
+    print(f"[parity] temporal flash T={T} S={S}: max|err| vs fp64 {err.max().item():.3e} (oracle bf16 {err_or.max().item():.3e}), "
+          f"bit-equal to oracle {(got == want).float().mean().item()*100:.1f} %")
+    assert (err <= 2.0**-7 * exact.abs().clamp_min(0.02) + 2e-3).all()
+    assert err.mean().item() <= 2.0 * err_or.mean().item() + 1e-5
+
+
+def test_tensor_map_cache_hits():
+    """The second identical launch re-uses the encoded tensor maps (no host cuTensorMapEncodeTiled)."""
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    a = synth.normalish("tm.a", (256, 128)).to(BF).to(dev)
+    w = synth.normalish("tm.w", (192, 128), std=0.05).to(BF).to(dev)
+    out = torch.empty(256, 192, dtype=BF, device=dev)
+    K.gemm_bias_act(a, w, None, out=out)
+    h0, m0 = K.tmap_cache_stats()
+    ref = out.clone()
+    K.gemm_bias_act(a, w, None, out=out)
+    h1, m1 = K.tmap_cache_stats()
+    assert m1 == m0 and h1 == h0 + 3, (h0, m0, h1, m1)
+    assert torch.equal(out, ref)

@@ -26,6 +26,8 @@ for g in "$@"; do
     refgpu) timeout 600 python tests/bench_reference_gpu.py > gpurun_out/refgpu.log 2>&1; echo "refgpu exit $? $(tail -n 1 gpurun_out/refgpu.log | cut -c1-300)" | tee -a gpurun_out/summary.txt ;;
     mmab) timeout 120 tools/_bin/mma_microbench > gpurun_out/mma_microbench.txt 2>&1; echo "mmab exit $?" | tee -a gpurun_out/summary.txt ;;
     atrace) timeout 300 python tools/attn_trace.py > gpurun_out/attn_trace.log 2>&1; echo "atrace exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/attn_trace.log ;;
+    kbattn) KB_ONLY=attn timeout 600 python tools/kernel_bench.py > gpurun_out/kernel_bench_attn.log 2>&1; echo "kbattn exit $?" | tee -a gpurun_out/summary.txt; tail -n 3 gpurun_out/kernel_bench_attn.log ;;
+    kernels) run kernels 900 tests/test_kernels_gpu.py ;;
     kbench) timeout 600 python tools/kernel_bench.py > gpurun_out/kernel_bench.log 2>&1; echo "kbench exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/kernel_bench.log | tail -12 ;;
     mbenchnccl*) n=${g#mbenchnccl}; echo "=== bench N=$n (NCCL a2a) ===" | tee -a gpurun_out/summary.txt
            VSB_DSP_P2P=0 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29534 \
@@ -49,17 +51,17 @@ for g in "$@"; do
            echo "benchpab exit $? : $(tail -c 400 gpurun_out/benchpab.json)" | tee -a gpurun_out/summary.txt ;;
     benchref) timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/benchref.json 2> gpurun_out/benchref.err
            echo "benchref exit $? : $(tail -c 400 gpurun_out/benchref.json)" | tee -a gpurun_out/summary.txt ;;
-    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 3000 --csv --log-file gpurun_out/launches.csv \
-              python bench.py --steps 1 --warmup 1 --depth 2 --no-cpu-baseline > gpurun_out/ncu_list.log 2>&1
+    ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv \
+              python bench.py --steps 1 --warmup 1 --depth 2 --no-cpu-baseline --no-gpu-baseline --no-graph > gpurun_out/ncu_list.log 2>&1
            echo "ncu_list exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm2_bf16 -s 14 -c 4 -o gpurun_out/prof_gemm -f \
-              python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
+              python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline --no-gpu-baseline --no-graph > gpurun_out/ncu_gemm.log 2>&1
            echo "ncu_gemm exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_short) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_short -c 1 -o gpurun_out/prof_short -f \
               python tools/kernel_bench.py > gpurun_out/ncu_short.log 2>&1
            echo "ncu_short exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_flash -s 2 -c 2 -o gpurun_out/prof_attn -f \
-              python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline > gpurun_out/ncu_attn.log 2>&1
+              python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline --no-gpu-baseline --no-graph $NCU_BENCH_ARGS > gpurun_out/ncu_attn.log 2>&1
            echo "ncu_attn exit $?" | tee -a gpurun_out/summary.txt ;;
     *)     run "custom" 600 $g ;;
   esac

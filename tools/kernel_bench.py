@@ -72,7 +72,27 @@ def cross(var, poly):
     K.attn_flash(qx, kvx[:, :, 0], kvx[:, :, 1], 2, 72000, 300, H, D, C, 72000 * C, 2 * C, 300 * 2 * C, D**-0.5)
 
 
-VARIANTS = {"kt128_pingpong": (0, 0), "kt64": (2, 0), "kt64_poly25": (2, 1), "kt64_poly37": (2, 2), "kt64p": (3, 0), "kt64p_poly25": (3, 1), "kt64p_poly37": (3, 2)}
+VARIANTS = {"kt128_pingpong": (0, 0), "kt64": (2, 0), "kt64_poly25": (2, 1), "kt64_poly37": (2, 2), "kt64p": (3, 0), "kt64p_poly25": (3, 1),
+            "kt64_qtmem": (4, 0), "kt64_qtmem_poly25": (4, 1), "kt64_qtmem_poly37": (4, 2), "kt64_qtmem_poly50": (4, 3)}
+# cuDNN's fused attention on the same problem, inside the same round-robin (a yardstick: never on the product path)
+from torch.nn.attention import SDPBackend, sdpa_kernel  # noqa: E402
+
+q_l, k_l, v_l = qkv.permute(2, 0, 3, 1, 4).unbind(0)
+
+
+def cudnn_spatial():
+    with sdpa_kernel([SDPBackend.CUDNN_ATTENTION]):
+        torch.nn.functional.scaled_dot_product_attention(q_l, k_l, v_l)
+
+
+try:
+    cudnn_spatial()
+    torch.cuda.synchronize()
+    HAVE_CUDNN = True
+except Exception as e:  # noqa: BLE001
+    print("cudnn sdpa unavailable:", type(e).__name__, str(e)[:120])
+    HAVE_CUDNN = False
+cudnn_ts = []
 for _ in range(600):  # ~2.5 s of attention: clocks settle under the power cap
     spatial(2, 0)
 torch.cuda.synchronize()
@@ -81,7 +101,12 @@ for rnd in range(24):
     for nm, (var, poly) in VARIANTS.items():
         acc[nm][0].append(timeit(lambda: spatial(var, poly), iters=3, warm=1))
         acc[nm][1].append(timeit(lambda: cross(var, poly), iters=6, warm=1))
+    if HAVE_CUDNN:
+        cudnn_ts.append(timeit(cudnn_spatial, iters=3, warm=1))
 r = {}
+if cudnn_ts:
+    cudnn_ts.sort()
+    r["cudnn_sdpa_interleaved"] = round(fl / cudnn_ts[len(cudnn_ts) // 2] / 1e12, 1)
 for nm, (ts, tx) in acc.items():
     ts, tx = sorted(ts), sorted(tx)
     r["ours_" + nm] = round(fl / ts[len(ts) // 2] / 1e12, 1)                       # median of 24 interleaved rounds
