@@ -54,7 +54,8 @@ int vsb_set_option(const char* name, int value);
  * timestamps (profiling aid, NULL disables). */
 int vsb_debug_attn_trace(void* device_buffer);
 /*   "attn_variant" 4 = variant 2 with the query rows resident in TMEM (S = Q K^T issued as TS MMAs: the A operand no
- *   longer re-read from shared memory on every K step) and 8 instead of 6 K/V stages.
+ *   longer re-read from shared memory on every K step) and 8 instead of 6 K/V stages; 5 = 4 with the softmax row sum
+ *   accumulated by the tensor core (ones written into the zero padding column d = 72 of every V tile; head_dim 72).
  *   "dsp_rowwise" (default 1): vsb_dsp_scatter decodes indices once per token row; 0 = the first version (per vector). */
 
 /* ---- AdaLN: LayerNorm(eps, no affine) -> x*(1+scale)+shift with per-frame t / t0 select --------------------

@@ -347,7 +347,8 @@ def test_attn_flash_cross(nb, nq, nk, H, D, lens):
 
 @pytest.mark.parametrize("opts", [dict(attn_variant=0), dict(attn_variant=0, attn_pingpong=0), dict(attn_variant=2, attn_poly_exp=1),
                                   dict(attn_variant=2, attn_poly_exp=3), dict(attn_variant=3), dict(attn_variant=3, attn_poly_exp=2),
-                                  dict(attn_variant=4), dict(attn_variant=4, attn_poly_exp=1)])
+                                  dict(attn_variant=4), dict(attn_variant=4, attn_poly_exp=1), dict(attn_variant=5),
+                                  dict(attn_variant=5, attn_poly_exp=2)])
 def test_attn_flash_schedule_options(opts):
     """Every schedule of vsb_attn_flash (vsb_set_option knobs) gives the same attention within tolerance."""
     from videosys_b200 import kernels as K
@@ -396,7 +397,7 @@ def test_attn_flash_large_max_growth():
     assert (err <= 2.0**-7 * exact.abs().clamp_min(0.02) + 4e-3).all()
 
 
-@pytest.mark.parametrize("variant", [2, 3, 4])
+@pytest.mark.parametrize("variant", [2, 3, 4, 5])
 @pytest.mark.parametrize("case", ["self_ragged", "cross_lens", "tails"])
 def test_attn_flash_many_items(variant, case):
     """More (batch, head, query-pair) items than SMs, so a persistent CTA (variant 3) walks several items: pairs whose
@@ -428,6 +429,9 @@ def test_attn_flash_q_in_tmem_720p_sequence():
         K.set_option("attn_variant", 4)
         _flash_check("qt3600", 1, 3600, 3600, 2, 72)
         _flash_check("qt64", 2, 700, 700, 2, 64)
+        K.set_option("attn_variant", 5)  # + the row sum accumulated by the tensor core (ones in V's padding column)
+        _flash_check("qs3600", 1, 3600, 3600, 2, 72)
+        _flash_check("qs64", 2, 700, 700, 2, 64)  # head_dim 64 has no padding column: falls back to variant 4's sums
     finally:
         K.set_option("attn_variant", -1)
 

@@ -392,7 +392,8 @@ extern "C" int vsb_attn_flash_strided(const vsb_bf16* q, const vsb_bf16* k, cons
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (variant == 3) return attn_flash_kt64p_launch(tm, prm, D, g_opt_attn_poly, st);
-  if (variant == 2 || variant == 4) return attn_flash_kt64_launch(tm, prm, D, g_opt_attn_poly, variant == 4, st);
+  if (variant == 2 || variant == 4 || variant == 5)
+    return attn_flash_kt64_launch(tm, prm, D, g_opt_attn_poly, variant == 5 ? 2 : (variant == 4 ? 1 : 0), st);
   dim3 grid((nq + 255) / 256, H, nb);
   static bool attr = false;
   if (!attr) {

@@ -52,13 +52,18 @@ __host__ __device__ constexpr uint32_t c_s(int x, int buf) { return uint32_t(x) 
 __host__ __device__ constexpr uint32_t c_o(int x) { return 256u + uint32_t(x) * 80u; }
 __host__ __device__ constexpr uint32_t c_q(int x) { return 416u + uint32_t(x) * 40u; }  // Q_x as bf16 pairs: 80 / 2 columns
 
-template <int D, int kPoly, bool kQTm>
+// kSumMMA (head_dim 72 only): the softmax row sum comes out of the tensor core.  The V tile's zero padding column d = 72
+// is overwritten with ones by the issuer warp, so O[:, 72] accumulates sum_j bf16(p_j) -- exactly the weights that
+// multiply V -- and the 64 FADDs per thread per key tile (a quarter of the softmax warps' FMA-pipe work, which becomes
+// the co-limiter once part of the exp2 moves off the MUFU pipe) disappear.
+template <int D, int kPoly, bool kQTm, bool kSumMMA>
 __global__ void __launch_bounds__(kT64Threads, 1)
 attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qb,
                        const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_kb,
                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_vb,
                        const __grid_constant__ AttnParams p) {
   constexpr bool kHasB = (D > 64);
+  static_assert(!kSumMMA || D == 72, "the ones column lives in the padding of head_dim 72");
   constexpr int kQTx = kHasB ? kQT : kQA;
   constexpr int kKTx = kHasB ? kKT : kKA;
   constexpr int ST = kQTm ? kT64StagesQT : kT64Stages;
@@ -193,6 +198,18 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const int s2 = (t + 2) % ST;
       // operands first (they land long before P is ready: these waits are off the critical path) ...
       mbar_wait(&v_full[s], (t / ST) & 1);
+      if (kSumMMA) {
+        // V_B chunk: 64 keys x 16 bf16 (32-byte rows, SWIZZLE_32B: the 16-byte half is XORed with address bit 7 = key
+        // bit 2): element d = 72 is the first of the upper half.  Both query tiles' issuers write it (same value).
+        unsigned char* vb = sKV + s * kStage + kKT + kKA;
+#pragma unroll
+        for (int rr = 0; rr < 2; ++rr) {
+          const int r = lane + rr * 32;
+          *reinterpret_cast<uint16_t*>(vb + r * 32 + ((1 ^ ((r >> 2) & 1)) << 4)) = 0x3F80;  // bf16 1.0
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+      }
       if (t + 2 < n_tiles) mbar_wait(&k_full[s2], ((t + 2) / ST) & 1);
       // ... then the softmax warps' P_x(t)
       mbar_wait(&p_full[x * 2 + par], (t >> 1) & 1);
@@ -326,10 +343,12 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
           for (int i = 0; i < 32; i += 4) {
             const float p0 = __uint_as_float(a[c - 1][i]), p1 = __uint_as_float(a[c - 1][i + 1]);
             const float p2 = __uint_as_float(a[c - 1][i + 2]), p3 = __uint_as_float(a[c - 1][i + 3]);
-            s0 += p0;
-            s1 += p1;
-            s2 += p2;
-            s3 += p3;
+            if (!kSumMMA) {
+              s0 += p0;
+              s1 += p1;
+              s2 += p2;
+              s3 += p3;
+            }
             pk[i >> 1] = pack_bf16x2(p0, p1);
             pk[(i >> 1) + 1] = pack_bf16x2(p2, p3);
           }
@@ -349,6 +368,12 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     mbar_wait(&o_full[x], 0);
     tc_fence_after();
     const int qrow = q0 + x * 128 + row;
+    if (kSumMMA) {  // the row sum accumulated by the tensor core in O's column 72
+      uint32_t r8[8];
+      tmem_ld8(tO + 72, r8);
+      tmem_wait_ld();
+      l_run = __uint_as_float(r8[0]);
+    }
     const float inv = 1.f / l_run;
     bf16* dst = p.out + (size_t)b * p.out_batch_stride + (size_t)(qrow < p.nq ? qrow : 0) * p.out_row_stride + (size_t)h * D;
 #pragma unroll 1
@@ -372,18 +397,18 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   if (warp == 0) tmem_dealloc<512>(tmem_base);
 }
 
-template <int D, int kPoly, bool kQTm>
+template <int D, int kPoly, bool kQTm, bool kSumMMA = false>
 static int launch_kt64(const CUtensorMap* tm, const AttnParams& prm, cudaStream_t st) {
   constexpr int smem = kQTm ? kT64SmemQT : kT64Smem;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_flash_kt64_kernel<D, kPoly, kQTm>,
+    cudaError_t e = cudaFuncSetAttribute(attn_flash_kt64_kernel<D, kPoly, kQTm, kSumMMA>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash(kt64): smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
   dim3 grid((prm.nq + 255) / 256, prm.H, prm.nb);
-  attn_flash_kt64_kernel<D, kPoly, kQTm><<<grid, kT64Threads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+  attn_flash_kt64_kernel<D, kPoly, kQTm, kSumMMA><<<grid, kT64Threads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
   return check_launch("attn_flash(kt64)");
 }
 
@@ -401,6 +426,14 @@ static int dispatch_kt64(const CUtensorMap* tm, const AttnParams& prm, int D, in
 }
 
 int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, int q_tmem, cudaStream_t st) {
+  if (q_tmem == 2 && D == 72) {  // variant 5: Q in TMEM + row sum on the tensor core
+    switch (poly) {
+      case 1: return launch_kt64<72, 1, true, true>(tm, prm, st);
+      case 2: return launch_kt64<72, 2, true, true>(tm, prm, st);
+      case 3: return launch_kt64<72, 3, true, true>(tm, prm, st);
+      default: return launch_kt64<72, 0, true, true>(tm, prm, st);
+    }
+  }
   return q_tmem ? dispatch_kt64<true>(tm, prm, D, poly, st) : dispatch_kt64<false>(tm, prm, D, poly, st);
 }
 
