@@ -49,6 +49,35 @@ for name, (N, Kd, act) in SHAPES.items():
     del a, w, o
 K.set_option("gemm_2sm", 1)
 
+# gate + residual fused into the GEMM epilogue (residual tile TMA-prefetched into the staging buffer) vs the two kernels
+if ONLY != "attn":
+    xres = torch.randn(2, 72000, 1152, device=dev, dtype=bf)
+    modg = torch.randn(2, 2, 6, 1152, device=dev, dtype=bf)
+    m8g = torch.ones(2, 20, dtype=torch.uint8, device=dev)
+    for name, Kd in (("proj", 1152), ("fc2", 4608)):
+        a = torch.randn(M, Kd, device=dev, dtype=bf)
+        w = torch.randn(1152, Kd, device=dev, dtype=bf) * 0.02
+        b = torch.randn(1152, device=dev, dtype=bf)
+        yb = torch.empty(M, 1152, device=dev, dtype=bf)
+
+        def unfused():
+            K.gemm_bias_act(a, w, b, out=yb)
+            K.gate_residual(xres, yb.view(2, 72000, 1152), modg, m8g, 2, 2, 20, 3600, out=xres)
+
+        def fused():
+            K.gemm_bias_residual(a, w, b, xres, modg, m8g, 2, 2, 20, 3600)
+
+        tu, tf = [], []
+        for _ in range(6):
+            tu.append(timeit(unfused, iters=8, warm=2))
+            tf.append(timeit(fused, iters=8, warm=2))
+        tg = timeit(lambda: K.gemm_bias_act(a, w, b, out=yb), iters=8, warm=2)
+        out["fused_epilogue_" + name] = {"gemm_plus_gate_residual_ms": round(sorted(tu)[3] * 1e3, 4), "fused_ms": round(sorted(tf)[3] * 1e3, 4),
+                                          "gemm_alone_ms": round(tg * 1e3, 4)}
+        print("fused epilogue", name, out["fused_epilogue_" + name], flush=True)
+        del a, w, yb
+    del xres
+
 # attention: spatial 720p (40 x 16 heads x 3600 x 72), cross (2 x 16 x 72000 x 300)
 C, H, D = 1152, 16, 72
 qkv = torch.randn(40, 3600, 3, H, D, device=dev, dtype=bf)
