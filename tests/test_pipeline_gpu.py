@@ -26,9 +26,9 @@ def test_engine_generate_latents_and_pab_speedup_path():
     for blk in eng.driver_worker.transformer.temporal_blocks:
         for lin in (blk.attn.proj, blk.cross_attn.proj, blk.mlp.fc2):
             torch.nn.init.normal_(lin.weight, std=0.02)
-    n0 = kernels.launch_count()
+    n0 = kernels.executed_launch_count()
     out = eng.generate("Sunset over the sea.", resolution="144p", aspect_ratio="9:16", num_frames=17, seed=0, verbose=False)
-    n_plain = kernels.launch_count() - n0
+    n_plain = kernels.executed_launch_count() - n0
     lat = out.video
     assert lat.shape == (1, 4, 5, 18, 32) and torch.isfinite(lat).all()
     out2 = eng.generate("Sunset over the sea.", resolution="144p", aspect_ratio="9:16", num_frames=17, seed=0, verbose=False)
@@ -39,9 +39,9 @@ def test_engine_generate_latents_and_pab_speedup_path():
     pab = OpenSoraPABConfig(spatial_threshold=(0, 1001), temporal_threshold=(0, 1001), cross_threshold=(0, 1001))
     eng = VideoSysEngine(_cfg(enable_pab=True, pab_config=pab))
     try:
-        n0 = kernels.launch_count()
+        n0 = kernels.executed_launch_count()
         out3 = eng.generate("Sunset over the sea.", resolution="144p", aspect_ratio="9:16", num_frames=17, seed=0, verbose=False)
-        n_pab = kernels.launch_count() - n0
+        n_pab = kernels.executed_launch_count() - n0
         assert torch.isfinite(out3.video).all() and out3.video.shape == lat.shape
         print(f"[pipeline] kernels launched: plain {n_plain}, PAB {n_pab}")
         assert n_pab < n_plain

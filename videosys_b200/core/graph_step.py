@@ -79,9 +79,11 @@ class StepGraph:
                 st["x_mask"] = torch.empty_like(xm)
             st["x_mask"].copy_(xm)
             args["x_mask"] = st["x_mask"]
+        from .. import kernels
+
         g = self._graphs.get(key)
+        fresh = g is None
         if g is None:
-            from .. import kernels
 
             g = torch.cuda.CUDAGraph()
             if self._pool is None:
@@ -97,4 +99,6 @@ class StepGraph:
         g.replay()
         self.replays += 1
         self.replayed_launches += self.launches_per_graph[key]
+        if not fresh:  # the capture itself advanced vsb_launch_count once for these kernels
+            kernels.GRAPH_REPLAYED_LAUNCHES += self.launches_per_graph[key]
         return self._outs[key].clone()

@@ -312,7 +312,7 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
 long long* g_attn_trace = nullptr;  // vsb_debug_attn_trace(device buffer of 3*16*4 int64)
 int g_opt_attn_poly = 0;            // variant 2 only: every fourth exp2 as a polynomial on the FMA pipe
 int g_opt_attn_pingpong = 1;        // variant 0 only: softmax warpgroups alternate on the MUFU phase
-int g_opt_attn_variant = -1;        // -1 = auto (3 for short key sequences, else 2); 0 = 128-key tiles, ping-pong;
+int g_opt_attn_variant = -1;        // -1 = auto (3 for short key sequences, else 5 / 4); 0 = 128-key tiles, ping-pong;
                                     // 2 = 64-key tiles, double-buffered S, one CTA per query pair; 3 = 2 + persistent CTAs
 
 }  // namespace vsb
@@ -371,7 +371,9 @@ extern "C" int vsb_attn_flash_strided(const vsb_bf16* q, const vsb_bf16* k, cons
   // Two tensor maps per operand: the 64-wide SWIZZLE_128B chunk and (head_dim 72 only) the 16-wide SWIZZLE_32B
   // chunk at d = 64..79.  The inner extent is D, so TMA zero-fills 72..79 and rows past nq / nk.
   // auto: text cross-attention (a handful of key tiles per query pair) is dominated by per-CTA fixed costs
-  const int variant = g_opt_attn_variant >= 0 ? g_opt_attn_variant : (nk <= 1024 ? 3 : 2);
+  // ... long key sequences: Q resident in TMEM (+8 % on the 720p spatial shape), head_dim 72 also takes the row sum from
+  // the tensor core (interleaved microbenchmark, profiles/r02_kernel_bench.json: 670 -> 726 / 729 TFLOP/s)
+  const int variant = g_opt_attn_variant >= 0 ? g_opt_attn_variant : (nk <= 1024 ? 3 : (D == 72 ? 5 : 4));
   CUtensorMap tm[6];
   const vsb_bf16* base[3] = {q, k, v};
   for (int i = 0; i < 3; ++i) {

@@ -84,6 +84,16 @@ def launch_count() -> int:
     return int(_lib.load().vsb_launch_count())
 
 
+# kernels executed by replaying captured CUDA graphs (core/graph_step.py adds a graph's launch count on every replay
+# after the first; the first replay's launches were counted by vsb_launch_count at capture time)
+GRAPH_REPLAYED_LAUNCHES = 0
+
+
+def executed_launch_count() -> int:
+    """Kernels of this library that have run: host launches + launches inside replayed CUDA graphs."""
+    return launch_count() + GRAPH_REPLAYED_LAUNCHES
+
+
 def tmap_cache_stats():
     """(hits, misses) of the encoded-tensor-map cache; misses = host cuTensorMapEncodeTiled calls made."""
     lib = _lib.load()
