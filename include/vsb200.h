@@ -206,6 +206,45 @@ int vsb_ipc_get_handle(void* devptr, void* out_handle64);
 int vsb_ipc_open_handle(const void* handle64, void** out_devptr);
 int vsb_ipc_close_handle(void* devptr);
 
+/* ---- IEEE fp16 twins ----------------------------------------------------------------------------------------------
+ * The reference runs CogVideoX-2b and Latte in torch.float16 (pipelines/cogvideox/pipeline_cogvideox.py:138-139,
+ * pipelines/latte/pipeline_latte.py:201).  Every kernel entry above that touches activations exists a second time with
+ * the suffix _f16: same arguments, same tile schedules, fp32 accumulation and rounding points, the 16-bit storage type
+ * being IEEE half instead of bfloat16 (each kernel source is compiled twice: csrc/vsb_common.cuh, -DVSB_HALF).  The
+ * DSP entries are bf16 only (sequence parallelism is an OpenSora path). */
+typedef uint16_t vsb_f16;
+int vsb_ln_modulate_f16(const vsb_f16* x, vsb_f16* out, const vsb_f16* mod, const uint8_t* x_mask, int shift_row,
+                    int scale_row, int B, int T, int S, int C, float eps, void* stream);
+int vsb_ln_modulate_affine_f16(const vsb_f16* x, vsb_f16* out, const vsb_f16* mod, const uint8_t* x_mask,
+                           const vsb_f16* gamma, const vsb_f16* beta, int shift_row, int scale_row, int B, int T, int S,
+                           int C, float eps, void* stream);
+int vsb_modulation_table_f16(const vsb_f16* table, const vsb_f16* t, const vsb_f16* t0, vsb_f16* mod, int B, int C,
+                         int rows, void* stream);
+int vsb_gate_residual_f16(const vsb_f16* x, const vsb_f16* y, vsb_f16* out, vsb_f16* cache_out, const vsb_f16* mod,
+                      const uint8_t* x_mask, int gate_row, int B, int T, int S, int C, void* stream);
+int vsb_residual_add_f16(const vsb_f16* x, const vsb_f16* y, vsb_f16* out, size_t n, void* stream);
+int vsb_qk_rmsnorm_f16(vsb_f16* qkv, const vsb_f16* wq, const vsb_f16* wk, size_t rows, int H, int D, float eps,
+                   void* stream);
+int vsb_qk_rmsnorm_rope_f16(vsb_f16* qkv, const vsb_f16* wq, const vsb_f16* wk, size_t rows, int H, int D, float eps,
+                        const float* rope_cos, const float* rope_sin, int pos_div, int pos_mod, void* stream);
+int vsb_qk_layernorm_f16(vsb_f16* qkv, const vsb_f16* wq, const vsb_f16* bq, const vsb_f16* wk, const vsb_f16* bk,
+                     size_t rows, int H, int D, float eps, void* stream);
+int vsb_attn_short_f16(const vsb_f16* qkv, vsb_f16* out, const vsb_f16* wq, const vsb_f16* wk, const float* rope_cos,
+                   const float* rope_sin, int n_outer, int n_inner, long long outer_stride, long long inner_stride,
+                   long long tok_stride, int n, int H, int D, float eps, float scale, int flags, void* stream);
+int vsb_gemm_bias_act_f16(const vsb_f16* A, const vsb_f16* W, const vsb_f16* bias, vsb_f16* out, int M, int N, int K,
+                      int act, void* stream);
+int vsb_gemm_bias_residual_f16(const vsb_f16* A, const vsb_f16* W, const vsb_f16* bias, const vsb_f16* resid,
+                           vsb_f16* out, const vsb_f16* mod, const uint8_t* x_mask, int gate_row, int M, int N, int K,
+                           int B, int T, int S, void* stream);
+int vsb_attn_flash_f16(const vsb_f16* q, const vsb_f16* k, const vsb_f16* v, vsb_f16* out, int nb, int nq, int nk,
+                   int H, int D, long long q_row_stride, long long q_batch_stride, long long kv_row_stride,
+                   long long kv_batch_stride, const int* host_kv_lens, float scale, void* stream);
+int vsb_attn_flash_strided_f16(const vsb_f16* q, const vsb_f16* k, const vsb_f16* v, vsb_f16* out, int nb, int nq, int nk,
+                           int H, int D, long long q_row_stride, long long q_batch_stride, long long kv_row_stride,
+                           long long kv_batch_stride, long long out_row_stride, long long out_batch_stride,
+                           const int* host_kv_lens, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -316,9 +316,25 @@ def test_step_graph_replay_is_bit_identical():
             eager, _ = run(False, pab)
             graphed, st = run(True, pab)
             assert st.replays >= len(ts), "the graph path was not taken"
+            n = len(ts)
+            if not pab:  # without PAB history the second pass over the schedule must reproduce the first, in each mode
+                for i in range(n):
+                    assert torch.equal(eager[i], eager[i + n]), f"EAGER is not deterministic: step {i} differs between passes"
+                    assert torch.equal(graphed[i], graphed[i + n]), f"GRAPH replay is not deterministic: step {i}"
             for i, (a, b) in enumerate(zip(eager, graphed)):
                 assert torch.equal(a, b), f"pab={pab} step {i}: replayed graph differs from eager"
             print(f"[parity] step graph pab={pab}: {len(st._graphs)} graphs, {st.replays} replays, bit-identical to eager")
     finally:
         P.set_pab_manager(None)
         net.reset_pab_state()
+
+
+def test_forward_is_deterministic():
+    """The same forward, 25 times: bit-identical outputs (no kernel may depend on scheduling order or timing)."""
+    cfg = cases.small_model_cfg(depth=2)
+    net, sd = _build(cfg)
+    dev = _dev()
+    inp = _to(cases.forward_inputs(BF), dev)
+    ref = net(**inp)
+    bad = [i for i in range(25) if not torch.equal(net(**inp), ref)]
+    assert not bad, f"forward differs from its first run on repetitions {bad}"

@@ -48,6 +48,13 @@ SIGNATURES = {
     "vsb_ipc_close_handle": (_i, [_vp]),
 }
 
+# fp16 twins (include/vsb200.h "IEEE fp16 twins"): same signatures, suffix _f16
+F16_TWINS = ("vsb_ln_modulate", "vsb_ln_modulate_affine", "vsb_modulation_table", "vsb_gate_residual", "vsb_residual_add",
+             "vsb_qk_rmsnorm", "vsb_qk_rmsnorm_rope", "vsb_qk_layernorm", "vsb_attn_short", "vsb_gemm_bias_act",
+             "vsb_gemm_bias_residual", "vsb_attn_flash", "vsb_attn_flash_strided")
+for _n in F16_TWINS:
+    SIGNATURES[_n + "_f16"] = SIGNATURES[_n]
+
 _lib = None
 
 

@@ -6,8 +6,14 @@
 
 #include "vsb_host.h"
 
-namespace vsb {
+namespace vsbs {
 thread_local char g_err[512] = "";
+int g_opt_gemm_2sm = 1;       // CTA-pair GEMM for M >= 1024
+int g_opt_attn_variant = -1;  // -1 = auto
+int g_opt_attn_pingpong = 1;  // variant 0 only
+int g_opt_attn_poly = 0;      // variants 2-5: fraction of exp2 on the FMA pipe
+int g_opt_dsp_rowwise = 1;    // 0: the first (per-vector) reshard kernel
+long long* g_attn_trace = nullptr;
 std::atomic<unsigned long long> g_launches{0};
 static EncodeTiledFn g_encode = nullptr;
 static int g_sms = 0;
@@ -44,6 +50,7 @@ struct TmapKey {
   unsigned long long dims[5], strides[4];
   unsigned box[5];
   int rank, swz;
+  int dtype, pad_;
   bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
 };
 struct TmapKeyHash {
@@ -63,17 +70,18 @@ static std::mutex g_tmap_mu;
 static std::atomic<unsigned long long> g_tmap_hits{0}, g_tmap_misses{0};
 static int g_opt_tmap_cache = 1;
 
-static int make_tmap_bf16_uncached(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+static int make_tmap_bf16_uncached(int dtype, CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
                                    const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz);
 
-int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+int make_tmap_elem(int dtype, CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
                    const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz) {
-  if (!g_opt_tmap_cache || rank < 1 || rank > 5) return make_tmap_bf16_uncached(m, base, rank, dims, strides_bytes, box, swz);
+  if (!g_opt_tmap_cache || rank < 1 || rank > 5) return make_tmap_bf16_uncached(dtype, m, base, rank, dims, strides_bytes, box, swz);
   TmapKey key;
   memset(&key, 0, sizeof(key));
   key.base = base;
   key.rank = rank;
   key.swz = (int)swz;
+  key.dtype = dtype;
   for (int i = 0; i < rank; ++i) {
     key.dims[i] = dims[i];
     key.box[i] = box[i];
@@ -88,7 +96,7 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned lo
       return VSB_OK;
     }
   }
-  int rc = make_tmap_bf16_uncached(m, base, rank, dims, strides_bytes, box, swz);
+  int rc = make_tmap_bf16_uncached(dtype, m, base, rank, dims, strides_bytes, box, swz);
   if (rc) return rc;
   g_tmap_misses.fetch_add(1, std::memory_order_relaxed);
   std::lock_guard<std::mutex> g(g_tmap_mu);
@@ -97,7 +105,7 @@ int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned lo
   return VSB_OK;
 }
 
-static int make_tmap_bf16_uncached(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+static int make_tmap_bf16_uncached(int dtype, CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
                                    const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz) {
   int rc = load_encode();
   if (rc) return rc;
@@ -113,15 +121,15 @@ static int make_tmap_bf16_uncached(CUtensorMap* m, const void* base, int rank, c
       if (gstr[i - 1] % 16) return fail(VSB_ERR_UNSUPPORTED, "tensor map stride %llu not a multiple of 16 bytes", (unsigned long long)gstr[i - 1]);
     }
   }
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
+  CUresult r = g_encode(m, dtype ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim,
                         estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(VSB_ERR_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
   return VSB_OK;
 }
-}  // namespace vsb
+}  // namespace vsbs
 
-using namespace vsb;
+using namespace vsbs;
 
 extern "C" int vsb_version(void) { return 100; }
 extern "C" const char* vsb_last_error(void) { return g_err; }
@@ -144,13 +152,6 @@ extern "C" int vsb_init(int device) {
   return load_encode();
 }
 
-namespace vsb {
-extern int g_opt_gemm_2sm;
-extern int g_opt_attn_variant;
-extern int g_opt_attn_pingpong;
-extern int g_opt_attn_poly;
-extern int g_opt_dsp_rowwise;
-}
 extern "C" int vsb_set_option(const char* name, int value) {
   if (!name) return fail(VSB_ERR_INVALID, "set_option: null name");
   if (!strcmp(name, "gemm_2sm")) {

@@ -24,7 +24,7 @@ constexpr int kMaxWarps = 16;
 
 union Vec8s {
   uint4 u;
-  __nv_bfloat162 h[4];
+  elem2 h[4];
 };
 
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
@@ -45,12 +45,12 @@ __device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const void* p) {
 }
 __device__ __forceinline__ void mma_k16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      "mma.sync.aligned.m16n8k16.row.col.f32." VSB_MMA_T "." VSB_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 __device__ __forceinline__ void mma_k8(float (&c)[4], const uint32_t (&a)[2], uint32_t b) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32." VSB_MMA_T "." VSB_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(b));
 }
@@ -148,7 +148,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
             v[c].u = *reinterpret_cast<const uint4*>(rowp + c * 8);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(v[c].h[j]);
+              const float2 f = e2_to_float2(v[c].h[j]);
               ss = fmaf(f.x, f.x, ss);
               ss = fmaf(f.y, f.y, ss);
             }
@@ -166,11 +166,11 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
             w.u = do_norm ? __ldg(reinterpret_cast<const uint4*>(wrow + c * 8)) : make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 f = __bfloat1622float2(v[c].h[j]);
+              const float2 f = e2_to_float2(v[c].h[j]);
               // normalization.py:28-33: h = bf16(x*rstd); y = bf16(w*h)
-              __nv_bfloat162 y2 = do_norm ? __hmul2_rn(w.h[j], __floats2bfloat162_rn(f.x * rs, f.y * rs)) : v[c].h[j];
+              elem2 y2 = do_norm ? __hmul2_rn(w.h[j], floats_to_e2(f.x * rs, f.y * rs)) : v[c].h[j];
               if (has_rope || (which == 0 && !sdpa_math)) {
-                float2 y = __bfloat1622float2(y2);
+                float2 y = e2_to_float2(y2);
                 if (has_rope) {
                   // rotate_queries_or_keys: t*cos + rotate_half(t)*sin in fp32, pairs (2i, 2i+1): rot = (-x2, x1)
                   const int d = (part * CPL + c) * 8 + 2 * j;
@@ -178,13 +178,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
                   const float2 sn = *reinterpret_cast<const float2*>(s_sin + r * D + d);
                   const float o0 = __fadd_rn(__fmul_rn(y.x, cs.x), __fmul_rn(-y.y, sn.x));
                   const float o1 = __fadd_rn(__fmul_rn(y.y, cs.y), __fmul_rn(y.x, sn.y));
-                  y = __bfloat1622float2(__floats2bfloat162_rn(o0, o1));
+                  y = e2_to_float2(floats_to_e2(o0, o1));
                 }
                 if (which == 0 && !sdpa_math) {  // q = bf16(q * scale)  (attentions.py:113)
                   y.x *= scale;
                   y.y *= scale;
                 }
-                y2 = __floats2bfloat162_rn(y.x, y.y);
+                y2 = floats_to_e2(y.x, y.y);
               }
               o.h[j] = y2;
             }
@@ -357,7 +357,7 @@ static int launch_short(const bf16* qkv, bf16* out, const bf16* wq, const bf16* 
 
 using namespace vsb;
 
-extern "C" int vsb_attn_short(const vsb_bf16* qkv, vsb_bf16* out, const vsb_bf16* wq, const vsb_bf16* wk,
+extern "C" int VSB_API(vsb_attn_short)(const vsb_bf16* qkv, vsb_bf16* out, const vsb_bf16* wq, const vsb_bf16* wk,
                               const float* rope_cos, const float* rope_sin, int n_outer, int n_inner,
                               long long outer_stride, long long inner_stride, long long tok_stride, int n, int H,
                               int D, float eps, float scale, int flags, void* stream) {

@@ -309,30 +309,28 @@ attn_flash_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constan
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
-long long* g_attn_trace = nullptr;  // vsb_debug_attn_trace(device buffer of 3*16*4 int64)
-int g_opt_attn_poly = 0;            // variant 2 only: every fourth exp2 as a polynomial on the FMA pipe
-int g_opt_attn_pingpong = 1;        // variant 0 only: softmax warpgroups alternate on the MUFU phase
-int g_opt_attn_variant = -1;        // -1 = auto (3 for short key sequences, else 5 / 4); 0 = 128-key tiles, ping-pong;
-                                    // 2 = 64-key tiles, double-buffered S, one CTA per query pair; 3 = 2 + persistent CTAs
+// g_attn_trace and the attn_* options live in api.cu (namespace vsbs, shared with the fp16 twin)
 
 }  // namespace vsb
 
 using namespace vsb;
 
+#ifndef VSB_HALF
 extern "C" int vsb_debug_attn_trace(void* device_buffer) {
   g_attn_trace = (long long*)device_buffer;
   return VSB_OK;
 }
+#endif
 
-extern "C" int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb, int nq,
+extern "C" int VSB_API(vsb_attn_flash)(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb, int nq,
                               int nk, int H, int D, long long q_row_stride, long long q_batch_stride,
                               long long kv_row_stride, long long kv_batch_stride, const int* host_kv_lens, float scale,
                               void* stream) {
-  return vsb_attn_flash_strided(q, k, v, out, nb, nq, nk, H, D, q_row_stride, q_batch_stride, kv_row_stride,
+  return VSB_API(vsb_attn_flash_strided)(q, k, v, out, nb, nq, nk, H, D, q_row_stride, q_batch_stride, kv_row_stride,
                                 kv_batch_stride, (long long)H * D, (long long)nq * H * D, host_kv_lens, scale, stream);
 }
 
-extern "C" int vsb_attn_flash_strided(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb,
+extern "C" int VSB_API(vsb_attn_flash_strided)(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb,
                                       int nq, int nk, int H, int D, long long q_row_stride, long long q_batch_stride,
                                       long long kv_row_stride, long long kv_batch_stride, long long out_row_stride,
                                       long long out_batch_stride, const int* host_kv_lens, float scale, void* stream) {

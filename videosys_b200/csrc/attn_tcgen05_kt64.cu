@@ -205,7 +205,7 @@ attn_flash_kt64_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
           const int r = lane + rr * 32;
-          *reinterpret_cast<uint16_t*>(vb + r * 32 + ((1 ^ ((r >> 2) & 1)) << 4)) = 0x3F80;  // bf16 1.0
+          *reinterpret_cast<uint16_t*>(vb + r * 32 + ((1 ^ ((r >> 2) & 1)) << 4)) = VSB_ONE_BITS;  // 1.0 in the element type
         }
         fence_proxy_async_smem();
         __syncwarp();

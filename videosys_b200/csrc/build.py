@@ -8,7 +8,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SOURCES = ["api.cu", "elementwise.cu", "attn_short.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2sm.cu", "attn_tcgen05.cu", "attn_tcgen05_kt64.cu", "attn_tcgen05_kt64p.cu", "dsp_p2p.cu"]
-HEADERS = ["vsb_common.cuh", "vsb_host.h", "attn_params.cuh", os.path.join("..", "..", "include", "vsb200.h")]
+# every kernel file below is compiled twice: bf16 (as is) and IEEE fp16 (-DVSB_HALF -> *.f16.o, entries suffixed _f16)
+TWINNED = ["elementwise.cu", "attn_short.cu", "gemm_tcgen05.cu", "gemm_tcgen05_2sm.cu", "attn_tcgen05.cu", "attn_tcgen05_kt64.cu", "attn_tcgen05_kt64p.cu"]
+HEADERS = ["vsb_common.cuh", "vsb_host.h", "attn_params.cuh", "dsp_common.cuh", os.path.join("..", "..", "include", "vsb200.h")]
 LIB = os.path.join(HERE, "libvsb200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -28,13 +30,14 @@ def _stale(obj, src):
 def build(force=False, verbose=False):
     objs = []
     procs = []
-    for s in SOURCES:
+    jobs = [(s, s.replace(".cu", ".o"), []) for s in SOURCES] + [(s, s.replace(".cu", ".f16.o"), ["-DVSB_HALF"]) for s in TWINNED]
+    for s, o, extra in jobs:
         src = os.path.join(HERE, s)
-        obj = os.path.join(HERE, s.replace(".cu", ".o"))
+        obj = os.path.join(HERE, o)
         objs.append(obj)
         if force or _stale(obj, src):
-            cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
-            procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+            cmd = [NVCC, *FLAGS, *extra, "-c", src, "-o", obj]
+            procs.append((o, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for s, p in procs:
         out, _ = p.communicate()

@@ -10,7 +10,7 @@
 
 namespace vsb {
 
-int g_opt_dsp_rowwise = 1;  // 1: one warp per token row (default); 0: the first version (decode per 16-byte vector)
+// option dsp_rowwise (api.cu): 1 = one warp per token row (default); 0 = the first version (decode per 16-byte vector)
 
 // dir 0: local [B, T, Sl, C] -> rank d receives frames [d*Tl, (d+1)*Tl) into [B, Tl, S, C] at columns rank*Sl + sl
 // dir 1: local [B, Tl, S, C] -> rank d receives columns [d*Sl, (d+1)*Sl) into [B, T, Sl, C] at frames rank*Tl + tl

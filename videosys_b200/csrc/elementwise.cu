@@ -10,7 +10,7 @@ namespace vsb {
 
 union Vec8 {
   uint4 u;
-  __nv_bfloat162 h[4];
+  elem2 h[4];
 };
 
 __device__ __forceinline__ uint4 ld_stream(const void* p) {
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
       if (lane + i * 32 < nvec) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float2 f = __bfloat1622float2(v[i].h[j]);
+          float2 f = e2_to_float2(v[i].h[j]);
           sum += f.x + f.y;
         }
       }
@@ -97,14 +97,14 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
       if (lane + i * 32 < nvec) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float2 f = __bfloat1622float2(v[i].h[j]);
+          float2 f = e2_to_float2(v[i].h[j]);
           float a = f.x - mean, c = f.y - mean;
           sq += a * a + c * c;
         }
       }
     }
     const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
-    const __nv_bfloat162 one2 = __floats2bfloat162_rn(1.f, 1.f);
+    const elem2 one2 = floats_to_e2(1.f, 1.f);
     bf16* orow = out + (size_t)row * C;
     bool send = true;
     if (kDsp) {
@@ -124,18 +124,18 @@ __global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict
         sc.u = __ldg(reinterpret_cast<const uint4*>(scale + vi * 8));
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float2 f = __bfloat1622float2(v[i].h[j]);
+          float2 f = e2_to_float2(v[i].h[j]);
           // eager chain on packed bf16 (each op = exact result rounded once, like the eager bf16 kernels):
           // n = bf16(LN(x)); g = bf16(1 + scale); m = bf16(n * g); out = bf16(m + shift)
           float n0 = (f.x - mean) * rstd, n1 = (f.y - mean) * rstd;
           if (gamma != nullptr) {  // nn.LayerNorm with affine: one rounding after weight and bias (CogVideoXLayerNormZero)
-            const float2 gw = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(gamma + vi * 8 + 2 * j));
-            const float2 gb = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(beta + vi * 8 + 2 * j));
+            const float2 gw = e2_to_float2(*reinterpret_cast<const elem2*>(gamma + vi * 8 + 2 * j));
+            const float2 gb = e2_to_float2(*reinterpret_cast<const elem2*>(beta + vi * 8 + 2 * j));
             n0 = n0 * gw.x + gb.x;
             n1 = n1 * gw.y + gb.y;
           }
-          const __nv_bfloat162 n2 = __floats2bfloat162_rn(n0, n1);
-          const __nv_bfloat162 g2 = __hadd2_rn(one2, sc.h[j]);
+          const elem2 n2 = floats_to_e2(n0, n1);
+          const elem2 g2 = __hadd2_rn(one2, sc.h[j]);
           o.h[j] = __hadd2_rn(__hmul2_rn(n2, g2), sh.h[j]);
         }
         if (!kDsp || send) st_stream(orow + vi * 8, o.u);
@@ -168,8 +168,8 @@ __global__ void modulation_table_kernel(const bf16* __restrict__ table, const bf
     int b = (i / (C * rows)) % B;
     int s = i / (C * rows * B);
     const bf16* src = (s == 1 && t0 != nullptr) ? t0 : t;
-    float v = __bfloat162float(table[r * C + c]) + __bfloat162float(src[(size_t)b * rows * C + r * C + c]);
-    mod[i] = __float2bfloat16_rn(v);
+    float v = e_to_float(table[r * C + c]) + e_to_float(src[(size_t)b * rows * C + r * C + c]);
+    mod[i] = float_to_e(v);
   }
 }
 
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv,
       if (active[u]) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float2 f = __bfloat1622float2(v[u].h[j]);
+          float2 f = e2_to_float2(v[u].h[j]);
           ss += f.x * f.x + f.y * f.y;
         }
       }
@@ -333,19 +333,19 @@ __global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv,
         Vec8 o;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float2 f = __bfloat1622float2(v[u].h[j]);
+          float2 f = e2_to_float2(v[u].h[j]);
           // eager: h = bf16(x * rstd); out = bf16(w * h)
-          o.h[j] = __hmul2_rn(wv[which[u]].h[j], __floats2bfloat162_rn(f.x * r, f.y * r));
+          o.h[j] = __hmul2_rn(wv[which[u]].h[j], floats_to_e2(f.x * r, f.y * r));
           if (rope_cos != nullptr) {
             // rotate_queries_or_keys (attentions.py:76-78): t*cos + rotate_half(t)*sin in fp32 on interleaved pairs
             // (2i, 2i+1), rot = (-x2, x1), cast back to bf16; position = the token's frame index
-            const float2 y = __bfloat1622float2(o.h[j]);
+            const float2 y = e2_to_float2(o.h[j]);
             const int d = l * 8 + 2 * j;
             const float2 cs = *reinterpret_cast<const float2*>(rope_cos + (size_t)pos[u] * D + d);
             const float2 sn = *reinterpret_cast<const float2*>(rope_sin + (size_t)pos[u] * D + d);
             const float o0 = __fadd_rn(__fmul_rn(y.x, cs.x), __fmul_rn(-y.y, sn.x));
             const float o1 = __fadd_rn(__fmul_rn(y.y, cs.y), __fmul_rn(y.x, sn.y));
-            o.h[j] = __floats2bfloat162_rn(o0, o1);
+            o.h[j] = floats_to_e2(o0, o1);
           }
         }
         *reinterpret_cast<uint4*>(p[u]) = o.u;
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256) qk_layernorm_kernel(bf16* __restrict__ qk
       v.u = *reinterpret_cast<const uint4*>(p);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(v.h[j]);
+        float2 f = e2_to_float2(v.h[j]);
         s1 += f.x + f.y;
       }
     }
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(256) qk_layernorm_kernel(bf16* __restrict__ qk
     if (active) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(v.h[j]);
+        float2 f = e2_to_float2(v.h[j]);
         s2 += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
       }
     }
@@ -414,9 +414,9 @@ __global__ void __launch_bounds__(256) qk_layernorm_kernel(bf16* __restrict__ qk
       Vec8 o;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float2 f = __bfloat1622float2(v.h[j]);
-        float2 w = __bfloat1622float2(wv[which].h[j]), b = __bfloat1622float2(bv[which].h[j]);
-        o.h[j] = __floats2bfloat162_rn((f.x - mean) * r * w.x + b.x, (f.y - mean) * r * w.y + b.y);
+        float2 f = e2_to_float2(v.h[j]);
+        float2 w = e2_to_float2(wv[which].h[j]), b = e2_to_float2(bv[which].h[j]);
+        o.h[j] = floats_to_e2((f.x - mean) * r * w.x + b.x, (f.y - mean) * r * w.y + b.y);
       }
       *reinterpret_cast<uint4*>(p) = o.u;
     }
@@ -462,12 +462,13 @@ static int ln_modulate_launch(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* 
   return check_launch("ln_modulate");
 }
 
-extern "C" int vsb_ln_modulate_affine(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
+extern "C" int VSB_API(vsb_ln_modulate_affine)(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
                                       const vsb_bf16* gamma, const vsb_bf16* beta, int shift_row, int scale_row, int B,
                                       int T, int S, int C, float eps, void* stream) {
   return ln_modulate_launch(x, out, mod, x_mask, gamma, beta, shift_row, scale_row, B, T, S, C, eps, nullptr, stream);
 }
 
+#ifndef VSB_HALF  // the DSP-fused entries exist in the bf16 build only (sequence parallelism is an OpenSora / bf16 path)
 namespace vsb {
 int dsp_fill_peers(DspPeers* peers, void* const* host_peer_recv, void* const* host_peer_flags, int world, const char* what);
 }
@@ -516,12 +517,14 @@ extern "C" int vsb_gate_residual_dsp(const vsb_bf16* x, void* const* host_peer_y
   return check_launch("gate_residual_dsp");
 }
 
-extern "C" int vsb_ln_modulate(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
+#endif  // !VSB_HALF
+
+extern "C" int VSB_API(vsb_ln_modulate)(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask,
                                int shift_row, int scale_row, int B, int T, int S, int C, float eps, void* stream) {
-  return vsb_ln_modulate_affine(x, out, mod, x_mask, nullptr, nullptr, shift_row, scale_row, B, T, S, C, eps, stream);
+  return VSB_API(vsb_ln_modulate_affine)(x, out, mod, x_mask, nullptr, nullptr, shift_row, scale_row, B, T, S, C, eps, stream);
 }
 
-extern "C" int vsb_modulation_table(const vsb_bf16* table, const vsb_bf16* t, const vsb_bf16* t0, vsb_bf16* mod,
+extern "C" int VSB_API(vsb_modulation_table)(const vsb_bf16* table, const vsb_bf16* t, const vsb_bf16* t0, vsb_bf16* mod,
                                     int B, int C, int rows, void* stream) {
   if (!table || !t || !mod || B <= 0 || C <= 0 || rows <= 0) return fail(VSB_ERR_INVALID, "modulation_table: bad args");
   int total = 2 * B * rows * C;
@@ -531,7 +534,7 @@ extern "C" int vsb_modulation_table(const vsb_bf16* table, const vsb_bf16* t, co
   return check_launch("modulation_table");
 }
 
-extern "C" int vsb_gate_residual(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* out, vsb_bf16* cache_out,
+extern "C" int VSB_API(vsb_gate_residual)(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* out, vsb_bf16* cache_out,
                                  const vsb_bf16* mod, const uint8_t* x_mask, int gate_row, int B, int T, int S, int C,
                                  void* stream) {
   if (!x || !y || !out || !mod || B <= 0 || T <= 0 || S <= 0 || C <= 0)
@@ -546,7 +549,7 @@ extern "C" int vsb_gate_residual(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16*
   return check_launch("gate_residual");
 }
 
-extern "C" int vsb_residual_add(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* out, size_t n, void* stream) {
+extern "C" int VSB_API(vsb_residual_add)(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* out, size_t n, void* stream) {
   if (!x || !y || !out || n == 0) return fail(VSB_ERR_INVALID, "residual_add: bad args");
   if (n % 8 || !aligned16(x) || !aligned16(y) || !aligned16(out))
     return fail(VSB_ERR_UNSUPPORTED, "residual_add: need n %% 8 == 0 and 16B-aligned pointers");
@@ -556,12 +559,12 @@ extern "C" int vsb_residual_add(const vsb_bf16* x, const vsb_bf16* y, vsb_bf16* 
   return check_launch("residual_add");
 }
 
-extern "C" int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D,
+extern "C" int VSB_API(vsb_qk_rmsnorm)(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D,
                               float eps, void* stream) {
-  return vsb_qk_rmsnorm_rope(qkv, wq, wk, rows, H, D, eps, nullptr, nullptr, 1, 1, stream);
+  return VSB_API(vsb_qk_rmsnorm_rope)(qkv, wq, wk, rows, H, D, eps, nullptr, nullptr, 1, 1, stream);
 }
 
-extern "C" int vsb_qk_rmsnorm_rope(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D,
+extern "C" int VSB_API(vsb_qk_rmsnorm_rope)(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D,
                                    float eps, const float* rope_cos, const float* rope_sin, int pos_div, int pos_mod,
                                    void* stream) {
   if (!qkv || !wq || !wk || rows == 0 || H <= 0) return fail(VSB_ERR_INVALID, "qk_rmsnorm: bad args");
@@ -584,7 +587,7 @@ extern "C" int vsb_qk_rmsnorm_rope(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_
   return check_launch("qk_rmsnorm");
 }
 
-extern "C" int vsb_qk_layernorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* bq, const vsb_bf16* wk,
+extern "C" int VSB_API(vsb_qk_layernorm)(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* bq, const vsb_bf16* wk,
                                 const vsb_bf16* bk, size_t rows, int H, int D, float eps, void* stream) {
   if (!qkv || !wq || !bq || !wk || !bk || rows == 0 || H <= 0) return fail(VSB_ERR_INVALID, "qk_layernorm: bad args");
   if (!aligned16(qkv) || !aligned16(wq) || !aligned16(bq) || !aligned16(wk) || !aligned16(bk))

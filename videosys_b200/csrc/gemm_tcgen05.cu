@@ -176,7 +176,7 @@ gemm_bf16_tn_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_const
             const int col = j * 8 + e;
             const float a = __uint_as_float(col < 32 ? r0[col] : r1[col - 32]);
             const int gcol = ncol0 + col;
-            const float b = (bias != nullptr && gcol < N) ? __bfloat162float(__ldg(bias + gcol)) : 0.f;
+            const float b = (bias != nullptr && gcol < N) ? e_to_float(__ldg(bias + gcol)) : 0.f;
             float x = a + b;
             if (ACT == 1) x = gelu_tanh_f(rbf(x));
             v[e] = x;
@@ -234,13 +234,12 @@ int gemm2_dispatch(const void* A, const void* W, const void* bias, void* out, in
 int gemm2_residual(const void* A, const void* W, const void* bias, const void* resid, void* out, const void* mod,
                    const unsigned char* x_mask, int gate_row, int M, int N, int K, int B, int T, int S,
                    cudaStream_t st);
-int g_opt_gemm_2sm = 1;  // CTA-pair kernel for large problems (vsb_set_option("gemm_2sm", 0) selects 1-CTA tiles)
 
 }  // namespace vsb
 
 using namespace vsb;
 
-extern "C" int vsb_gemm_bias_act(const vsb_bf16* A, const vsb_bf16* W, const vsb_bf16* bias, vsb_bf16* out, int M,
+extern "C" int VSB_API(vsb_gemm_bias_act)(const vsb_bf16* A, const vsb_bf16* W, const vsb_bf16* bias, vsb_bf16* out, int M,
                                  int N, int K, int act, void* stream) {
   if (!A || !W || !out || M <= 0 || N <= 0 || K <= 0) return fail(VSB_ERR_INVALID, "gemm: bad args");
   if (K % 8 || N % 8 || !aligned16(A) || !aligned16(W) || !aligned16(out))
@@ -284,7 +283,7 @@ extern "C" int vsb_gemm_bias_act(const vsb_bf16* A, const vsb_bf16* W, const vsb
 
 // Fused epilogue: out = resid + [gate *] (A @ W^T + bias), see include/vsb200.h.  Returns 1 (nothing launched) when
 // the CTA-pair kernel does not take this shape; the caller then runs vsb_gemm_bias_act + vsb_gate_residual.
-extern "C" int vsb_gemm_bias_residual(const vsb_bf16* A, const vsb_bf16* W, const vsb_bf16* bias, const vsb_bf16* resid,
+extern "C" int VSB_API(vsb_gemm_bias_residual)(const vsb_bf16* A, const vsb_bf16* W, const vsb_bf16* bias, const vsb_bf16* resid,
                                       vsb_bf16* out, const vsb_bf16* mod, const uint8_t* x_mask, int gate_row, int M,
                                       int N, int K, int B, int T, int S, void* stream) {
   if (!A || !W || !resid || !out || M <= 0 || N <= 0 || K <= 0) return fail(VSB_ERR_INVALID, "gemm_residual: bad args");

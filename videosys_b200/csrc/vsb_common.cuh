@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -11,9 +12,43 @@
 #define VSB_SM100 1
 #endif
 
+// ---- element type of this translation unit -------------------------------------------------------------------------
+// Every kernel file is compiled twice: as is (bf16: OpenSora, CogVideoX-5b) and with -DVSB_HALF (IEEE fp16: the dtype the
+// reference runs CogVideoX-2b and Latte in, pipeline_cogvideox.py:138-139, pipeline_latte.py:201).  The fp16 twin lives
+// in namespace vsbh and exports every kernel entry with the suffix _f16 (same signatures).  `bf16` below is therefore
+// "the 16-bit storage type of this build"; fp32 accumulation, rounding points and tile schedules are identical.
+#ifdef VSB_HALF
+#define vsb vsbh
+#define VSB_API(name) name##_f16
+#define VSB_MMA_T "f16"
+#define VSB_ONE_BITS 0x3C00  // 1.0
+#define VSB_TMAP_DTYPE 1
+#else
+#define VSB_API(name) name
+#define VSB_MMA_T "bf16"
+#define VSB_ONE_BITS 0x3F80  // 1.0
+#define VSB_TMAP_DTYPE 0
+#endif
+
 namespace vsb {
 
+#ifdef VSB_HALF
+typedef __half bf16;
+typedef __half2 elem2;
+__device__ __forceinline__ float2 e2_to_float2(elem2 v) { return __half22float2(v); }
+__device__ __forceinline__ elem2 floats_to_e2(float lo, float hi) { return __floats2half2_rn(lo, hi); }
+__device__ __forceinline__ bf16 float_to_e(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ float e_to_float(bf16 x) { return __half2float(x); }
+constexpr uint32_t kUmmaFmtBits = 0u;  // a_format = b_format = F16
+#else
 typedef __nv_bfloat16 bf16;
+typedef __nv_bfloat162 elem2;
+__device__ __forceinline__ float2 e2_to_float2(elem2 v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ elem2 floats_to_e2(float lo, float hi) { return __floats2bfloat162_rn(lo, hi); }
+__device__ __forceinline__ bf16 float_to_e(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float e_to_float(bf16 x) { return __bfloat162float(x); }
+constexpr uint32_t kUmmaFmtBits = (1u << 7) | (1u << 10);  // a_format = b_format = BF16
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -21,15 +56,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
 // round-to-nearest-even float -> bf16 -> float (the rounding point of an eager bf16 op)
-__device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+__device__ __forceinline__ float rbf(float x) { return e_to_float(float_to_e(x)); }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
+  elem2 v = floats_to_e2(lo, hi);  // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
-  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
-  return __bfloat1622float2(v);
+  elem2 v = *reinterpret_cast<elem2*>(&u);
+  return e2_to_float2(v);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -310,7 +345,7 @@ __device__ __forceinline__ void tma_load_4d_w(uint32_t elected, const CUtensorMa
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32 (cute/arch/mma_sm100_desc.hpp InstrDescriptor bit layout).
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                      // c_format = F32
-         | (1u << 7) | (1u << 10)       // a_format = b_format = BF16
+         | kUmmaFmtBits                 // a_format = b_format = BF16 (F16 in the fp16 twin)
          | (uint32_t(a_mn_major) << 15) | (uint32_t(b_mn_major) << 16) | (uint32_t(N >> 3) << 17) |
          (uint32_t(M >> 4) << 24);
 }

@@ -9,9 +9,13 @@
 
 #include "../../include/vsb200.h"
 
-namespace vsb {
+// Host state shared by the bf16 build and its fp16 twin (namespace vsbs is never renamed; api.cu defines it once).
+namespace vsbs {
 extern thread_local char g_err[512];
 extern std::atomic<unsigned long long> g_launches;
+// run-time kernel selection knobs (vsb_set_option)
+extern int g_opt_gemm_2sm, g_opt_attn_variant, g_opt_attn_pingpong, g_opt_attn_poly, g_opt_dsp_rowwise;
+extern long long* g_attn_trace;
 
 inline int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -34,8 +38,20 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled();
 
-// bf16 tensor map, rank <= 5; dims/strides innermost first; strides in BYTES for dims 1..rank-1.
-int make_tmap_bf16(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+// 16-bit tensor map (dtype 0 = bf16, 1 = fp16), rank <= 5; dims/strides innermost first; strides in BYTES for dims
+// 1..rank-1.  Cached by (dtype, base, shape, strides, box, swizzle).
+int make_tmap_elem(int dtype, CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
                    const unsigned long long* strides_bytes, const unsigned* box, CUtensorMapSwizzle swz);
 int num_sms();
-}  // namespace vsb
+}  // namespace vsbs
+
+#ifndef VSB_TMAP_DTYPE
+#define VSB_TMAP_DTYPE 0
+#endif
+#define make_tmap_bf16(...) make_tmap_elem(VSB_TMAP_DTYPE, __VA_ARGS__)
+
+#ifdef VSB_HALF
+namespace vsbh { using namespace vsbs; }
+#else
+namespace vsb { using namespace vsbs; }
+#endif

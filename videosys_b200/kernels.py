@@ -72,8 +72,28 @@ def _p(t):
 
 
 def _bf16(t, name):
-    if t is not None and t.dtype != torch.bfloat16:
-        raise _lib.VsbError(f"{name} must be bfloat16")
+    if t is not None and t.dtype not in (torch.bfloat16, torch.float16):
+        raise _lib.VsbError(f"{name} must be bfloat16 or float16")
+
+
+def _fn(lib, name, ref):
+    """The entry for ref's dtype: bf16 -> `name`, IEEE fp16 -> its twin `name_f16` (include/vsb200.h)."""
+    if ref.dtype == torch.float16:
+        return getattr(lib, name + "_f16")
+    if ref.dtype != torch.bfloat16:
+        raise _lib.VsbError(f"vsb200 kernels take bfloat16 or float16 tensors, got {ref.dtype}")
+    return getattr(lib, name)
+
+
+def _same_dtype(*tensors):
+    dt = None
+    for t in tensors:
+        if t is None or not t.dtype.is_floating_point or t.dtype == torch.float32:
+            continue
+        if dt is None:
+            dt = t.dtype
+        elif t.dtype != dt:
+            raise _lib.VsbError(f"vsb200 kernels need one 16-bit dtype per call, got {dt} and {t.dtype}")
 
 
 def set_option(name: str, value: int) -> None:
@@ -105,8 +125,9 @@ def modulation_table(table: torch.Tensor, t: torch.Tensor, t0: Optional[torch.Te
     lib, st = _prep(table, t, t0)
     rows, Cc = table.shape
     B = t.shape[0]
-    mod = torch.empty(2, B, rows, Cc, dtype=torch.bfloat16, device=table.device)
-    _lib.check(lib.vsb_modulation_table(_p(table), _p(t), _p(t0), _p(mod), B, Cc, rows, st), "modulation_table")
+    _same_dtype(table, t, t0)
+    mod = torch.empty(2, B, rows, Cc, dtype=table.dtype, device=table.device)
+    _lib.check(_fn(lib, "vsb_modulation_table", table)(_p(table), _p(t), _p(t0), _p(mod), B, Cc, rows, st), "modulation_table")
     return mod
 
 
@@ -114,11 +135,12 @@ def ln_modulate(x, mod, x_mask_u8, shift_row, scale_row, B, T, S, out=None, eps=
     """LayerNorm (optionally affine: gamma/beta) + modulate + per-frame select; x viewed as [B, T, S, C]."""
     lib, st = _prep(x, mod, x_mask_u8, out, gamma, beta)
     _bf16(x, "x")
+    _same_dtype(x, mod, out, gamma, beta)
     Cc = x.shape[-1]
     out = torch.empty_like(x) if out is None else out
     with _Timed("ln_modulate", 2 * x.numel() * 2):
         _lib.check(
-            lib.vsb_ln_modulate_affine(_p(x), _p(out), _p(mod), _p(x_mask_u8), _p(gamma), _p(beta), shift_row,
+            _fn(lib, "vsb_ln_modulate_affine", x)(_p(x), _p(out), _p(mod), _p(x_mask_u8), _p(gamma), _p(beta), shift_row,
                                        scale_row, B, T, S, Cc, eps, st),
             "ln_modulate",
         )
@@ -127,11 +149,12 @@ def ln_modulate(x, mod, x_mask_u8, shift_row, scale_row, B, T, S, out=None, eps=
 
 def gate_residual(x, y, mod, x_mask_u8, gate_row, B, T, S, out=None, cache_out=None):
     lib, st = _prep(x, y, mod, x_mask_u8, out, cache_out)
+    _same_dtype(x, y, mod, out, cache_out)
     Cc = x.shape[-1]
     out = torch.empty_like(x) if out is None else out
     with _Timed("gate_residual", (3 + (cache_out is not None)) * x.numel() * 2):
         _lib.check(
-            lib.vsb_gate_residual(_p(x), _p(y), _p(out), _p(cache_out), _p(mod), _p(x_mask_u8), gate_row, B, T, S, Cc,
+            _fn(lib, "vsb_gate_residual", x)(_p(x), _p(y), _p(out), _p(cache_out), _p(mod), _p(x_mask_u8), gate_row, B, T, S, Cc,
                                   st),
             "gate_residual",
         )
@@ -140,9 +163,10 @@ def gate_residual(x, y, mod, x_mask_u8, gate_row, B, T, S, out=None, cache_out=N
 
 def residual_add(x, y, out=None):
     lib, st = _prep(x, y, out)
+    _same_dtype(x, y, out)
     out = torch.empty_like(x) if out is None else out
     with _Timed("residual_add", 3 * x.numel() * 2):
-        _lib.check(lib.vsb_residual_add(_p(x), _p(y), _p(out), x.numel(), st), "residual_add")
+        _lib.check(_fn(lib, "vsb_residual_add", x)(_p(x), _p(y), _p(out), x.numel(), st), "residual_add")
     return out
 
 
@@ -151,7 +175,7 @@ def qk_rmsnorm_(qkv, wq, wk, H, D, eps=1e-6, rope_cos=None, rope_sin=None, pos_d
     lib, st = _prep(qkv, wq, wk, rope_cos, rope_sin)
     rows = qkv.numel() // (3 * H * D)
     with _Timed("qk_rmsnorm", 4 * rows * H * D * 2):
-        _lib.check(lib.vsb_qk_rmsnorm_rope(_p(qkv), _p(wq), _p(wk), rows, H, D, eps, _p(rope_cos), _p(rope_sin),
+        _lib.check(_fn(lib, "vsb_qk_rmsnorm_rope", qkv)(_p(qkv), _p(wq), _p(wk), rows, H, D, eps, _p(rope_cos), _p(rope_sin),
                                            int(pos_div), int(pos_mod), st), "qk_rmsnorm")
     return qkv
 
@@ -160,7 +184,7 @@ def qk_layernorm_(qkv, wq, bq, wk, bk, H, D, eps=1e-6):
     lib, st = _prep(qkv, wq, bq, wk, bk)
     rows = qkv.numel() // (3 * H * D)
     with _Timed("qk_rmsnorm", 4 * rows * H * D * 2):
-        _lib.check(lib.vsb_qk_layernorm(_p(qkv), _p(wq), _p(bq), _p(wk), _p(bk), rows, H, D, eps, st), "qk_layernorm")
+        _lib.check(_fn(lib, "vsb_qk_layernorm", qkv)(_p(qkv), _p(wq), _p(bq), _p(wk), _p(bk), rows, H, D, eps, st), "qk_layernorm")
     return qkv
 
 
@@ -168,10 +192,10 @@ def attn_short(qkv, wq, wk, rope_cos, rope_sin, n_outer, n_inner, outer_stride, 
                scale, out=None, eps=1e-6, flags: int = 0):
     lib, st = _prep(qkv, wq, wk, rope_cos, rope_sin, out)
     rows = qkv.numel() // (3 * H * D)
-    out = torch.empty(rows, H * D, dtype=torch.bfloat16, device=qkv.device) if out is None else out
+    out = torch.empty(rows, H * D, dtype=qkv.dtype, device=qkv.device) if out is None else out
     with _Timed("attn_short", 4 * rows * H * D * 2):
         _lib.check(
-            lib.vsb_attn_short(_p(qkv), _p(out), _p(wq), _p(wk), _p(rope_cos), _p(rope_sin), n_outer, n_inner,
+            _fn(lib, "vsb_attn_short", qkv)(_p(qkv), _p(out), _p(wq), _p(wk), _p(rope_cos), _p(rope_sin), n_outer, n_inner,
                                outer_stride, inner_stride, tok_stride, n, H, D, eps, scale, flags, st),
             "attn_short",
         )
@@ -187,9 +211,10 @@ def gemm_bias_act(a, w, bias=None, act: int = 0, out=None):
     N = w.shape[0]
     if w.shape[1] != K:
         raise _lib.VsbError("gemm: K mismatch")
-    out = torch.empty(*a.shape[:-1], N, dtype=torch.bfloat16, device=a.device) if out is None else out
+    _same_dtype(a, w, bias, out)
+    out = torch.empty(*a.shape[:-1], N, dtype=a.dtype, device=a.device) if out is None else out
     with _Timed("gemm", 2 * M * N * K):
-        _lib.check(lib.vsb_gemm_bias_act(_p(a), _p(w), _p(bias), _p(out), M, N, K, act, st), "gemm_bias_act")
+        _lib.check(_fn(lib, "vsb_gemm_bias_act", a)(_p(a), _p(w), _p(bias), _p(out), M, N, K, act, st), "gemm_bias_act")
     return out
 
 
@@ -202,7 +227,7 @@ def gemm_bias_residual(a, w, bias, resid, mod=None, x_mask_u8=None, gate_row: in
     N = w.shape[0]
     out = resid if out is None else out
     with _Timed("gemm", 2 * M * N * K) as tm:
-        rc = lib.vsb_gemm_bias_residual(_p(a), _p(w), _p(bias), _p(resid), _p(out), _p(mod), _p(x_mask_u8), gate_row, M,
+        rc = _fn(lib, "vsb_gemm_bias_residual", a)(_p(a), _p(w), _p(bias), _p(resid), _p(out), _p(mod), _p(x_mask_u8), gate_row, M,
                                         N, K, B, T, S, st)
         if rc == 1:
             tm.cancel()
@@ -222,13 +247,14 @@ def attn_flash(q, k, v, nb, nq, nk, H, D, q_row_stride, q_batch_stride, kv_row_s
         raise _lib.VsbError("vsb200 kernels need CUDA tensors (no CPU fallback)")
     _init_dev(lib, q.device.index)
     st = torch.cuda.current_stream().cuda_stream
-    out = torch.empty(nb, nq, H * D, dtype=torch.bfloat16, device=q.device) if out is None else out
+    _same_dtype(q, k, v, out)
+    out = torch.empty(nb, nq, H * D, dtype=q.dtype, device=q.device) if out is None else out
     lens = None
     if kv_lens is not None:
         lens = (C.c_int * len(kv_lens))(*[int(v_) for v_ in kv_lens])
     with _Timed("attn_flash", 4 * nb * H * nq * nk * D):
         _lib.check(
-            lib.vsb_attn_flash_strided(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), nb, nq, nk, H, D,
+            _fn(lib, "vsb_attn_flash_strided", q)(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), nb, nq, nk, H, D,
                                        q_row_stride, q_batch_stride, kv_row_stride, kv_batch_stride,
                                        H * D if out_row_stride is None else out_row_stride,
                                        nq * H * D if out_batch_stride is None else out_batch_stride, lens, scale, st),

@@ -12,9 +12,12 @@ attention processor :88-175, sp = 1, no rotary = the 2B model) on the kernels:
     attention over 226 + 17 550 tokens is vsb_attn_flash (head_dim 64);
   * PAB (spatial gate only, :284-295) caches the un-gated attention output, as the reference does.
 
-Compute dtype is bf16 (the reference runs the 2B model in fp16, pipeline_cogvideox.py:138-139; an fp16 instantiation
-of the kernels is future work).  The time/patch embedders and the output head are diffusers classes, not restated.
+Compute dtype: IEEE fp16 (what the reference runs the 2B model in, pipeline_cogvideox.py:138-139; the *_f16 kernel
+twins) or bf16 (the 5B model's dtype).  ``CogVideoXTransformer3DModel`` below adds the embedders and the output head
+(reference :315-589; the diffusers pieces -- Timesteps, TimestepEmbedding, get_3d_sincos_pos_embed, AdaLayerNorm --
+restated from their published semantics, diffusers==0.30.0: parity unpinned for those).
 """
+import math
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -67,11 +70,12 @@ class CogVideoXBlock(nn.Module):
         self._qkv = None
 
     def fused_qkv(self):
-        if self._qkv is None:
-            a = self.attn1
-            self._qkv = (torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight], 0).contiguous(),
+        a = self.attn1
+        key = tuple((t.data_ptr(), t._version, t.dtype) for t in (a.to_q.weight, a.to_k.weight, a.to_v.weight, a.to_q.bias))
+        if self._qkv is None or self._qkv[0] != key:  # rebuilt after load_state_dict / .to(dtype or device)
+            self._qkv = (key, torch.cat([a.to_q.weight, a.to_k.weight, a.to_v.weight], 0).contiguous(),
                          torch.cat([a.to_q.bias, a.to_k.bias, a.to_v.bias], 0).contiguous())
-        return self._qkv
+        return self._qkv[1], self._qkv[2]
 
 
 class CogVideoXBlockStack(nn.Module):
@@ -106,10 +110,11 @@ class CogVideoXBlockStack(nn.Module):
         return mod
 
     @torch.no_grad()
-    def forward(self, hidden: torch.Tensor, enc: torch.Tensor, temb: torch.Tensor, timestep=None):
-        """hidden [B, Nv, C], enc [B, Nt, C] (bf16, CUDA), temb [B, time_embed_dim]; returns the two streams."""
-        if not hidden.is_cuda or hidden.dtype != torch.bfloat16:
-            raise RuntimeError("videosys_b200 CogVideoX blocks run on sm_100a CUDA devices in bf16 only (no CPU path)")
+    def forward(self, hidden: torch.Tensor, enc: torch.Tensor, temb: torch.Tensor, timestep=None, ts_int=None):
+        """hidden [B, Nv, C], enc [B, Nt, C] (fp16 / bf16, CUDA), temb [B, time_embed_dim]; returns the two streams.
+        ts_int: host integer timestep for the PAB gate (else one D2H read of timestep[0], as the reference does)."""
+        if not hidden.is_cuda or hidden.dtype not in (torch.bfloat16, torch.float16):
+            raise RuntimeError("videosys_b200 CogVideoX blocks run on sm_100a CUDA devices in fp16 / bf16 only (no CPU path)")
         K = kernels
         B, Nv, C = hidden.shape
         Nt = enc.shape[1]
@@ -119,7 +124,8 @@ class CogVideoXBlockStack(nn.Module):
         en = enc.contiguous().clone()
         ncat = torch.empty(B, N, C, dtype=hid.dtype, device=hid.device)
         pab_on = pab_mgr.enable_pab()
-        ts_int = int(timestep[0]) if (pab_on and timestep is not None) else None
+        if ts_int is None:
+            ts_int = int(timestep[0]) if (pab_on and timestep is not None) else None
         for blk in self.transformer_blocks:
             mod = self._norm_zero(blk.norm1, hid, en, temb, ncat, B, Nv, Nt, C)
             reuse = False
@@ -149,3 +155,141 @@ class CogVideoXBlockStack(nn.Module):
                 K.gate_residual(hid[b], f[b, Nt:], mb, None, 2, 1, 1, Nv, out=hid[b])
                 K.gate_residual(en[b], f[b, :Nt], mb, None, 5, 1, 1, Nt, out=en[b])
         return hid, en
+
+
+# ---- the whole denoiser (reference CogVideoXTransformer3DModel :315-589), 2B configuration --------------------------------
+def _sincos_1d(embed_dim: int, pos: torch.Tensor) -> torch.Tensor:
+    """diffusers get_1d_sincos_pos_embed_from_grid: [sin(pos * w) | cos(pos * w)], w = 10000^(-2i/embed_dim), float64."""
+    omega = 1.0 / 10000 ** (torch.arange(embed_dim // 2, dtype=torch.float64) / (embed_dim / 2.0))
+    out = pos.reshape(-1).double()[:, None] * omega[None]
+    return torch.cat([out.sin(), out.cos()], dim=1)
+
+
+def get_3d_sincos_pos_embed(embed_dim, spatial_size, temporal_size, spatial_interpolation_scale=1.0,
+                            temporal_interpolation_scale=1.0) -> torch.Tensor:
+    """diffusers.models.embeddings.get_3d_sincos_pos_embed (0.30.0), call site reference :412-418: a quarter of the
+    channels encodes the frame, three quarters the (w-first meshgrid) 2-D position.  Returns [T, H*W, D] float32."""
+    assert embed_dim % 4 == 0
+    W, H = spatial_size
+    d_sp, d_t = 3 * embed_dim // 4, embed_dim // 4
+    gh = torch.arange(H, dtype=torch.float32) / spatial_interpolation_scale
+    gw = torch.arange(W, dtype=torch.float32) / spatial_interpolation_scale
+    grid_w, grid_h = torch.meshgrid(gw, gh, indexing="xy")  # np.meshgrid(grid_w, grid_h): both [H, W]
+    emb_h = _sincos_1d(d_sp // 2, grid_w)  # the library feeds grid[0] (= the w coordinates) to its "emb_h"
+    emb_w = _sincos_1d(d_sp // 2, grid_h)
+    sp = torch.cat([emb_h, emb_w], dim=1)  # [H*W, d_sp]
+    tm = _sincos_1d(d_t, torch.arange(temporal_size, dtype=torch.float32) / temporal_interpolation_scale)  # [T, d_t]
+    out = torch.cat([tm[:, None, :].expand(-1, H * W, -1), sp[None].expand(temporal_size, -1, -1)], dim=-1)
+    return out.float()
+
+
+class _TimestepEmbedding(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, cout)
+        self.linear_2 = nn.Linear(cout, cout)
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch, cin, dim, text_dim):
+        super().__init__()
+        self.proj = nn.Conv2d(cin, dim, kernel_size=(patch, patch), stride=patch, bias=True)
+        self.text_proj = nn.Linear(text_dim, dim)
+
+
+class _AdaLayerNorm(nn.Module):
+    def __init__(self, cond, dim, eps):
+        super().__init__()
+        self.linear = nn.Linear(cond, 2 * dim)
+        self.norm = nn.LayerNorm(dim, eps, True)
+
+
+class CogVideoXTransformer3DModel(nn.Module):
+    """State-dict compatible with the reference / HF ``THUDM/CogVideoX-2b`` transformer (same module names), forward
+    on the vsb200 kernels.  One GPU: the reference's head-scatter sequence parallelism needs 30 % sp == 0 and the
+    BASELINE configuration for this model is 1 GPU."""
+
+    def __init__(self, num_attention_heads=30, attention_head_dim=64, in_channels=16, out_channels=16, flip_sin_to_cos=True,
+                 freq_shift=0, time_embed_dim=512, text_embed_dim=4096, num_layers=30, sample_width=90, sample_height=60,
+                 sample_frames=49, patch_size=2, temporal_compression_ratio=4, max_text_seq_length=226, norm_eps=1e-5,
+                 spatial_interpolation_scale=1.875, temporal_interpolation_scale=1.0,
+                 use_rotary_positional_embeddings=False, **unused):
+        super().__init__()
+        if use_rotary_positional_embeddings:
+            raise NotImplementedError("rotary position embeddings (CogVideoX-5b) are not built; the 2b model is the BASELINE config")
+        dim = num_attention_heads * attention_head_dim
+        self.config = type("Cfg", (), dict(in_channels=in_channels, out_channels=out_channels, patch_size=patch_size,
+                                           max_text_seq_length=max_text_seq_length, sample_width=sample_width,
+                                           sample_height=sample_height, sample_frames=sample_frames,
+                                           use_rotary_positional_embeddings=False, num_attention_heads=num_attention_heads,
+                                           attention_head_dim=attention_head_dim, time_embed_dim=time_embed_dim,
+                                           text_embed_dim=text_embed_dim, num_layers=num_layers))()
+        self.inner_dim, self.flip, self.freq_shift, self.eps = dim, flip_sin_to_cos, freq_shift, norm_eps
+        ph, pw = sample_height // patch_size, sample_width // patch_size
+        frames = (sample_frames - 1) // temporal_compression_ratio + 1
+        self.num_patches = ph * pw * frames
+        self.patch_embed = _PatchEmbed(patch_size, in_channels, dim, text_embed_dim)
+        pos = torch.zeros(1, max_text_seq_length + self.num_patches, dim)
+        pos[:, max_text_seq_length:] = get_3d_sincos_pos_embed(dim, (pw, ph), frames, spatial_interpolation_scale,
+                                                               temporal_interpolation_scale).flatten(0, 1)
+        self.register_buffer("pos_embedding", pos, persistent=False)
+        self.time_embedding = _TimestepEmbedding(dim, time_embed_dim)
+        stack = CogVideoXBlockStack(num_attention_heads, attention_head_dim, num_layers, time_embed_dim)
+        self.transformer_blocks = stack.transformer_blocks
+        self._stack = [stack]  # not a registered child twice: shares the blocks above
+        self.norm_final = nn.LayerNorm(dim, norm_eps, True)
+        self.norm_out = _AdaLayerNorm(time_embed_dim, dim, norm_eps)
+        self.proj_out = nn.Linear(dim, patch_size * patch_size * out_channels)
+        self.parallel_manager = None
+
+    def enable_parallel(self, dp_size=None, sp_size=None, enable_cp=None):
+        if (sp_size or 1) > 1:
+            raise NotImplementedError("CogVideoX runs on one GPU here (reference head-scatter SP: 30 heads, sp in {2,3,5,6})")
+
+    def reset_pab_state(self):
+        self._stack[0].reset_pab_state()
+
+    def _time_proj(self, timesteps: torch.Tensor) -> torch.Tensor:
+        """diffusers Timesteps(dim, flip_sin_to_cos, freq_shift): fp32 [cos | sin] (flipped) sinusoid."""
+        half = self.inner_dim // 2
+        exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=timesteps.device) / (half - self.freq_shift)
+        emb = timesteps[:, None].float() * exponent.exp()[None]
+        emb = torch.cat([emb.sin(), emb.cos()], dim=-1)
+        return torch.cat([emb[:, half:], emb[:, :half]], dim=-1) if self.flip else emb
+
+    @torch.no_grad()
+    def forward(self, hidden_states, encoder_hidden_states, timestep, timestep_cond=None, image_rotary_emb=None,
+                return_dict=True, ts_int=None):
+        """hidden_states [B, F, C, H, W] latents, encoder_hidden_states [B, 226, 4096], timestep [B]."""
+        if not hidden_states.is_cuda:
+            raise RuntimeError("videosys_b200 CogVideoX runs on sm_100a CUDA devices only (no CPU path)")
+        K = kernels
+        dt = self.proj_out.weight.dtype
+        B, Fr, Cin, H, W = hidden_states.shape
+        p, C = self.config.patch_size, self.inner_dim
+        te = self.time_embedding
+        t_emb = self._time_proj(timestep).to(dt)
+        emb = K.gemm_bias_act(F.silu(K.gemm_bias_act(t_emb, te.linear_1.weight, te.linear_1.bias)), te.linear_2.weight,
+                              te.linear_2.bias)  # [B, 512]
+        txt = K.gemm_bias_act(encoder_hidden_states.to(dt).contiguous(), self.patch_embed.text_proj.weight,
+                              self.patch_embed.text_proj.bias)  # [B, Nt, C]
+        img = self.patch_embed.proj(hidden_states.to(dt).reshape(-1, Cin, H, W))  # conv: cuDNN (glue, once per step)
+        img = img.view(B, Fr, C, -1).transpose(2, 3).flatten(1, 2)  # [B, F*h*w, C]
+        Nt, Nv = txt.shape[1], img.shape[1]
+        pos = self.pos_embedding[:, : Nt + Nv].to(dt)
+        enc = txt + pos[:, :Nt]
+        hid = img + pos[:, Nt:]
+        hid, enc = self._stack[0](hid, enc, emb, timestep, ts_int=ts_int)
+        # norm_final (plain affine LayerNorm = modulate with shift = scale = 0), then norm_out (AdaLayerNorm, chunk_dim 1:
+        # rows shift, scale) and the 1920 -> 64 projection
+        zero = torch.zeros(1, B, 6, C, dtype=dt, device=hid.device)
+        hid = K.ln_modulate(hid, zero, None, 0, 1, B, 1, Nv, eps=self.eps, gamma=self.norm_final.weight, beta=self.norm_final.bias)
+        no = self.norm_out
+        ss = K.gemm_bias_act(F.silu(emb), no.linear.weight, no.linear.bias).view(B, 2, C)  # [shift | scale]
+        mod = torch.zeros(1, B, 6, C, dtype=dt, device=hid.device)
+        mod[0, :, :2] = ss
+        hid = K.ln_modulate(hid, mod, None, 0, 1, B, 1, Nv, eps=self.eps, gamma=no.norm.weight, beta=no.norm.bias)
+        out = K.gemm_bias_act(hid, self.proj_out.weight, self.proj_out.bias)  # [B, Nv, p*p*Cout]
+        Co = self.config.out_channels
+        out = out.reshape(B, Fr, H // p, W // p, Co, p, p).permute(0, 1, 4, 2, 5, 3, 6).flatten(5, 6).flatten(3, 4)
+        return (out,) if not return_dict else type("Out", (), {"sample": out})()
