@@ -9,7 +9,13 @@ from their published semantics as the reference configures them (cogvideox_trans
     to_q/to_k/to_v Linears, ``norm_q``/``norm_k`` = nn.LayerNorm(dim_head, eps=1e-6) (affine), to_out[0] Linear;
   * ``FeedForward(dim, activation_fn="gelu-approximate", final_dropout=True, bias=True)``: Linear -> tanh-GELU -> Linear.
 Those two are PARITY UNPINNED.  2B configuration: no rotary embedding (use_rotary_positional_embeddings False), sp = 1.
+
+``transformer_forward`` restates CogVideoXTransformer3DModel.forward (:479-589) around the block: the in-tree pieces
+(CogVideoXPatchEmbed models/modules/embeddings.py:14-51, AdaLayerNorm normalization.py:60-114, unpatchify :578-581) as
+written, the diffusers pieces (``Timesteps`` / ``TimestepEmbedding`` / ``get_3d_sincos_pos_embed``, diffusers==0.30.0)
+from their published semantics: PARITY UNPINNED for those three.
 """
+import math
 from typing import Dict
 
 import torch
@@ -80,3 +86,63 @@ def block(sd, p: str, hidden: Tensor, enc: Tensor, temb: Tensor, heads: int, pab
     hidden = hidden + gate_ff * ff[:, text_len:]
     enc = enc + e_gate_ff * ff[:, :text_len]
     return hidden, enc
+
+
+def _sincos_1d(embed_dim: int, pos: Tensor) -> Tensor:
+    omega = 1.0 / 10000 ** (torch.arange(embed_dim // 2, dtype=torch.float64) / (embed_dim / 2.0))
+    out = pos.reshape(-1).double()[:, None] * omega[None]
+    return torch.cat([out.sin(), out.cos()], dim=1)
+
+
+def sincos_3d(embed_dim, spatial_size, temporal_size, spatial_scale=1.0, temporal_scale=1.0) -> Tensor:
+    """diffusers get_3d_sincos_pos_embed(embed_dim, (W, H), T, ...): [T, H*W, D] (temporal quarter first)."""
+    W, H = spatial_size
+    d_sp, d_t = 3 * embed_dim // 4, embed_dim // 4
+    gh = torch.arange(H, dtype=torch.float32) / spatial_scale
+    gw = torch.arange(W, dtype=torch.float32) / spatial_scale
+    grid_w, grid_h = torch.meshgrid(gw, gh, indexing="xy")
+    sp = torch.cat([_sincos_1d(d_sp // 2, grid_w), _sincos_1d(d_sp // 2, grid_h)], dim=1)
+    tm = _sincos_1d(d_t, torch.arange(temporal_size, dtype=torch.float32) / temporal_scale)
+    return torch.cat([tm[:, None, :].expand(-1, H * W, -1), sp[None].expand(temporal_size, -1, -1)], dim=-1).float()
+
+
+def timestep_sinusoid(timesteps: Tensor, dim: int, flip_sin_to_cos=True, freq_shift=0) -> Tensor:
+    """diffusers get_timestep_embedding (fp32)."""
+    half = dim // 2
+    exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32) / (half - freq_shift)
+    emb = timesteps[:, None].float() * exponent.exp()[None]
+    emb = torch.cat([emb.sin(), emb.cos()], dim=-1)
+    return torch.cat([emb[:, half:], emb[:, :half]], dim=-1) if flip_sin_to_cos else emb
+
+
+def transformer_forward(sd, cfg: dict, hidden: Tensor, enc: Tensor, timestep: Tensor, pab=None, pab_states=None):
+    """CogVideoXTransformer3DModel.forward (:479-589), 2B configuration; cfg: heads, head_dim, layers, patch,
+    max_text, sample_width/height/frames, spatial_scale, temporal_scale, out_channels, eps."""
+    dt = sd["proj_out.weight"].dtype
+    heads, D, p = cfg["heads"], cfg["head_dim"], cfg["patch"]
+    C = heads * D
+    B, Fr, Cin, H, W = hidden.shape
+    t_emb = timestep_sinusoid(timestep, C).to(dt)
+    emb = F.linear(F.silu(F.linear(t_emb, sd["time_embedding.linear_1.weight"], sd["time_embedding.linear_1.bias"])),
+                   sd["time_embedding.linear_2.weight"], sd["time_embedding.linear_2.bias"])
+    txt = F.linear(enc.to(dt), sd["patch_embed.text_proj.weight"], sd["patch_embed.text_proj.bias"])
+    img = F.conv2d(hidden.to(dt).reshape(-1, Cin, H, W), sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], stride=p)
+    img = img.view(B, Fr, C, -1).transpose(2, 3).flatten(1, 2)
+    x = torch.cat([txt, img], dim=1)
+    Nt = txt.shape[1]
+    frames = (cfg["sample_frames"] - 1) // 4 + 1
+    pos = torch.zeros(1, cfg["max_text"] + (cfg["sample_height"] // p) * (cfg["sample_width"] // p) * frames, C)
+    pos[:, cfg["max_text"]:] = sincos_3d(C, (cfg["sample_width"] // p, cfg["sample_height"] // p), frames,
+                                         cfg.get("spatial_scale", 1.875), cfg.get("temporal_scale", 1.0)).flatten(0, 1)
+    x = x + pos[:, : x.shape[1]].to(dt)
+    e, h = x[:, :Nt], x[:, Nt:]
+    ts_int = int(timestep[0]) if pab is not None else None
+    for i in range(cfg["layers"]):
+        h, e = block(sd, f"transformer_blocks.{i}.", h, e, emb, heads, pab, pab_states[i] if pab_states else None, ts_int)
+    eps = cfg.get("eps", 1e-5)
+    h = F.layer_norm(h, (C,), sd["norm_final.weight"], sd["norm_final.bias"], eps)
+    shift, scale = F.linear(F.silu(emb), sd["norm_out.linear.weight"], sd["norm_out.linear.bias"]).chunk(2, dim=1)
+    h = F.layer_norm(h, (C,), sd["norm_out.norm.weight"], sd["norm_out.norm.bias"], eps) * (1 + scale)[:, None, :] + shift[:, None, :]
+    h = F.linear(h, sd["proj_out.weight"], sd["proj_out.bias"])
+    Co = cfg.get("out_channels", Cin)
+    return h.reshape(B, Fr, H // p, W // p, Co, p, p).permute(0, 1, 4, 2, 5, 3, 6).flatten(5, 6).flatten(3, 4)

@@ -30,7 +30,7 @@ class StepGraph:
         self._seen: Dict[tuple, int] = {}
         self._graphs: Dict[tuple, torch.cuda.CUDAGraph] = {}
         self._pool = None
-        self._static: Optional[dict] = None
+        self._static: Dict[tuple, dict] = {}  # per graph: a captured graph reads the buffers it was captured with, for ever
         self.launches_per_graph: Dict[tuple, int] = {}
         self.replays = 0
         self.replayed_launches = 0
@@ -45,11 +45,12 @@ class StepGraph:
         v = uncond + self.guidance_scale * (cond - uncond)
         return z + v * dt[:, None, None, None, None]
 
-    def _key(self, z, fwd_args, plan, ts_int):
+    def _key(self, z, t, dt, fwd_args, plan):
         ids = tuple((k, v.data_ptr(), tuple(v.shape), v._version) if torch.is_tensor(v) else (k, repr(v))
                     for k, v in sorted(fwd_args.items()) if k != "x_mask")
         # without PAB the timestep never reaches the host and one graph serves every step
-        return (tuple(z.shape), z.dtype, "x_mask" in fwd_args and fwd_args["x_mask"] is not None, plan, ids)
+        xm = fwd_args.get("x_mask")
+        return (tuple(z.shape), z.dtype, t.dtype, dt.dtype, None if xm is None else (tuple(xm.shape), xm.dtype), plan, ids)
 
     def step(self, z, t, dt, fwd_args, ts_int: Optional[int] = None):
         """z [1,C,T,H,W], t [1], dt [1] device tensors; fwd_args as RFLOW.step passes them (x_mask may change per step);
@@ -61,22 +62,24 @@ class StepGraph:
             plan = self.model.pab_plan(ts_int)
         if not self.enabled:
             return self._compute(z, t, dt, fwd_args, plan)
-        key = self._key(z, fwd_args, plan, ts_int)
+        key = self._key(z, t, dt, fwd_args, plan)
         n = self._seen.get(key, 0)
         self._seen[key] = n + 1
         if n == 0:  # first sight: eager (allocations, lazily built windows, library warm-up)
             return self._compute(z, t, dt, fwd_args, plan)
-        st = self._static
-        if st is None or st["z"].shape != z.shape or st["z"].dtype != z.dtype:
-            st = self._static = {"z": torch.empty_like(z), "t": torch.empty_like(t), "dt": torch.empty_like(dt), "x_mask": None}
+        # static input buffers belong to the KEY (shape / dtype of z are part of it): the first version kept one set and
+        # re-allocated it when z's dtype changed (bf16 initial latent, fp32 after the first Euler update), leaving the
+        # already captured graph reading freed memory
+        st = self._static.get(key)
+        xm = fwd_args.get("x_mask")
+        if st is None:
+            st = self._static[key] = {"z": torch.empty_like(z), "t": torch.empty_like(t), "dt": torch.empty_like(dt),
+                                      "x_mask": None if xm is None else torch.empty_like(xm)}
         st["z"].copy_(z)
         st["t"].copy_(t)
         st["dt"].copy_(dt)
         args = dict(fwd_args)
-        xm = fwd_args.get("x_mask")
         if xm is not None:
-            if st["x_mask"] is None or st["x_mask"].shape != xm.shape:
-                st["x_mask"] = torch.empty_like(xm)
             st["x_mask"].copy_(xm)
             args["x_mask"] = st["x_mask"]
         from .. import kernels

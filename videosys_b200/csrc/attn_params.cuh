@@ -43,6 +43,8 @@ struct AttnParams {
 // attn_tcgen05_kt64.cu.  tm = {q64, q16, k64, k16, v64, v16} with 64-row key boxes.
 // q_tmem: Q rows resident in TMEM, S = Q K^T issued as TS MMAs (attn_variant 4)
 int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, int q_tmem, cudaStream_t st);
+// attn_tcgen05_kvres.cu: nk <= 320, K/V resident in shared memory, 160-key score tiles.  tm key boxes have 160 rows.
+int attn_flash_kvres_launch(const CUtensorMap* tm, const AttnParams& prm, int D, cudaStream_t st);
 // attn_tcgen05_kt64p.cu: the same tiles under persistent CTAs.
 int attn_flash_kt64p_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st);
 

@@ -371,7 +371,9 @@ extern "C" int VSB_API(vsb_attn_flash_strided)(const vsb_bf16* q, const vsb_bf16
   // auto: text cross-attention (a handful of key tiles per query pair) is dominated by per-CTA fixed costs
   // ... long key sequences: Q resident in TMEM (+8 % on the 720p spatial shape), head_dim 72 also takes the row sum from
   // the tensor core (interleaved microbenchmark, profiles/r02_kernel_bench.json: 670 -> 726 / 729 TFLOP/s)
-  const int variant = g_opt_attn_variant >= 0 ? g_opt_attn_variant : (nk <= 1024 ? 3 : (D == 72 ? 5 : 4));
+  // ... and up to 320 keys (text cross-attention): K/V of a (batch, head) resident in shared memory (variant 6)
+  int variant = g_opt_attn_variant >= 0 ? g_opt_attn_variant : (nk <= 320 ? 6 : (nk <= 1024 ? 3 : (D == 72 ? 5 : 4)));
+  if (variant == 6 && nk > 320) variant = 3;
   CUtensorMap tm[6];
   const vsb_bf16* base[3] = {q, k, v};
   for (int i = 0; i < 3; ++i) {
@@ -379,7 +381,7 @@ extern "C" int VSB_API(vsb_attn_flash_strided)(const vsb_bf16* q, const vsb_bf16
     unsigned long long dims[4] = {(unsigned long long)D, (unsigned long long)H, (unsigned long long)(i == 0 ? nq : nk),
                                   (unsigned long long)nb};
     unsigned long long str[3] = {(unsigned long long)D * 2, (unsigned long long)rs * 2, (unsigned long long)bs * 2};
-    const unsigned rows = (i > 0 && variant >= 2) ? 64u : 128u;  // key tile of the selected schedule
+    const unsigned rows = i == 0 ? 128u : (variant == 6 ? 160u : (variant >= 2 ? 64u : 128u));  // key tile of the schedule
     unsigned boxA[4] = {64, 1, rows, 1}, boxB[4] = {16, 1, rows, 1};
     int rc = make_tmap_bf16(&tm[2 * i], base[i], 4, dims, str, boxA, CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc) return rc;
@@ -391,6 +393,7 @@ extern "C" int VSB_API(vsb_attn_flash_strided)(const vsb_bf16* q, const vsb_bf16
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (variant == 6) return attn_flash_kvres_launch(tm, prm, D, st);
   if (variant == 3) return attn_flash_kt64p_launch(tm, prm, D, g_opt_attn_poly, st);
   if (variant == 2 || variant == 4 || variant == 5)
     return attn_flash_kt64_launch(tm, prm, D, g_opt_attn_poly, variant == 5 ? 2 : (variant == 4 ? 1 : 0), st);

@@ -1,0 +1,372 @@
+// vsb200 -- flash attention forward on tcgen05 for SHORT key sequences (nk <= 320): K/V resident (attn_variant = 6).
+//
+// Text cross-attention (open_sora_transformer_3d.py:234-240 -> attentions.py:152-185,259-270) has 72 000 query rows per
+// sample but only <= 300 keys.  Under the long-sequence schedules (attn_tcgen05_kt64*.cu) a (batch, head, query-pair)
+// item is 5 key tiles = ~7k cycles of work wrapped in ~10k cycles of per-item latency (Q round trip, first S, the
+// drain before the epilogue) -- ncu: tensor pipe 20 %, 0.59 ms per launch against a MUFU floor of ~0.2 ms
+// (profiles/r02_attn_ncu.txt).  Here the whole K and V of a (batch, head) -- 2 x 320 keys x 80 x 2 B = 100 KB -- live in
+// shared memory for as long as the CTA stays on that (batch, head); a persistent CTA (one per SM) walks a CONTIGUOUS
+// range of (batch, head, query-pair) items, so K/V are loaded two or three times per CTA instead of once per item, and
+// the score tile of a query tile covers 160 keys at a time (one N = 160 MMA per K step): two softmax passes per item
+// instead of five, with an exact (not lazy) online rescale between them.
+//
+//   warp 0 / 1    MMA issuer of query tile A / B:  S0 = Q K[0:160]^T -> wait P0 -> O = P0 V[0:160] -> S1 = Q K[160:320]^T
+//                 -> wait P1 -> O += P1 V[160:320] -> commit o_full.  The two tiles are independent pipelines that share K/V:
+//                 while warpgroup A exponentiates, the tensor pipe runs B's MMAs and vice versa.
+//   warp 2        TMA producer: K/V halves when the (batch, head) changes, Q tiles into two buffers (one item ahead)
+//   warp 3        TMEM allocation
+//   warps 4..7    softmax warpgroup A (thread = query row), warps 8..11 warpgroup B: per half, pass 1 = row max over the
+//                 160 score columns (tcgen05.ld in 32-column chunks), pass 2 = exp2 / row sum / bf16 P written over the
+//                 head of the score buffer chunk by chunk (P chunk c lands on columns [16c, 16c+16), all of which were
+//                 read before); half 1 first rescales O by exp2(m0 - m1) (P0 V has retired: S1's commit covers it).
+//   TMEM          S_x at x*256 (160 columns), O_x at x*256 + 160 (80 columns).
+#include "attn_params.cuh"
+
+namespace vsb {
+
+constexpr int kRThreads = 384;
+constexpr int kRH = 160;                 // keys per half
+constexpr int kRQA = 128 * 128;          // Q: 128 rows x 64, SWIZZLE_128B
+constexpr int kRQB = 128 * 32;           // Q: 128 rows x 16, SWIZZLE_32B
+constexpr int kRQT = kRQA + kRQB;
+constexpr int kRKA = kRH * 128;          // K / V half: 160 keys x 64, SWIZZLE_128B
+constexpr int kRKB = kRH * 32;           // K / V half: 160 keys x 16, SWIZZLE_32B
+constexpr int kRKT = kRKA + kRKB;
+constexpr int kRSmem = 4 * kRKT + 4 * kRQT + 1024 + 512;  // K0 K1 V0 V1 | 2 Q buffers x 2 tiles | barriers
+
+__host__ __device__ constexpr uint32_t r_s(int x) { return uint32_t(x) * 256u; }
+__host__ __device__ constexpr uint32_t r_o(int x) { return uint32_t(x) * 256u + 160u; }
+
+struct RItem {
+  int b, h, bh, q0, kv_len, n_halves, nx;
+};
+__device__ __forceinline__ RItem ritem_of(const AttnParams& p, int item, int n_pairs) {
+  RItem it;
+  it.bh = item / n_pairs;
+  it.q0 = (item - it.bh * n_pairs) * 256;
+  it.b = it.bh / p.H;
+  it.h = it.bh - it.b * p.H;
+  it.kv_len = p.has_lens ? p.lens[it.b] : p.nk;
+  it.n_halves = it.kv_len > kRH ? 2 : 1;
+  it.nx = (it.q0 + 128 < p.nq) ? 2 : 1;
+  return it;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kRThreads, 1)
+attn_flash_kvres_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_qb,
+                        const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_kb,
+                        const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_vb,
+                        const __grid_constant__ AttnParams p) {
+  constexpr bool kHasB = (D > 64);
+  constexpr int kQTx = kHasB ? kRQT : kRQA;
+  constexpr int kKTx = kHasB ? kRKT : kRKA;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* sK = smem;                  // [half][K_A | K_B]
+  unsigned char* sV = smem + 2 * kRKT;       // [half][V_A | V_B]
+  unsigned char* sQ = smem + 4 * kRKT;       // [q buffer][x][Q_A | Q_B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sQ + 4 * kRQT);
+  uint64_t* kv_full = bars;          // [1]
+  uint64_t* kv_empty = bars + 1;     // [1] 2 commits: both issuers' last MMA on this (batch, head)
+  uint64_t* q_full = bars + 2;       // [2]
+  uint64_t* q_empty = bars + 4;      // [2] 2 commits: both issuers' last S MMA of the item
+  uint64_t* s_full = bars + 6;       // [x]
+  uint64_t* p_full = bars + 8;       // [x] 4 softmax warps
+  uint64_t* o_full = bars + 10;      // [x]
+  uint64_t* o_free = bars + 12;      // [x] 4 softmax warps: the epilogue has read O_x
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_pairs = (p.nq + 255) / 256;
+  const int total = p.nb * p.H * n_pairs;
+  // contiguous item ranges: a CTA stays on one (batch, head) for as long as possible
+  const int per = (total + gridDim.x - 1) / gridDim.x;
+  const int i0 = blockIdx.x * per;
+  const int i1 = min(total, i0 + per);
+
+  if (warp == 2 && lane == 0) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    if (kHasB) {
+      tma_prefetch_desc(&tm_qb);
+      tma_prefetch_desc(&tm_kb);
+      tma_prefetch_desc(&tm_vb);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 2);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 2);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 3) tmem_alloc<512>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 2) {
+    // =============================== TMA producer ===============================
+    const uint32_t elected = elect_one();
+    int cur_bh = -1, n_kv = 0;
+    for (int item = i0, li = 0; item < i1; ++item, ++li) {
+      const RItem it = ritem_of(p, item, n_pairs);
+      if (it.bh != cur_bh) {
+        if (n_kv > 0) mbar_wait(kv_empty, (n_kv - 1) & 1);  // every MMA on the previous (batch, head) has retired
+        const int nh_load = p.nk > kRH ? 2 : 1;  // a half that starts past the last key is never read
+        mbar_arrive_expect_tx_w(elected, kv_full, 2 * nh_load * kKTx);
+        for (int hf = 0; hf < nh_load; ++hf) {
+          tma_load_4d_w(elected, &tm_k, kv_full, sK + hf * kRKT, 0, it.h, hf * kRH, it.b);
+          if (kHasB) tma_load_4d_w(elected, &tm_kb, kv_full, sK + hf * kRKT + kRKA, 64, it.h, hf * kRH, it.b);
+          tma_load_4d_w(elected, &tm_v, kv_full, sV + hf * kRKT, 0, it.h, hf * kRH, it.b);
+          if (kHasB) tma_load_4d_w(elected, &tm_vb, kv_full, sV + hf * kRKT + kRKA, 64, it.h, hf * kRH, it.b);
+        }
+        cur_bh = it.bh;
+        ++n_kv;
+      }
+      const int qb = li & 1;
+      mbar_wait(&q_empty[qb], ((li >> 1) & 1) ^ 1);
+      mbar_arrive_expect_tx_w(elected, &q_full[qb], it.nx * kQTx);
+      for (int x = 0; x < it.nx; ++x) {
+        unsigned char* dst = sQ + (qb * 2 + x) * kRQT;
+        tma_load_4d_w(elected, &tm_q, &q_full[qb], dst, 0, it.h, it.q0 + x * 128, it.b);
+        if (kHasB) tma_load_4d_w(elected, &tm_qb, &q_full[qb], dst + kRQA, 64, it.h, it.q0 + x * 128, it.b);
+      }
+    }
+  } else if (warp < 2) {
+    // =============================== MMA issuer of query tile x = warp ===============================
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, kRH, 0, 0);   // S = Q K^T (128 x 160), both K-major
+    constexpr uint32_t idesc_o64 = umma_idesc_bf16(128, 64, 0, 1);  // O[:, 0:64]  += P V, V MN-major
+    constexpr uint32_t idesc_o16 = umma_idesc_bf16(128, 16, 0, 1);  // O[:, 64:80] += P V
+    constexpr uint32_t hi128 = umma_desc_hi(1024, 2);
+    constexpr uint32_t hi32 = umma_desc_hi(256, 6);
+    const int x = warp;
+    const uint32_t elected = elect_one();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t q_lo = umma_desc_lo(smem_u32(sQ), 16);
+    const uint32_t k_lo = umma_desc_lo(smem_u32(sK), 16);
+    const uint32_t v_lo = umma_desc_lo(smem_u32(sV), 16);
+    auto issue_S = [&](int qb, int hf) {
+      const uint32_t qa = q_lo + (qb * 2 + x) * (kRQT >> 4);
+      const uint32_t ka = k_lo + hf * (kRKT >> 4);
+      const uint32_t d = tb + r_s(x);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_ss_w(elected, d, desc_pack(qa + 2 * k, hi128), desc_pack(ka + 2 * k, hi128), idesc_s, k > 0 ? 1u : 0u);
+      if (kHasB) umma_ss_w(elected, d, desc_pack(qa + (kRQA >> 4), hi32), desc_pack(ka + (kRKA >> 4), hi32), idesc_s, 1u);
+    };
+    auto issue_PV = [&](int hf, bool first) {
+      // V halves are MN-major (d contiguous): LBO = stride between d atoms, unused with a single atom
+      const uint32_t va = v_lo + hf * (kRKT >> 4) - (1u << 16) + ((uint32_t(kRKA) >> 4) << 16);
+      const uint32_t vb = v_lo + hf * (kRKT >> 4) + (kRKA >> 4) - (1u << 16) + ((uint32_t(kRKB) >> 4) << 16);
+      const uint32_t pt = tb + r_s(x);
+      const uint32_t d = tb + r_o(x);
+#pragma unroll
+      for (int ks = 0; ks < kRH / 16; ++ks) {  // 16 keys per step: +2048 B in the 128B-swizzled chunk, +512 B in the 32B one
+        umma_ts_w(elected, d, pt + ks * 8, desc_pack(va + ks * 128, hi128), idesc_o64, (first && ks == 0) ? 0u : 1u);
+        if (kHasB) umma_ts_w(elected, d + 64, pt + ks * 8, desc_pack(vb + ks * 32, hi32), idesc_o16, (first && ks == 0) ? 0u : 1u);
+      }
+    };
+    int cur_bh = -1, n_kv = 0, n_s = 0, n_mine = 0;
+    for (int item = i0, li = 0; item < i1; ++item, ++li) {
+      const RItem it = ritem_of(p, item, n_pairs);
+      const int qb = li & 1;
+      const bool live = x < it.nx;                       // tile B of a ragged last pair holds no rows
+      const bool last_of_bh = (item + 1 >= i1) || (ritem_of(p, item + 1, n_pairs).bh != it.bh);
+      if (it.bh != cur_bh) {
+        mbar_wait(kv_full, n_kv & 1);
+        cur_bh = it.bh;
+        ++n_kv;
+      }
+      // Both issuers take part in the two-party barriers (q_empty, kv_empty) of EVERY item, live or not, and only after
+      // seeing the item's q_full: an idle issuer can then never arrive twice in one phase of a barrier.
+      mbar_wait(&q_full[qb], (li >> 1) & 1);
+      if (!live) {
+        umma_commit_w(elected, &q_empty[qb]);
+        if (last_of_bh) umma_commit_w(elected, kv_empty);  // completes when my earlier MMAs on this K/V have retired
+        continue;
+      }
+      {
+        tc_fence_after();
+        issue_S(qb, 0);
+        if (it.n_halves == 1) umma_commit_w(elected, &q_empty[qb]);
+        umma_commit_w(elected, &s_full[x]);
+        mbar_wait(&p_full[x], n_s & 1);
+        ++n_s;
+        if (n_mine > 0) mbar_wait(&o_free[x], (n_mine - 1) & 1);  // the previous item's epilogue has read O_x
+        tc_fence_after();
+        issue_PV(0, true);
+        if (it.n_halves == 2) {
+          issue_S(qb, 1);
+          umma_commit_w(elected, &q_empty[qb]);
+          umma_commit_w(elected, &s_full[x]);  // also: P0 V0 has retired (the softmax warps may rescale O_x)
+          mbar_wait(&p_full[x], n_s & 1);
+          ++n_s;
+          tc_fence_after();
+          issue_PV(1, false);
+        }
+        umma_commit_w(elected, &o_full[x]);
+        ++n_mine;
+        if (last_of_bh) umma_commit_w(elected, kv_empty);
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== softmax warpgroups ===============================
+    const int x = (warp - 4) >> 2;
+    const int ew = warp & 3;
+    const int row = ew * 32 + lane;
+    const uint32_t lane_off = uint32_t(ew * 32) << 16;
+    const uint32_t tS = tmem_base + lane_off + r_s(x);
+    const uint32_t tO = tmem_base + lane_off + r_o(x);
+    const float sl2 = p.scale_log2;
+    int n_s = 0, n_mine = 0;
+    for (int item = i0; item < i1; ++item) {
+      const RItem it = ritem_of(p, item, n_pairs);
+      if (x >= it.nx) continue;
+      float l_run = 0.f, m_run = -INFINITY;
+      for (int hf = 0; hf < it.n_halves; ++hf) {
+        mbar_wait(&s_full[x], n_s & 1);
+        ++n_s;
+        tc_fence_after();
+        const int valid = it.kv_len - hf * kRH;  // >= 160: every column; else columns >= valid are masked
+        // ---- pass 1: row max ----
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < kRH / 32; ++c) {
+          uint32_t a[32];
+          tmem_ld32(tS + c * 32, a);
+          tmem_wait_ld();
+          if (valid >= (c + 1) * 32) {
+            float m0 = fmax3(__uint_as_float(a[0]), __uint_as_float(a[1]), __uint_as_float(a[2]));
+            float m1 = fmax3(__uint_as_float(a[3]), __uint_as_float(a[4]), __uint_as_float(a[5]));
+#pragma unroll
+            for (int i = 6; i < 30; i += 4) {
+              m0 = fmax3(m0, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+              m1 = fmax3(m1, __uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
+            }
+            m0 = fmax3(m0, __uint_as_float(a[30]), __uint_as_float(a[31]));
+            mx = fmax3(mx, m0, m1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(a[i]));
+          }
+        }
+        const float m_new = fmaxf(m_run, mx);
+        if (hf > 0) {
+          // exact online softmax: O_x and l carry exp2((s - m0) * sl2); bring them to the new max
+          const float alpha = fast_exp2((m_run - m_new) * sl2);
+          if (__any_sync(0xffffffffu, alpha != 1.f)) {
+#pragma unroll 1
+            for (int c = 0; c < (kHasB ? 5 : 4); ++c) {
+              uint32_t o[16];
+              tmem_ld16(tO + c * 16, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+              tmem_st16(tO + c * 16, o);
+            }
+          }
+          l_run *= alpha;
+        }
+        m_run = m_new;
+        const float mb = m_run * sl2;
+        // ---- pass 2: p = exp2(s*sl2 - m*sl2), row sum, bf16 P over the head of the score buffer ----
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < kRH / 32; ++c) {
+          uint32_t a[32];
+          tmem_ld32(tS + c * 32, a);
+          tmem_wait_ld();
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            float e0 = fast_exp2(fmaf(__uint_as_float(a[i]), sl2, -mb));
+            float e1 = fast_exp2(fmaf(__uint_as_float(a[i + 1]), sl2, -mb));
+            float e2 = fast_exp2(fmaf(__uint_as_float(a[i + 2]), sl2, -mb));
+            float e3 = fast_exp2(fmaf(__uint_as_float(a[i + 3]), sl2, -mb));
+            if (valid < (c + 1) * 32) {
+              if (c * 32 + i >= valid) e0 = 0.f;
+              if (c * 32 + i + 1 >= valid) e1 = 0.f;
+              if (c * 32 + i + 2 >= valid) e2 = 0.f;
+              if (c * 32 + i + 3 >= valid) e3 = 0.f;
+            }
+            s0 += e0;
+            s1 += e1;
+            s2 += e2;
+            s3 += e3;
+            pk[i >> 1] = pack_bf16x2(e0, e1);
+            pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);
+          }
+          tmem_st16(tS + c * 16, pk);  // P chunk c over score columns [16c, 16c+16): all read already
+        }
+        l_run += (s0 + s1) + (s2 + s3);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[x]);
+      }
+      // ---- epilogue: O / l -> bf16 -> global ----
+      mbar_wait(&o_full[x], n_mine & 1);
+      ++n_mine;
+      tc_fence_after();
+      const int qrow = it.q0 + x * 128 + row;
+      const float inv = 1.f / l_run;
+      bf16* dst = p.out + (size_t)it.b * p.out_batch_stride + (size_t)(qrow < p.nq ? qrow : 0) * p.out_row_stride + (size_t)it.h * D;
+#pragma unroll
+      for (int c = 0; c < D / 8; ++c) {
+        uint32_t r[8];
+        tmem_ld8(tO + c * 8, r);
+        tmem_wait_ld();
+        if (c == D / 8 - 1) {  // O_x is in registers: the issuer may start the next item's P V
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_free[x]);
+        }
+        if (qrow < p.nq) {
+          uint4 u;
+          u.x = pack_bf16x2(__uint_as_float(r[0]) * inv, __uint_as_float(r[1]) * inv);
+          u.y = pack_bf16x2(__uint_as_float(r[2]) * inv, __uint_as_float(r[3]) * inv);
+          u.z = pack_bf16x2(__uint_as_float(r[4]) * inv, __uint_as_float(r[5]) * inv);
+          u.w = pack_bf16x2(__uint_as_float(r[6]) * inv, __uint_as_float(r[7]) * inv);
+          *reinterpret_cast<uint4*>(dst + c * 8) = u;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 3) tmem_dealloc<512>(tmem_base);
+}
+
+template <int D>
+static int launch_kvres(const CUtensorMap* tm, const AttnParams& prm, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attn_flash_kvres_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRSmem);
+    if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_flash(kvres): smem attr: %s", cudaGetErrorString(e));
+    attr = true;
+  }
+  const int total = prm.nb * prm.H * ((prm.nq + 255) / 256);
+  int grid = num_sms();
+  if (grid > total) grid = total;
+  attn_flash_kvres_kernel<D><<<grid, kRThreads, kRSmem, st>>>(tm[0], tm[1], tm[2], tm[3], tm[4], tm[5], prm);
+  return check_launch("attn_flash(kvres)");
+}
+
+// tm = {q64, q16, k64, k16, v64, v16} with 128-row query boxes and 160-row key boxes; requires prm.nk <= 320.
+int attn_flash_kvres_launch(const CUtensorMap* tm, const AttnParams& prm, int D, cudaStream_t st) {
+  return D == 72 ? launch_kvres<72>(tm, prm, st) : launch_kvres<64>(tm, prm, st);
+}
+
+}  // namespace vsb
