@@ -28,6 +28,10 @@ for g in "$@"; do
     atrace) timeout 300 python tools/attn_trace.py > gpurun_out/attn_trace.log 2>&1; echo "atrace exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/attn_trace.log ;;
     kbattn) KB_ONLY=attn timeout 600 python tools/kernel_bench.py > gpurun_out/kernel_bench_attn.log 2>&1; echo "kbattn exit $?" | tee -a gpurun_out/summary.txt; tail -n 3 gpurun_out/kernel_bench_attn.log ;;
     kernels) run kernels 900 tests/test_kernels_gpu.py ;;
+    cogx) run cogx 600 tests/test_cogvideox_gpu.py ;;
+    latte) run latte 600 tests/test_latte_gpu.py ;;
+    benchcogx) timeout 900 python bench.py --workload cogvideox_2b_49f_480x720_50step $BENCH_ARGS > gpurun_out/benchcogx.json 2> gpurun_out/benchcogx.err
+           echo "benchcogx exit $? : $(tail -c 500 gpurun_out/benchcogx.json)" | tee -a gpurun_out/summary.txt; tail -n 3 gpurun_out/benchcogx.err ;;
     kbench) timeout 600 python tools/kernel_bench.py > gpurun_out/kernel_bench.log 2>&1; echo "kbench exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/kernel_bench.log | tail -12 ;;
     mbenchnccl*) n=${g#mbenchnccl}; echo "=== bench N=$n (NCCL a2a) ===" | tee -a gpurun_out/summary.txt
            VSB_DSP_P2P=0 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29534 \

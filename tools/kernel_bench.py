@@ -103,7 +103,7 @@ def cross(var, poly):
 
 VARIANTS = {"kt128_pingpong": (0, 0), "kt64": (2, 0), "kt64_poly25": (2, 1), "kt64_poly37": (2, 2), "kt64p": (3, 0), "kt64p_poly25": (3, 1),
             "kt64_qtmem": (4, 0), "kt64_qtmem_poly25": (4, 1), "kt64_qtmem_poly37": (4, 2), "kt64_qtmem_poly50": (4, 3),
-            "kt64_qtsum": (5, 0), "kt64_qtsum_poly25": (5, 1), "kt64_qtsum_poly37": (5, 2), "kt64_qtsum_poly50": (5, 3)}
+            "kvres_cross_only": (6, 0), "kt64_qtsum": (5, 0), "kt64_qtsum_poly25": (5, 1), "kt64_qtsum_poly37": (5, 2), "kt64_qtsum_poly50": (5, 3)}
 # cuDNN's fused attention on the same problem, inside the same round-robin (a yardstick: never on the product path)
 from torch.nn.attention import SDPBackend, sdpa_kernel  # noqa: E402
 
