@@ -322,7 +322,9 @@ def test_step_graph_replay_is_bit_identical():
                     assert torch.equal(eager[i], eager[i + n]), f"EAGER is not deterministic: step {i} differs between passes"
                     assert torch.equal(graphed[i], graphed[i + n]), f"GRAPH replay is not deterministic: step {i}"
             for i, (a, b) in enumerate(zip(eager, graphed)):
-                assert torch.equal(a, b), f"pab={pab} step {i}: replayed graph differs from eager"
+                assert torch.equal(a, b), (f"pab={pab} step {i}: replayed graph differs from eager: max abs diff "
+                                           f"{(a.float() - b.float()).abs().max().item():.3e}, "
+                                           f"{(a != b).float().mean().item() * 100:.2f} % of the elements")
             print(f"[parity] step graph pab={pab}: {len(st._graphs)} graphs, {st.replays} replays, bit-identical to eager")
     finally:
         P.set_pab_manager(None)

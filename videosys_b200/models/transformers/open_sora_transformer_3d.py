@@ -111,11 +111,15 @@ class STDiT3Block(nn.Module):
         self.block_idx = block_idx
         self.reset_pab()
 
-    def reset_pab(self):
+    def reset_pab(self, drop_caches: bool = False):
+        """Counters back to zero.  The cache BUFFERS are kept (a count of 0 recomputes and rewrites a cache before any
+        step can replay it): captured step graphs hold their addresses, and re-allocating 37 GB of caches per video is
+        pointless.  drop_caches=True frees them (shape change, memory pressure)."""
         self.attn_count = 0
         self.cross_count = 0
-        self.last_attn = None
-        self.last_cross = None
+        if drop_caches or not hasattr(self, "last_attn"):
+            self.last_attn = None
+            self.last_cross = None
 
 
 class _Embed2(nn.Module):
@@ -230,9 +234,9 @@ class STDiT3(nn.Module):
         for blk in [*self.spatial_blocks, *self.temporal_blocks]:
             blk.parallel_manager = self.parallel_manager
 
-    def reset_pab_state(self):
+    def reset_pab_state(self, drop_caches: bool = False):
         for blk in [*self.spatial_blocks, *self.temporal_blocks]:
-            blk.reset_pab()
+            blk.reset_pab(drop_caches)
 
     def get_dynamic_size(self, x):
         _, _, T, H, W = x.size()
