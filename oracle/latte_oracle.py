@@ -11,7 +11,13 @@ two diffusers classes as the reference uses them:
     one, pipeline_latte.py:854-862), to_out[0] Linear, dropout 0, rescale_output_factor 1;
   * ``GELU(dim, inner, approximate="tanh")`` = Linear then tanh-GELU.
 Configuration: norm_type "ada_norm_single", norm_elementwise_affine False, eps 1e-6, activation "gelu-approximate".
+
+``transformer_forward`` restates LatteT2V.forward around the block loop (:1144-1466): the in-tree glue (rearranges, output
+head :1436-1443, unpatchify :1446-1456, temp_pos_embed :1468-1470) as written, the diffusers pieces (``PatchEmbed`` with
+its 2-D sincos table, ``AdaLayerNormSingle`` -> ``PixArtAlphaCombinedTimestepSizeEmbeddings`` -> ``Timesteps`` /
+``TimestepEmbedding``, ``PixArtAlphaTextProjection``) from their published semantics: PARITY UNPINNED.
 """
+import math
 from typing import Dict, Optional
 
 import torch
@@ -85,3 +91,47 @@ def block_stack(sd, x: Tensor, enc: Tensor, timestep6: Tensor, heads: int, depth
         h = temporal_block(sd, f"temporal_transformer_blocks.{i}.", h, t_tm, heads)
         h = h.reshape(B, S, Fr, C).permute(0, 2, 1, 3).reshape(B * Fr, S, C).contiguous()
     return h.reshape(B, Fr, S, C)
+
+
+def _sincos_1d(embed_dim: int, pos: Tensor) -> Tensor:
+    omega = 1.0 / 10000 ** (torch.arange(embed_dim // 2, dtype=torch.float64) / (embed_dim / 2.0))
+    out = pos.reshape(-1).double()[:, None] * omega[None]
+    return torch.cat([out.sin(), out.cos()], dim=1)
+
+
+def sincos_2d(embed_dim: int, grid_size: int, base_size: int, interpolation_scale: float = 1.0) -> Tensor:
+    """diffusers get_2d_sincos_pos_embed as PatchEmbed calls it (w-first meshgrid): [grid*grid, D] float32."""
+    g = torch.arange(grid_size, dtype=torch.float32) / (grid_size / base_size) / interpolation_scale
+    gw, gh = torch.meshgrid(g, g, indexing="xy")
+    return torch.cat([_sincos_1d(embed_dim // 2, gw), _sincos_1d(embed_dim // 2, gh)], dim=1).float()
+
+
+def transformer_forward(sd, cfg: dict, latents: Tensor, timestep: Tensor, text: Tensor) -> Tensor:
+    """LatteT2V.forward, inference, sp = 1, ada_norm_single, no micro-conditions (sample_size != 128).
+    cfg: heads, head_dim, layers, patch, sample_size, out_channels, video_length."""
+    dt = sd["proj_out.weight"].dtype
+    heads, D, p = cfg["heads"], cfg["head_dim"], cfg["patch"]
+    C = heads * D
+    B, Cin, Fr, H, W = latents.shape
+    h, w = H // p, W // p
+    x = latents.to(dt).permute(0, 2, 1, 3, 4).reshape(B * Fr, Cin, H, W)
+    x = F.conv2d(x, sd["pos_embed.proj.weight"], sd["pos_embed.proj.bias"], stride=p).flatten(2).transpose(1, 2)
+    grid = cfg["sample_size"] // p
+    x = (x + sincos_2d(C, h, base_size=grid, interpolation_scale=max(cfg["sample_size"] // 64, 1))[None].to(dt)).reshape(B, Fr, h * w, C)
+    half = 128
+    e = timestep[:, None].float() * (-math.log(10000.0) * torch.arange(half, dtype=torch.float32) / half).exp()[None]
+    t_emb = torch.cat([e.cos(), e.sin()], dim=-1).to(dt)  # Timesteps(256, flip_sin_to_cos=True, freq_shift=0)
+    pre = "adaln_single.emb.timestep_embedder."
+    emb = F.linear(F.silu(F.linear(t_emb, sd[pre + "linear_1.weight"], sd[pre + "linear_1.bias"])), sd[pre + "linear_2.weight"],
+                   sd[pre + "linear_2.bias"])
+    t6 = F.linear(F.silu(emb), sd["adaln_single.linear.weight"], sd["adaln_single.linear.bias"])
+    enc = F.linear(F.gelu(F.linear(text.to(dt), sd["caption_projection.linear_1.weight"], sd["caption_projection.linear_1.bias"]),
+                          approximate="tanh"), sd["caption_projection.linear_2.weight"], sd["caption_projection.linear_2.bias"])
+    tpe = _sincos_1d(C, torch.arange(cfg["video_length"]).float()).float()[None][:, :Fr].to(dt)
+    x = block_stack(sd, x, enc, t6, heads, cfg["layers"], tpe if Fr > 1 else None)
+    shift, scale = (sd["scale_shift_table"][None] + emb[:, None]).chunk(2, dim=1)  # per sample, broadcast over frames
+    y = _ln(x.reshape(B, Fr * h * w, C)) * (1 + scale) + shift
+    y = F.linear(y, sd["proj_out.weight"], sd["proj_out.bias"])
+    Co = cfg["out_channels"]
+    y = torch.einsum("nhwpqc->nchpwq", y.reshape(B * Fr, h, w, p, p, Co)).reshape(B * Fr, Co, h * p, w * p)
+    return y.reshape(B, Fr, Co, h * p, w * p).permute(0, 2, 1, 3, 4).contiguous()

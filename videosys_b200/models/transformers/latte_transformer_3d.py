@@ -11,15 +11,20 @@ models/transformers/latte_transformer_3d.py:1312-1425 (inference, use_image_num 
     norm, SDPA rounding); cross attention = one kv GEMM per sample (the reference repeats the text per frame and
     recomputes it F times: latte_transformer_3d.py:1290-1296) + vsb_attn_flash.
 
-The embedders around the blocks (PatchEmbed, PixArtAlphaCombinedTimestepSizeEmbeddings, caption projection, output
-head) are diffusers classes and are not restated this round.
+``LatteT2V`` adds the embedders and the output head (reference :846-1470); the diffusers pieces (PatchEmbed's 2-D sincos
+table, Timesteps / TimestepEmbedding inside PixArtAlphaCombinedTimestepSizeEmbeddings, PixArtAlphaTextProjection) are
+restated from their published semantics (diffusers==0.30.0: parity unpinned for those).  Compute dtype:
+fp16 (the reference's, pipeline_latte.py:201) or bf16.  PAB: spatial / temporal / cross broadcast and the MLP skip.
 """
+import math
 from typing import Optional
 
 import torch
 import torch.nn as nn
+import torch.nn.functional as F
 
 from ... import kernels
+from ...core.pab import pab_mgr
 
 
 class _Attn(nn.Module):
@@ -45,23 +50,33 @@ class _FF(nn.Module):
 
 
 class LatteBlock(nn.Module):
-    def __init__(self, dim, heads, temporal):
+    def __init__(self, dim, heads, temporal, block_idx=0):
         super().__init__()
         self.temporal = temporal
+        self.block_idx = block_idx
         self.attn1 = _Attn(dim)
         if not temporal:
             self.attn2 = _Attn(dim, dim)
         self.ff = _FF(dim)
         self.scale_shift_table = nn.Parameter(torch.randn(6, dim) / dim**0.5)
         self._fused = {}
+        self.reset_pab()
+
+    def reset_pab(self):
+        # reference attributes: spatial_count / count (temporal), cross_count, mlp_count; spatial_last / last_out, cross_last
+        self.attn_count = self.cross_count = self.mlp_count = 0
+        self.last_attn = self.last_cross = None
 
     def fused(self, which: str):
-        """Concatenated projection weights (built once; call ``invalidate()`` after loading new weights)."""
-        if which not in self._fused:
-            a = self.attn1 if which == "qkv" else self.attn2
-            mods = (a.to_q, a.to_k, a.to_v) if which == "qkv" else (a.to_k, a.to_v)
-            self._fused[which] = (torch.cat([m.weight for m in mods], 0).contiguous(), torch.cat([m.bias for m in mods], 0).contiguous())
-        return self._fused[which]
+        """Concatenated projection weights, rebuilt when the parameters change (load_state_dict / .to)."""
+        a = self.attn1 if which == "qkv" else self.attn2
+        mods = (a.to_q, a.to_k, a.to_v) if which == "qkv" else (a.to_k, a.to_v)
+        key = tuple((m.weight.data_ptr(), m.weight._version, m.weight.dtype) for m in mods)
+        c = self._fused.get(which)
+        if c is None or c[0] != key:
+            c = self._fused[which] = (key, torch.cat([m.weight for m in mods], 0).contiguous(),
+                                      torch.cat([m.bias for m in mods], 0).contiguous())
+        return c[1], c[2]
 
     def invalidate(self):
         self._fused = {}
@@ -71,20 +86,21 @@ class LatteBlockStack(nn.Module):
     def __init__(self, hidden_size=1152, num_heads=16, depth=28):
         super().__init__()
         self.hidden_size, self.num_heads, self.depth = hidden_size, num_heads, depth
-        self.transformer_blocks = nn.ModuleList([LatteBlock(hidden_size, num_heads, False) for _ in range(depth)])
-        self.temporal_transformer_blocks = nn.ModuleList([LatteBlock(hidden_size, num_heads, True) for _ in range(depth)])
+        self.transformer_blocks = nn.ModuleList([LatteBlock(hidden_size, num_heads, False, i) for i in range(depth)])
+        self.temporal_transformer_blocks = nn.ModuleList([LatteBlock(hidden_size, num_heads, True, i) for i in range(depth)])
 
-    def load_state_dict(self, *a, **k):
-        r = super().load_state_dict(*a, **k)
+    def reset_pab_state(self):
         for b in [*self.transformer_blocks, *self.temporal_transformer_blocks]:
-            b.invalidate()
-        return r
+            b.reset_pab()
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor, enc: torch.Tensor, timestep6: torch.Tensor, temp_pos_embed: Optional[torch.Tensor] = None):
-        """x [B, F, S, C] bf16 (CUDA), enc [B, L, C], timestep6 [B, 6C]; returns [B, F, S, C]."""
-        if not x.is_cuda or x.dtype != torch.bfloat16:
-            raise RuntimeError("videosys_b200 Latte blocks run on sm_100a CUDA devices in bf16 only (no CPU path)")
+    def forward(self, x: torch.Tensor, enc: torch.Tensor, timestep6: torch.Tensor, temp_pos_embed: Optional[torch.Tensor] = None,
+                ts_int: Optional[int] = None, all_timesteps=None):
+        """x [B, F, S, C] fp16 / bf16 (CUDA), enc [B, L, C], timestep6 [B, 6C]; returns [B, F, S, C].
+        PAB (reference blocks :372-517, :700-824): ts_int = int(org_timestep[0]) on the host, all_timesteps = the
+        scheduler's timestep list (python ints) for the MLP skip windows."""
+        if not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16):
+            raise RuntimeError("videosys_b200 Latte blocks run on sm_100a CUDA devices in fp16 / bf16 only (no CPU path)")
         K = kernels
         B, Fr, S, C = x.shape
         H = self.num_heads
@@ -93,37 +109,224 @@ class LatteBlockStack(nn.Module):
         x = x.contiguous().clone()
         enc2 = enc.reshape(B * L, C).contiguous()
         xf = x.view(B, Fr * S, C)
+        pab_on = pab_mgr.enable_pab()
+        if pab_on and ts_int is None:
+            raise RuntimeError("PAB needs the host integer timestep (ts_int)")
         for i in range(self.depth):
             for blk in (self.transformer_blocks[i], self.temporal_transformer_blocks[i]):
                 if blk.temporal and i == 0 and Fr > 1 and temp_pos_embed is not None:
                     x.add_(temp_pos_embed.reshape(1, Fr, 1, C).to(x.dtype))  # glue op (once per forward)
                 mod = K.modulation_table(blk.scale_shift_table, timestep6, None)
-                xm = K.ln_modulate(xf, mod, None, 0, 1, B, Fr, S)
-                wqkv, bqkv = blk.fused("qkv")
-                qkv = K.gemm_bias_act(xm, wqkv, bqkv)
-                if blk.temporal:
-                    if Fr < 30:
-                        o = K.attn_short(qkv.view(-1, 3, H, D), None, None, None, None, B, S, Fr * S, 1, S, Fr, H, D, D**-0.5, flags=3)
-                    else:
-                        raise RuntimeError("temporal sequences >= 30 frames are not supported by vsb_attn_short")
+                # ---- self attention (spatial over S per frame / temporal over F per patch) ----
+                reuse = False
+                if pab_on:
+                    gate = pab_mgr.if_broadcast_temporal if blk.temporal else pab_mgr.if_broadcast_spatial
+                    reuse, blk.attn_count = gate(ts_int, blk.attn_count)
+                if reuse:
+                    K.residual_add(xf, blk.last_attn, out=xf)  # the cached value is the GATED output (:422-430)
                 else:
-                    q3 = qkv.view(-1, 3, C)
-                    if S >= 30:
-                        o = K.attn_flash(q3[:, 0], q3[:, 1], q3[:, 2], B * Fr, S, S, H, D, 3 * C, S * 3 * C, 3 * C, S * 3 * C, D**-0.5)
+                    xm = K.ln_modulate(xf, mod, None, 0, 1, B, Fr, S)
+                    wqkv, bqkv = blk.fused("qkv")
+                    qkv = K.gemm_bias_act(xm, wqkv, bqkv)
+                    if blk.temporal:
+                        if Fr <= 32:
+                            o = K.attn_short(qkv.view(-1, 3, H, D), None, None, None, None, B, S, Fr * S, 1, S, Fr, H, D, D**-0.5, flags=3)
+                        else:  # long videos: the flash kernel over strided views (batch = patch, row = frame)
+                            o = torch.empty(B * Fr * S, C, dtype=x.dtype, device=x.device)
+                            q3 = qkv.view(B, Fr * S, 3, C)
+                            for b in range(B):
+                                K.attn_flash(q3[b, :, 0], q3[b, :, 1], q3[b, :, 2], S, Fr, Fr, H, D, S * 3 * C, 3 * C, S * 3 * C, 3 * C,
+                                             D**-0.5, out=o[b * Fr * S:], out_row_stride=S * C, out_batch_stride=C)
                     else:
-                        o = K.attn_short(qkv.view(-1, 3, H, D), None, None, None, None, B * Fr, 1, S, 0, 1, S, H, D, D**-0.5, flags=3)
-                y = K.gemm_bias_act(o.view(-1, C), blk.attn1.to_out[0].weight, blk.attn1.to_out[0].bias)
-                K.gate_residual(xf, y.view(B, Fr * S, C), mod, None, 2, B, Fr, S, out=xf)
+                        q3 = qkv.view(-1, 3, C)
+                        if S >= 30:
+                            o = K.attn_flash(q3[:, 0], q3[:, 1], q3[:, 2], B * Fr, S, S, H, D, 3 * C, S * 3 * C, 3 * C, S * 3 * C, D**-0.5)
+                        else:
+                            o = K.attn_short(qkv.view(-1, 3, H, D), None, None, None, None, B * Fr, 1, S, 0, 1, S, H, D, D**-0.5, flags=3)
+                    y = K.gemm_bias_act(o.view(-1, C), blk.attn1.to_out[0].weight, blk.attn1.to_out[0].bias)
+                    cache = None
+                    if pab_on:
+                        if blk.last_attn is None or blk.last_attn.shape != xf.shape:
+                            blk.last_attn = torch.empty_like(xf)
+                        cache = blk.last_attn
+                    K.gate_residual(xf, y.view(B, Fr * S, C), mod, None, 2, B, Fr, S, out=xf, cache_out=cache)
+                # ---- text cross attention (spatial blocks only) ----
                 if not blk.temporal:
-                    a2 = blk.attn2
-                    q = K.gemm_bias_act(xf, a2.to_q.weight, a2.to_q.bias)
-                    wkv, bkv = blk.fused("kv")
-                    kv = K.gemm_bias_act(enc2, wkv, bkv).view(-1, 2, C)
-                    o = K.attn_flash(q, kv[:, 0], kv[:, 1], B, Fr * S, L, H, D, C, Fr * S * C, 2 * C, L * 2 * C, D**-0.5)
-                    xc = K.gemm_bias_act(o, a2.to_out[0].weight, a2.to_out[0].bias)
-                    K.residual_add(xf, xc.view(B, Fr * S, C), out=xf)
-                xm = K.ln_modulate(xf, mod, None, 3, 4, B, Fr, S)
-                h = K.gemm_bias_act(xm, blk.ff.net[0].proj.weight, blk.ff.net[0].proj.bias, act=1)
-                y = K.gemm_bias_act(h, blk.ff.net[2].weight, blk.ff.net[2].bias)
-                K.gate_residual(xf, y, mod, None, 5, B, Fr, S, out=xf)
+                    reuse = False
+                    if pab_on:
+                        reuse, blk.cross_count = pab_mgr.if_broadcast_cross(ts_int, blk.cross_count)
+                    if reuse:
+                        K.residual_add(xf, blk.last_cross, out=xf)
+                    else:
+                        a2 = blk.attn2
+                        q = K.gemm_bias_act(xf, a2.to_q.weight, a2.to_q.bias)
+                        wkv, bkv = blk.fused("kv")
+                        kv = K.gemm_bias_act(enc2, wkv, bkv).view(-1, 2, C)
+                        o = K.attn_flash(q, kv[:, 0], kv[:, 1], B, Fr * S, L, H, D, C, Fr * S * C, 2 * C, L * 2 * C, D**-0.5)
+                        out = blk.last_cross if (pab_on and blk.last_cross is not None and blk.last_cross.shape == xf.shape) else None
+                        xc = K.gemm_bias_act(o, a2.to_out[0].weight, a2.to_out[0].bias, out=out)
+                        if pab_on:
+                            blk.last_cross = xc
+                        K.residual_add(xf, xc.view(B, Fr * S, C), out=xf)
+                # ---- feed-forward, with the PAB MLP skip (Latte enables it: pipeline_latte.py:48-61) ----
+                skip = keep = False
+                rng = None
+                if pab_on:
+                    skip, cnt, keep, rng = pab_mgr.if_broadcast_mlp(ts_int, blk.mlp_count, blk.block_idx, all_timesteps, blk.temporal)
+                    if cnt is not None:
+                        blk.mlp_count = cnt
+                if skip:
+                    ff = pab_mgr.get_mlp_output(rng, ts_int, blk.block_idx, blk.temporal)  # stored GATED output
+                    K.residual_add(xf, ff, out=xf)
+                else:
+                    xm = K.ln_modulate(xf, mod, None, 3, 4, B, Fr, S)
+                    h = K.gemm_bias_act(xm, blk.ff.net[0].proj.weight, blk.ff.net[0].proj.bias, act=1)
+                    y = K.gemm_bias_act(h, blk.ff.net[2].weight, blk.ff.net[2].bias)
+                    ffc = torch.empty_like(xf) if keep else None
+                    K.gate_residual(xf, y, mod, None, 5, B, Fr, S, out=xf, cache_out=ffc)
+                    if keep:
+                        pab_mgr.save_mlp_output(ts_int, blk.block_idx, ffc, blk.temporal)
         return x
+
+
+# ---- the whole denoiser (reference LatteT2V :846-1470, ada_norm_single / PixArt-alpha conditioning) ------------------------
+def _sincos_1d(embed_dim: int, pos: torch.Tensor) -> torch.Tensor:
+    """diffusers get_1d_sincos_pos_embed_from_grid: [sin | cos], float64 omega."""
+    omega = 1.0 / 10000 ** (torch.arange(embed_dim // 2, dtype=torch.float64) / (embed_dim / 2.0))
+    out = pos.reshape(-1).double()[:, None] * omega[None]
+    return torch.cat([out.sin(), out.cos()], dim=1)
+
+
+def get_2d_sincos_pos_embed(embed_dim: int, grid_size: int, base_size: int = 16, interpolation_scale: float = 1.0) -> torch.Tensor:
+    """diffusers.models.embeddings.get_2d_sincos_pos_embed (0.30.0) as PatchEmbed uses it: [grid*grid, D] float32."""
+    g = torch.arange(grid_size, dtype=torch.float32) / (grid_size / base_size) / interpolation_scale
+    grid_w, grid_h = torch.meshgrid(g, g, indexing="xy")  # np.meshgrid(grid_w, grid_h): w first
+    return torch.cat([_sincos_1d(embed_dim // 2, grid_w), _sincos_1d(embed_dim // 2, grid_h)], dim=1).float()
+
+
+class _TimestepEmbedder(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, cout)
+        self.linear_2 = nn.Linear(cout, cout)
+
+
+class _CombinedEmb(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.timestep_embedder = _TimestepEmbedder(256, dim)
+
+
+class _AdaLNSingle(nn.Module):
+    def __init__(self, dim):
+        super().__init__()
+        self.emb = _CombinedEmb(dim)
+        self.linear = nn.Linear(dim, 6 * dim)
+
+
+class _CaptionProjection(nn.Module):
+    def __init__(self, cin, dim):
+        super().__init__()
+        self.linear_1 = nn.Linear(cin, dim)
+        self.linear_2 = nn.Linear(dim, dim)
+
+
+class _PatchEmbed2D(nn.Module):
+    def __init__(self, patch, cin, dim):
+        super().__init__()
+        self.proj = nn.Conv2d(cin, dim, kernel_size=(patch, patch), stride=patch, bias=True)
+
+
+class LatteT2V(nn.Module):
+    """State-dict compatible with the reference / HF ``maxin-cn/Latte-1`` transformer (same parameter names), forward on the
+    vsb200 kernels, sequence parallelism off (the BASELINE configuration for Latte is the plumbing run)."""
+
+    def __init__(self, num_attention_heads=16, attention_head_dim=72, in_channels=4, out_channels=8, num_layers=28,
+                 cross_attention_dim=1152, attention_bias=True, sample_size=64, patch_size=2, activation_fn="gelu-approximate",
+                 norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6, caption_channels=4096,
+                 video_length=16, **unused):
+        super().__init__()
+        if norm_type != "ada_norm_single" or activation_fn != "gelu-approximate" or norm_elementwise_affine:
+            raise NotImplementedError("vsb200 LatteT2V implements the Latte-1 configuration (ada_norm_single, tanh-GELU)")
+        if sample_size == 128:
+            raise NotImplementedError("resolution / aspect-ratio micro-conditions (sample_size 128) are not built")
+        dim = num_attention_heads * attention_head_dim
+        self.config = type("Cfg", (), dict(in_channels=in_channels, out_channels=out_channels, patch_size=patch_size,
+                                           sample_size=sample_size, video_length=video_length, caption_channels=caption_channels,
+                                           num_attention_heads=num_attention_heads, attention_head_dim=attention_head_dim,
+                                           num_layers=num_layers))()
+        self.inner_dim, self.patch_size, self.out_channels, self.eps = dim, patch_size, out_channels, norm_eps
+        self.pos_embed = _PatchEmbed2D(patch_size, in_channels, dim)
+        grid = sample_size // patch_size
+        self.register_buffer("pos_table", get_2d_sincos_pos_embed(dim, grid, base_size=grid,
+                                                                  interpolation_scale=max(sample_size // 64, 1))[None], persistent=False)
+        self.adaln_single = _AdaLNSingle(dim)
+        self.caption_projection = _CaptionProjection(caption_channels, dim)
+        stack = LatteBlockStack(dim, num_attention_heads, num_layers)
+        self.transformer_blocks = stack.transformer_blocks
+        self.temporal_transformer_blocks = stack.temporal_transformer_blocks
+        self._stack = [stack]
+        self.scale_shift_table = nn.Parameter(torch.randn(2, dim) / dim**0.5)
+        self.proj_out = nn.Linear(dim, patch_size * patch_size * out_channels)
+        self.register_buffer("temp_pos_embed", _sincos_1d(dim, torch.arange(video_length).float()).float()[None], persistent=False)
+        self.parallel_manager = None
+
+    def enable_parallel(self, dp_size=None, sp_size=None, enable_cp=None):
+        if (sp_size or 1) > 1:
+            raise NotImplementedError("Latte sequence parallelism (T-shard DSP, reference :826-843) is not built: 1 GPU")
+
+    def reset_pab_state(self):
+        self._stack[0].reset_pab_state()
+
+    @staticmethod
+    def _time_proj(timesteps: torch.Tensor, dim: int = 256) -> torch.Tensor:
+        """diffusers Timesteps(256, flip_sin_to_cos=True, downscale_freq_shift=0): fp32 [cos | sin]."""
+        half = dim // 2
+        exponent = -math.log(10000.0) * torch.arange(half, dtype=torch.float32, device=timesteps.device) / half
+        emb = timesteps[:, None].float() * exponent.exp()[None]
+        return torch.cat([emb.cos(), emb.sin()], dim=-1)
+
+    @torch.no_grad()
+    def forward(self, hidden_states, timestep=None, all_timesteps=None, encoder_hidden_states=None, added_cond_kwargs=None,
+                class_labels=None, cross_attention_kwargs=None, attention_mask=None, encoder_attention_mask=None,
+                use_image_num: int = 0, enable_temporal_attentions: bool = True, return_dict: bool = True, ts_int=None):
+        """hidden_states [B, C, F, H, W] latents, timestep [B], encoder_hidden_states [B, L, 4096] (reference :1144-1466)."""
+        if not hidden_states.is_cuda:
+            raise RuntimeError("videosys_b200 LatteT2V runs on sm_100a CUDA devices only (no CPU path)")
+        if attention_mask is not None or encoder_attention_mask is not None or use_image_num or not enable_temporal_attentions:
+            raise NotImplementedError("masks / joint image training / spatial-only mode are outside the inference path "
+                                      "(the reference pipeline never passes them: pipeline_latte.py:854-862)")
+        K = kernels
+        dt = self.proj_out.weight.dtype
+        B, Cin, Fr, H, W = hidden_states.shape
+        p, C = self.patch_size, self.inner_dim
+        h, w = H // p, W // p
+        S = h * w
+        x = hidden_states.to(dt).permute(0, 2, 1, 3, 4).reshape(B * Fr, Cin, H, W)
+        x = self.pos_embed.proj(x).flatten(2).transpose(1, 2)  # conv: cuDNN (glue, once per step)  [B*F, S, C]
+        pos = self.pos_table if S == self.pos_table.shape[1] else get_2d_sincos_pos_embed(
+            C, h, base_size=self.config.sample_size // p, interpolation_scale=max(self.config.sample_size // 64, 1))[None].to(x.device)
+        x = (x + pos.to(dt)).reshape(B, Fr, S, C)
+        te = self.adaln_single.emb.timestep_embedder
+        t_emb = self._time_proj(timestep).to(dt)
+        embedded = K.gemm_bias_act(F.silu(K.gemm_bias_act(t_emb, te.linear_1.weight, te.linear_1.bias)), te.linear_2.weight,
+                                   te.linear_2.bias)  # [B, C]
+        t6 = K.gemm_bias_act(F.silu(embedded), self.adaln_single.linear.weight, self.adaln_single.linear.bias)  # [B, 6C]
+        cp = self.caption_projection
+        enc = K.gemm_bias_act(K.gemm_bias_act(encoder_hidden_states.to(dt).contiguous(), cp.linear_1.weight, cp.linear_1.bias, act=1),
+                              cp.linear_2.weight, cp.linear_2.bias)  # [B, L, C]
+        if pab_mgr.enable_pab() and ts_int is None:
+            ts_int = int(timestep[0])
+        if all_timesteps is not None and torch.is_tensor(all_timesteps):
+            all_timesteps = all_timesteps.tolist()
+        x = self._stack[0](x, enc, t6, self.temp_pos_embed[:, :Fr] if Fr > 1 else None, ts_int=ts_int, all_timesteps=all_timesteps)
+        # output head (:1436-1443): LayerNorm (no affine) -> * (1 + scale) + shift with table + embedded timestep -> proj_out
+        tab6 = torch.cat([self.scale_shift_table, self.scale_shift_table.new_zeros(4, C)], 0)
+        mod = K.modulation_table(tab6, torch.cat([embedded, embedded, embedded.new_zeros(B, 4 * C)], 1).contiguous(), None)
+        y = K.ln_modulate(x.view(B, Fr * S, C), mod, None, 0, 1, B, Fr, S, eps=self.eps)
+        y = K.gemm_bias_act(y, self.proj_out.weight, self.proj_out.bias)  # [B, F*S, p*p*Cout]
+        Co = self.out_channels
+        y = y.reshape(B * Fr, h, w, p, p, Co)
+        y = torch.einsum("nhwpqc->nchpwq", y).reshape(B * Fr, Co, h * p, w * p)
+        out = y.reshape(B, Fr, Co, h * p, w * p).permute(0, 2, 1, 3, 4).contiguous()
+        return (out,) if not return_dict else type("Out", (), {"sample": out})()
