@@ -19,7 +19,7 @@
 //                 160 score columns (tcgen05.ld in 32-column chunks), pass 2 = exp2 / row sum / bf16 P written over the
 //                 head of the score buffer chunk by chunk (P chunk c lands on columns [16c, 16c+16), all of which were
 //                 read before); the running max is lazy (rescale of O only when it grew by > 2^8: P0 V has retired by then,
-//                 S1's commit covers it); each tcgen05.ld of the two passes is issued one chunk ahead.
+//                 S1's commit covers it).
 //   TMEM          S_x at x*256 (160 columns), O_x at x*256 + 160 (80 columns).
 #include "attn_params.cuh"
 
@@ -239,39 +239,35 @@ attn_flash_kvres_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         ++n_s;
         tc_fence_after();
         const int valid = it.kv_len - hf * kRH;  // >= 160: every column; else columns >= valid are masked
-        // ---- pass 1: row max (the next chunk's tcgen05.ld is in flight while this one is reduced) ----
+        // ---- pass 1: row max ----
         float mx = -INFINITY;
-        uint32_t a[2][32];
-        tmem_ld32(tS, a[0]);
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < kRH / 32; ++c) {
+          uint32_t a[32];
+          tmem_ld32(tS + c * 32, a);
           tmem_wait_ld();
-          if (c + 1 < kRH / 32) tmem_ld32(tS + (c + 1) * 32, a[(c + 1) & 1]);
-          const uint32_t* v = a[c & 1];
           if (valid >= (c + 1) * 32) {
-            float m0 = fmax3(__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]));
-            float m1 = fmax3(__uint_as_float(v[3]), __uint_as_float(v[4]), __uint_as_float(v[5]));
+            float m0 = fmax3(__uint_as_float(a[0]), __uint_as_float(a[1]), __uint_as_float(a[2]));
+            float m1 = fmax3(__uint_as_float(a[3]), __uint_as_float(a[4]), __uint_as_float(a[5]));
 #pragma unroll
             for (int i = 6; i < 30; i += 4) {
-              m0 = fmax3(m0, __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-              m1 = fmax3(m1, __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+              m0 = fmax3(m0, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+              m1 = fmax3(m1, __uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
             }
-            m0 = fmax3(m0, __uint_as_float(v[30]), __uint_as_float(v[31]));
+            m0 = fmax3(m0, __uint_as_float(a[30]), __uint_as_float(a[31]));
             mx = fmax3(mx, m0, m1);
           } else {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+              if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(a[i]));
           }
         }
-        tmem_ld32(tS, a[0]);  // pass 2's first chunk: in flight during the max bookkeeping below
         // lazy rescale (as in the long-sequence kernels): keep the stale max unless it grew by more than 2^8, so that the
-        // 80-column read-modify-write of O_x is the rare path (p stays <= 256: exact in bf16 and fp16 range)
+        // 80-column read-modify-write of O_x is the rare path (p stays <= 256: exact in bf16 and inside the fp16 range)
         const float m_new = fmaxf(m_run, mx);
         const bool grow = (m_new - m_run) * sl2 > 8.f;  // first half: m_run = -inf -> true (nothing to rescale yet)
         if (hf > 0 && __any_sync(0xffffffffu, grow)) {
           const float alpha = grow ? fast_exp2((m_run - m_new) * sl2) : 1.f;
-          tmem_wait_ld();  // O_x columns below must not race the outstanding score load's wait accounting
 #pragma unroll 1
           for (int c = 0; c < (kHasB ? 5 : 4); ++c) {  // P0 V0 has retired: S1's commit covers it
             uint32_t o[16];
@@ -286,19 +282,22 @@ attn_flash_kvres_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
         if (grow) m_run = m_new;
         const float mb = m_run * sl2;
         // ---- pass 2: p = exp2(s*sl2 - m*sl2), row sum, bf16 P over the head of the score buffer ----
+        // (software-pipelining the tcgen05.ld of the two passes one chunk ahead was measured SLOWER: 0.58 vs 0.49 ms per
+        // 720p cross-attention launch -- 168 registers with spills instead of 122, and the two warpgroups already overlap
+        // each other's load latency)
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < kRH / 32; ++c) {
+          uint32_t a[32];
+          tmem_ld32(tS + c * 32, a);
           tmem_wait_ld();
-          if (c + 1 < kRH / 32) tmem_ld32(tS + (c + 1) * 32, a[(c + 1) & 1]);
-          const uint32_t* v = a[c & 1];
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
-            float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), sl2, -mb));
-            float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), sl2, -mb));
-            float e2 = fast_exp2(fmaf(__uint_as_float(v[i + 2]), sl2, -mb));
-            float e3 = fast_exp2(fmaf(__uint_as_float(v[i + 3]), sl2, -mb));
+            float e0 = fast_exp2(fmaf(__uint_as_float(a[i]), sl2, -mb));
+            float e1 = fast_exp2(fmaf(__uint_as_float(a[i + 1]), sl2, -mb));
+            float e2 = fast_exp2(fmaf(__uint_as_float(a[i + 2]), sl2, -mb));
+            float e3 = fast_exp2(fmaf(__uint_as_float(a[i + 3]), sl2, -mb));
             if (valid < (c + 1) * 32) {
               if (c * 32 + i >= valid) e0 = 0.f;
               if (c * 32 + i + 1 >= valid) e1 = 0.f;
@@ -312,8 +311,7 @@ attn_flash_kvres_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
             pk[i >> 1] = pack_bf16x2(e0, e1);
             pk[(i >> 1) + 1] = pack_bf16x2(e2, e3);
           }
-          // P chunk c over score columns [16c, 16c+16): read already (chunk c+1, in flight, covers [32c+32, 32c+64))
-          tmem_st16(tS + c * 16, pk);
+          tmem_st16(tS + c * 16, pk);  // P chunk c over score columns [16c, 16c+16): all read already
         }
         l_run += (s0 + s1) + (s2 + s3);
         tmem_wait_st();
