@@ -260,3 +260,60 @@ def test_bench_line_contract():
     assert abs(line["value"] - 68 / (50 * 0.437)) < 1e-9 and abs(line["ms_per_step"] - 437.0) < 1e-6
     assert set(line["e2e"]) >= {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"}
     assert line["config"]["workload"] == args.workload and "model" not in line["config"]
+
+
+def test_from_pretrained_local_snapshot(tmp_path):
+    """the three denoisers load hub-style LOCAL snapshots (config.json + safetensors / .bin) strictly, under
+    the reference's parameter names; a path that is not a directory fails loudly (no hub download)."""
+    import json
+
+    import torch
+    from safetensors.torch import save_file
+
+    from videosys_b200.models.transformers.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+    from videosys_b200.models.transformers.latte_transformer_3d import LatteT2V
+    from videosys_b200.models.transformers.open_sora_transformer_3d import STDiT3, STDiT3Config
+
+    cfg = dict(hidden_size=144, num_heads=2, depth=1, caption_channels=32, model_max_length=8)
+    src = STDiT3(STDiT3Config(**cfg))
+    d = tmp_path / "stdit3"
+    d.mkdir()
+    (d / "config.json").write_text(json.dumps(dict(cfg, _name_or_path="x", architectures=["STDiT3"], model_type="STDiT3")))
+    save_file({k: v.contiguous() for k, v in src.state_dict().items()}, str(d / "model.safetensors"))
+    got = STDiT3.from_pretrained(str(d), enable_flash_attn=True)
+    assert got.config.enable_flash_attn is True and got.depth == 1
+    for k, v in src.state_dict().items():
+        assert torch.equal(got.state_dict()[k], v), k
+
+    cx = dict(num_attention_heads=2, attention_head_dim=64, in_channels=4, out_channels=4, time_embed_dim=32, text_embed_dim=16,
+              num_layers=1, sample_width=8, sample_height=8, sample_frames=5, max_text_seq_length=4)
+    srcx = CogVideoXTransformer3DModel(**cx)
+    dx = tmp_path / "cogx" / "transformer"
+    dx.mkdir(parents=True)
+    (dx / "config.json").write_text(json.dumps(dict(cx, _class_name="CogVideoXTransformer3DModel")))
+    torch.save(srcx.state_dict(), str(dx / "diffusion_pytorch_model.bin"))
+    gotx = CogVideoXTransformer3DModel.from_pretrained(str(tmp_path / "cogx"))
+    assert all(torch.equal(gotx.state_dict()[k], v) for k, v in srcx.state_dict().items())
+
+    lt = dict(num_attention_heads=2, attention_head_dim=72, num_layers=1, sample_size=8, caption_channels=16)
+    srcl = LatteT2V(**lt, video_length=4)
+    dl = tmp_path / "latte" / "transformer"
+    dl.mkdir(parents=True)
+    (dl / "config.json").write_text(json.dumps(lt))
+    sd = {k: v.contiguous() for k, v in srcl.state_dict().items()}
+    half = len(sd) // 2
+    keys = list(sd)
+    save_file({k: sd[k] for k in keys[:half]}, str(dl / "a.safetensors"))
+    save_file({k: sd[k] for k in keys[half:]}, str(dl / "b.safetensors"))
+    (dl / "diffusion_pytorch_model.safetensors.index.json").write_text(json.dumps(
+        {"weight_map": {**{k: "a.safetensors" for k in keys[:half]}, **{k: "b.safetensors" for k in keys[half:]}}}))
+    gotl = LatteT2V.from_pretrained(str(tmp_path / "latte"), video_length=4)
+    assert all(torch.equal(gotl.state_dict()[k], v) for k, v in srcl.state_dict().items())
+
+    with pytest.raises(FileNotFoundError):
+        STDiT3.from_pretrained("hpcai-tech/OpenSora-STDiT-v3")
+    bad = dict(src.state_dict())
+    bad.pop("t_block.1.bias")
+    save_file({k: v.contiguous() for k, v in bad.items()}, str(d / "model.safetensors"))
+    with pytest.raises(RuntimeError):
+        STDiT3.from_pretrained(str(d))

@@ -242,6 +242,13 @@ class CogVideoXTransformer3DModel(nn.Module):
         self.proj_out = nn.Linear(dim, patch_size * patch_size * out_channels)
         self.parallel_manager = None
 
+    @classmethod
+    def from_pretrained(cls, path, subfolder: str = "transformer", **config_overrides):
+        """Reference pipeline_cogvideox.py:143-145, for a LOCAL snapshot directory (videosys_b200/utils/checkpoint.py)."""
+        from ...utils.checkpoint import build_from_pretrained
+
+        return build_from_pretrained(cls, path, subfolder, **config_overrides)
+
     def enable_parallel(self, dp_size=None, sp_size=None, enable_cp=None):
         if (sp_size or 1) > 1:
             raise NotImplementedError("CogVideoX runs on one GPU here (reference head-scatter SP: 30 heads, sp in {2,3,5,6})")

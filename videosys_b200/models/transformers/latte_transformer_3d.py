@@ -271,6 +271,13 @@ class LatteT2V(nn.Module):
         self.register_buffer("temp_pos_embed", _sincos_1d(dim, torch.arange(video_length).float()).float()[None], persistent=False)
         self.parallel_manager = None
 
+    @classmethod
+    def from_pretrained(cls, path, subfolder: str = "transformer", **config_overrides):
+        """Reference pipeline_latte.py:196-199 (``video_length=16``), for a LOCAL snapshot directory."""
+        from ...utils.checkpoint import build_from_pretrained
+
+        return build_from_pretrained(cls, path, subfolder, **config_overrides)
+
     def enable_parallel(self, dp_size=None, sp_size=None, enable_cp=None):
         if (sp_size or 1) > 1:
             raise NotImplementedError("Latte sequence parallelism (T-shard DSP, reference :826-843) is not built: 1 GPU")

@@ -223,6 +223,14 @@ class STDiT3(nn.Module):
             nn.init.zeros_(blk.cross_attn.proj.weight)
             nn.init.zeros_(blk.mlp.fc2.weight)
 
+    @classmethod
+    def from_pretrained(cls, path, subfolder: str = "", **config_overrides):
+        """STDiT3.from_pretrained (reference pipeline_open_sora.py:222-224) for a LOCAL snapshot directory (config.json +
+        safetensors / .bin; videosys_b200/utils/checkpoint.py): the reference's parameter names load strictly."""
+        from ...utils.checkpoint import build_from_pretrained
+
+        return build_from_pretrained(cls, path, subfolder, config_cls=STDiT3Config, **config_overrides)
+
     def enable_parallel(self, dp_size=None, sp_size=None, enable_cp=None, parallel_mgr=None):
         if parallel_mgr is not None:
             self.parallel_manager = parallel_mgr
@@ -650,5 +658,5 @@ class STDiT3(nn.Module):
 
 def STDiT3_XL_2(from_pretrained=None, **kwargs):
     if from_pretrained is not None:
-        raise NotImplementedError("checkpoint download is out of scope; build the model and load_state_dict()")
+        return STDiT3.from_pretrained(from_pretrained, **kwargs)
     return STDiT3(STDiT3Config(depth=28, hidden_size=1152, patch_size=(1, 2, 2), num_heads=16, **kwargs))

@@ -57,7 +57,12 @@ class CogVideoXPipeline:
         if config.model_path == "THUDM/CogVideoX-2b":
             dtype = torch.float16  # reference :138-139
         self._dtype = dtype
-        self.transformer = CogVideoXTransformer3DModel(**(config.transformer_config or {})).to(dtype)
+        import os
+
+        if config.transformer_config is None and config.state_dict is None and os.path.isdir(str(config.model_path)):
+            self.transformer = CogVideoXTransformer3DModel.from_pretrained(config.model_path, subfolder="transformer").to(dtype)
+        else:
+            self.transformer = CogVideoXTransformer3DModel(**(config.transformer_config or {})).to(dtype)
         if config.state_dict is not None:
             self.transformer.load_state_dict(config.state_dict)
         self.transformer = self.transformer.to(self._device).eval()

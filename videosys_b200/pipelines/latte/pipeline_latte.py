@@ -66,7 +66,12 @@ class LattePipeline:
         self._config = config
         self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._dtype = dtype
-        self.transformer = LatteT2V(**(config.transformer_config or {})).to(dtype)
+        import os
+
+        if config.transformer_config is None and config.state_dict is None and os.path.isdir(str(config.model_path)):
+            self.transformer = LatteT2V.from_pretrained(config.model_path, subfolder="transformer", video_length=16).to(dtype)
+        else:
+            self.transformer = LatteT2V(**(config.transformer_config or {})).to(dtype)
         if config.state_dict is not None:
             self.transformer.load_state_dict(config.state_dict)
         self.transformer = self.transformer.to(self._device).eval()

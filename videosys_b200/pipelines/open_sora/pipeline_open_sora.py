@@ -101,8 +101,14 @@ class OpenSoraPipeline:
             raise RuntimeError("videosys_b200 pipelines need an sm_100a GPU (no CPU path)")
         self._config = config
         self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        tcfg = config.transformer_config or STDiT3Config(depth=28, hidden_size=1152, num_heads=16)
-        self.transformer = STDiT3(tcfg).to(torch.bfloat16)
+        import os
+
+        if config.transformer_config is None and config.state_dict is None and os.path.isdir(str(config.transformer)):
+            # a local snapshot of hpcai-tech/OpenSora-STDiT-v3 (reference :222-224 downloads it)
+            self.transformer = STDiT3.from_pretrained(config.transformer, enable_flash_attn=config.enable_flash_attn).to(torch.bfloat16)
+        else:
+            tcfg = config.transformer_config or STDiT3Config(depth=28, hidden_size=1152, num_heads=16)
+            self.transformer = STDiT3(tcfg).to(torch.bfloat16)
         if config.state_dict is not None:
             self.transformer.load_state_dict(config.state_dict)
         self.transformer = self.transformer.to(self._device).eval()
