@@ -516,8 +516,18 @@ def run_ours(args):
                          peaks, cfg["depth"], z_host.numel() * 4, out_host.numel() * 4, extra)
         print(json.dumps(line), flush=True)
     if world > 1:
+        # the captured step graphs hold NCCL work (the final gather): release them before the communicator goes away --
+        # destroying the process group under live graphs hung the N = 2 run after its line had been printed
+        import gc
+
+        del stepper, eager
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)  # every rank has passed the barrier; no communicator / interpreter teardown that could wait on a peer
 
 
 def _dsp_parity(net, sched, z0, timesteps, dts, fwd_args, dev, dist, args):
