@@ -38,7 +38,7 @@ for g in "$@"; do
               bench.py --gpus $n $BENCH_ARGS > gpurun_out/bench_nccl_n$n.json 2> gpurun_out/bench_nccl_n$n.err
            echo "exit $? : $(tail -c 1500 gpurun_out/bench_nccl_n$n.json | cut -c1-300)" | tee -a gpurun_out/summary.txt ;;
     mbench*) n=${g#mbench}; echo "=== bench N=$n ===" | tee -a gpurun_out/summary.txt
-           timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 \
+           timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 \
               bench.py --gpus $n $BENCH_ARGS > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
            echo "exit $? : $(tail -c 1500 gpurun_out/bench_n$n.json | cut -c1-400)" | tee -a gpurun_out/summary.txt
            tail -n 8 gpurun_out/bench_n$n.err ;;
