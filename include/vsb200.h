@@ -56,7 +56,11 @@ int vsb_debug_attn_trace(void* device_buffer);
 /*   "attn_variant" 4 = variant 2 with the query rows resident in TMEM (S = Q K^T issued as TS MMAs: the A operand no
  *   longer re-read from shared memory on every K step) and 8 instead of 6 K/V stages; 5 = 4 with the softmax row sum
  *   accumulated by the tensor core (ones written into the zero padding column d = 72 of every V tile; head_dim 72).
- *   "dsp_rowwise" (default 1): vsb_dsp_scatter decodes indices once per token row; 0 = the first version (per vector). */
+ *   6 = up to 320 keys (text cross-attention): K/V of a (batch, head) resident in shared memory, 160-key score tiles
+ *   (auto for nk <= 320).
+ *   "dsp_rowwise" (default 1): vsb_dsp_scatter decodes indices once per token row; 0 = the first version (per vector).
+ *   "ln_occupancy" (default 3): 4 = vsb_ln_modulate compiled for 4 resident blocks per SM (64 registers).
+ *   "tmap_cache" (default 1): cache of encoded TMA tensor maps. */
 
 /* ---- AdaLN: LayerNorm(eps, no affine) -> x*(1+scale)+shift with per-frame t / t0 select --------------------
  * replaces norm1/norm2 + t2i_modulate + t_mask_select: models/transformers/open_sora_transformer_3d.py:47-48,

@@ -58,7 +58,7 @@ for g in "$@"; do
     ncu_list) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file gpurun_out/launches.csv \
               python bench.py --steps 1 --warmup 1 --depth 2 --no-cpu-baseline --no-gpu-baseline --no-graph > gpurun_out/ncu_list.log 2>&1
            echo "ncu_list exit $?" | tee -a gpurun_out/summary.txt ;;
-    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm2_bf16 -s 14 -c 4 -o gpurun_out/prof_gemm -f \
+    ncu_gemm) timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm2_bf16 -s 36 -c 12 -o gpurun_out/prof_gemm -f \
               python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline --no-gpu-baseline --no-graph > gpurun_out/ncu_gemm.log 2>&1
            echo "ncu_gemm exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_short) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_short -c 1 -o gpurun_out/prof_short -f \

@@ -170,6 +170,9 @@ o = torch.empty_like(x)
 nb = x.numel() * 2
 r = {}
 t = timeit(lambda: K.ln_modulate(x, mod, m8, 0, 1, 2, 20, 3600, out=o)); r["ln_modulate_GBs"] = round(2 * nb / t / 1e9)
+K.set_option("ln_occupancy", 4)
+t = timeit(lambda: K.ln_modulate(x, mod, m8, 0, 1, 2, 20, 3600, out=o)); r["ln_modulate_occ4_GBs"] = round(2 * nb / t / 1e9)
+K.set_option("ln_occupancy", 3)
 t = timeit(lambda: K.gate_residual(x, y, mod, m8, 2, 2, 20, 3600, out=o)); r["gate_residual_GBs"] = round(3 * nb / t / 1e9)
 t = timeit(lambda: K.residual_add(x, y, out=o)); r["residual_add_GBs"] = round(3 * nb / t / 1e9)
 t = timeit(lambda: o.copy_(x)); r["torch_copy_GBs"] = round(2 * nb / t / 1e9)

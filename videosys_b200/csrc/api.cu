@@ -13,6 +13,7 @@ int g_opt_attn_variant = -1;  // -1 = auto
 int g_opt_attn_pingpong = 1;  // variant 0 only
 int g_opt_attn_poly = 0;      // variants 2-5: fraction of exp2 on the FMA pipe
 int g_opt_dsp_rowwise = 1;    // 0: the first (per-vector) reshard kernel
+int g_opt_ln_occupancy = 3;   // ln_modulate: resident 256-thread blocks per SM the kernel is compiled for (3 or 4)
 long long* g_attn_trace = nullptr;
 std::atomic<unsigned long long> g_launches{0};
 static EncodeTiledFn g_encode = nullptr;
@@ -176,6 +177,10 @@ extern "C" int vsb_set_option(const char* name, int value) {
   }
   if (!strcmp(name, "dsp_rowwise")) {
     g_opt_dsp_rowwise = value;
+    return VSB_OK;
+  }
+  if (!strcmp(name, "ln_occupancy")) {
+    g_opt_ln_occupancy = value;
     return VSB_OK;
   }
   return fail(VSB_ERR_INVALID, "set_option: unknown option '%s'", name);

@@ -46,8 +46,10 @@ struct LnDspArgs {
   unsigned epoch;
 };
 
-template <int kMaxVec, bool kDsp>
-__global__ void __launch_bounds__(256) ln_modulate_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
+// kMinBlocks: 3 = 80 registers, 24 resident warps per SM (one 2.3 KB row in flight each); 4 = capped at 64 registers
+// (~100 bytes of spills) for 32 resident warps: option "ln_occupancy" picks, bench decides (profiles/r02_kernel_bench.json).
+template <int kMaxVec, bool kDsp, int kMinBlocks>
+__global__ void __launch_bounds__(256, kMinBlocks) ln_modulate_kernel(const bf16* __restrict__ x, bf16* __restrict__ out,
                                                           const bf16* __restrict__ mod,
                                                           const uint8_t* __restrict__ x_mask, int shift_row,
                                                           int scale_row, int B, int T, int S, int C, float eps,
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(256) gate_residual_dsp_kernel(const bf16* __re
 // In-place RMSNorm of the q and k heads of a packed [rows, 3, H, D] buffer.  A group of D/8 lanes owns one
 // (row, q|k, head) vector of D elements (D=72 -> 9 lanes, D=64 -> 8 lanes); groups are packed 3 per warp.
 template <int D>
-__global__ void __launch_bounds__(256) qk_rmsnorm_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ wq,
+__global__ void __launch_bounds__(256, 4) qk_rmsnorm_kernel(bf16* __restrict__ qkv, const bf16* __restrict__ wq,
                                                          const bf16* __restrict__ wk, long long rows, int H, float eps,
                                                          const float* __restrict__ rope_cos,
                                                          const float* __restrict__ rope_sin, unsigned pos_div,
@@ -449,14 +451,16 @@ static int ln_modulate_launch(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* 
   cudaStream_t st = (cudaStream_t)stream;
   LnDspArgs none;
   memset(&none, 0, sizeof(none));
-#define VSB_LN_LAUNCH(MV, DSP, ARGS)                                                                                   \
-  ln_modulate_kernel<MV, DSP><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, (const bf16*)mod, x_mask, shift_row,   \
-                                                     scale_row, B, T, S, C, eps, rows, (const bf16*)gamma,              \
-                                                     (const bf16*)beta, ARGS)
+#define VSB_LN_LAUNCH(MV, DSP, OCC, ARGS)                                                                              \
+  ln_modulate_kernel<MV, DSP, OCC><<<grid, 256, 0, st>>>((const bf16*)x, (bf16*)out, (const bf16*)mod, x_mask,         \
+                                                          shift_row, scale_row, B, T, S, C, eps, rows,                  \
+                                                          (const bf16*)gamma, (const bf16*)beta, ARGS)
   if (dsp) {
-    if (C <= 1280) VSB_LN_LAUNCH(5, true, *dsp); else VSB_LN_LAUNCH(8, true, *dsp);
+    if (C <= 1280) VSB_LN_LAUNCH(5, true, 3, *dsp); else VSB_LN_LAUNCH(8, true, 2, *dsp);
+  } else if (C <= 1280) {
+    if (g_opt_ln_occupancy >= 4) VSB_LN_LAUNCH(5, false, 4, none); else VSB_LN_LAUNCH(5, false, 3, none);
   } else {
-    if (C <= 1280) VSB_LN_LAUNCH(5, false, none); else VSB_LN_LAUNCH(8, false, none);
+    VSB_LN_LAUNCH(8, false, 2, none);
   }
 #undef VSB_LN_LAUNCH
   return check_launch("ln_modulate");

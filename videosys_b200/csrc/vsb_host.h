@@ -14,7 +14,7 @@ namespace vsbs {
 extern thread_local char g_err[512];
 extern std::atomic<unsigned long long> g_launches;
 // run-time kernel selection knobs (vsb_set_option)
-extern int g_opt_gemm_2sm, g_opt_attn_variant, g_opt_attn_pingpong, g_opt_attn_poly, g_opt_dsp_rowwise;
+extern int g_opt_gemm_2sm, g_opt_attn_variant, g_opt_attn_pingpong, g_opt_attn_poly, g_opt_dsp_rowwise, g_opt_ln_occupancy;
 extern long long* g_attn_trace;
 
 inline int fail(int code, const char* fmt, ...) {
