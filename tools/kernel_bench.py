@@ -86,7 +86,7 @@ fl = 4.0 * 40 * H * 3600 * 3600 * D
 # after the other, whichever ran first on a cool GPU looked 20-40 % faster than it is inside a denoising step.
 def spatial(var, poly):
     K.set_option("attn_variant", var)
-    K.set_option("attn_poly_exp", poly)
+    K.set_option("attn_poly_exp", poly if var != 6 else 0)
     K.attn_flash(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], 40, 3600, 3600, H, D, 3 * C, 3600 * 3 * C, 3 * C, 3600 * 3 * C, D**-0.5)
 
 
@@ -97,13 +97,14 @@ flx = 4.0 * 2 * H * 72000 * 300 * D
 
 def cross(var, poly):
     K.set_option("attn_variant", var)
-    K.set_option("attn_poly_exp", poly)
+    K.set_option("attn_poly_exp", poly if var != 6 else 0)
+    K.set_option("attn_pingpong", 0 if (var == 6 and poly == 9) else 1)  # variant 6: poly slot 9 = pipelines NOT staggered
     K.attn_flash(qx, kvx[:, :, 0], kvx[:, :, 1], 2, 72000, 300, H, D, C, 72000 * C, 2 * C, 300 * 2 * C, D**-0.5)
 
 
 VARIANTS = {"kt128_pingpong": (0, 0), "kt64": (2, 0), "kt64_poly25": (2, 1), "kt64_poly37": (2, 2), "kt64p": (3, 0), "kt64p_poly25": (3, 1),
             "kt64_qtmem": (4, 0), "kt64_qtmem_poly25": (4, 1), "kt64_qtmem_poly37": (4, 2), "kt64_qtmem_poly50": (4, 3),
-            "kvres_cross_only": (6, 0), "kt64_qtsum": (5, 0), "kt64_qtsum_poly25": (5, 1), "kt64_qtsum_poly37": (5, 2), "kt64_qtsum_poly50": (5, 3)}
+            "kvres_cross_only": (6, 0), "kvres_cross_only_nostagger": (6, 9), "kt64_qtsum": (5, 0), "kt64_qtsum_poly25": (5, 1), "kt64_qtsum_poly37": (5, 2), "kt64_qtsum_poly50": (5, 3)}
 # cuDNN's fused attention on the same problem, inside the same round-robin (a yardstick: never on the product path)
 from torch.nn.attention import SDPBackend, sdpa_kernel  # noqa: E402
 

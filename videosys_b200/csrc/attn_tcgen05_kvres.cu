@@ -230,6 +230,11 @@ attn_flash_kvres_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     const uint32_t tO = tmem_base + lane_off + r_o(x);
     const float sl2 = p.scale_log2;
     int n_s = 0, n_mine = 0;
+    // Stagger the two query-tile pipelines (option "attn_pingpong", default on): both tiles of an item become ready at
+    // the same instant, so left alone the two warpgroups exponentiate at the same time (each at half the MUFU rate)
+    // while the tensor pipe idles, then both wait for their MMAs.  Warpgroup B starts its first softmax only when A has
+    // published its first P: from then on A's exp2 phases run against B's MMA phases and vice versa.
+    if (p.pingpong && x == 1 && i0 < i1 && ritem_of(p, i0, n_pairs).nx == 2) mbar_wait(&p_full[0], 0);
     for (int item = i0; item < i1; ++item) {
       const RItem it = ritem_of(p, item, n_pairs);
       if (x >= it.nx) continue;
