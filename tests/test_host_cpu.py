@@ -317,3 +317,38 @@ def test_from_pretrained_local_snapshot(tmp_path):
     save_file({k: v.contiguous() for k, v in bad.items()}, str(d / "model.safetensors"))
     with pytest.raises(RuntimeError):
         STDiT3.from_pretrained(str(d))
+
+
+def test_pab_plan_matches_known_answer_schedules(golden_dir):
+    """STDiT3.pab_plan (the per-step skip decisions taken on the host before anything is launched = the key of the step
+    graphs) reproduces the reference's skip bitmaps (generated by executing the reference) for every
+    block over two consecutive 50-step videos, and the number of distinct plans is what core/graph_step.py captures."""
+    from videosys_b200.core.pab import pab_mgr as P
+    from videosys_b200.models.transformers.open_sora_transformer_3d import STDiT3, STDiT3Config
+    from videosys_b200.pipelines.open_sora.pipeline_open_sora import OpenSoraPABConfig
+
+    kat = json.load(open(os.path.join(golden_dir, "pab_schedules.json")))["720p_68f_50"]
+    net = STDiT3(STDiT3Config(hidden_size=144, num_heads=2, depth=3, caption_channels=32, model_max_length=8))
+    assert net.pab_plan(500) is None  # PAB off
+    try:
+        P.set_pab_manager(OpenSoraPABConfig())
+        P.update_steps(50)
+        rows = {"spatial": [], "temporal": [], "cross": []}
+        plans = set()
+        for rep in range(2):
+            for t in kat["timesteps"]:
+                plan = net.pab_plan(t)
+                plans.add(plan)
+                assert len(plan) == 2 * net.depth
+                for d in range(net.depth):
+                    (sa, sc), (ta, tc) = plan[2 * d], plan[2 * d + 1]
+                    assert (sa, sc, ta, tc) == (plan[0][0], plan[0][1], plan[1][0], plan[1][1])  # every block pair alike
+                    assert sc == tc  # one cross gate per block, same counter history
+                rows["spatial"].append("1" if plan[0][0] else "0")
+                rows["temporal"].append("1" if plan[1][0] else "0")
+                rows["cross"].append("1" if plan[0][1] else "0")
+        for kind in rows:
+            assert "".join(rows[kind][:50]) == kat[kind] and "".join(rows[kind][50:]) == kat[kind + "_second_run"], kind
+        assert 2 <= len(plans) <= 13, len(plans)  # lcm(2, 4, 6) = 12 skip patterns + "nothing reused"
+    finally:
+        P.set_pab_manager(None)

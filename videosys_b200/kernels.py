@@ -139,11 +139,12 @@ def ln_modulate(x, mod, x_mask_u8, shift_row, scale_row, B, T, S, out=None, eps=
     Cc = x.shape[-1]
     out = torch.empty_like(x) if out is None else out
     with _Timed("ln_modulate", 2 * x.numel() * 2):
-        _lib.check(
-            _fn(lib, "vsb_ln_modulate_affine", x)(_p(x), _p(out), _p(mod), _p(x_mask_u8), _p(gamma), _p(beta), shift_row,
-                                       scale_row, B, T, S, Cc, eps, st),
-            "ln_modulate",
-        )
+        if gamma is None and beta is None:  # STDiT3 / Latte: LayerNorm without affine parameters
+            rc = _fn(lib, "vsb_ln_modulate", x)(_p(x), _p(out), _p(mod), _p(x_mask_u8), shift_row, scale_row, B, T, S, Cc, eps, st)
+        else:  # CogVideoXLayerNormZero / norm_final / AdaLayerNorm: nn.LayerNorm with weight and bias in front
+            rc = _fn(lib, "vsb_ln_modulate_affine", x)(_p(x), _p(out), _p(mod), _p(x_mask_u8), _p(gamma), _p(beta), shift_row,
+                                                       scale_row, B, T, S, Cc, eps, st)
+        _lib.check(rc, "ln_modulate")
     return out
 
 
