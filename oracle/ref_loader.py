@@ -120,3 +120,40 @@ def build_stdit3(depth=1, hidden_size=1152, num_heads=16, dtype=torch.float32, *
     for b in [*net.spatial_blocks, *net.temporal_blocks]:
         b.parallel_manager = SingleRankPM()
     return net
+
+
+def load_cogvideox_scheduler():
+    """The reference's CogVideoXDDIMScheduler class (schedulers/scheduling_ddim_cogvideox.py), imported unmodified with
+    the three diffusers base names it needs stubbed (ConfigMixin / register_to_config: keep the constructor kwargs as
+    ``self.config``; SchedulerMixin; BaseOutput).  All scheduler arithmetic is the reference's own."""
+    import functools
+    import inspect
+
+    if not available():
+        raise RuntimeError(f"reference tree not present at {REF}")
+    if "videosys" not in sys.modules:
+        pkg = _mod("videosys")
+        pkg.__path__ = [REF + "/videosys"]
+
+    def register_to_config(init):
+        @functools.wraps(init)
+        def wrapper(self, *a, **kw):
+            sig = inspect.signature(init)
+            bound = sig.bind(self, *a, **kw)
+            bound.apply_defaults()
+            self.config = types.SimpleNamespace(**{k: v for k, v in bound.arguments.items() if k != "self"})
+            init(self, *a, **kw)
+
+        return wrapper
+
+    class BaseOutput:
+        def __init_subclass__(cls, **kw):
+            super().__init_subclass__(**kw)
+
+    for name in ("diffusers", "diffusers.schedulers"):
+        if name not in sys.modules:
+            _mod(name)
+    _mod("diffusers.configuration_utils", ConfigMixin=type("ConfigMixin", (), {}), register_to_config=register_to_config)
+    _mod("diffusers.schedulers.scheduling_utils", KarrasDiffusionSchedulers=[], SchedulerMixin=type("SchedulerMixin", (), {}))
+    _mod("diffusers.utils", BaseOutput=BaseOutput)
+    return importlib.import_module("videosys.schedulers.scheduling_ddim_cogvideox").CogVideoXDDIMScheduler

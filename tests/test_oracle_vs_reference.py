@@ -181,3 +181,32 @@ def test_cogvideox_layernorm_zero(dtype):
         got = CO.layer_norm_zero(sd, "n.", h, e, t)
     for a, b in zip(ref, got):
         assert torch.equal(a, b)
+
+
+def test_cogvideox_ddim_scheduler_vs_reference():
+    """videosys_b200's CogVideoXDDIMScheduler against the reference's own class (executed unmodified): trailing timesteps,
+    the SNR-shifted / zero-terminal-SNR alphas, and 50 v-prediction steps on random tensors."""
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    from videosys_b200.schedulers.scheduling_ddim_cogvideox import CogVideoXDDIMScheduler as Ours
+
+    Ref = ref_loader.load_cogvideox_scheduler()
+    kw = dict(num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+              set_alpha_to_one=True, steps_offset=0, prediction_type="v_prediction", timestep_spacing="trailing",
+              rescale_betas_zero_snr=True, snr_shift_scale=3.0)
+    ref, ours = Ref(**kw), Ours(**kw)
+    assert torch.equal(ref.alphas_cumprod, ours.alphas_cumprod)
+    for n in (50, 30, 7):
+        ref.set_timesteps(n)
+        ours.set_timesteps(n)
+        assert ref.timesteps.tolist() == ours.timesteps.tolist()
+    ref.set_timesteps(50)
+    ours.set_timesteps(50)
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 3, 4, 6, 6, generator=g)
+    xr, xo = x.clone(), x.clone()
+    for t in ref.timesteps:
+        v = torch.randn(x.shape, generator=g)
+        xr = ref.step(v, t, xr, return_dict=False)[0]
+        xo = ours.step(v, int(t), xo)[0]
+        assert torch.allclose(xr.float(), xo.float(), rtol=1e-5, atol=1e-6), int(t)
