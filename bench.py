@@ -579,7 +579,10 @@ def _dsp_parity(net, sched, z0, timesteps, dts, fwd_args, dev, dist, args):
 
 def run_cogvideox(args):
     """configs[3]: one DDIM step of CogVideoX-2B = CFG pair through CogVideoXTransformer3DModel (30 blocks, joint text + video
-    attention over 226 + 17 550 tokens, fp16 as the reference runs it), guidance, DDIM update.  1 GPU."""
+    attention over 226 + 17 550 tokens, fp16 as the reference runs it), guidance, DDIM update.  N > 1: the reference's
+    head-scatter sequence parallelism (30 heads: N in {2, 3, 5, 6}), or with --cp its CFG parallelism (N = 2)."""
+    import torch.distributed as dist
+
     import videosys_b200  # noqa: F401
     from videosys_b200 import kernels
     from videosys_b200.core.pab import pab_mgr
@@ -587,11 +590,18 @@ def run_cogvideox(args):
     from videosys_b200.pipelines.cogvideox.pipeline_cogvideox import CogVideoXPABConfig
     from videosys_b200.schedulers.scheduling_ddim_cogvideox import CogVideoXDDIMScheduler
 
-    if args.gpus != 1:
-        raise SystemExit("the CogVideoX workload is a 1-GPU configuration (BASELINE.json configs[3])")
+    from videosys_b200.core.distributed.parallel_mgr import initialize
+
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    rank = int(os.environ.get("RANK", 0))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run for N > 1")
     W = COGVIDEOX
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(local)
+    if world > 1:
+        initialize(rank=rank, world_size=world)
     dt = torch.float16
     torch.manual_seed(0)
     layers = args.depth or W["layers"]
@@ -600,6 +610,10 @@ def run_cogvideox(args):
         if prm.ndim >= 2:
             torch.nn.init.normal_(prm, std=0.02)
     net = net.to(dt).to(dev).eval()
+    if world > 1:
+        net.enable_parallel(1, world, enable_cp=args.cp)
+    pm = net.parallel_manager
+    par = "single" if world == 1 else (f"cp{pm.cp_size}" if pm.sp_size == 1 else (f"sp{pm.sp_size}" if pm.cp_size == 1 else f"cp{pm.cp_size}xsp{pm.sp_size}"))
     sched = CogVideoXDDIMScheduler()
     sched.set_timesteps(W["steps"], dev)
     ts = [int(v) for v in sched.timesteps.tolist()]
@@ -631,20 +645,49 @@ def run_cogvideox(args):
         zdev.copy_(z_host, non_blocking=True)
         out_host.copy_(one(zdev.to(dt), (first + i) % len(ts)).float(), non_blocking=True)
 
-    def timed(fn, n):
+    def sync_all():
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n):
             fn(i)
         e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / 1e3
+        sync_all()
+        sec = e0.elapsed_time(e1) / 1e3
+        if world > 1:
+            t = torch.tensor([sec], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = t.item()
+        return sec
+
+    sp_parity = None
+    if world > 1:  # sharded == single GPU, bit for bit, on this workload's shapes (2 blocks), before anything is timed
+        z0 = state["z"]
+        tt0 = torch.full((2,), ts[0], device=dev, dtype=torch.int64)
+        keep, blocks = net._stack[0].transformer_blocks, net._stack[0].transformer_blocks
+        net._stack[0].transformer_blocks = torch.nn.ModuleList(list(blocks)[:2])
+        try:
+            a = net(torch.cat([z0, z0]), pe, tt0, return_dict=False)[0]
+            net.parallel_manager = None
+            b = net(torch.cat([z0, z0]), pe, tt0, return_dict=False)[0]
+        finally:
+            net.parallel_manager = pm
+            net._stack[0].transformer_blocks = keep
+        flag = torch.tensor([1 if torch.equal(a, b) else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        sp_parity = {"mode": par, "depth2_forward": "bit_equal" if int(flag.item()) else "MISMATCH", "ranks": world}
+        del a, b
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
     net.reset_pab_state()
-    sampler = ClockSampler(0)
+    sampler = ClockSampler(local)
     sampler.start()
     l0 = kernels.launch_count()
     sec = timed(step_resident, args.steps)
@@ -671,13 +714,13 @@ def run_cogvideox(args):
     a_tf = at[1] / (at[0] * 1e-3) / 1e12
     per = sec / args.steps
     line = {
-        "metric": "frames/sec", "value": W["frames"] / (W["steps"] * per), "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+        "metric": "frames/sec", "value": W["frames"] / (W["steps"] * per), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f16", "data": "synthetic",
         "config": {"workload": "cogvideox_2b_49f_480x720_50step", "resolution": "480x720", "frames": 49, "sampling_steps": 50,
                    "latent": list(W["lat"]), "cfg_batch": 2, "text_tokens": 226, "joint_sequence": 226 + 13 * 30 * 45,
                    "architecture": "CogVideoX-2B transformer (hidden 1920, 30 heads x 64, 30 blocks)", "pab": bool(args.pab),
-                   "parallelism": "single", "first_schedule_index": first,
+                   "parallelism": par, "first_schedule_index": first,
                    "l2": "per-step working set (136 MB per activation tensor, 30 blocks) exceeds the 126 MB L2; no flush needed"},
         "e2e": {"value": W["frames"] / (W["steps"] * sec_e2e / args.steps), "unit": "frames/s",
                 "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
@@ -696,8 +739,16 @@ def run_cogvideox(args):
     if args.depth:
         line["config"]["depth_override"] = args.depth
         line["invalid"] = "reduced depth (debug run): not a bench value"
-    print(json.dumps(line), flush=True)
+    if sp_parity is not None:
+        line["sp_parity"] = sp_parity
+    if rank == 0:
+        print(json.dumps(line), flush=True)
     pab_mgr.set_pab_manager(None)
+    if world > 1:
+        sync_all()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
@@ -708,6 +759,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="opensora_720p_68f_50step", choices=sorted(WORKLOADS) + ["cogvideox_2b_49f_480x720_50step"])
     ap.add_argument("--pab", action="store_true", help="enable Pyramid Attention Broadcast (config 5)")
+    ap.add_argument("--cp", action="store_true", help="CogVideoX workload, N > 1: CFG parallelism instead of a factor 2 of sequence parallelism")
     ap.add_argument("--depth", type=int, default=0, help="debug only: fewer block pairs (marks the line invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-baseline", action="store_true", help="skip the eager torch/cuBLAS/SDPA baseline (N = 1)")

@@ -187,6 +187,55 @@ def test_dsp_comm_gloo_world2(T, S):
         assert torch.equal(g, full)
 
 
+def _ulysses_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    try:
+        from videosys_b200.core.distributed import comm
+        from videosys_b200.core.distributed.parallel_mgr import ParallelManager, initialize
+
+        initialize(rank, world)
+        pm = ParallelManager(1, 1, world)
+        B, Nt, Nv, H, D = 2, 3, 8, 4, 2
+        full = synth.normalish("ulysses", (B, Nt + Nv, 3, H, D))
+        Nl = Nv // world
+        mine = torch.cat([full[:, :Nt], full[:, Nt + rank * Nl : Nt + (rank + 1) * Nl]], 1).contiguous()
+        a = comm.ulysses_scatter_heads(mine, Nt, pm.sp_group)  # every row, my heads
+        o = a[:, :, 0].reshape(B, Nt + Nv, -1).contiguous()    # stand-in attention output: my heads of q
+        back = comm.ulysses_gather_heads(o, Nt, pm.sp_group)    # my rows, every head
+        q.put((rank, a, back, None))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # pragma: no cover
+        import traceback
+
+        q.put((rank, None, None, traceback.format_exc()))
+
+
+def test_ulysses_head_scatter_gloo_world2():
+    """CogVideoX's head-scatter exchange (reference cogvideox_transformer_3d.py:44-165): after the scatter a rank holds
+    every row of its head group, after the way back its own rows (text + its chunk) with every head."""
+    world, port = 2, 29800 + (os.getpid() % 150)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ulysses_worker, args=(r, world, port, q)) for r in range(world)]
+    [p.start() for p in procs]
+    res = {}
+    for _ in range(world):
+        r, a, back, err = q.get(timeout=120)
+        assert err is None, err
+        res[r] = (a.clone(), back.clone())
+    [p.join(timeout=60) for p in procs]
+    B, Nt, Nv, H, D = 2, 3, 8, 4, 2
+    full = synth.normalish("ulysses", (B, Nt + Nv, 3, H, D))
+    Hn, Nl = H // world, Nv // world
+    for r in range(world):
+        a, back = res[r]
+        assert torch.equal(a, full[:, :, :, r * Hn : (r + 1) * Hn])
+        rows = torch.cat([full[:, :Nt, 0], full[:, Nt + r * Nl : Nt + (r + 1) * Nl, 0]], 1)  # q of my rows, every head
+        assert torch.equal(back, rows.reshape(B, Nt + Nl, H * D))
+
+
 def test_rflow_timesteps_match_reference_known_answers(golden_dir):
     """The scheduler mirror reproduces the reference's transformed timesteps: int(bf16(t)) == SURVEY Appendix A."""
     from videosys_b200.schedulers.scheduling_rflow_open_sora import RFLOW

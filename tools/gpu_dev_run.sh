@@ -23,6 +23,12 @@ for g in "$@"; do
     model) run model 600 tests/test_model_gpu.py ;;
     all)   run all 900 tests ;;
     dsp)   run dsp 600 tests/test_dsp_gpu.py ;;
+    spmodels) run spmodels 600 tests/test_sp_models_gpu.py ;;
+    mcogx*) n=${g#mcogx}; echo "=== bench cogvideox N=$n ($COGX_ARGS) ===" | tee -a gpurun_out/summary.txt
+           timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29535 \
+              bench.py --gpus $n --workload cogvideox_2b_49f_480x720_50step $COGX_ARGS > gpurun_out/benchcogx_n$n.json 2> gpurun_out/benchcogx_n$n.err
+           echo "exit $? : $(tail -c 1500 gpurun_out/benchcogx_n$n.json | cut -c1-400)" | tee -a gpurun_out/summary.txt
+           tail -n 8 gpurun_out/benchcogx_n$n.err ;;
     refgpu) timeout 600 python tests/bench_reference_gpu.py > gpurun_out/refgpu.log 2>&1; echo "refgpu exit $? $(tail -n 1 gpurun_out/refgpu.log | cut -c1-300)" | tee -a gpurun_out/summary.txt ;;
     mmab) timeout 120 tools/_bin/mma_microbench > gpurun_out/mma_microbench.txt 2>&1; echo "mmab exit $?" | tee -a gpurun_out/summary.txt ;;
     atrace) timeout 300 python tools/attn_trace.py > gpurun_out/attn_trace.log 2>&1; echo "atrace exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/attn_trace.log ;;

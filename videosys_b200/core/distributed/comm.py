@@ -2,7 +2,8 @@
 
 Same function names / argument meaning as the reference (set_pad/get_pad :268-279, split_sequence /
 gather_sequence :148-190,256-261, all_to_all_with_pad :282-304, all_to_all_comm :139-140,
-split/gather_from_second_dim :307-318), inference only (no autograd functions).
+split/gather_from_second_dim :307-318), inference only (no autograd functions); ``ulysses_scatter_heads`` /
+``ulysses_gather_heads`` are CogVideoX's head-scatter exchange on the packed qkv (cogvideox_transformer_3d.py:44-165).
 
 Two transports for the dimension switch:
   * ``DspP2P`` (B200 path): one sm_100a kernel stores every 16-byte vector straight into the destination rank's
@@ -98,6 +99,44 @@ def gather_from_second_dim(x, batch_size, parallel_group):
     x = x.view(batch_size, -1, *x.shape[1:])
     x = gather_sequence(x, parallel_group, dim=1, grad_scale="up", pad=get_pad("temporal"))
     return x.reshape(-1, *x.shape[2:])
+
+
+def ulysses_scatter_heads(qkv: torch.Tensor, n_text: int, process_group) -> torch.Tensor:
+    """Head-scatter all-to-all of CogVideoX's joint attention (reference cogvideox_transformer_3d.py:112-122 followed by
+    ``_remove_extra_encoder`` :44-62), on the PACKED projection.
+
+    qkv: [B, n_text + Nl, 3, H, D] -- this rank's rows (the replicated text rows, then its 1/world chunk of the video
+    rows), every head.  Returns [B, n_text + world * Nl, 3, H / world, D]: every row, this rank's head group.  The
+    reference ships the text rows to every peer and drops all copies but the first; each rank already holds those rows
+    (computed from the replicated text stream), so only the video rows travel: one ``all_to_all_single``."""
+    world = dist.get_world_size(process_group)
+    rank = dist.get_rank(process_group)
+    B, L, three, H, D = qkv.shape
+    assert H % world == 0, f"Number of heads {H} must be divisible by sequence parallel size {world}"
+    Hn, Nl = H // world, L - n_text
+    send = qkv[:, n_text:].reshape(B, Nl, three, world, Hn, D).permute(3, 0, 1, 2, 4, 5).contiguous()
+    recv = torch.empty_like(send)  # [source rank, B, Nl, 3, Hn, D]
+    dist.all_to_all_single(recv, send, group=process_group)
+    out = qkv.new_empty(B, n_text + world * Nl, three, Hn, D)
+    out[:, :n_text] = qkv[:, :n_text, :, rank * Hn : (rank + 1) * Hn]
+    out[:, n_text:].view(B, world, Nl, three, Hn, D).copy_(recv.permute(1, 0, 2, 3, 4, 5))
+    return out
+
+
+def ulysses_gather_heads(o: torch.Tensor, n_text: int, process_group) -> torch.Tensor:
+    """The way back (reference :162-165: ``_add_extra_encoder`` then all_to_all scatter rows / gather heads).
+
+    o: [B, n_text + world * Nl, Hn * D] -- every row, this rank's heads.  Returns [B, n_text + Nl, world * Hn * D]: the
+    text rows and this rank's video rows with every head (head group g in columns [g * Hn * D, (g + 1) * Hn * D))."""
+    world = dist.get_world_size(process_group)
+    B, L, Cn = o.shape
+    Nl = (L - n_text) // world
+    send = torch.empty(world, B, n_text + Nl, Cn, dtype=o.dtype, device=o.device)
+    send[:, :, :n_text] = o[:, :n_text]  # the text rows go to every peer (the reference's "extra encoder")
+    send[:, :, n_text:] = o[:, n_text:].view(B, world, Nl, Cn).transpose(0, 1)
+    recv = torch.empty_like(send)  # [head group, B, n_text + Nl, Cn]
+    dist.all_to_all_single(recv, send, group=process_group)
+    return recv.permute(1, 2, 0, 3).reshape(B, n_text + Nl, world * Cn)
 
 
 class DspP2P:

@@ -23,6 +23,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ... import kernels
+from ...core.distributed import comm
+from ...core.distributed.parallel_mgr import ParallelManager
 from ...core.pab import pab_mgr
 
 
@@ -110,9 +112,14 @@ class CogVideoXBlockStack(nn.Module):
         return mod
 
     @torch.no_grad()
-    def forward(self, hidden: torch.Tensor, enc: torch.Tensor, temb: torch.Tensor, timestep=None, ts_int=None):
+    def forward(self, hidden: torch.Tensor, enc: torch.Tensor, temb: torch.Tensor, timestep=None, ts_int=None,
+                sp_group=None, n_video: int = None):
         """hidden [B, Nv, C], enc [B, Nt, C] (fp16 / bf16, CUDA), temb [B, time_embed_dim]; returns the two streams.
-        ts_int: host integer timestep for the PAB gate (else one D2H read of timestep[0], as the reference does)."""
+        ts_int: host integer timestep for the PAB gate (else one D2H read of timestep[0], as the reference does).
+        sp_group: sequence-parallel group; ``hidden`` is then this rank's chunk of the (zero-padded) video rows and
+        ``n_video`` the unpadded global row count.  Everything but the attention core is row-wise and runs on the local
+        rows; the joint attention runs on H / sp heads over every row after the head-scatter exchange (reference
+        :112-122, :138-143, :162-165), pad rows excluded as keys (:58-62) and zero in the output (:66-72)."""
         if not hidden.is_cuda or hidden.dtype not in (torch.bfloat16, torch.float16):
             raise RuntimeError("videosys_b200 CogVideoX blocks run on sm_100a CUDA devices in fp16 / bf16 only (no CPU path)")
         K = kernels
@@ -138,8 +145,20 @@ class CogVideoXBlockStack(nn.Module):
                 qkv = K.gemm_bias_act(ncat.view(B * N, C), w, bias)
                 at = blk.attn1
                 K.qk_layernorm_(qkv, at.norm_q.weight, at.norm_q.bias, at.norm_k.weight, at.norm_k.bias, H, D, eps=1e-6)
-                q3 = qkv.view(-1, 3, C)
-                o = K.attn_flash(q3[:, 0], q3[:, 1], q3[:, 2], B, N, N, H, D, 3 * C, N * 3 * C, 3 * C, N * 3 * C, D**-0.5)
+                if sp_group is None:
+                    q3 = qkv.view(-1, 3, C)
+                    o = K.attn_flash(q3[:, 0], q3[:, 1], q3[:, 2], B, N, N, H, D, 3 * C, N * 3 * C, 3 * C, N * 3 * C, D**-0.5)
+                else:
+                    full = comm.ulysses_scatter_heads(qkv.view(B, N, 3, H, D), Nt, sp_group)  # every row, H / sp heads
+                    Lf, Hn = full.shape[1], full.shape[3]
+                    Cn, Lv = Hn * D, Nt + n_video
+                    f3 = full.view(B * Lf, 3, Cn)
+                    of = torch.empty(B, Lf, Cn, dtype=qkv.dtype, device=qkv.device)
+                    if Lf > Lv:
+                        of[:, Lv:].zero_()
+                    K.attn_flash(f3[:, 0], f3[:, 1], f3[:, 2], B, Lv, Lv, Hn, D, 3 * Cn, Lf * 3 * Cn, 3 * Cn, Lf * 3 * Cn,
+                                 D**-0.5, out=of, out_row_stride=Cn, out_batch_stride=Lf * Cn)
+                    o = comm.ulysses_gather_heads(of, Nt, sp_group).contiguous()  # my rows, every head
                 a = K.gemm_bias_act(o, at.to_out[0].weight, at.to_out[0].bias)  # [B, N, C] = [text | video]
                 if pab_on:
                     blk.last_attn = a
@@ -206,8 +225,8 @@ class _AdaLayerNorm(nn.Module):
 
 class CogVideoXTransformer3DModel(nn.Module):
     """State-dict compatible with the reference / HF ``THUDM/CogVideoX-2b`` transformer (same module names), forward
-    on the vsb200 kernels.  One GPU: the reference's head-scatter sequence parallelism needs 30 % sp == 0 and the
-    BASELINE configuration for this model is 1 GPU."""
+    on the vsb200 kernels.  ``enable_parallel`` as the reference: head-scatter sequence parallelism (30 % sp == 0:
+    sp in {2, 3, 5, 6, ...}) and CFG parallelism (cp = 2)."""
 
     def __init__(self, num_attention_heads=30, attention_head_dim=64, in_channels=16, out_channels=16, flip_sin_to_cos=True,
                  freq_shift=0, time_embed_dim=512, text_embed_dim=4096, num_layers=30, sample_width=90, sample_height=60,
@@ -250,8 +269,15 @@ class CogVideoXTransformer3DModel(nn.Module):
         return build_from_pretrained(cls, path, subfolder, **config_overrides)
 
     def enable_parallel(self, dp_size=None, sp_size=None, enable_cp=None):
-        if (sp_size or 1) > 1:
-            raise NotImplementedError("CogVideoX runs on one GPU here (reference head-scatter SP: 30 heads, sp in {2,3,5,6})")
+        """Reference :462-474: CFG parallelism takes a factor 2 out of an even sp_size when ``enable_cp``."""
+        dp_size, sp_size = dp_size or 1, sp_size or 1
+        cp_size = 1
+        if enable_cp and sp_size % 2 == 0:
+            sp_size, cp_size = sp_size // 2, 2
+        if self.config.num_attention_heads % sp_size:
+            raise ValueError(f"Number of heads {self.config.num_attention_heads} must be divisible by sequence parallel "
+                             f"size {sp_size}")
+        self.parallel_manager = ParallelManager(dp_size, cp_size, sp_size)
 
     def reset_pab_state(self):
         self._stack[0].reset_pab_state()
@@ -272,6 +298,12 @@ class CogVideoXTransformer3DModel(nn.Module):
             raise RuntimeError("videosys_b200 CogVideoX runs on sm_100a CUDA devices only (no CPU path)")
         K = kernels
         dt = self.proj_out.weight.dtype
+        pm = self.parallel_manager
+        cp = pm is not None and pm.cp_size > 1
+        sp = pm is not None and pm.sp_size > 1
+        if cp:  # reference :488-503: the CFG pair is split across the cp group
+            hidden_states, encoder_hidden_states, timestep = (
+                comm.split_sequence(v, pm.cp_group, dim=0) for v in (hidden_states, encoder_hidden_states, timestep))
         B, Fr, Cin, H, W = hidden_states.shape
         p, C = self.config.patch_size, self.inner_dim
         te = self.time_embedding
@@ -286,7 +318,12 @@ class CogVideoXTransformer3DModel(nn.Module):
         pos = self.pos_embedding[:, : Nt + Nv].to(dt)
         enc = txt + pos[:, :Nt]
         hid = img + pos[:, Nt:]
-        hid, enc = self._stack[0](hid, enc, emb, timestep, ts_int=ts_int)
+        if sp:  # reference :531-533: the video rows are split (zero-padded to a multiple of sp), the text rows replicated
+            comm.set_pad("pad", Nv, pm.sp_group)
+            hid = comm.split_sequence(hid, pm.sp_group, dim=1, pad=comm.get_pad("pad"))
+        hid, enc = self._stack[0](hid, enc, emb, timestep, ts_int=ts_int, sp_group=pm.sp_group if sp else None, n_video=Nv)
+        Nv_all, Nv = Nv, hid.shape[1]  # the output head is row-wise: it runs on the local rows, its 30x narrower
+        # result is gathered (the reference gathers the C-wide rows first, :563-564: same values)
         # norm_final (plain affine LayerNorm = modulate with shift = scale = 0), then norm_out (AdaLayerNorm, chunk_dim 1:
         # rows shift, scale) and the 1920 -> 64 projection
         zero = torch.zeros(1, B, 6, C, dtype=dt, device=hid.device)
@@ -297,6 +334,11 @@ class CogVideoXTransformer3DModel(nn.Module):
         mod[0, :, :2] = ss
         hid = K.ln_modulate(hid, mod, None, 0, 1, B, 1, Nv, eps=self.eps, gamma=no.norm.weight, beta=no.norm.bias)
         out = K.gemm_bias_act(hid, self.proj_out.weight, self.proj_out.bias)  # [B, Nv, p*p*Cout]
+        if sp:
+            out = comm.gather_sequence(out, pm.sp_group, dim=1, pad=comm.get_pad("pad"))
+            Nv = Nv_all
         Co = self.config.out_channels
         out = out.reshape(B, Fr, H // p, W // p, Co, p, p).permute(0, 1, 4, 2, 5, 3, 6).flatten(5, 6).flatten(3, 4)
+        if cp:  # reference :584-585
+            out = comm.gather_sequence(out, pm.cp_group, dim=0)
         return (out,) if not return_dict else type("Out", (), {"sample": out})()

@@ -24,6 +24,8 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from ... import kernels
+from ...core.distributed import comm
+from ...core.distributed.parallel_mgr import ParallelManager
 from ...core.pab import pab_mgr
 
 
@@ -95,10 +97,13 @@ class LatteBlockStack(nn.Module):
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, enc: torch.Tensor, timestep6: torch.Tensor, temp_pos_embed: Optional[torch.Tensor] = None,
-                ts_int: Optional[int] = None, all_timesteps=None):
+                ts_int: Optional[int] = None, all_timesteps=None, sp_group=None):
         """x [B, F, S, C] fp16 / bf16 (CUDA), enc [B, L, C], timestep6 [B, 6C]; returns [B, F, S, C].
         PAB (reference blocks :372-517, :700-824): ts_int = int(org_timestep[0]) on the host, all_timesteps = the
-        scheduler's timestep list (python ints) for the MLP skip windows."""
+        scheduler's timestep list (python ints) for the MLP skip windows.
+        sp_group: Latte's flavour of DSP (reference :734-745, :826-843): x (and temp_pos_embed) hold this rank's FRAMES;
+        spatial blocks are local; a temporal block switches its modulated input to a patch shard with every frame for
+        the attention (qkv, softmax, out projection) and switches the result back (pads: comm.get_pad)."""
         if not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16):
             raise RuntimeError("videosys_b200 Latte blocks run on sm_100a CUDA devices in fp16 / bf16 only (no CPU path)")
         K = kernels
@@ -114,7 +119,7 @@ class LatteBlockStack(nn.Module):
             raise RuntimeError("PAB needs the host integer timestep (ts_int)")
         for i in range(self.depth):
             for blk in (self.transformer_blocks[i], self.temporal_transformer_blocks[i]):
-                if blk.temporal and i == 0 and Fr > 1 and temp_pos_embed is not None:
+                if blk.temporal and i == 0 and temp_pos_embed is not None:  # the caller passes it for F > 1 (:1391)
                     x.add_(temp_pos_embed.reshape(1, Fr, 1, C).to(x.dtype))  # glue op (once per forward)
                 mod = K.modulation_table(blk.scale_shift_table, timestep6, None)
                 # ---- self attention (spatial over S per frame / temporal over F per patch) ----
@@ -126,17 +131,25 @@ class LatteBlockStack(nn.Module):
                     K.residual_add(xf, blk.last_attn, out=xf)  # the cached value is the GATED output (:422-430)
                 else:
                     xm = K.ln_modulate(xf, mod, None, 0, 1, B, Fr, S)
+                    switch = blk.temporal and sp_group is not None
+                    Ft, St = Fr, S  # extents the temporal attention sees
+                    if switch:  # frame shard -> patch shard (scatter S, gather F)
+                        xm = comm.all_to_all_with_pad(xm.view(B, Fr, S, C), sp_group, scatter_dim=2, gather_dim=1,
+                                                      scatter_pad=comm.get_pad("spatial"),
+                                                      gather_pad=comm.get_pad("temporal")).contiguous()
+                        Ft, St = xm.shape[1], xm.shape[2]
+                        xm = xm.view(B * Ft * St, C)
                     wqkv, bqkv = blk.fused("qkv")
                     qkv = K.gemm_bias_act(xm, wqkv, bqkv)
                     if blk.temporal:
-                        if Fr <= 32:
-                            o = K.attn_short(qkv.view(-1, 3, H, D), None, None, None, None, B, S, Fr * S, 1, S, Fr, H, D, D**-0.5, flags=3)
+                        if Ft <= 32:
+                            o = K.attn_short(qkv.view(-1, 3, H, D), None, None, None, None, B, St, Ft * St, 1, St, Ft, H, D, D**-0.5, flags=3)
                         else:  # long videos: the flash kernel over strided views (batch = patch, row = frame)
-                            o = torch.empty(B * Fr * S, C, dtype=x.dtype, device=x.device)
-                            q3 = qkv.view(B, Fr * S, 3, C)
+                            o = torch.empty(B * Ft * St, C, dtype=x.dtype, device=x.device)
+                            q3 = qkv.view(B, Ft * St, 3, C)
                             for b in range(B):
-                                K.attn_flash(q3[b, :, 0], q3[b, :, 1], q3[b, :, 2], S, Fr, Fr, H, D, S * 3 * C, 3 * C, S * 3 * C, 3 * C,
-                                             D**-0.5, out=o[b * Fr * S:], out_row_stride=S * C, out_batch_stride=C)
+                                K.attn_flash(q3[b, :, 0], q3[b, :, 1], q3[b, :, 2], St, Ft, Ft, H, D, St * 3 * C, 3 * C, St * 3 * C, 3 * C,
+                                             D**-0.5, out=o[b * Ft * St:], out_row_stride=St * C, out_batch_stride=C)
                     else:
                         q3 = qkv.view(-1, 3, C)
                         if S >= 30:
@@ -144,6 +157,10 @@ class LatteBlockStack(nn.Module):
                         else:
                             o = K.attn_short(qkv.view(-1, 3, H, D), None, None, None, None, B * Fr, 1, S, 0, 1, S, H, D, D**-0.5, flags=3)
                     y = K.gemm_bias_act(o.view(-1, C), blk.attn1.to_out[0].weight, blk.attn1.to_out[0].bias)
+                    if switch:  # patch shard -> frame shard (scatter F, gather S)
+                        y = comm.all_to_all_with_pad(y.view(B, Ft, St, C), sp_group, scatter_dim=1, gather_dim=2,
+                                                     scatter_pad=comm.get_pad("temporal"),
+                                                     gather_pad=comm.get_pad("spatial")).contiguous()
                     cache = None
                     if pab_on:
                         if blk.last_attn is None or blk.last_attn.shape != xf.shape:
@@ -239,7 +256,8 @@ class _PatchEmbed2D(nn.Module):
 
 class LatteT2V(nn.Module):
     """State-dict compatible with the reference / HF ``maxin-cn/Latte-1`` transformer (same parameter names), forward on the
-    vsb200 kernels, sequence parallelism off (the BASELINE configuration for Latte is the plumbing run)."""
+    vsb200 kernels.  ``enable_parallel`` as the reference (:1127-1139): frame-sharded DSP (temporal blocks switch to a
+    patch shard and back) and CFG parallelism."""
 
     def __init__(self, num_attention_heads=16, attention_head_dim=72, in_channels=4, out_channels=8, num_layers=28,
                  cross_attention_dim=1152, attention_bias=True, sample_size=64, patch_size=2, activation_fn="gelu-approximate",
@@ -279,8 +297,12 @@ class LatteT2V(nn.Module):
         return build_from_pretrained(cls, path, subfolder, **config_overrides)
 
     def enable_parallel(self, dp_size=None, sp_size=None, enable_cp=None):
-        if (sp_size or 1) > 1:
-            raise NotImplementedError("Latte sequence parallelism (T-shard DSP, reference :826-843) is not built: 1 GPU")
+        """Reference :1127-1139: CFG parallelism takes a factor 2 out of an even sp_size when ``enable_cp``."""
+        dp_size, sp_size = dp_size or 1, sp_size or 1
+        cp_size = 1
+        if enable_cp and sp_size % 2 == 0:
+            sp_size, cp_size = sp_size // 2, 2
+        self.parallel_manager = ParallelManager(dp_size, cp_size, sp_size)
 
     def reset_pab_state(self):
         self._stack[0].reset_pab_state()
@@ -305,6 +327,12 @@ class LatteT2V(nn.Module):
                                       "(the reference pipeline never passes them: pipeline_latte.py:854-862)")
         K = kernels
         dt = self.proj_out.weight.dtype
+        pm = self.parallel_manager
+        cpar = pm is not None and pm.cp_size > 1
+        sp = pm is not None and pm.sp_size > 1
+        if cpar:  # reference :1198-1216: the CFG pair is split across the cp group
+            hidden_states, timestep, encoder_hidden_states = (
+                comm.split_sequence(v, pm.cp_group, dim=0) for v in (hidden_states, timestep, encoder_hidden_states))
         B, Cin, Fr, H, W = hidden_states.shape
         p, C = self.patch_size, self.inner_dim
         h, w = H // p, W // p
@@ -326,14 +354,28 @@ class LatteT2V(nn.Module):
             ts_int = int(timestep[0])
         if all_timesteps is not None and torch.is_tensor(all_timesteps):
             all_timesteps = all_timesteps.tolist()
-        x = self._stack[0](x, enc, t6, self.temp_pos_embed[:, :Fr] if Fr > 1 else None, ts_int=ts_int, all_timesteps=all_timesteps)
+        tpe = self.temp_pos_embed[:, :Fr] if Fr > 1 else None
+        Fg = Fr
+        if sp:  # reference :1300-1308: frames are split (zero-padded to a multiple of sp), the text stays whole
+            comm.set_pad("temporal", Fr, pm.sp_group)
+            comm.set_pad("spatial", S, pm.sp_group)
+            x = comm.split_sequence(x, pm.sp_group, dim=1, pad=comm.get_pad("temporal"))
+            if tpe is not None:
+                tpe = comm.split_sequence(tpe, pm.sp_group, dim=1, pad=comm.get_pad("temporal"))
+            Fr = x.shape[1]
+        x = self._stack[0](x, enc, t6, tpe, ts_int=ts_int, all_timesteps=all_timesteps, sp_group=pm.sp_group if sp else None)
         # output head (:1436-1443): LayerNorm (no affine) -> * (1 + scale) + shift with table + embedded timestep -> proj_out
         tab6 = torch.cat([self.scale_shift_table, self.scale_shift_table.new_zeros(4, C)], 0)
         mod = K.modulation_table(tab6, torch.cat([embedded, embedded, embedded.new_zeros(B, 4 * C)], 1).contiguous(), None)
         y = K.ln_modulate(x.view(B, Fr * S, C), mod, None, 0, 1, B, Fr, S, eps=self.eps)
         y = K.gemm_bias_act(y, self.proj_out.weight, self.proj_out.bias)  # [B, F*S, p*p*Cout]
+        if sp:  # the head is row-wise: run on the local frames, gather its 36x narrower output (reference gathers first, :1428-1429)
+            y = comm.gather_sequence(y.view(B, Fr, S, -1), pm.sp_group, dim=1, pad=comm.get_pad("temporal"))
+            Fr = Fg
         Co = self.out_channels
         y = y.reshape(B * Fr, h, w, p, p, Co)
         y = torch.einsum("nhwpqc->nchpwq", y).reshape(B * Fr, Co, h * p, w * p)
         out = y.reshape(B, Fr, Co, h * p, w * p).permute(0, 2, 1, 3, 4).contiguous()
+        if cpar:  # reference :1459-1461
+            out = comm.gather_sequence(out, pm.cp_group, dim=0)
         return (out,) if not return_dict else type("Out", (), {"sample": out})()

@@ -14,6 +14,7 @@ import torch
 from ...core.pab.pab_mgr import PABConfig, enable_pab, set_pab_manager, update_steps
 from ...models.transformers.cogvideox_transformer_3d import CogVideoXTransformer3DModel
 from ...schedulers.scheduling_ddim_cogvideox import CogVideoXDDIMScheduler
+from .._common import ParallelPipelineMixin
 from ..open_sora.pipeline_open_sora import VideoSysPipelineOutput
 
 
@@ -41,17 +42,13 @@ class CogVideoXConfig:
         self.vae_decode_fn = vae_decode_fn
 
 
-class CogVideoXPipeline:
+class CogVideoXPipeline(ParallelPipelineMixin):
     vae_scale_factor_spatial = 8
     vae_scale_factor_temporal = 4
 
     def __init__(self, config: CogVideoXConfig, device=None, dtype: torch.dtype = torch.bfloat16):
         if not torch.cuda.is_available():
             raise RuntimeError("videosys_b200 pipelines need an sm_100a GPU (no CPU path)")
-        import torch.distributed as dist
-
-        if (dist.get_world_size() if dist.is_initialized() else 1) > 1:
-            raise NotImplementedError("CogVideoX runs on one GPU here (reference head-scatter SP needs 30 % sp == 0)")
         self._config = config
         self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         if config.model_path == "THUDM/CogVideoX-2b":
@@ -69,6 +66,7 @@ class CogVideoXPipeline:
         self.scheduler = CogVideoXDDIMScheduler()
         if config.enable_pab:
             set_pab_manager(config.pab_config)
+        self._set_parallel()
 
     def _embeds(self, prompt, negative_prompt, max_sequence_length):
         cfg = self.transformer.config
@@ -101,9 +99,7 @@ class CogVideoXPipeline:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
         update_steps(num_inference_steps)
         self.transformer.reset_pab_state()
-        if seed is not None and seed >= 0:
-            torch.manual_seed(seed)
-            torch.cuda.manual_seed(seed)
+        self._maybe_seed(seed)
         dev, dt = self._device, self._dtype
         if prompt_embeds is None:
             prompt_embeds, negative_prompt_embeds = self._embeds(prompt, negative_prompt, max_sequence_length)

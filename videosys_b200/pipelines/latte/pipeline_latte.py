@@ -14,6 +14,7 @@ import torch
 from ...core.pab.pab_mgr import PABConfig, enable_pab, set_pab_manager, update_steps
 from ...models.transformers.latte_transformer_3d import LatteT2V
 from ...schedulers.scheduling_ddim import DDIMScheduler
+from .._common import ParallelPipelineMixin
 from ..open_sora.pipeline_open_sora import VideoSysPipelineOutput
 
 _MLP_CFG = {k: {"block": [0, 1, 2, 3, 4], "skip_count": 2} for k in (720, 640, 560, 480, 400)}
@@ -53,16 +54,12 @@ class LatteConfig:
         self.vae_decode_fn = vae_decode_fn
 
 
-class LattePipeline:
+class LattePipeline(ParallelPipelineMixin):
     vae_scale_factor = 8
 
     def __init__(self, config: LatteConfig, device=None, dtype: torch.dtype = torch.float16):
         if not torch.cuda.is_available():
             raise RuntimeError("videosys_b200 pipelines need an sm_100a GPU (no CPU path)")
-        import torch.distributed as dist
-
-        if (dist.get_world_size() if dist.is_initialized() else 1) > 1:
-            raise NotImplementedError("Latte runs on one GPU here (its T-shard DSP flavour, reference :826-843, is not built)")
         self._config = config
         self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self._dtype = dtype
@@ -79,6 +76,7 @@ class LattePipeline:
                                        variance_type=config.variance_type, clip_sample=False)
         if config.enable_pab:
             set_pab_manager(config.pab_config)
+        self._set_parallel()
 
     def _embeds(self, prompt, negative_prompt, L=120):
         cfg = self.transformer.config
@@ -98,9 +96,7 @@ class LattePipeline:
         that the tests can run a small model."""
         update_steps(num_inference_steps)
         self.transformer.reset_pab_state()
-        if seed is not None and seed >= 0:
-            torch.manual_seed(seed)
-            torch.cuda.manual_seed(seed)
+        self._maybe_seed(seed)
         dev, dt = self._device, self._dtype
         if prompt_embeds is None:
             prompt_embeds, negative_prompt_embeds = self._embeds(prompt, negative_prompt)
