@@ -85,6 +85,19 @@ int vsb_ln_modulate_affine(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* mod
 int vsb_modulation_table(const vsb_bf16* table, const vsb_bf16* t, const vsb_bf16* t0, vsb_bf16* mod, int B, int C,
                          int rows, void* stream);
 
+/* ---- patch embedding of the latent + position embedding + sequence-parallel split ------------------------------
+ * replaces open_sora_transformer_3d.py:568-572 (x_embedder: Conv3d kernel = stride = (1, ph, pw); rearrange; + pos_emb)
+ * and :577 (split_sequence along the patch axis); the same for Latte's 2-D PatchEmbed (latte_transformer_3d.py:1245).
+ *   z    latent, element (b, c, t, y, x) at b*batch_stride + c*chan_stride + t*frame_stride + y*W + x (elements);
+ *        rows / columns beyond H / W read as zero (the reference pads to the patch grid)
+ *   w    [C, Cin*ph*pw] (= conv.weight storage, taps ordered (c, ky, kx)); bias [C] or NULL; pos [S_total, C] or NULL
+ *   out  [B, T, S_local, C]: patch columns s0 .. s0+S_local-1 of every (batch, frame); columns >= S_total are zero
+ * Rounds like the eager chain: conv (fp32 accumulate) -> bf16, + bias -> bf16, + pos -> bf16.
+ * Returns 1 without launching unless Cin*ph*pw == 16, C % 8 == 0 and C <= 2048. */
+int vsb_patch_embed(const vsb_bf16* z, const vsb_bf16* w, const vsb_bf16* bias, const vsb_bf16* pos, vsb_bf16* out, int B,
+                    int Cin, int T, int H, int W, long long batch_stride, long long chan_stride, long long frame_stride,
+                    int ph, int pw, int C, int s0, int S_local, void* stream);
+
 /* ---- gate * y (+ per-frame select) + residual, optional PAB cache write ---------------------------------------
  * replaces open_sora_transformer_3d.py:219-228 and :270-284.  gated = bf16(gate*y); out = bf16(x + gated).
  *   cache_out (nullable): receives `gated` (what the reference keeps as last_attn, :224-225). */
@@ -224,6 +237,9 @@ int vsb_ln_modulate_affine_f16(const vsb_f16* x, vsb_f16* out, const vsb_f16* mo
                            int C, float eps, void* stream);
 int vsb_modulation_table_f16(const vsb_f16* table, const vsb_f16* t, const vsb_f16* t0, vsb_f16* mod, int B, int C,
                          int rows, void* stream);
+int vsb_patch_embed_f16(const vsb_f16* z, const vsb_f16* w, const vsb_f16* bias, const vsb_f16* pos, vsb_f16* out, int B,
+                    int Cin, int T, int H, int W, long long batch_stride, long long chan_stride, long long frame_stride,
+                    int ph, int pw, int C, int s0, int S_local, void* stream);
 int vsb_gate_residual_f16(const vsb_f16* x, const vsb_f16* y, vsb_f16* out, vsb_f16* cache_out, const vsb_f16* mod,
                       const uint8_t* x_mask, int gate_row, int B, int T, int S, int C, void* stream);
 int vsb_residual_add_f16(const vsb_f16* x, const vsb_f16* y, vsb_f16* out, size_t n, void* stream);

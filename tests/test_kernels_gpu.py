@@ -29,7 +29,7 @@ def _bf16_ulp(x, bits=8):
     return torch.ldexp(torch.ones_like(x), e - bits)
 
 
-def _ulp_report(name, got, want, min_equal=0.99, max_ulps=1.0, row_floor=0.0):
+def _ulp_report(name, got, want, min_equal=0.99, max_ulps=1.0, row_floor=0.0, bits=8):
     """bit-equal fraction + max error in TRUE bf16 ulps.  row_floor > 0 measures the ulp at
     max(|want|, row_floor * rowmax|want|): outputs of a reduction carry the rounding error of the
     row's magnitude even where the result itself cancels to ~0."""
@@ -39,7 +39,7 @@ def _ulp_report(name, got, want, min_equal=0.99, max_ulps=1.0, row_floor=0.0):
     mag = want.abs()
     if row_floor > 0:
         mag = torch.maximum(mag, row_floor * want.abs().amax(dim=-1, keepdim=True))
-    rel = ((got - want).abs() / _bf16_ulp(mag)).max().item()
+    rel = ((got - want).abs() / _bf16_ulp(mag, bits)).max().item()
     print(f"[parity] {name}: bit-equal {eq*100:.3f} %  max diff {rel:.2f} ulp  max abs {(got-want).abs().max().item():.3e}")
     assert eq >= min_equal, f"{name}: only {eq*100:.2f} % bit-equal"
     assert rel <= max_ulps + 1e-3, f"{name}: {rel:.2f} ulp"
@@ -701,3 +701,42 @@ def test_attn_flash_kv_resident_self_and_f16():
         _flash_check("kvres_h", 2, 900, 226, 3, 64, packed_qkv=False, BF=torch.float16)
     finally:
         K.set_option("attn_variant", -1)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("B,Cin,T,H,W,C,ph,pw", [(2, 4, 3, 12, 16, 1152, 2, 2),   # exact patch grid
+                                                   (1, 4, 2, 9, 15, 288, 2, 2),     # H, W not multiples of the patch: zero pad
+                                                   (2, 4, 15, 30, 53, 1152, 2, 2),  # OpenSora 240p latent
+                                                   (1, 16, 2, 6, 10, 64, 1, 1)])    # 16 channels, 1 x 1 patch
+def test_patch_embed(B, Cin, T, H, W, C, ph, pw, dt):
+    """vsb_patch_embed against the eager chain it replaces (open_sora_transformer_3d.py:568-577): strided conv (fp32
+    accumulation, here in float64: the summation order of 16 products is the only freedom), + bias, + pos, each rounded
+    to the storage dtype; then the sequence-parallel split with its zero padding."""
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    z = synth.normalish(f"pe.z{H}{W}", (B, Cin, T, H, W)).to(dt)
+    w = synth.normalish(f"pe.w{C}", (C, Cin, 1, ph, pw), std=0.3).to(dt)
+    bias = synth.normalish(f"pe.b{C}", (C,), std=0.2).to(dt)
+    Hn, Wn = -(-H // ph), -(-W // pw)
+    S = Hn * Wn
+    pos = synth.normalish(f"pe.p{S}{C}", (S, C)).to(dt)
+    got = K.patch_embed(z.to(dev), w.to(dev), bias.to(dev), pos.to(dev), ph, pw)
+    assert got is not None and got.shape == (B, T, S, C)
+    zp = torch.nn.functional.pad(z.double(), (0, Wn * pw - W, 0, Hn * ph - H))
+    conv = torch.nn.functional.conv3d(zp, w.double(), None, stride=(1, ph, pw))  # [B, C, T, Hn, Wn]
+    tok = conv.permute(0, 2, 3, 4, 1).reshape(B, T, S, C)
+    want = ((tok.float().to(dt).float() + bias.float()).to(dt).float() + pos.float()).to(dt)
+    _ulp_report(f"patch_embed {dt} [{B},{Cin},{T},{H},{W}]->{C}", got, want, min_equal=0.998, max_ulps=1.0,
+                bits=8 if dt == torch.bfloat16 else 11)
+    # the rank-local form: 3 ranks, the last one's tail columns are padding (zeros)
+    world = 3
+    Sl = -(-S // world)
+    for r in range(world):
+        part = K.patch_embed(z.to(dev), w.to(dev), bias.to(dev), pos.to(dev), ph, pw, s0=r * Sl, s_local=Sl).cpu()
+        full = torch.cat([got.cpu(), torch.zeros(B, T, world * Sl - S, C, dtype=dt)], 2)
+        assert torch.equal(part, full[:, :, r * Sl : (r + 1) * Sl]), f"rank {r} of {world}"
+    # and the torch / cuDNN chain on the same GPU (different accumulation order: equal up to rare one-ulp flips)
+    conv_g = torch.nn.functional.conv3d(zp.to(dt).to(dev), w.to(dev), bias.to(dev), stride=(1, ph, pw))
+    eager = conv_g.flatten(2).transpose(1, 2).reshape(B, T, S, C) + pos.to(dev)
+    _ulp_report(f"patch_embed {dt} vs cuDNN chain", got, eager, min_equal=0.99, max_ulps=1.0, bits=8 if dt == torch.bfloat16 else 11)

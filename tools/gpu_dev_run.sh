@@ -13,7 +13,7 @@ run() {  # name, timeout, pytest args...
 for g in "$@"; do
   case $g in
     elem)  run elem 300 tests/test_kernels_gpu.py -k "ln_modulate or gate_residual or qk_rmsnorm" ;;
-    short) run short 300 tests/test_kernels_gpu.py -k "attn_short" ;;
+    short) run short 300 tests/test_kernels_gpu.py -k "attn_short or patch_embed or temporal" ;;
     gemm)  run gemm 300 tests/test_kernels_gpu.py -k "gemm and not cta_pair" ;;
     gemm2) run gemm2 300 tests/test_kernels_gpu.py -k "cta_pair or single_cta or fused_residual" ;;
     pipe)  run pipe 300 tests/test_pipeline_gpu.py ;;
@@ -33,6 +33,7 @@ for g in "$@"; do
     mmab) timeout 120 tools/_bin/mma_microbench > gpurun_out/mma_microbench.txt 2>&1; echo "mmab exit $?" | tee -a gpurun_out/summary.txt ;;
     atrace) timeout 300 python tools/attn_trace.py > gpurun_out/attn_trace.log 2>&1; echo "atrace exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/attn_trace.log ;;
     kbattn) KB_ONLY=attn timeout 600 python tools/kernel_bench.py > gpurun_out/kernel_bench_attn.log 2>&1; echo "kbattn exit $?" | tee -a gpurun_out/summary.txt; tail -n 3 gpurun_out/kernel_bench_attn.log ;;
+    kbelem) KB_ONLY=elem timeout 300 python tools/kernel_bench.py > gpurun_out/kernel_bench_elem.log 2>&1; echo "kbelem exit $?" | tee -a gpurun_out/summary.txt; tail -n 3 gpurun_out/kernel_bench_elem.log ;;
     kernels) run kernels 900 tests/test_kernels_gpu.py ;;
     cogx) run cogx 600 tests/test_cogvideox_gpu.py ;;
     latte) run latte 600 tests/test_latte_gpu.py ;;
@@ -68,7 +69,7 @@ for g in "$@"; do
               python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline --no-gpu-baseline --no-graph > gpurun_out/ncu_gemm.log 2>&1
            echo "ncu_gemm exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_short) timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_short -c 1 -o gpurun_out/prof_short -f \
-              python tools/kernel_bench.py > gpurun_out/ncu_short.log 2>&1
+              env KB_ONLY=elem python tools/kernel_bench.py > gpurun_out/ncu_short.log 2>&1
            echo "ncu_short exit $?" | tee -a gpurun_out/summary.txt ;;
     ncu_attn) timeout 900 ncu --set full --clock-control none --import-source on -k regex:attn_flash -s 2 -c 2 -o gpurun_out/prof_attn -f \
               python bench.py --steps 1 --warmup 1 --depth 1 --no-cpu-baseline --no-gpu-baseline --no-graph $NCU_BENCH_ARGS > gpurun_out/ncu_attn.log 2>&1

@@ -29,6 +29,48 @@ def timeit(fn, iters=20, warm=3):
 
 out = {}
 M = 144000
+
+
+def elem_section():
+    C, H, D = 1152, 16, 72
+    x = torch.randn(2, 72000, C, device=dev, dtype=bf)
+    y = torch.randn(2, 72000, C, device=dev, dtype=bf)
+    mod = torch.randn(2, 2, 6, C, device=dev, dtype=bf)
+    m8 = torch.ones(2, 20, dtype=torch.uint8, device=dev)
+    o = torch.empty_like(x)
+    nb = x.numel() * 2
+    r = {}
+    t = timeit(lambda: K.ln_modulate(x, mod, m8, 0, 1, 2, 20, 3600, out=o)); r["ln_modulate_GBs"] = round(2 * nb / t / 1e9)
+    K.set_option("ln_occupancy", 4)
+    t = timeit(lambda: K.ln_modulate(x, mod, m8, 0, 1, 2, 20, 3600, out=o)); r["ln_modulate_occ4_GBs"] = round(2 * nb / t / 1e9)
+    K.set_option("ln_occupancy", 3)
+    t = timeit(lambda: K.gate_residual(x, y, mod, m8, 2, 2, 20, 3600, out=o)); r["gate_residual_GBs"] = round(3 * nb / t / 1e9)
+    t = timeit(lambda: K.residual_add(x, y, out=o)); r["residual_add_GBs"] = round(3 * nb / t / 1e9)
+    t = timeit(lambda: o.copy_(x)); r["torch_copy_GBs"] = round(2 * nb / t / 1e9)
+    qkv = torch.randn(144000, 3, H, D, device=dev, dtype=bf)
+    wq = torch.ones(D, device=dev, dtype=bf)
+    t = timeit(lambda: K.qk_rmsnorm_(qkv, wq, wq, H, D)); r["qk_rmsnorm_GBs"] = round(4 * 144000 * C * 2 / t / 1e9)
+    cos = torch.randn(20, D, device=dev); sin = torch.randn(20, D, device=dev)
+    t = timeit(lambda: K.attn_short(qkv, wq, wq, cos, sin, 2, 3600, 20 * 3600, 1, 3600, 20, H, D, D**-0.5, out=o.view(-1, C)))
+    r["attn_short_GBs"] = round(4 * 144000 * C * 2 / t / 1e9); r["attn_short_ms"] = round(t * 1e3, 3)
+    # patch embedding (vsb_patch_embed) against the torch / cuDNN chain it replaces, 720p CFG pair
+    z = torch.randn(2, 4, 20, 90, 160, device=dev, dtype=bf)
+    conv = torch.nn.Conv3d(4, C, (1, 2, 2), (1, 2, 2)).to(dev, bf)
+    pos = torch.randn(1, 3600, C, device=dev, dtype=bf)
+    t = timeit(lambda: K.patch_embed(z, conv.weight, conv.bias, pos[0], 2, 2)); r["patch_embed_ms"] = round(t * 1e3, 4)
+    r["patch_embed_GBs"] = round(2 * 72000 * C * 2 / t / 1e9)
+    with torch.no_grad():
+        t = timeit(lambda: (conv(z).flatten(2).transpose(1, 2).reshape(2, 20, 3600, C) + pos).reshape(2, 72000, C).contiguous())
+    r["patch_embed_torch_chain_ms"] = round(t * 1e3, 4)
+    return r
+
+
+if os.environ.get("KB_ONLY", "") == "elem":
+    out["elementwise"] = elem_section()
+    print("elementwise", out["elementwise"], flush=True)
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(out, open("gpurun_out/kernel_bench_elem.json", "w"), indent=1)
+    sys.exit(0)
 ONLY = os.environ.get("KB_ONLY", "")  # "attn": skip the GEMM and elementwise sections
 SHAPES = {} if ONLY == "attn" else {"qkv": (3456, 1152, 0), "proj": (1152, 1152, 0), "fc1": (4608, 1152, 1), "fc2": (1152, 4608, 0)}
 for name, (N, Kd, act) in SHAPES.items():
@@ -163,26 +205,7 @@ del qkv
 if ONLY == "attn":
     json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "kernel_bench_attn.json"), "w"), indent=1)
     sys.exit(0)
-x = torch.randn(2, 72000, C, device=dev, dtype=bf)
-y = torch.randn(2, 72000, C, device=dev, dtype=bf)
-mod = torch.randn(2, 2, 6, C, device=dev, dtype=bf)
-m8 = torch.ones(2, 20, dtype=torch.uint8, device=dev)
-o = torch.empty_like(x)
-nb = x.numel() * 2
-r = {}
-t = timeit(lambda: K.ln_modulate(x, mod, m8, 0, 1, 2, 20, 3600, out=o)); r["ln_modulate_GBs"] = round(2 * nb / t / 1e9)
-K.set_option("ln_occupancy", 4)
-t = timeit(lambda: K.ln_modulate(x, mod, m8, 0, 1, 2, 20, 3600, out=o)); r["ln_modulate_occ4_GBs"] = round(2 * nb / t / 1e9)
-K.set_option("ln_occupancy", 3)
-t = timeit(lambda: K.gate_residual(x, y, mod, m8, 2, 2, 20, 3600, out=o)); r["gate_residual_GBs"] = round(3 * nb / t / 1e9)
-t = timeit(lambda: K.residual_add(x, y, out=o)); r["residual_add_GBs"] = round(3 * nb / t / 1e9)
-t = timeit(lambda: o.copy_(x)); r["torch_copy_GBs"] = round(2 * nb / t / 1e9)
-qkv = torch.randn(144000, 3, H, D, device=dev, dtype=bf)
-wq = torch.ones(D, device=dev, dtype=bf)
-t = timeit(lambda: K.qk_rmsnorm_(qkv, wq, wq, H, D)); r["qk_rmsnorm_GBs"] = round(4 * 144000 * C * 2 / t / 1e9)
-cos = torch.randn(20, D, device=dev); sin = torch.randn(20, D, device=dev)
-t = timeit(lambda: K.attn_short(qkv, wq, wq, cos, sin, 2, 3600, 20 * 3600, 1, 3600, 20, H, D, D**-0.5, out=o.view(-1, C)))
-r["attn_short_GBs"] = round(4 * 144000 * C * 2 / t / 1e9); r["attn_short_ms"] = round(t * 1e3, 3)
+r = elem_section()
 out["elementwise"] = r
 print("elementwise", r, flush=True)
 os.makedirs("gpurun_out", exist_ok=True)

@@ -14,6 +14,8 @@
 // arithmetic, 12 warps per SM: 1.08 ms for the 720p launch, 15 % of HBM peak -- profiles/r01_attn_short_ncu_full.txt.)
 // Rounding follows the reference's eager op order (attentions.py:111-120): bf16(q*scale), bf16(q@k^T),
 // fp32 softmax, bf16(probs), bf16(probs@v).
+#include <type_traits>
+
 #include "vsb_common.cuh"
 #include "vsb_host.h"
 
@@ -73,9 +75,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
   // [mbarriers | rope cos | rope sin] (fp32, n x D each, shared by the block) then per warp q[rq] | k[rq] | v[32].
   // ldmatrix of Q rows >= rq runs on into K / V (valid memory, results unused); V rows n..31 are zero.
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
-  float* s_cos = reinterpret_cast<float*>(smem_raw + 128);
-  float* s_sin = s_cos + kMaxN * D;
-  bf16* sq = reinterpret_cast<bf16*>(s_sin + kMaxN * D) + (size_t)warp * (2 * rq + kMaxN) * D;
+  // rope table, one float4 per rotated pair (2i, 2i+1) of a position: (cos[2i], cos[2i+1], sin[2i], sin[2i+1])
+  float4* s_rope = reinterpret_cast<float4*>(smem_raw + 128);
+  bf16* sq = reinterpret_cast<bf16*>(s_rope + kMaxN * (D / 2)) + (size_t)warp * (2 * rq + kMaxN) * D;
   bf16* sk = sq + (size_t)rq * D;
   bf16* sv = sk + (size_t)rq * D;
   uint64_t* bar = &bars[warp];
@@ -84,10 +86,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
   const bool sdpa_math = (flags & 2) != 0; // flag bit 1: F.scaled_dot_product_attention rounding (fp32 scores,
                                            // scale inside the softmax) instead of native_attention's bf16 steps
   if (has_rope) {
-    for (int i = threadIdx.x; i < n * D; i += blockDim.x) {
-      s_cos[i] = rope_cos[i];
-      s_sin[i] = rope_sin[i];
-    }
+    for (int i = threadIdx.x; i < n * (D / 2); i += blockDim.x)
+      s_rope[i] = make_float4(rope_cos[2 * i], rope_cos[2 * i + 1], rope_sin[2 * i], rope_sin[2 * i + 1]);
   }
   // zero V's padding rows once (P is 0 there, but 0 * garbage could be NaN); the TMA boxes never touch them
   for (int i = lane; i < (kMaxN - n) * VPR; i += 32)
@@ -126,72 +126,77 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
       for (int c = lane; c < VPR; c += 32)
         *reinterpret_cast<uint4*>(sq + c * 8) = *reinterpret_cast<const uint4*>(sv + c * 8);
     } else {
-    // ---- 2. RMSNorm (+RoPE, q scale) in place.  LPR lanes share one row (CPL 16-byte chunks each); the 2n rows
-    //         (q rows then k rows) are walked 32/LPR at a time; the sum of squares crosses lanes by shuffle ----
+    // ---- 2. RMSNorm (+RoPE, q scale) in place.  LPR lanes share one row (CPL 16-byte chunks each); the n query rows,
+    //         then the n key rows, are walked 32/LPR at a time (two instantiations: the q-only scale is compile-time and a
+    //         pass never mixes q and k rows, so no lane diverges); the sum of squares crosses lanes by shuffle ----
     if (do_norm || has_rope || !sdpa_math) {
       constexpr int LPR = (D == 72) ? 3 : 2;  // lanes per row
       constexpr int CPL = VPR / LPR;          // chunks per lane (3 or 4)
       constexpr int RPP = 32 / LPR;           // rows per pass
       const int gi = lane / LPR, part = lane - gi * LPR;
       const int gbase = (gi < RPP ? gi : 0) * LPR;
-      for (int vr0 = 0; vr0 < 2 * n; vr0 += RPP) {
-        const int vr = vr0 + gi;
-        const bool act = (gi < RPP) && (vr < 2 * n);
-        const int which = (act && vr >= n) ? 1 : 0;
-        const int r = act ? (vr - which * n) : 0;
-        bf16* rowp = (which ? sk : sq) + r * D + part * CPL * 8;
-        Vec8s v[CPL];
-        float ss = 0.f;
-        if (act) {
+      auto norm_rows = [&](auto is_q_c) {
+        constexpr bool kIsQ = decltype(is_q_c)::value;
+        const bool scale_q = kIsQ && !sdpa_math;  // q = bf16(q * scale)  (attentions.py:113)
+        if (!do_norm && !has_rope && !scale_q) return;
+        const bf16* wrow = (kIsQ ? wq : wk) + part * CPL * 8;
+        for (int r0 = 0; r0 < n; r0 += RPP) {
+          const int r = r0 + gi;
+          const bool act = (gi < RPP) && (r < n);
+          bf16* rowp = (kIsQ ? sq : sk) + (act ? r : 0) * D + part * CPL * 8;
+          Vec8s v[CPL];
+          float ss = 0.f;
+          if (act) {
 #pragma unroll
-          for (int c = 0; c < CPL; ++c) {
-            v[c].u = *reinterpret_cast<const uint4*>(rowp + c * 8);
+            for (int c = 0; c < CPL; ++c) {
+              v[c].u = *reinterpret_cast<const uint4*>(rowp + c * 8);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = e2_to_float2(v[c].h[j]);
-              ss = fmaf(f.x, f.x, ss);
-              ss = fmaf(f.y, f.y, ss);
-            }
-          }
-        }
-        float tot = 0.f;
-#pragma unroll
-        for (int i = 0; i < LPR; ++i) tot += __shfl_sync(0xffffffffu, ss, gbase + i);
-        if (act) {
-          const float rs = do_norm ? rsqrtf(tot / (float)D + eps) : 1.f;
-          const bf16* wrow = (which ? wk : wq) + part * CPL * 8;
-#pragma unroll
-          for (int c = 0; c < CPL; ++c) {
-            Vec8s w, o;
-            w.u = do_norm ? __ldg(reinterpret_cast<const uint4*>(wrow + c * 8)) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = e2_to_float2(v[c].h[j]);
-              // normalization.py:28-33: h = bf16(x*rstd); y = bf16(w*h)
-              elem2 y2 = do_norm ? __hmul2_rn(w.h[j], floats_to_e2(f.x * rs, f.y * rs)) : v[c].h[j];
-              if (has_rope || (which == 0 && !sdpa_math)) {
-                float2 y = e2_to_float2(y2);
-                if (has_rope) {
-                  // rotate_queries_or_keys: t*cos + rotate_half(t)*sin in fp32, pairs (2i, 2i+1): rot = (-x2, x1)
-                  const int d = (part * CPL + c) * 8 + 2 * j;
-                  const float2 cs = *reinterpret_cast<const float2*>(s_cos + r * D + d);
-                  const float2 sn = *reinterpret_cast<const float2*>(s_sin + r * D + d);
-                  const float o0 = __fadd_rn(__fmul_rn(y.x, cs.x), __fmul_rn(-y.y, sn.x));
-                  const float o1 = __fadd_rn(__fmul_rn(y.y, cs.y), __fmul_rn(y.x, sn.y));
-                  y = e2_to_float2(floats_to_e2(o0, o1));
-                }
-                if (which == 0 && !sdpa_math) {  // q = bf16(q * scale)  (attentions.py:113)
-                  y.x *= scale;
-                  y.y *= scale;
-                }
-                y2 = floats_to_e2(y.x, y.y);
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = e2_to_float2(v[c].h[j]);
+                ss = fmaf(f.x, f.x, ss);
+                ss = fmaf(f.y, f.y, ss);
               }
-              o.h[j] = y2;
             }
-            *reinterpret_cast<uint4*>(rowp + c * 8) = o.u;
+          }
+          float tot = 0.f;
+#pragma unroll
+          for (int i = 0; i < LPR; ++i) tot += __shfl_sync(0xffffffffu, ss, gbase + i);
+          if (act) {
+            const float rs = do_norm ? rsqrtf(tot / (float)D + eps) : 1.f;
+            const float4* rp = s_rope + (size_t)r * (D / 2) + part * CPL * 4;
+#pragma unroll
+            for (int c = 0; c < CPL; ++c) {
+              Vec8s w, o;
+              w.u = do_norm ? __ldg(reinterpret_cast<const uint4*>(wrow + c * 8)) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const float2 f = e2_to_float2(v[c].h[j]);
+                // normalization.py:28-33: h = bf16(x*rstd); y = bf16(w*h)
+                elem2 y2 = do_norm ? __hmul2_rn(w.h[j], floats_to_e2(f.x * rs, f.y * rs)) : v[c].h[j];
+                if (has_rope || scale_q) {
+                  float2 y = e2_to_float2(y2);
+                  if (has_rope) {
+                    // rotate_queries_or_keys: t*cos + rotate_half(t)*sin in fp32, pairs (2i, 2i+1): rot = (-x2, x1)
+                    const float4 cs = rp[c * 4 + j];
+                    const float o0 = __fadd_rn(__fmul_rn(y.x, cs.x), __fmul_rn(-y.y, cs.z));
+                    const float o1 = __fadd_rn(__fmul_rn(y.y, cs.y), __fmul_rn(y.x, cs.w));
+                    y = scale_q ? e2_to_float2(floats_to_e2(o0, o1)) : make_float2(o0, o1);
+                  }
+                  if (scale_q) {
+                    y.x *= scale;
+                    y.y *= scale;
+                  }
+                  y2 = floats_to_e2(y.x, y.y);
+                }
+                o.h[j] = y2;
+              }
+              *reinterpret_cast<uint4*>(rowp + c * 8) = o.u;
+            }
           }
         }
-      }
+      };
+      norm_rows(std::true_type{});
+      norm_rows(std::false_type{});
     }
     __syncwarp();
 
@@ -246,11 +251,13 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
       float d0 = 0.f, d1 = 0.f;
+      const bool rows_hi = mt * 16 + 8 < n;  // rows g + 8 of this m-tile exist (warp-uniform): else their P stays unused
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float p = expf(sacc[j][e] - (e < 2 ? mx0 : mx1));  // exp(-inf) = 0 for masked keys
+          // exp(-inf) = 0 for masked keys; key tiles beyond the sequence and absent rows skip the exponential
+          const float p = (j < nt && (e < 2 || rows_hi)) ? expf(sacc[j][e] - (e < 2 ? mx0 : mx1)) : 0.f;
           sacc[j][e] = p;
           if (e < 2) d0 += p; else d1 += p;
         }
@@ -260,13 +267,15 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
       d1 += __shfl_xor_sync(0xffffffffu, d1, 1);
       d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
       // P (bf16) as A fragments of the two k16 steps
+      // one correctly rounded reciprocal per row, then a multiply (vs p / d: <= 1.5 fp32 ulp before the bf16 rounding of P)
+      const float i0 = 1.f / d0, i1 = rows_hi ? 1.f / d1 : 0.f;
       uint32_t pa[2][4];
 #pragma unroll
       for (int kb = 0; kb < 2; ++kb) {
-        pa[kb][0] = pack_bf16x2(sacc[2 * kb][0] / d0, sacc[2 * kb][1] / d0);
-        pa[kb][1] = pack_bf16x2(sacc[2 * kb][2] / d1, sacc[2 * kb][3] / d1);
-        pa[kb][2] = pack_bf16x2(sacc[2 * kb + 1][0] / d0, sacc[2 * kb + 1][1] / d0);
-        pa[kb][3] = pack_bf16x2(sacc[2 * kb + 1][2] / d1, sacc[2 * kb + 1][3] / d1);
+        pa[kb][0] = pack_bf16x2(sacc[2 * kb][0] * i0, sacc[2 * kb][1] * i0);
+        pa[kb][1] = pack_bf16x2(sacc[2 * kb][2] * i1, sacc[2 * kb][3] * i1);
+        pa[kb][2] = pack_bf16x2(sacc[2 * kb + 1][0] * i0, sacc[2 * kb + 1][1] * i0);
+        pa[kb][3] = pack_bf16x2(sacc[2 * kb + 1][2] * i1, sacc[2 * kb + 1][3] * i1);
       }
       float oacc[ND][4];
 #pragma unroll

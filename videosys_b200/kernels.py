@@ -131,6 +131,29 @@ def modulation_table(table: torch.Tensor, t: torch.Tensor, t0: Optional[torch.Te
     return mod
 
 
+def patch_embed(z, weight, bias, pos, ph: int, pw: int, s0: int = 0, s_local: Optional[int] = None):
+    """Tokens [B, T, S_local, C] of a latent z [B, Cin, T, H, W] (contiguous): the (1, ph, pw)-strided patch convolution
+    (weight = conv.weight, any [C, Cin, (1,) ph, pw] shape), + bias, + pos [S, C], for patch columns s0 .. s0+S_local-1
+    (columns beyond the grid are zero).  Returns None when the kernel does not take the shape (Cin*ph*pw != 16)."""
+    lib, st = _prep(z, weight, bias, pos)
+    _bf16(z, "z")
+    _same_dtype(z, weight, bias, pos)
+    B, Cin, T, H, W = z.shape
+    Cc = weight.shape[0]
+    S = -(-H // ph) * -(-W // pw)
+    s_local = S if s_local is None else s_local
+    out = torch.empty(B, T, s_local, Cc, dtype=z.dtype, device=z.device)
+    with _Timed("patch_embed", out.numel() * 2) as tm:
+        rc = _fn(lib, "vsb_patch_embed", z)(_p(z), _p(weight), _p(bias), _p(pos), _p(out), B, Cin, T, H, W, Cin * T * H * W,
+                                            T * H * W, H * W, ph, pw, Cc, s0, s_local, st)
+        if rc == 1:
+            tm.cancel()
+    if rc == 1:
+        return None
+    _lib.check(rc, "patch_embed")
+    return out
+
+
 def ln_modulate(x, mod, x_mask_u8, shift_row, scale_row, B, T, S, out=None, eps=1e-6, gamma=None, beta=None):
     """LayerNorm (optionally affine: gamma/beta) + modulate + per-frame select; x viewed as [B, T, S, C]."""
     lib, st = _prep(x, mod, x_mask_u8, out, gamma, beta)

@@ -337,11 +337,15 @@ class LatteT2V(nn.Module):
         p, C = self.patch_size, self.inner_dim
         h, w = H // p, W // p
         S = h * w
-        x = hidden_states.to(dt).permute(0, 2, 1, 3, 4).reshape(B * Fr, Cin, H, W)
-        x = self.pos_embed.proj(x).flatten(2).transpose(1, 2)  # conv: cuDNN (glue, once per step)  [B*F, S, C]
         pos = self.pos_table if S == self.pos_table.shape[1] else get_2d_sincos_pos_embed(
-            C, h, base_size=self.config.sample_size // p, interpolation_scale=max(self.config.sample_size // 64, 1))[None].to(x.device)
-        x = (x + pos.to(dt)).reshape(B, Fr, S, C)
+            C, h, base_size=self.config.sample_size // p, interpolation_scale=max(self.config.sample_size // 64, 1))[None].to(hidden_states.device)
+        # PatchEmbed (:1245): 2 x 2 conv per frame + 2-D sincos table; one kernel on the [B, C, F, H, W] latent as it is
+        x = K.patch_embed(hidden_states.to(dt).contiguous(), self.pos_embed.proj.weight, self.pos_embed.proj.bias,
+                          pos[0].to(dt).contiguous(), p, p)
+        if x is None:  # not a 16-tap embedding: the eager chain (cuDNN conv, once per step)
+            x = hidden_states.to(dt).permute(0, 2, 1, 3, 4).reshape(B * Fr, Cin, H, W)
+            x = self.pos_embed.proj(x).flatten(2).transpose(1, 2)
+            x = (x + pos.to(dt)).reshape(B, Fr, S, C)
         te = self.adaln_single.emb.timestep_embedder
         t_emb = self._time_proj(timestep).to(dt)
         embedded = K.gemm_bias_act(F.silu(K.gemm_bias_act(t_emb, te.linear_1.weight, te.linear_1.bias)), te.linear_2.weight,

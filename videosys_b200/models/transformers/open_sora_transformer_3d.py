@@ -568,24 +568,35 @@ class STDiT3(nn.Module):
 
         text = self._text_state(y, mask, B, dtype)
 
-        # patch embed (right/bottom zero pad to the patch grid, then a strided conv)
+        # patch embed + position embedding + this rank's patch columns: one kernel (vsb_patch_embed) for temporal patch 1
+        # and 16 taps; otherwise the reference's chain (zero pad to the patch grid, strided conv, add, split)
         p = self.patch_size
-        if Wx % p[2]:
-            x = F.pad(x, (0, p[2] - Wx % p[2]))
-        if Hx % p[1]:
-            x = F.pad(x, (0, 0, 0, p[1] - Hx % p[1]))
-        if Tx % p[0]:
-            x = F.pad(x, (0, 0, 0, 0, 0, p[0] - Tx % p[0]))
-        h = self.x_embedder.proj(x).flatten(2).transpose(1, 2)
-        h = h.reshape(B, T, S, C) + pos
-
         Tg, Sg = T, S
+        s_pad = 0
         if sp > 1:
             comm.set_pad("temporal", T, pm.sp_group)
             comm.set_pad("spatial", S, pm.sp_group)
             comm.set_pad("batch", B, pm.sp_group)
-            h = comm.split_sequence(h, pm.sp_group, dim=2, grad_scale="down", pad=comm.get_pad("spatial"))
-            S = h.shape[2]
+            s_pad = comm.get_pad("spatial")
+        Sl = (S + s_pad) // sp
+        h = None
+        if p[0] == 1 and os.environ.get("VSB_PATCH_EMBED", "1") != "0":
+            proj = self.x_embedder.proj
+            h = kernels.patch_embed(x.contiguous(), proj.weight, proj.bias, pos.reshape(S, C), p[1], p[2],
+                                    s0=(pm.sp_rank * Sl if sp > 1 else 0), s_local=Sl)
+        if h is None:
+            if Wx % p[2]:
+                x = F.pad(x, (0, p[2] - Wx % p[2]))
+            if Hx % p[1]:
+                x = F.pad(x, (0, 0, 0, p[1] - Hx % p[1]))
+            if Tx % p[0]:
+                x = F.pad(x, (0, 0, 0, 0, 0, p[0] - Tx % p[0]))
+            h = self.x_embedder.proj(x).flatten(2).transpose(1, 2)
+            h = h.reshape(B, T, S, C) + pos
+            if sp > 1:
+                h = comm.split_sequence(h, pm.sp_group, dim=2, grad_scale="down", pad=s_pad)
+        S = h.shape[2]
+        if sp > 1:
             self._ensure_dsp(B, T, S, C, x.device)
         h = h.reshape(B, T * S, C).contiguous()
 
