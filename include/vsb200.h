@@ -117,7 +117,9 @@ int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t
  * pairs, fp32 math, cast back): the pre-pass of TEMPORAL attention over >= 30 frames, where the reference leaves
  * native_attention for F.scaled_dot_product_attention (attentions.py:95-100) and vsb_attn_short's 32-token limit is
  * exceeded.  rope_cos / rope_sin [pos_mod, D] fp32; token row r sits at position (r / pos_div) % pos_mod
- * (token-major [B, T, S] activation: pos_div = S, pos_mod = T). */
+ * (token-major [B, T, S] activation: pos_div = S, pos_mod = T).
+ * wq == wk == NULL: RoPE only (q / k stay un-normalised): the temporal attention of Vchitect beyond 32 frames
+ * (attentions.py:688-701 apply_rotary_emb, complex multiply on the same interleaved pairs; no q/k norm). */
 int vsb_qk_rmsnorm_rope(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D, float eps,
                         const float* rope_cos, const float* rope_sin, int pos_div, int pos_mod, void* stream);
 

@@ -210,3 +210,70 @@ def test_cogvideox_ddim_scheduler_vs_reference():
         xr = ref.step(v, t, xr, return_dict=False)[0]
         xo = ours.step(v, int(t), xo)[0]
         assert torch.allclose(xr.float(), xo.float(), rtol=1e-5, atol=1e-6), int(t)
+
+
+def _vchitect_ref_attention(C, H, context_pre_only, dtype):
+    A = ref_loader.load().attentions
+    attn = A.VchitectAttention(query_dim=C, cross_attention_dim=None, added_kv_proj_dim=C, dim_head=C // H, heads=H,
+                               out_dim=C, context_pre_only=context_pre_only, bias=True, processor=A.VchitectAttnProcessor())
+    attn = attn.to(dtype).eval()
+    attn.parallel_manager = ref_loader.SingleRankPM()
+    sd = synth.fill_state_dict(attn.state_dict(), "vchattn.")
+    attn.load_state_dict(sd)
+    return attn, {"a." + k: v for k, v in sd.items()}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Fr,S,L,pre_only", [(5, 12, 7, False), (5, 12, 7, True), (1, 12, 7, False)])
+def test_vchitect_attention_vs_reference(Fr, S, L, pre_only, dtype):
+    """oracle/vchitect_oracle.attention against the reference's own VchitectAttention + VchitectAttnProcessor
+    (models/modules/attentions.py:321-949, executed unmodified): temporal (RoPE), cross (frame-0 text keys) and spatial
+    joint attention, the 1.1 mix, the output projections of both streams; bit for bit."""
+    from oracle import vchitect_oracle as VO
+
+    C, H = 64, 4
+    attn, sd = _vchitect_ref_attention(C, H, pre_only, dtype)
+    nh = synth.normalish("vch.h", (Fr, S, C)).to(dtype)
+    ne = synth.normalish("vch.e", (Fr, L, C)).to(dtype)
+    fc = VO.freqs_cis(C // H, 64, theta=1e6)
+    with torch.no_grad():
+        rv, re = attn(hidden_states=nh, encoder_hidden_states=ne, freqs_cis=fc, full_seqlen=Fr, Frame=Fr,
+                      timestep=torch.tensor([500]))
+        ov, oe = VO.attention(sd, "a.", nh, ne, fc, H, Fr, pre_only)
+    assert torch.equal(rv, ov)
+    assert torch.equal(re, oe)
+
+
+def test_vchitect_attention_pab_vs_reference():
+    """The three PAB gates of the processor (:838-895: temporal, cross, spatial, in this order) over 8 steps."""
+    from oracle import vchitect_oracle as VO
+
+    ref = ref_loader.load()
+    P = ref.pab_mgr
+    C, H, Fr, S, L = 64, 4, 4, 10, 6
+    attn, sd = _vchitect_ref_attention(C, H, False, torch.float32)
+    cfg = P.PABConfig(spatial_broadcast=True, spatial_threshold=[100, 800], spatial_range=2, temporal_broadcast=True,
+                      temporal_threshold=[100, 800], temporal_range=3, cross_broadcast=True, cross_threshold=[100, 800],
+                      cross_range=4)
+    P.set_pab_manager(cfg)
+    P.update_steps(8)
+    try:
+        fc = VO.freqs_cis(C // H, 64, theta=1e6)
+        counts = {"spatial": 0, "temporal": 0, "cross": 0}
+        cache = {}
+        G = pab_oracle.PABGate((True, (100, 800), 2), (True, (100, 800), 3), (True, (100, 800), 4), 8)
+        for step, t in enumerate([900, 700, 650, 600, 550, 500, 450, 50]):
+            nh = synth.normalish(f"vchp.h{step}", (Fr, S, C))
+            ne = synth.normalish(f"vchp.e{step}", (Fr, L, C))
+
+            def gate(kind, t=t):
+                hit, counts[kind] = G.gate(kind, t, counts[kind])
+                return hit
+
+            with torch.no_grad():
+                rv, re = attn(hidden_states=nh, encoder_hidden_states=ne, freqs_cis=fc, full_seqlen=Fr, Frame=Fr,
+                              timestep=torch.tensor([t]))
+                ov, oe = VO.attention(sd, "a.", nh, ne, fc, H, Fr, False, gate, cache)
+            assert torch.equal(rv, ov) and torch.equal(re, oe), step
+    finally:
+        P.PAB_MANAGER = None

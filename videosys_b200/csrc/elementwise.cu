@@ -291,9 +291,10 @@ __global__ void __launch_bounds__(256, 4) qk_rmsnorm_kernel(bf16* __restrict__ q
   const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
   const unsigned ngroups = (unsigned)rows * 2u * H;  // (row, which in {q,k}, head)
   const unsigned H2 = 2u * H;
+  const bool do_norm = wq != nullptr;  // NULL weights: RoPE only (attention without q/k norm: Vchitect temporal)
   Vec8 wv[2];
-  wv[0].u = __ldg(reinterpret_cast<const uint4*>(wq + l * 8));
-  wv[1].u = __ldg(reinterpret_cast<const uint4*>(wk + l * 8));
+  wv[0].u = do_norm ? __ldg(reinterpret_cast<const uint4*>(wq + l * 8)) : make_uint4(0, 0, 0, 0);
+  wv[1].u = do_norm ? __ldg(reinterpret_cast<const uint4*>(wk + l * 8)) : make_uint4(0, 0, 0, 0);
   for (unsigned base = warp * (GPW * U); base < ngroups; base += nwarps * (GPW * U)) {
     Vec8 v[U];
     bf16* p[U];
@@ -337,7 +338,7 @@ __global__ void __launch_bounds__(256, 4) qk_rmsnorm_kernel(bf16* __restrict__ q
         for (int j = 0; j < 4; ++j) {
           float2 f = e2_to_float2(v[u].h[j]);
           // eager: h = bf16(x * rstd); out = bf16(w * h)
-          o.h[j] = __hmul2_rn(wv[which[u]].h[j], floats_to_e2(f.x * r, f.y * r));
+          o.h[j] = do_norm ? __hmul2_rn(wv[which[u]].h[j], floats_to_e2(f.x * r, f.y * r)) : v[u].h[j];
           if (rope_cos != nullptr) {
             // rotate_queries_or_keys (attentions.py:76-78): t*cos + rotate_half(t)*sin in fp32 on interleaved pairs
             // (2i, 2i+1), rot = (-x2, x1), cast back to bf16; position = the token's frame index
@@ -571,9 +572,11 @@ extern "C" int VSB_API(vsb_qk_rmsnorm)(vsb_bf16* qkv, const vsb_bf16* wq, const 
 extern "C" int VSB_API(vsb_qk_rmsnorm_rope)(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D,
                                    float eps, const float* rope_cos, const float* rope_sin, int pos_div, int pos_mod,
                                    void* stream) {
-  if (!qkv || !wq || !wk || rows == 0 || H <= 0) return fail(VSB_ERR_INVALID, "qk_rmsnorm: bad args");
+  if (!qkv || rows == 0 || H <= 0 || ((wq == nullptr) != (wk == nullptr)))
+    return fail(VSB_ERR_INVALID, "qk_rmsnorm: bad args");
   if ((rope_cos == nullptr) != (rope_sin == nullptr) || pos_div <= 0 || pos_mod <= 0)
     return fail(VSB_ERR_INVALID, "qk_rmsnorm: rope tables / position map");
+  if (wq == nullptr && rope_cos == nullptr) return fail(VSB_ERR_INVALID, "qk_rmsnorm: neither norm weights nor rope tables");
   if (!aligned16(qkv) || !aligned16(wq) || !aligned16(wk)) return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: alignment");
   long long groups = (long long)rows * 2 * H;
   if (groups >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: %lld head vectors", groups);

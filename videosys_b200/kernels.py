@@ -71,6 +71,12 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
+def require_cuda(t, what: str = "vsb200"):
+    """The model front ends call this first: there is no CPU execution path."""
+    if not t.is_cuda:
+        raise RuntimeError(f"videosys_b200 {what} runs on sm_100a CUDA devices only (no CPU path)")
+
+
 def _bf16(t, name):
     if t is not None and t.dtype not in (torch.bfloat16, torch.float16):
         raise _lib.VsbError(f"{name} must be bfloat16 or float16")
