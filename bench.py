@@ -40,6 +40,10 @@ WORKLOADS = {
 MODEL = dict(hidden_size=1152, num_heads=16, depth=28, caption_channels=4096, model_max_length=300)
 # BASELINE.json configs[3]: CogVideoX-2B, 49 frames 480x720, 50 DDIM steps, fp16, 1 GPU (PAB with --pab)
 COGVIDEOX = dict(frames=49, steps=50, h=480, w=720, lat=(13, 16, 60, 90), text=(226, 4096), heads=30, head_dim=64, layers=30)
+# not a BASELINE.json config (SURVEY section 8 (f)4 widening): Vchitect-2.0-2B, the reference's example call (40 frames 288x480,
+# 100 steps, pipeline_vchitect.py:84-93), bf16, 1 GPU
+VCHITECT = dict(frames=40, steps=100, h=288, w=480, lat=(40, 16, 36, 60), text=(333, 4096), pooled=2048, heads=24, head_dim=64,
+                layers=24)
 
 
 def _peaks():
@@ -751,13 +755,139 @@ def run_cogvideox(args):
         os._exit(0)
 
 
+def run_vchitect(args):
+    """One denoising step of Vchitect-2.0-2B as the reference runs it (pipeline_vchitect.py:916-954): the unconditional and
+    the text forward (batch 1 each) through VchitectXLTransformerModel (24 MMDiT blocks, three joint attentions each),
+    cosine-ramped guidance, flow-match Euler update.  1 GPU."""
+    import videosys_b200  # noqa: F401
+    from videosys_b200 import kernels
+    from videosys_b200.core.pab import pab_mgr
+    from videosys_b200.models.transformers.vchitect_transformer_3d import VchitectXLTransformerModel
+    from videosys_b200.pipelines.vchitect.pipeline_vchitect import VchitectPABConfig
+    from videosys_b200.schedulers.scheduling_flow_match_euler import FlowMatchEulerDiscreteScheduler
+
+    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", 1)) != 1:
+        raise SystemExit("the Vchitect workload runs on 1 GPU (frame-sharded sequence parallelism is not built)")
+    W = VCHITECT
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    dt = torch.bfloat16
+    torch.manual_seed(0)
+    layers = args.depth or W["layers"]
+    net = VchitectXLTransformerModel(num_layers=layers, num_attention_heads=W["heads"], attention_head_dim=W["head_dim"],
+                                     caption_projection_dim=W["heads"] * W["head_dim"])
+    for prm in net.parameters():  # random-init weights of the named architecture (incl. the three zero-initialised projections)
+        if prm.ndim >= 2:
+            torch.nn.init.normal_(prm, std=0.02)
+    net = net.to(dt).to(dev).eval()
+    sched = FlowMatchEulerDiscreteScheduler(shift=3.0)
+    sched.set_timesteps(W["steps"], dev)
+    ts = [float(v) for v in sched.timesteps.tolist()]
+    if args.pab:
+        pab_mgr.set_pab_manager(VchitectPABConfig())
+        pab_mgr.update_steps(W["steps"])
+    g = torch.Generator(device="cpu").manual_seed(1)
+    z_host = torch.randn(1, *W["lat"], generator=g).pin_memory()
+    pe = [torch.randn(1, *W["text"], generator=g).to(dev, dt) for _ in range(2)]
+    pp = [torch.randn(1, W["pooled"], generator=g).to(dev, dt) for _ in range(2)]
+    first = args.first_step if args.first_step >= 0 else (20 if args.pab else 0)
+    state = {"z": z_host.to(dev, dt)}
+
+    def one(z, k):
+        t = ts[k]
+        tt = sched.timesteps[k].expand(1)
+        un, tx = (net(z, encoder_hidden_states=e, pooled_projections=p, timestep=tt, return_dict=False,
+                      ts_int=int(t) if args.pab else None)[0] for e, p in zip(pe, pp))
+        sched._step_index = k
+        return sched.step(un + 7.5 * (tx - un), t, z)[0]
+
+    def step_resident(i):
+        state["z"] = one(state["z"], (first + i) % len(ts))
+
+    out_host = torch.empty(1, *W["lat"], dtype=torch.float32).pin_memory()
+    zdev = torch.empty(1, *W["lat"], device=dev, dtype=torch.float32)
+
+    def step_e2e(i):
+        zdev.copy_(z_host, non_blocking=True)
+        out_host.copy_(one(zdev.to(dt), (first + i) % len(ts)).float(), non_blocking=True)
+
+    def timed(fn, n):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / 1e3
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    net.reset_pab_state()
+    sampler = ClockSampler(0)
+    sampler.start()
+    l0 = kernels.launch_count()
+    sec = timed(step_resident, args.steps)
+    launches = kernels.launch_count() - l0
+    net.reset_pab_state()
+    sec_e2e = timed(step_e2e, args.steps)
+    clocks = sampler.stop()
+    net.reset_pab_state()
+    kernels.PROFILE, kernels.PROFILE_KINDS = [], None
+    sec_prof = timed(step_resident, args.steps)
+    prof, kernels.PROFILE = kernels.PROFILE, None
+    by = {}
+    for kind, a, b, work in prof:
+        d = by.setdefault(kind, [0.0, 0.0, 0])
+        d[0] += a.elapsed_time(b)
+        d[1] += work
+        d[2] += 1
+    peaks = _peaks()
+    tf = ("gemm", "attn_flash")
+    shares = kernel_fractions({k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
+                                   "achieved": v[1] / (v[0] * 1e-3) / (1e12 if k in tf else 1e9),
+                                   "unit": "TFLOP/s" if k in tf else "GB/s"} for k, v in by.items()}, peaks)
+    gm = by.get("gemm", [1e-9, 0.0, 1])
+    g_tf = gm[1] / (gm[0] * 1e-3) / 1e12
+    per = sec / args.steps
+    S, L = (W["h"] // 16) * (W["w"] // 16), W["text"][0]
+    line = {
+        "metric": "frames/sec", "value": W["frames"] / (W["steps"] * per), "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "vchitect_2b_40f_288x480_100step", "resolution": "288x480", "frames": 40, "sampling_steps": 100,
+                   "latent": list(W["lat"]), "forwards_per_step": 2, "text_tokens": L, "tokens_per_frame": S + L,
+                   "architecture": "Vchitect-2.0-2B transformer (hidden 1536, 24 heads x 64, 24 MMDiT blocks)",
+                   "pab": bool(args.pab), "parallelism": "single", "first_schedule_index": first,
+                   "l2": "per-step working set (107 MB per joint activation tensor, 24 blocks) exceeds what stays in the 126 MB L2 "
+                         "across a block; no flush needed"},
+        "e2e": {"value": W["frames"] / (W["steps"] * sec_e2e / args.steps), "unit": "frames/s",
+                "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
+                "ms_per_step": sec_e2e / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "gemm2_bf16_tn_kernel / gemm_bf16_tn_kernel (every Linear of the two forwards)", "bound": "tensor",
+                     "achieved": g_tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": g_tf / peaks["tflops"], "traffic": None,
+                     "peak_source": peaks["src"], "launches_timed": gm[2],
+                     "timed_in": "a second pass of the same steps with CUDA-event pairs around every launch",
+                     "share_of_step": gm[0] / (sec_prof * 1e3)},
+        "kernels": shares, "cpu_baseline": None,
+        "cpu_baseline_note": "not sampled for this workload (not a BASELINE.json config); the headline workload carries the CPU arm",
+        "clocks": clocks, "cuda_graph": False,
+    }
+    if args.depth:
+        line["config"]["depth_override"] = args.depth
+        line["invalid"] = "reduced depth (debug run): not a bench value"
+    print(json.dumps(line), flush=True)
+    pab_mgr.set_pab_manager(None)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="opensora_720p_68f_50step", choices=sorted(WORKLOADS) + ["cogvideox_2b_49f_480x720_50step"])
+    ap.add_argument("--workload", default="opensora_720p_68f_50step", choices=sorted(WORKLOADS) + ["cogvideox_2b_49f_480x720_50step", "vchitect_2b_40f_288x480_100step"])
     ap.add_argument("--pab", action="store_true", help="enable Pyramid Attention Broadcast (config 5)")
     ap.add_argument("--cp", action="store_true", help="CogVideoX workload, N > 1: CFG parallelism instead of a factor 2 of sequence parallelism")
     ap.add_argument("--depth", type=int, default=0, help="debug only: fewer block pairs (marks the line invalid)")
@@ -772,6 +902,11 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm is defined for the OpenSora workloads"}))
         else:
             run_cogvideox(args)
+    elif args.workload.startswith("vchitect"):
+        if args.impl == "reference":
+            print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm is defined for the OpenSora workloads"}))
+        else:
+            run_vchitect(args)
     elif args.impl == "reference":
         run_reference(args)
     else:

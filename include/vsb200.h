@@ -123,6 +123,16 @@ int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t
 int vsb_qk_rmsnorm_rope(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D, float eps,
                         const float* rope_cos, const float* rope_sin, int pos_div, int pos_mod, void* stream);
 
+/* Half-rotation RoPE on q and k in place (Open-Sora-Plan RoPE1D / RoPE2D / RoPE3D:
+ * models/transformers/open_sora_plan_v110_transformer_3d.py:136-252 applied :1217-1232,
+ * open_sora_plan_v120_transformer_3d.py:63-118 applied :921-925): every head is cut into D / (2*half) blocks (one per
+ * position axis), inside a block out[d] = x[d]*cos + rotate_half(x)[d]*sin with rotate_half = (-second half, first half),
+ * each product and the sum rounded to the 16-bit dtype as the reference's eager ops do.
+ *   rope_cos, rope_sin_signed [pos_mod, D] fp32: row p holds, for every channel of a head, the reference's 16-bit cos / sin
+ *   of that channel's axis position (sin negated on the first half of each block); token row r uses table row
+ *   (r / pos_div) % pos_mod.  half even, D a multiple of 2*half. */
+int vsb_qk_rope_halves(vsb_bf16* qkv, size_t rows, int H, int D, int half, const float* rope_cos,
+                       const float* rope_sin_signed, int pos_div, int pos_mod, void* stream);
 /* Per-head LayerNorm(D, eps, affine) of q and k in place (CogVideoX: diffusers Attention(qk_norm="layer_norm"),
  * models/transformers/cogvideox_transformer_3d.py:241-242 -> processor :130-133).  wq,bq,wk,bk [D] bf16. */
 int vsb_qk_layernorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* bq, const vsb_bf16* wk, const vsb_bf16* bk,
@@ -249,6 +259,8 @@ int vsb_qk_rmsnorm_f16(vsb_f16* qkv, const vsb_f16* wq, const vsb_f16* wk, size_
                    void* stream);
 int vsb_qk_rmsnorm_rope_f16(vsb_f16* qkv, const vsb_f16* wq, const vsb_f16* wk, size_t rows, int H, int D, float eps,
                         const float* rope_cos, const float* rope_sin, int pos_div, int pos_mod, void* stream);
+int vsb_qk_rope_halves_f16(vsb_f16* qkv, size_t rows, int H, int D, int half, const float* rope_cos,
+                           const float* rope_sin_signed, int pos_div, int pos_mod, void* stream);
 int vsb_qk_layernorm_f16(vsb_f16* qkv, const vsb_f16* wq, const vsb_f16* bq, const vsb_f16* wk, const vsb_f16* bk,
                      size_t rows, int H, int D, float eps, void* stream);
 int vsb_attn_short_f16(const vsb_f16* qkv, vsb_f16* out, const vsb_f16* wq, const vsb_f16* wk, const float* rope_cos,

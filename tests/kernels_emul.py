@@ -92,6 +92,20 @@ def qk_rmsnorm_(qkv, wq, wk, H, D, eps=1e-6, rope_cos=None, rope_sin=None, pos_d
     return qkv
 
 
+def qk_rope_halves_(qkv, rope_cos, rope_sin_signed, H, D, half, pos_div=1, pos_mod=1):
+    rows = qkv.numel() // (3 * H * D)
+    v = qkv.view(rows, 3, H, D)
+    pos = (torch.arange(rows) // pos_div) % pos_mod
+    c = rope_cos[pos].view(rows, 1, D).to(qkv.dtype)
+    s = rope_sin_signed[pos].view(rows, 1, D).to(qkv.dtype)
+    for i in (0, 1):
+        t = v[:, i]
+        blk = t.reshape(rows, H, D // (2 * half), 2, half)
+        partner = blk.flip(3).reshape(rows, H, D)  # the other half of every rotation block
+        v[:, i] = t * c + partner * s
+    return qkv
+
+
 def qk_layernorm_(qkv, wq, bq, wk, bk, H, D, eps=1e-6):
     rows = qkv.numel() // (3 * H * D)
     v = qkv.view(rows, 3, H, D)
@@ -164,11 +178,11 @@ def patch_embed(*a, **k):
     return None  # "shape not taken": the callers run their torch convolution
 
 
-def require_cuda(t, what="vsb200"):
+def require_cuda(t, what="vsb200", half_only=False):
     return None
 
 
-NAMES = ["ln_modulate", "gate_residual", "residual_add", "gemm_bias_act", "gemm_bias_residual", "qk_rmsnorm_", "qk_layernorm_",
+NAMES = ["ln_modulate", "gate_residual", "residual_add", "gemm_bias_act", "gemm_bias_residual", "qk_rmsnorm_", "qk_rope_halves_", "qk_layernorm_",
          "attn_short", "attn_flash", "modulation_table", "patch_embed", "require_cuda"]
 
 

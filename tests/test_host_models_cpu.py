@@ -80,3 +80,91 @@ def test_vchitect_pab_host_logic(monkeypatch):
         assert hits > 0
     finally:
         pab_mgr.set_pab_manager(None)
+
+
+@pytest.mark.parametrize("name", ["small_rope", "small_norope"])
+def test_osp_v110_host_logic_vs_reference_golden(monkeypatch, golden_dir, name):
+    """The Open-Sora-Plan v1.1.0 front end on the torch stand-ins, fp32, against the fp32 output of the UNMODIFIED reference
+    model stored in tests/golden/osp_v110.pt (runs wherever the fixture is: no reference tree needed)."""
+    import os
+
+    from oracle import osp_cases as OC
+    from videosys_b200.models.transformers.open_sora_plan_v110_transformer_3d import LatteT2V
+
+    kernels_emul.emulate(monkeypatch)
+    gold = torch.load(os.path.join(golden_dir, "osp_v110.pt"))
+    net = LatteT2V(**OC.CASES[name][0])
+    net.load_state_dict(OC.weights(net.state_dict(), name, torch.float32))
+    x, enc, m, tt = OC.inputs(name, torch.float32)
+    out = net.eval()(x, timestep=tt, all_timesteps=[900, 500], encoder_hidden_states=enc, encoder_attention_mask=m,
+                     return_dict=False)[0]
+    assert torch.allclose(out, gold[f"{name}.fp32"], rtol=1e-4, atol=1e-5), (out - gold[f"{name}.fp32"]).abs().max()
+
+
+def test_osp_v110_pab_host_logic_vs_reference_golden(monkeypatch, golden_dir):
+    import os
+
+    from oracle import osp_cases as OC
+    from videosys_b200.core.pab import pab_mgr
+    from videosys_b200.models.transformers.open_sora_plan_v110_transformer_3d import LatteT2V
+
+    kernels_emul.emulate(monkeypatch)
+    gold = torch.load(os.path.join(golden_dir, "osp_v110.pt"))
+    net = LatteT2V(**OC.CASES["small_rope"][0])
+    net.load_state_dict(OC.weights(net.state_dict(), "small_rope", torch.float32))
+    net.eval()
+    pab_mgr.set_pab_manager(pab_mgr.PABConfig(**OC.PAB_KW))
+    pab_mgr.update_steps(len(OC.PAB_TIMESTEPS))
+    net.reset_pab_state()
+    try:
+        for step, t in enumerate(OC.PAB_TIMESTEPS):
+            x, enc, m, _ = OC.inputs("small_rope", torch.float32, step)
+            out = net(x, timestep=torch.tensor([t, t]), all_timesteps=OC.PAB_TIMESTEPS, encoder_hidden_states=enc,
+                      encoder_attention_mask=m, return_dict=False)[0]
+            want = gold[f"pab.{step}.fp32"]
+            assert torch.allclose(out, want, rtol=1e-4, atol=1e-5), (step, (out - want).abs().max())
+    finally:
+        pab_mgr.set_pab_manager(None)
+
+
+def _bare_pipeline(cls, config, transformer, scheduler, dtype=torch.float32):
+    """A pipeline object without its CUDA-only constructor: generate()'s host logic (CFG batching, scheduler stepping,
+    timestep bookkeeping) runs on the CPU stand-ins."""
+    pipe = cls.__new__(cls)
+    pipe._config, pipe._device, pipe._dtype = config, torch.device("cpu"), dtype
+    pipe.transformer, pipe.scheduler = transformer, scheduler
+    return pipe
+
+
+def test_vchitect_pipeline_generate_host_logic(monkeypatch):
+    from videosys_b200 import VchitectConfig, VchitectXLPipeline
+    from videosys_b200.schedulers.scheduling_flow_match_euler import FlowMatchEulerDiscreteScheduler
+
+    kernels_emul.emulate(monkeypatch)
+    net, _ = _vchitect("vchg.")
+    pipe = _bare_pipeline(VchitectXLPipeline, VchitectConfig(transformer_config=VCH), net, FlowMatchEulerDiscreteScheduler(shift=3.0))
+    kw = dict(num_inference_steps=4, guidance_scale=7.5, seed=0, frames=3, height=96, width=128)
+    out = pipe.generate("Sunset over the sea.", **kw).video
+    assert out.shape == (1, 3, 4, 12, 16) and torch.isfinite(out).all()
+    assert torch.equal(pipe.generate("Sunset over the sea.", **kw).video, out)
+    assert not torch.equal(pipe.generate("A different prompt.", **kw).video, out)
+
+
+def test_osp_pipeline_generate_host_logic(monkeypatch):
+    from oracle import osp_cases as OC
+    from videosys_b200 import OpenSoraPlanConfig, OpenSoraPlanPipeline
+    from videosys_b200.models.transformers.open_sora_plan_v110_transformer_3d import LatteT2V
+    from videosys_b200.schedulers.scheduling_pndm import PNDMScheduler
+
+    kernels_emul.emulate(monkeypatch)
+    tc = OC.CASES["small_rope"][0]
+    net = LatteT2V(**tc)
+    net.load_state_dict(OC.weights(net.state_dict(), "small_rope", torch.float32))
+    cfg = OpenSoraPlanConfig(version="v110", transformer_type="65x512x512", transformer_config=tc)
+    pipe = _bare_pipeline(OpenSoraPlanPipeline, cfg, net.eval(), PNDMScheduler())
+    kw = dict(num_inference_steps=5, guidance_scale=7.5, seed=0, height=64, width=64, max_sequence_length=24)
+    out = pipe.generate("Sunset over the sea.", **kw).video
+    assert out.shape == (1, 4, 5, 8, 8) and torch.isfinite(out).all()
+    assert pipe.scheduler.counter == len(pipe.scheduler.timesteps) == 12 + 2  # 4 Runge-Kutta steps x 3 evaluations + 2 multi-step
+    assert torch.equal(pipe.generate("Sunset over the sea.", **kw).video, out)
+    assert OpenSoraPlanPipeline.latent_frames(65) == 17 and OpenSoraPlanPipeline.latent_frames(221) == 56

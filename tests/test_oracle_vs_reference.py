@@ -277,3 +277,112 @@ def test_vchitect_attention_pab_vs_reference():
             assert torch.equal(rv, ov) and torch.equal(re, oe), step
     finally:
         P.PAB_MANAGER = None
+
+
+# ---- Open-Sora-Plan v1.1.0: the product's host logic against the UNMODIFIED reference model --------------------------------
+OSP_SMALL = dict(num_attention_heads=2, attention_head_dim=72, in_channels=4, out_channels=8, num_layers=2,
+                 cross_attention_dim=144, attention_bias=True, sample_size=(8, 8), patch_size=2, activation_fn="gelu-approximate",
+                 norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6, caption_channels=32, video_length=5,
+                 attention_mode="math", use_rope=True)
+
+
+def _osp_pair(cfg, tag="osp."):
+    from videosys_b200.models.transformers.open_sora_plan_v110_transformer_3d import LatteT2V
+
+    ref = ref_loader.build_osp_v110(**cfg)
+    sd = synth.fill_state_dict(ref.state_dict(), tag)
+    ref.load_state_dict(sd)
+    net = LatteT2V(**cfg)
+    net.load_state_dict(sd)  # strict: same parameter / buffer names as the reference
+    return ref, net.eval()
+
+
+def _osp_inputs(B, Fr, HW, L=7, tag="osp."):
+    x = synth.normalish(tag + "x", (B, 4, Fr, *HW))
+    enc = synth.normalish(tag + "enc", (B, 1, L, 32))
+    m = torch.ones(B, 1, L)
+    m[B - 1, 0, L - 2:] = 0  # tokenizer padding on the last sample
+    return x, enc, m
+
+
+@pytest.mark.parametrize("use_rope,HW,scale1d", [(True, (8, 8), None), (False, (8, 8), None), (True, (12, 8), 2)])
+def test_osp_v110_mirror_vs_reference_model(monkeypatch, use_rope, HW, scale1d):
+    """videosys_b200's Open-Sora-Plan v1.1.0 front end, its kernel entries replaced by torch stand-ins
+    (tests/kernels_emul.py), against the reference's own LatteT2V executed unmodified (oracle/ref_loader.load_osp_v110):
+    RoPE tables (2-D / 1-D, linear scaling), position tables, text padding mask, block order, output head."""
+    from tests import kernels_emul
+
+    kernels_emul.emulate(monkeypatch)
+    ref, net = _osp_pair(dict(OSP_SMALL, use_rope=use_rope, interpolation_scale_1d=scale1d))
+    B, Fr = 2, 5
+    x, enc, m = _osp_inputs(B, Fr, HW)
+    t = torch.tensor([500, 500])
+    with torch.no_grad():
+        want = ref(x, timestep=t, all_timesteps=torch.tensor([900, 500]), encoder_hidden_states=enc,
+                   added_cond_kwargs={"resolution": None, "aspect_ratio": None}, attention_mask=torch.ones(B, Fr, *HW),
+                   encoder_attention_mask=m, return_dict=False)[0]
+    got = net(x, timestep=t, all_timesteps=[900, 500], encoder_hidden_states=enc, attention_mask=torch.ones(B, Fr, *HW),
+              encoder_attention_mask=m, return_dict=False)[0]
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+
+
+def test_osp_v110_pab_vs_reference_model(monkeypatch):
+    """Eight steps with PAB (attention broadcast on all three gates + the MLP skip windows) on both sides."""
+    from tests import kernels_emul
+    from videosys_b200.core.pab import pab_mgr as ours
+
+    kernels_emul.emulate(monkeypatch)
+    P = ref_loader.load().pab_mgr
+    ref, net = _osp_pair(OSP_SMALL, "ospp.")
+    ts = [900, 700, 650, 600, 550, 500, 450, 50]
+    mlp = {700: {"block": [0, 1], "skip_count": 2}, 550: {"block": [1], "skip_count": 1}}
+    kw = dict(spatial_broadcast=True, spatial_threshold=[100, 850], spatial_range=2, temporal_broadcast=True,
+              temporal_threshold=[100, 850], temporal_range=3, cross_broadcast=True, cross_threshold=[100, 850], cross_range=4,
+              mlp_broadcast=True, mlp_spatial_broadcast_config=mlp, mlp_temporal_broadcast_config=mlp)
+    P.set_pab_manager(P.PABConfig(**kw))
+    P.update_steps(len(ts))
+    ours.set_pab_manager(ours.PABConfig(**kw))
+    ours.update_steps(len(ts))
+    net.reset_pab_state()
+    try:
+        B, Fr, HW = 2, 5, (8, 8)
+        for step, t in enumerate(ts):
+            x, enc, m = _osp_inputs(B, Fr, HW, tag=f"ospp{step}.")
+            tt = torch.tensor([t, t])
+            with torch.no_grad():
+                want = ref(x, timestep=tt, all_timesteps=torch.tensor(ts), encoder_hidden_states=enc,
+                           added_cond_kwargs={"resolution": None, "aspect_ratio": None}, attention_mask=torch.ones(B, Fr, *HW),
+                           encoder_attention_mask=m, return_dict=False)[0]
+            got = net(x, timestep=tt, all_timesteps=ts, encoder_hidden_states=enc, encoder_attention_mask=m,
+                      return_dict=False)[0]
+            assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (step, (got - want).abs().max())
+    finally:
+        P.PAB_MANAGER = None
+        ours.set_pab_manager(None)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_osp_v110_rope_tables_vs_reference_classes(dtype):
+    """The cos / signed-sin tables of vsb_qk_rope_halves against LinearScalingRoPE2D / LinearScalingRoPE1D run on q itself:
+    q*cos + partner*sin_signed, evaluated op by op in the dtype, equals the reference's output bit for bit."""
+    from videosys_b200.models.transformers.open_sora_plan_v110_transformer_3d import rope_tables
+
+    M = ref_loader.load_osp_v110()
+    D, Hh, h, w, Fr = 72, 3, 5, 7, 9
+    q2 = synth.normalish("rope.q2", (2, Hh, h * w, D)).to(dtype)
+    pos2 = M.PositionGetter2D()(2, h, w, "cpu")
+    want2 = M.LinearScalingRoPE2D(scaling_factor=2)(q2, pos2)
+    yx = torch.cartesian_prod(torch.arange(h), torch.arange(w))
+    c, s, half = rope_tables(D, [yx[:, 0], yx[:, 1]], 2, dtype, "cpu")
+    assert half == 18
+
+    def apply(q, c, s, half):
+        partner = q.reshape(*q.shape[:-1], D // (2 * half), 2, half).flip(-2).reshape(q.shape)
+        return q * c.to(dtype) + partner * s.to(dtype)
+
+    assert torch.equal(apply(q2, c, s, half), want2)
+    q1 = synth.normalish("rope.q1", (4, Hh, Fr, D)).to(dtype)
+    want1 = M.LinearScalingRoPE1D(scaling_factor=2)(q1, M.PositionGetter1D()(4, Fr, "cpu"))
+    c, s, half = rope_tables(D, [torch.arange(Fr)], 2, dtype, "cpu")
+    assert half == 36 and torch.equal(apply(q1, c, s, half), want1)

@@ -38,6 +38,7 @@ SIGNATURES = {
                                 _vp]),
     "vsb_gate_residual_dsp": (_i, [_vp, C.POINTER(_vp), _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "vsb_qk_rmsnorm_rope": (_i, [_vp, _vp, _vp, _sz, _i, _i, _f, _vp, _vp, _i, _i, _vp]),
+    "vsb_qk_rope_halves": (_i, [_vp, _sz, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
     "vsb_attn_flash_strided": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _ll, _ll, _ll, C.POINTER(_i), _f,
                                    _vp]),
     "vsb_patch_embed": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _ll, _ll, _ll, _i, _i, _i, _i, _i, _vp]),
@@ -51,7 +52,7 @@ SIGNATURES = {
 
 # fp16 twins (include/vsb200.h "IEEE fp16 twins"): same signatures, suffix _f16
 F16_TWINS = ("vsb_ln_modulate", "vsb_ln_modulate_affine", "vsb_modulation_table", "vsb_gate_residual", "vsb_residual_add",
-             "vsb_qk_rmsnorm", "vsb_qk_rmsnorm_rope", "vsb_qk_layernorm", "vsb_attn_short", "vsb_gemm_bias_act",
+             "vsb_qk_rmsnorm", "vsb_qk_rmsnorm_rope", "vsb_qk_rope_halves", "vsb_qk_layernorm", "vsb_attn_short", "vsb_gemm_bias_act",
              "vsb_gemm_bias_residual", "vsb_attn_flash", "vsb_attn_flash_strided", "vsb_patch_embed")
 for _n in F16_TWINS:
     SIGNATURES[_n + "_f16"] = SIGNATURES[_n]

@@ -426,6 +426,43 @@ __global__ void __launch_bounds__(256) qk_layernorm_kernel(bf16* __restrict__ qk
   }
 }
 
+// Half-rotation RoPE ("rotate_half" inside blocks of 2*half channels of every head) on the q and k thirds of a packed
+// [rows, 3, H, D] buffer, in place: Open-Sora-Plan's RoPE1D / RoPE2D / RoPE3D
+// (open_sora_plan_v110_transformer_3d.py:136-252, open_sora_plan_v120_transformer_3d.py:63-118):
+//     out[d] = x[d] * cos[p, d] + rotate_half(x)[d] * sin[p, d],   evaluated in the 16-bit dtype op by op.
+// One thread owns two adjacent rotation pairs (d, d + half), (d + 1, d + 1 + half): it reads and writes the same four
+// elements, so the in-place update needs no ordering between threads.  The tables are fp32 copies of the 16-bit cos / sin
+// the reference computes (the sign of rotate_half folded into sin), so every product is exact in fp32 before its rounding.
+__global__ void __launch_bounds__(256) qk_rope_halves_kernel(bf16* __restrict__ qkv, unsigned items, unsigned per_vec,
+                                                             int H, int D, int half, const float* __restrict__ cosv,
+                                                             const float* __restrict__ sinv, unsigned pos_div,
+                                                             unsigned pos_mod) {
+  const unsigned per_head = (unsigned)D / 4u;      // thread slots per head (4 elements each)
+  const unsigned per_blk = (unsigned)half / 2u;    // thread slots per rotation block
+  for (unsigned it = blockIdx.x * blockDim.x + threadIdx.x; it < items; it += gridDim.x * blockDim.x) {
+    const unsigned rw = it / per_vec, j = it - rw * per_vec;  // (row, q|k), slot within the H*D vector
+    const unsigned row = rw >> 1, which = rw & 1u;
+    const unsigned h = j / per_head, q = j - h * per_head;
+    const unsigned b = q / per_blk, o2 = q - b * per_blk;
+    const unsigned d1 = b * 2u * (unsigned)half + 2u * o2, d2 = d1 + (unsigned)half;
+    bf16* base = qkv + ((size_t)row * 3 + which) * H * D + (size_t)h * D;
+    const unsigned p = (row / pos_div) % pos_mod;
+    const float* ct = cosv + (size_t)p * D;
+    const float* st = sinv + (size_t)p * D;
+    const float2 x1 = e2_to_float2(*reinterpret_cast<const elem2*>(base + d1));
+    const float2 x2 = e2_to_float2(*reinterpret_cast<const elem2*>(base + d2));
+    const float2 c1 = *reinterpret_cast<const float2*>(ct + d1), c2 = *reinterpret_cast<const float2*>(ct + d2);
+    const float2 s1 = *reinterpret_cast<const float2*>(st + d1), s2 = *reinterpret_cast<const float2*>(st + d2);
+    // first half: x1 * cos + (-x2) * sin (the table holds -sin there); second half: x2 * cos + x1 * sin
+    const float2 a1 = e2_to_float2(floats_to_e2(__fmul_rn(x1.x, c1.x), __fmul_rn(x1.y, c1.y)));
+    const float2 r1 = e2_to_float2(floats_to_e2(__fmul_rn(x2.x, s1.x), __fmul_rn(x2.y, s1.y)));
+    const float2 a2 = e2_to_float2(floats_to_e2(__fmul_rn(x2.x, c2.x), __fmul_rn(x2.y, c2.y)));
+    const float2 r2 = e2_to_float2(floats_to_e2(__fmul_rn(x1.x, s2.x), __fmul_rn(x1.y, s2.y)));
+    *reinterpret_cast<elem2*>(base + d1) = floats_to_e2(__fadd_rn(a1.x, r1.x), __fadd_rn(a1.y, r1.y));
+    *reinterpret_cast<elem2*>(base + d2) = floats_to_e2(__fadd_rn(a2.x, r2.x), __fadd_rn(a2.y, r2.y));
+  }
+}
+
 static int grid_for(long long work_items, int per_block) {
   long long blocks = (work_items + per_block - 1) / per_block;
   long long cap = (long long)num_sms() * 8;
@@ -592,6 +629,23 @@ extern "C" int VSB_API(vsb_qk_rmsnorm_rope)(vsb_bf16* qkv, const vsb_bf16* wq, c
   else
     return fail(VSB_ERR_UNSUPPORTED, "qk_rmsnorm: head_dim %d (72 or 64 only)", D);
   return check_launch("qk_rmsnorm");
+}
+
+extern "C" int VSB_API(vsb_qk_rope_halves)(vsb_bf16* qkv, size_t rows, int H, int D, int half, const float* rope_cos,
+                                           const float* rope_sin_signed, int pos_div, int pos_mod, void* stream) {
+  if (!qkv || !rope_cos || !rope_sin_signed || rows == 0 || H <= 0 || D <= 0 || pos_div <= 0 || pos_mod <= 0)
+    return fail(VSB_ERR_INVALID, "qk_rope_halves: bad args");
+  if (half <= 0 || (half & 1) || D % (2 * half) != 0)
+    return fail(VSB_ERR_UNSUPPORTED, "qk_rope_halves: head_dim %d is not a whole number of 2 x %d rotation blocks (half even)", D, half);
+  if (!aligned16(qkv) || (reinterpret_cast<uintptr_t>(rope_cos) & 7) || (reinterpret_cast<uintptr_t>(rope_sin_signed) & 7))
+    return fail(VSB_ERR_UNSUPPORTED, "qk_rope_halves: alignment");
+  const long long per_vec = (long long)H * D / 4;
+  const long long items = (long long)rows * 2 * per_vec;
+  if (items >= (1ll << 32) - (1ll << 24)) return fail(VSB_ERR_UNSUPPORTED, "qk_rope_halves: %lld thread slots", items);
+  qk_rope_halves_kernel<<<grid_for(items, 256 * 4), 256, 0, (cudaStream_t)stream>>>(
+      (bf16*)qkv, (unsigned)items, (unsigned)per_vec, H, D, half, rope_cos, rope_sin_signed, (unsigned)pos_div,
+      (unsigned)pos_mod);
+  return check_launch("qk_rope_halves");
 }
 
 extern "C" int VSB_API(vsb_qk_layernorm)(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* bq, const vsb_bf16* wk,

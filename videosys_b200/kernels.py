@@ -71,10 +71,12 @@ def _p(t):
     return None if t is None else t.data_ptr()
 
 
-def require_cuda(t, what: str = "vsb200"):
-    """The model front ends call this first: there is no CPU execution path."""
+def require_cuda(t, what: str = "vsb200", half_only: bool = False):
+    """The model front ends call this first: there is no CPU execution path (and the kernels take 16-bit activations)."""
     if not t.is_cuda:
         raise RuntimeError(f"videosys_b200 {what} runs on sm_100a CUDA devices only (no CPU path)")
+    if half_only and t.dtype not in (torch.bfloat16, torch.float16):
+        raise RuntimeError(f"videosys_b200 {what} runs in fp16 / bf16 only")
 
 
 def _bf16(t, name):
@@ -207,6 +209,17 @@ def qk_rmsnorm_(qkv, wq, wk, H, D, eps=1e-6, rope_cos=None, rope_sin=None, pos_d
     with _Timed("qk_rmsnorm", 4 * rows * H * D * 2):
         _lib.check(_fn(lib, "vsb_qk_rmsnorm_rope", qkv)(_p(qkv), _p(wq), _p(wk), rows, H, D, eps, _p(rope_cos), _p(rope_sin),
                                            int(pos_div), int(pos_mod), st), "qk_rmsnorm")
+    return qkv
+
+
+def qk_rope_halves_(qkv, rope_cos, rope_sin_signed, H, D, half, pos_div=1, pos_mod=1):
+    """In-place half-rotation RoPE of q and k (Open-Sora-Plan RoPE1D / 2D / 3D): tables [pos_mod, D] fp32, the sign of
+    rotate_half folded into the sin table; token row r uses table row (r // pos_div) % pos_mod."""
+    lib, st = _prep(qkv, rope_cos, rope_sin_signed)
+    rows = qkv.numel() // (3 * H * D)
+    with _Timed("qk_rmsnorm", 4 * rows * H * D * 2):
+        _lib.check(_fn(lib, "vsb_qk_rope_halves", qkv)(_p(qkv), rows, H, D, int(half), _p(rope_cos), _p(rope_sin_signed),
+                                                       int(pos_div), int(pos_mod), st), "qk_rope_halves")
     return qkv
 
 

@@ -97,16 +97,18 @@ class LatteBlockStack(nn.Module):
 
     @torch.no_grad()
     def forward(self, x: torch.Tensor, enc: torch.Tensor, timestep6: torch.Tensor, temp_pos_embed: Optional[torch.Tensor] = None,
-                ts_int: Optional[int] = None, all_timesteps=None, sp_group=None):
+                ts_int: Optional[int] = None, all_timesteps=None, sp_group=None, rope: Optional[dict] = None, enc_lens=None):
         """x [B, F, S, C] fp16 / bf16 (CUDA), enc [B, L, C], timestep6 [B, 6C]; returns [B, F, S, C].
         PAB (reference blocks :372-517, :700-824): ts_int = int(org_timestep[0]) on the host, all_timesteps = the
         scheduler's timestep list (python ints) for the MLP skip windows.
         sp_group: Latte's flavour of DSP (reference :734-745, :826-843): x (and temp_pos_embed) hold this rank's FRAMES;
         spatial blocks are local; a temporal block switches its modulated input to a patch shard with every frame for
-        the attention (qkv, softmax, out projection) and switches the result back (pads: comm.get_pad)."""
-        if not x.is_cuda or x.dtype not in (torch.bfloat16, torch.float16):
-            raise RuntimeError("videosys_b200 Latte blocks run on sm_100a CUDA devices in fp16 / bf16 only (no CPU path)")
+        the attention (qkv, softmax, out projection) and switches the result back (pads: comm.get_pad).
+        rope (Open-Sora-Plan v1.1.0, open_sora_plan_v110_transformer_3d.py:1217-1232): {"spatial": (cos, sin_signed, half),
+        "temporal": (...)} tables of ``vsb_qk_rope_halves`` indexed by the token's patch / frame; enc_lens: valid text tokens per
+        sample (the reference's -10000 bias on padded keys, :2440-2444)."""
         K = kernels
+        K.require_cuda(x, "Latte / Open-Sora-Plan blocks", half_only=True)
         B, Fr, S, C = x.shape
         H = self.num_heads
         D = C // H
@@ -141,6 +143,12 @@ class LatteBlockStack(nn.Module):
                         xm = xm.view(B * Ft * St, C)
                     wqkv, bqkv = blk.fused("qkv")
                     qkv = K.gemm_bias_act(xm, wqkv, bqkv)
+                    if rope is not None:
+                        rc, rs, half = rope["temporal" if blk.temporal else "spatial"]
+                        if blk.temporal:
+                            K.qk_rope_halves_(qkv, rc, rs, H, D, half, pos_div=St, pos_mod=Ft)
+                        else:
+                            K.qk_rope_halves_(qkv, rc, rs, H, D, half, pos_div=1, pos_mod=S)
                     if blk.temporal:
                         if Ft <= 32:
                             o = K.attn_short(qkv.view(-1, 3, H, D), None, None, None, None, B, St, Ft * St, 1, St, Ft, H, D, D**-0.5, flags=3)
@@ -179,7 +187,8 @@ class LatteBlockStack(nn.Module):
                         q = K.gemm_bias_act(xf, a2.to_q.weight, a2.to_q.bias)
                         wkv, bkv = blk.fused("kv")
                         kv = K.gemm_bias_act(enc2, wkv, bkv).view(-1, 2, C)
-                        o = K.attn_flash(q, kv[:, 0], kv[:, 1], B, Fr * S, L, H, D, C, Fr * S * C, 2 * C, L * 2 * C, D**-0.5)
+                        o = K.attn_flash(q, kv[:, 0], kv[:, 1], B, Fr * S, L, H, D, C, Fr * S * C, 2 * C, L * 2 * C, D**-0.5,
+                                         kv_lens=enc_lens)
                         out = blk.last_cross if (pab_on and blk.last_cross is not None and blk.last_cross.shape == xf.shape) else None
                         xc = K.gemm_bias_act(o, a2.to_out[0].weight, a2.to_out[0].bias, out=out)
                         if pab_on:
