@@ -1,19 +1,21 @@
 """TEST INFRASTRUCTURE ONLY -- CPU/torch restatement of the CogVideoX transformer block (block level).
 
-PARITY PARTLY PINNED: ``CogVideoXLayerNormZero`` (models/modules/normalization.py:36-57) is in the reference tree and is
-executed as-is by tests/test_oracle_vs_reference.py::test_cogvideox_layernorm_zero.  The attention processor
-(models/transformers/cogvideox_transformer_3d.py:88-175) is in-tree but drives a ``diffusers==0.30.0`` ``Attention``
-object (requirements.txt:25, not installed here), and the feed-forward is diffusers' ``FeedForward``; both are restated
-from their published semantics as the reference configures them (cogvideox_transformer_3d.py:237-261):
-  * ``Attention(query_dim, heads, dim_head, qk_norm="layer_norm", eps=1e-6, bias=attention_bias, out_bias=True)``:
-    to_q/to_k/to_v Linears, ``norm_q``/``norm_k`` = nn.LayerNorm(dim_head, eps=1e-6) (affine), to_out[0] Linear;
-  * ``FeedForward(dim, activation_fn="gelu-approximate", final_dropout=True, bias=True)``: Linear -> tanh-GELU -> Linear.
-Those two are PARITY UNPINNED.  2B configuration: no rotary embedding (use_rotary_positional_embeddings False), sp = 1.
+PINNED against the reference's own CogVideoXTransformer3DModel, executed unmodified (tests/test_oracle_vs_reference.py::
+test_cogvideox_oracle_vs_reference_model: fp32 within summation order, bf16 and fp16 bit for bit; also
+test_cogvideox_layernorm_zero and the DDIM scheduler test).  ``diffusers==0.30.0`` (requirements.txt:25) is not installed
+here; oracle/ref_loader.load_cogvideox supplies the leaf classes the reference file imports from it:
+  * ``Attention(query_dim, heads, dim_head, qk_norm="layer_norm", eps=1e-6, bias, out_bias)`` = the reference's own vendored
+    copy (VchitectAttention, models/modules/attentions.py:321-638: to_q/to_k/to_v Linears, ``norm_q``/``norm_k`` =
+    nn.LayerNorm(dim_head, eps=1e-6), to_out[0]), driven by the in-tree CogVideoXAttnProcessor2_0 (:88-175);
+  * ``FeedForward(dim, activation_fn="gelu-approximate", final_dropout=True, bias=True)`` = the vendored copy in
+    open_sora_plan_v110_transformer_3d.py:1312-1367 (Linear -> tanh-GELU -> Linear);
+  * ``Timesteps`` / ``TimestepEmbedding`` / GELU restated there (a few lines each);
+  * ``get_3d_sincos_pos_embed`` = ``sincos_3d`` below: the one piece of this model that stays PARITY UNPINNED (restated from
+    the library's published semantics; no copy of it exists in the reference tree).
+2B configuration: no rotary embedding (use_rotary_positional_embeddings False), sp = 1.
 
-``transformer_forward`` restates CogVideoXTransformer3DModel.forward (:479-589) around the block: the in-tree pieces
-(CogVideoXPatchEmbed models/modules/embeddings.py:14-51, AdaLayerNorm normalization.py:60-114, unpatchify :578-581) as
-written, the diffusers pieces (``Timesteps`` / ``TimestepEmbedding`` / ``get_3d_sincos_pos_embed``, diffusers==0.30.0)
-from their published semantics: PARITY UNPINNED for those three.
+``transformer_forward`` restates CogVideoXTransformer3DModel.forward (:479-589) around the block: CogVideoXPatchEmbed
+(models/modules/embeddings.py:14-51), AdaLayerNorm (normalization.py:60-114), unpatchify (:578-581).
 """
 import math
 from typing import Dict

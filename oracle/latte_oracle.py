@@ -1,11 +1,13 @@
 """TEST INFRASTRUCTURE ONLY -- CPU/torch restatement of the Latte transformer blocks (block level).
 
-PARITY UNPINNED: Latte's blocks lean on ``diffusers==0.30.0`` (``Attention`` + ``AttnProcessor2_0``, ``GELU``;
-requirements.txt:25), which is not installed in this image and not vendored in /root/reference, so the reference
-modules cannot be executed here.  This file restates the in-tree block code
+PINNED against the reference's own LatteT2V, executed unmodified (tests/test_oracle_vs_reference.py::
+test_latte_oracle_vs_reference_model: fp32 within summation order, bf16 bit for bit).  ``diffusers==0.30.0`` (requirements.txt:25)
+is not installed here, so the reference file's diffusers LEAF classes are supplied by oracle/ref_loader.load_latte from the
+reference's own vendored copies in open_sora_plan_v110_transformer_3d.py (Attention + AttnProcessor2_0, PatchEmbed,
+CombinedTimestepSizeEmbeddings, CaptionProjection, get_1d_sincos_pos_embed_from_grid) plus three restated ones (GELU,
+Timesteps, TimestepEmbedding: published semantics, a few lines each).  This file restates the in-tree block code
 (models/transformers/latte_transformer_3d.py:357-517 spatial ``BasicTransformerBlock``, :680-824 temporal
-``BasicTransformerBlock_``, local ``FeedForward`` :92-148, block loop :1312-1425) plus the published semantics of the
-two diffusers classes as the reference uses them:
+``BasicTransformerBlock_``, local ``FeedForward`` :92-148, block loop :1312-1425) and those leaves:
   * ``Attention(query_dim, heads, dim_head, bias=True, cross_attention_dim)`` with the default processor:
     to_q / to_k / to_v Linears, heads split, F.scaled_dot_product_attention (no mask: the Latte pipeline never passes
     one, pipeline_latte.py:854-862), to_out[0] Linear, dropout 0, rescale_output_factor 1;
@@ -15,7 +17,7 @@ Configuration: norm_type "ada_norm_single", norm_elementwise_affine False, eps 1
 ``transformer_forward`` restates LatteT2V.forward around the block loop (:1144-1466): the in-tree glue (rearranges, output
 head :1436-1443, unpatchify :1446-1456, temp_pos_embed :1468-1470) as written, the diffusers pieces (``PatchEmbed`` with
 its 2-D sincos table, ``AdaLayerNormSingle`` -> ``PixArtAlphaCombinedTimestepSizeEmbeddings`` -> ``Timesteps`` /
-``TimestepEmbedding``, ``PixArtAlphaTextProjection``) from their published semantics: PARITY UNPINNED.
+``TimestepEmbedding``, ``PixArtAlphaTextProjection``) from their published semantics; the whole forward is pinned as above.
 """
 import math
 from typing import Dict, Optional

@@ -192,8 +192,9 @@ class _RefTimesteps(nn.Module):
 class _RefTimestepEmbedding(nn.Module):
     """diffusers TimestepEmbedding(in_channels, time_embed_dim): linear_1 -> SiLU -> linear_2."""
 
-    def __init__(self, in_channels, time_embed_dim, **_):
+    def __init__(self, in_channels, time_embed_dim, act_fn="silu", **_):
         super().__init__()
+        assert act_fn == "silu"
         self.linear_1 = nn.Linear(in_channels, time_embed_dim)
         self.act = nn.SiLU()
         self.linear_2 = nn.Linear(time_embed_dim, time_embed_dim)
@@ -254,6 +255,218 @@ def load_osp_v110():
 def build_osp_v110(dtype=torch.float32, **cfg):
     M = load_osp_v110()
     net = M.LatteT2V(**cfg).eval().to(dtype)
+    net.parallel_manager = SingleRankPM()
+    for mod in net.modules():
+        if hasattr(mod, "parallel_manager"):
+            mod.parallel_manager = SingleRankPM()
+    return net
+
+
+def load_latte():
+    """The reference's models/transformers/latte_transformer_3d.py, imported unmodified.  Its diffusers leaf classes are
+    taken from the REFERENCE'S OWN vendored copies in open_sora_plan_v110_transformer_3d.py (same authors, same semantics:
+    Attention + AttnProcessor2_0 with RoPE off, PatchEmbed, CombinedTimestepSizeEmbeddings, CaptionProjection,
+    get_1d_sincos_pos_embed_from_grid) plus the three restated leaves of load_osp_v110 (GELU, Timesteps, TimestepEmbedding)."""
+    if "latte" in _LOADED:
+        return _LOADED["latte"]
+    O = load_osp_v110()
+
+    class Attention(O.Attention):  # diffusers' constructor signature -> the vendored class (RoPE / KV compression off)
+        def __init__(self, query_dim, cross_attention_dim=None, heads=8, dim_head=64, dropout=0.0, bias=False,
+                     upcast_attention=False, out_bias=True, **kw):
+            super().__init__(query_dim=query_dim, cross_attention_dim=cross_attention_dim, heads=heads, dim_head=dim_head,
+                             dropout=dropout, bias=bias, upcast_attention=upcast_attention, out_bias=out_bias,
+                             attention_mode="math", use_rope=False, rope_scaling=None, compress_kv_factor=None, **kw)
+
+    class PixArtAlphaTextProjection(O.CaptionProjection):  # the diffusers class has no y_embedding buffer
+        def __init__(self, in_features, hidden_size, **kw):
+            super().__init__(in_features, hidden_size)
+            del self._buffers["y_embedding"]
+
+    ph = lambda name: type(name, (nn.Module,), {})  # noqa: E731
+    sys.modules["diffusers.models.attention_processor"].Attention = Attention
+    emb = sys.modules["diffusers.models.embeddings"]
+    emb.ImagePositionalEmbeddings = ph("ImagePositionalEmbeddings")
+    emb.PatchEmbed = O.PatchEmbed
+    emb.PixArtAlphaCombinedTimestepSizeEmbeddings = O.CombinedTimestepSizeEmbeddings
+    emb.PixArtAlphaTextProjection = PixArtAlphaTextProjection
+    emb.get_1d_sincos_pos_embed_from_grid = O.get_1d_sincos_pos_embed_from_grid
+    sys.modules["diffusers.models.normalization"].AdaLayerNormContinuous = ph("AdaLayerNormContinuous")
+    m = importlib.import_module("videosys.models.transformers.latte_transformer_3d")
+    _LOADED["latte"] = m
+    return m
+
+
+def build_latte(dtype=torch.float32, **cfg):
+    M = load_latte()
+    net = M.LatteT2V(**cfg).eval().to(dtype)
+    net.parallel_manager = SingleRankPM()
+    for mod in net.modules():
+        if hasattr(mod, "parallel_manager"):
+            mod.parallel_manager = SingleRankPM()
+    return net
+
+
+def load_cogvideox():
+    """The reference's models/transformers/cogvideox_transformer_3d.py (+ its in-tree CogVideoXPatchEmbed,
+    CogVideoXLayerNormZero, AdaLayerNorm, CogVideoXAttnProcessor2_0), imported unmodified.  diffusers leaves:
+    ``Attention`` = the reference's own vendored copy (VchitectAttention, models/modules/attentions.py:321-638: same
+    to_q / to_k / to_v / norm_q / norm_k (qk_norm="layer_norm") / to_out members; its forward handed to the CogVideoX
+    processor), ``FeedForward`` = the vendored copy in open_sora_plan_v110_transformer_3d.py:1312-1367, Timesteps /
+    TimestepEmbedding restated (load_osp_v110), ``get_3d_sincos_pos_embed`` restated (oracle/cogvideox_oracle.sincos_3d:
+    the one leaf of this model that stays unpinned)."""
+    if "cogvideox" in _LOADED:
+        return _LOADED["cogvideox"]
+    O = load_osp_v110()
+    A = load().attentions
+    from . import cogvideox_oracle as CO
+
+    class Attention(A.VchitectAttention):
+        def __init__(self, query_dim, dim_head=64, heads=8, qk_norm=None, eps=1e-5, bias=False, out_bias=True, processor=None, **kw):
+            super().__init__(query_dim=query_dim, dim_head=dim_head, heads=heads, qk_norm=qk_norm, eps=eps, bias=bias,
+                             out_bias=out_bias, processor=processor, **kw)
+
+        def forward(self, hidden_states, encoder_hidden_states=None, attention_mask=None, **kw):
+            return self.processor(self, hidden_states, encoder_hidden_states=encoder_hidden_states,
+                                  attention_mask=attention_mask, **kw)
+
+    class FeedForward(O.FeedForward):
+        def __init__(self, dim, dropout=0.0, activation_fn="geglu", final_dropout=False, inner_dim=None, bias=True, **kw):
+            assert inner_dim is None and bias, "the vendored copy is the 4x / bias-on configuration"
+            super().__init__(dim, dropout=dropout, activation_fn=activation_fn, final_dropout=final_dropout)
+
+    def get_3d_sincos_pos_embed(embed_dim, spatial_size, temporal_size, spatial_interpolation_scale=1.0,
+                                temporal_interpolation_scale=1.0):
+        return CO.sincos_3d(embed_dim, spatial_size, temporal_size, spatial_interpolation_scale,
+                            temporal_interpolation_scale).numpy()
+
+    class Transformer2DModelOutput:
+        def __init__(self, sample):
+            self.sample = sample
+
+    _mod("diffusers.models.attention", Attention=Attention, FeedForward=FeedForward)
+    emb = sys.modules["diffusers.models.embeddings"]
+    emb.get_3d_sincos_pos_embed = get_3d_sincos_pos_embed
+    _mod("diffusers.models.modeling_outputs", Transformer2DModelOutput=Transformer2DModelOutput)
+    sys.modules["diffusers.utils"].is_torch_version = lambda *a, **k: True
+    m = importlib.import_module("videosys.models.transformers.cogvideox_transformer_3d")
+    _LOADED["cogvideox"] = m
+    return m
+
+
+def build_cogvideox(dtype=torch.float32, **cfg):
+    M = load_cogvideox()
+    net = M.CogVideoXTransformer3DModel(**cfg).eval().to(dtype)
+    net.parallel_manager = SingleRankPM()
+    for mod in net.modules():
+        if hasattr(mod, "parallel_manager"):
+            mod.parallel_manager = SingleRankPM()
+    return net
+
+
+# ---- Vchitect: the reference transformer file imported unmodified; five diffusers leaves restated here ------------------------
+class _RefAdaLayerNormZero(nn.Module):
+    """diffusers AdaLayerNormZero(embedding_dim) without class embedding: linear(silu(emb)) -> 6 chunks; LayerNorm 1e-6, no affine."""
+
+    def __init__(self, embedding_dim, num_embeddings=None):
+        super().__init__()
+        self.silu = nn.SiLU()
+        self.linear = nn.Linear(embedding_dim, 6 * embedding_dim, bias=True)
+        self.norm = nn.LayerNorm(embedding_dim, elementwise_affine=False, eps=1e-6)
+
+    def forward(self, x, timestep=None, class_labels=None, hidden_dtype=None, emb=None):
+        emb = self.linear(self.silu(emb))
+        shift_msa, scale_msa, gate_msa, shift_mlp, scale_mlp, gate_mlp = emb.chunk(6, dim=1)
+        x = self.norm(x) * (1 + scale_msa[:, None]) + shift_msa[:, None]
+        return x, gate_msa, shift_mlp, scale_mlp, gate_mlp
+
+
+class _RefAdaLayerNormContinuous(nn.Module):
+    """diffusers AdaLayerNormContinuous(dim, cond_dim, elementwise_affine, eps, bias, norm_type='layer_norm'): scale, shift."""
+
+    def __init__(self, embedding_dim, conditioning_embedding_dim, elementwise_affine=True, eps=1e-5, bias=True, norm_type="layer_norm"):
+        super().__init__()
+        self.silu = nn.SiLU()
+        self.linear = nn.Linear(conditioning_embedding_dim, embedding_dim * 2, bias=bias)
+        self.norm = nn.LayerNorm(embedding_dim, eps, elementwise_affine, bias)
+
+    def forward(self, x, conditioning_embedding):
+        emb = self.linear(self.silu(conditioning_embedding).to(x.dtype))
+        scale, shift = torch.chunk(emb, 2, dim=1)
+        return self.norm(x) * (1 + scale)[:, None, :] + shift[:, None, :]
+
+
+class _RefCombinedTimestepTextProj(nn.Module):
+    """diffusers CombinedTimestepTextProjEmbeddings(embedding_dim, pooled_projection_dim)."""
+
+    def __init__(self, embedding_dim, pooled_projection_dim):
+        super().__init__()
+        self.time_proj = _RefTimesteps(num_channels=256, flip_sin_to_cos=True, downscale_freq_shift=0)
+        self.timestep_embedder = _RefTimestepEmbedding(in_channels=256, time_embed_dim=embedding_dim)
+        self.text_embedder = _RefTimestepEmbedding(pooled_projection_dim, embedding_dim)  # PixArtAlphaTextProjection(act_fn="silu")
+
+    def forward(self, timestep, pooled_projection):
+        timesteps_emb = self.timestep_embedder(self.time_proj(timestep).to(dtype=pooled_projection.dtype))
+        return timesteps_emb + self.text_embedder(pooled_projection)
+
+
+class _RefPatchEmbedSD3(nn.Module):
+    """diffusers PatchEmbed with pos_embed_max_size (SD3): conv, flatten, + the centre crop of a max-size sin-cos table."""
+
+    def __init__(self, height=224, width=224, patch_size=16, in_channels=3, embed_dim=768, pos_embed_max_size=None, **_):
+        super().__init__()
+        import numpy as np
+
+        self.proj = nn.Conv2d(in_channels, embed_dim, kernel_size=(patch_size, patch_size), stride=patch_size, bias=True)
+        self.patch_size, self.pos_embed_max_size = patch_size, pos_embed_max_size
+        base = height // patch_size
+        g = np.arange(pos_embed_max_size, dtype=np.float32) / (pos_embed_max_size / base)
+        grid = np.stack(np.meshgrid(g, g), axis=0).reshape([2, 1, pos_embed_max_size, pos_embed_max_size])
+
+        def one(dim, pos):
+            omega = 1.0 / 10000 ** (np.arange(dim // 2, dtype=np.float64) / (dim / 2.0))
+            out = np.einsum("m,d->md", pos.reshape(-1), omega)
+            return np.concatenate([np.sin(out), np.cos(out)], axis=1)
+
+        pe = np.concatenate([one(embed_dim // 2, grid[0]), one(embed_dim // 2, grid[1])], axis=1)
+        self.register_buffer("pos_embed", torch.from_numpy(pe).float().unsqueeze(0), persistent=True)
+
+    def forward(self, latent):
+        h, w = latent.shape[-2] // self.patch_size, latent.shape[-1] // self.patch_size
+        latent = self.proj(latent).flatten(2).transpose(1, 2)
+        m = self.pos_embed_max_size
+        top, left = (m - h) // 2, (m - w) // 2
+        pe = self.pos_embed.reshape(1, m, m, -1)[:, top : top + h, left : left + w, :].reshape(1, -1, self.pos_embed.shape[-1])
+        return (latent + pe).to(latent.dtype)
+
+
+def load_vchitect():
+    """models/transformers/vchitect_transformer_3d.py imported unmodified (JointTransformerBlock, FeedForward,
+    VchitectXLTransformerModel incl. precompute_freqs_cis and forward) on top of the reference's own VchitectAttention +
+    processor; the five diffusers leaf classes above are restated from their published semantics."""
+    if "vchitect" in _LOADED:
+        return _LOADED["vchitect"]
+    load_osp_v110()  # shared stubs
+    ph = lambda name: type(name, (), {})  # noqa: E731
+    _mod("diffusers.loaders", FromOriginalModelMixin=ph("FromOriginalModelMixin"), PeftAdapterMixin=ph("PeftAdapterMixin"))
+    emb = sys.modules["diffusers.models.embeddings"]
+    emb.CombinedTimestepTextProjEmbeddings = _RefCombinedTimestepTextProj
+    emb.PatchEmbed = _RefPatchEmbedSD3
+    norm = sys.modules["diffusers.models.normalization"]
+    norm.AdaLayerNormContinuous = _RefAdaLayerNormContinuous
+    norm.AdaLayerNormZero = _RefAdaLayerNormZero
+    _mod("diffusers.models.transformers")
+    _mod("diffusers.models.transformers.transformer_2d",
+         Transformer2DModelOutput=type("Transformer2DModelOutput", (), {"__init__": lambda s, sample: setattr(s, "sample", sample)}))
+    sys.modules["diffusers.utils"].unscale_lora_layers = lambda *a, **k: None
+    m = importlib.import_module("videosys.models.transformers.vchitect_transformer_3d")
+    _LOADED["vchitect"] = m
+    return m
+
+
+def build_vchitect(dtype=torch.float32, **cfg):
+    M = load_vchitect()
+    net = M.VchitectXLTransformerModel(**cfg).eval().to(dtype)
     net.parallel_manager = SingleRankPM()
     for mod in net.modules():
         if hasattr(mod, "parallel_manager"):

@@ -386,3 +386,251 @@ def test_osp_v110_rope_tables_vs_reference_classes(dtype):
     want1 = M.LinearScalingRoPE1D(scaling_factor=2)(q1, M.PositionGetter1D()(4, Fr, "cpu"))
     c, s, half = rope_tables(D, [torch.arange(Fr)], 2, dtype, "cpu")
     assert half == 36 and torch.equal(apply(q1, c, s, half), want1)
+
+
+# ---- Latte: oracle and product host logic against the UNMODIFIED reference model ---------------------------------------------
+LATTE_SMALL = dict(num_attention_heads=2, attention_head_dim=72, in_channels=4, out_channels=8, num_layers=2,
+                   cross_attention_dim=144, attention_bias=True, sample_size=8, patch_size=2, activation_fn="gelu-approximate",
+                   norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6, caption_channels=32, video_length=6)
+LATTE_SMALL_O = dict(heads=2, head_dim=72, layers=2, patch=2, sample_size=8, out_channels=8, video_length=6)
+
+
+def _latte_ref(dtype=torch.float32, tag="lattep."):
+    ref = ref_loader.build_latte(dtype=dtype, **LATTE_SMALL)
+    sd = synth.fill_state_dict({k: v.float() for k, v in ref.state_dict().items()}, tag)
+    sd = {k: v.to(dtype) for k, v in sd.items()}
+    ref.load_state_dict(sd)
+    return ref, sd
+
+
+def _latte_call(ref, x, t, enc, all_ts=(900, 500)):
+    return ref(x, timestep=t, all_timesteps=torch.tensor(list(all_ts)), encoder_hidden_states=enc,
+               added_cond_kwargs={"resolution": None, "aspect_ratio": None}, enable_temporal_attentions=True,
+               return_dict=False)[0]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_latte_oracle_vs_reference_model(dtype):
+    """oracle/latte_oracle.transformer_forward against the reference's own LatteT2V (models/transformers/
+    latte_transformer_3d.py, executed unmodified; its diffusers leaves = the reference's vendored copies, ref_loader.load_latte):
+    the whole forward -- PatchEmbed + 2-D sin-cos table, AdaLayerNormSingle, caption projection, both block kinds,
+    temp_pos_embed, output head, un-patchify.  fp32: equal up to summation order; bf16: bit for bit."""
+    from oracle import latte_oracle as LO
+
+    ref, sd = _latte_ref(dtype)
+    x = synth.normalish("lattep.x", (2, 4, 6, 8, 8)).to(dtype)
+    enc = synth.normalish("lattep.enc", (2, 7, 32)).to(dtype)
+    t = torch.tensor([500, 500])
+    with torch.no_grad():
+        want = _latte_call(ref, x, t, enc)
+        got = LO.transformer_forward(sd, LATTE_SMALL_O, x, t, enc)
+    assert got.shape == want.shape
+    if dtype == torch.float32:
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+    else:
+        print(f"[pin] latte oracle bf16 vs reference bf16: bit-equal {(got == want).float().mean().item()*100:.1f} %")
+        assert torch.equal(got, want)
+
+
+def test_latte_mirror_vs_reference_model(monkeypatch):
+    """videosys_b200's LatteT2V (kernel entries = torch stand-ins) against the reference model, fp32, incl. 8 PAB steps with the
+    MLP skip on both sides."""
+    from tests import kernels_emul
+    from videosys_b200.core.pab import pab_mgr as ours
+    from videosys_b200.models.transformers.latte_transformer_3d import LatteT2V
+
+    kernels_emul.emulate(monkeypatch)
+    ref, sd = _latte_ref()
+    net = LatteT2V(**LATTE_SMALL)
+    net.load_state_dict(sd)
+    net.eval()
+    x = synth.normalish("lattep.x", (2, 4, 6, 8, 8))
+    enc = synth.normalish("lattep.enc", (2, 7, 32))
+    t = torch.tensor([500, 500])
+    with torch.no_grad():
+        want = _latte_call(ref, x, t, enc)
+    got = net(x, timestep=t, all_timesteps=[900, 500], encoder_hidden_states=enc, return_dict=False)[0]
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+    P = ref_loader.load().pab_mgr
+    ts = [900, 700, 650, 600, 550, 500, 450, 50]
+    mlp = {700: {"block": [0, 1], "skip_count": 2}, 550: {"block": [1], "skip_count": 1}}
+    kw = dict(spatial_broadcast=True, spatial_threshold=[100, 800], spatial_range=2, temporal_broadcast=True,
+              temporal_threshold=[100, 800], temporal_range=3, cross_broadcast=True, cross_threshold=[100, 800], cross_range=6,
+              mlp_broadcast=True, mlp_spatial_broadcast_config=mlp, mlp_temporal_broadcast_config=mlp)
+    P.set_pab_manager(P.PABConfig(**kw))
+    P.update_steps(len(ts))
+    ours.set_pab_manager(ours.PABConfig(**kw))
+    ours.update_steps(len(ts))
+    net.reset_pab_state()
+    try:
+        for step, tv in enumerate(ts):
+            x = synth.normalish(f"lattep.x{step}", (2, 4, 6, 8, 8))
+            tt = torch.tensor([tv, tv])
+            with torch.no_grad():
+                want = _latte_call(ref, x, tt, enc, ts)
+            got = net(x, timestep=tt, all_timesteps=ts, encoder_hidden_states=enc, return_dict=False)[0]
+            assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (step, (got - want).abs().max())
+    finally:
+        P.PAB_MANAGER = None
+        ours.set_pab_manager(None)
+
+
+# ---- CogVideoX: oracle and product host logic against the UNMODIFIED reference model ------------------------------------------
+COGX_SMALL = dict(num_attention_heads=4, attention_head_dim=64, in_channels=4, out_channels=4, time_embed_dim=64, text_embed_dim=48,
+                  num_layers=2, sample_width=16, sample_height=12, sample_frames=9, max_text_seq_length=16)
+COGX_SMALL_O = dict(heads=4, head_dim=64, layers=2, patch=2, max_text=16, sample_width=16, sample_height=12, sample_frames=9,
+                    out_channels=4)
+
+
+def _cogx_ref(dtype=torch.float32, tag="cogxp."):
+    ref = ref_loader.build_cogvideox(dtype=dtype, **COGX_SMALL)
+    sd = synth.fill_state_dict({k: v.float() for k, v in ref.state_dict().items()}, tag)
+    for k in sd:  # LayerNorm weights around 1 (fill_state_dict treats them as matrices)
+        if k.endswith("norm.weight") or k.endswith("norm_final.weight") or k.endswith("norm_q.weight") or k.endswith("norm_k.weight"):
+            sd[k] = 1.0 + 0.2 * synth.uniform(tag + k, tuple(sd[k].shape))
+    sd = {k: v.to(dtype) for k, v in sd.items()}
+    ref.load_state_dict(sd)
+    return ref, sd
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+def test_cogvideox_oracle_vs_reference_model(dtype):
+    """oracle/cogvideox_oracle.transformer_forward against the reference's own CogVideoXTransformer3DModel (executed
+    unmodified; diffusers Attention / FeedForward = the reference's vendored copies, ref_loader.load_cogvideox): patch / text
+    embedding, position table, LayerNormZero blocks with the joint-attention processor, norm_final + AdaLayerNorm head,
+    un-patchify."""
+    from oracle import cogvideox_oracle as CO
+
+    ref, sd = _cogx_ref(dtype)
+    lat = synth.normalish("cogxp.lat", (2, 3, 4, 12, 16)).to(dtype)
+    txt = synth.normalish("cogxp.txt", (2, 16, 48)).to(dtype)
+    ts = torch.tensor([499, 499])
+    with torch.no_grad():
+        want = ref(lat, txt, ts, return_dict=False)[0]
+        got = CO.transformer_forward(sd, COGX_SMALL_O, lat, txt, ts)
+    assert got.shape == want.shape
+    if dtype == torch.float32:
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+    else:
+        print(f"[pin] cogvideox oracle {dtype} vs reference: bit-equal {(got == want).float().mean().item()*100:.1f} %")
+        assert torch.equal(got, want)
+
+
+def test_cogvideox_mirror_vs_reference_model(monkeypatch):
+    """videosys_b200's CogVideoXTransformer3DModel (kernel entries = torch stand-ins) against the reference model, fp32, plain
+    and over 8 PAB steps."""
+    from tests import kernels_emul
+    from videosys_b200.core.pab import pab_mgr as ours
+    from videosys_b200.models.transformers.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+
+    kernels_emul.emulate(monkeypatch)
+    ref, sd = _cogx_ref()
+    net = CogVideoXTransformer3DModel(**COGX_SMALL)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not missing and all(".attn1.to_" in k and ("_temp" in k or "_cross" in k or "_context" in k or "temporal" in k)
+                               for k in unexpected), (missing, unexpected)  # the vendored Attention's Vchitect-only members
+    net.eval()
+    lat = synth.normalish("cogxp.lat", (2, 3, 4, 12, 16))
+    txt = synth.normalish("cogxp.txt", (2, 16, 48))
+    ts = torch.tensor([499, 499])
+    with torch.no_grad():
+        want = ref(lat, txt, ts, return_dict=False)[0]
+    got = net(lat, txt, ts, return_dict=False)[0]
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+    P = ref_loader.load().pab_mgr
+    kw = dict(spatial_broadcast=True, spatial_threshold=[100, 850], spatial_range=2)
+    steps = [900, 700, 650, 600, 550, 500, 450, 50]
+    P.set_pab_manager(P.PABConfig(**kw))
+    P.update_steps(len(steps))
+    ours.set_pab_manager(ours.PABConfig(**kw))
+    ours.update_steps(len(steps))
+    net.reset_pab_state()
+    try:
+        for step, tv in enumerate(steps):
+            lat = synth.normalish(f"cogxp.lat{step}", (2, 3, 4, 12, 16))
+            tt = torch.tensor([tv, tv])
+            with torch.no_grad():
+                want = ref(lat, txt, tt, return_dict=False)[0]
+            got = net(lat, txt, tt, return_dict=False)[0]
+            assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (step, (got - want).abs().max())
+    finally:
+        P.PAB_MANAGER = None
+        ours.set_pab_manager(None)
+
+
+# ---- Vchitect: oracle and product host logic against the UNMODIFIED reference transformer ---------------------------------------
+VCH_SMALL = dict(sample_size=8, patch_size=2, in_channels=4, num_layers=3, attention_head_dim=64, num_attention_heads=2,
+                 joint_attention_dim=48, caption_projection_dim=128, pooled_projection_dim=40, out_channels=4, pos_embed_max_size=12)
+VCH_SMALL_O = dict(heads=2, head_dim=64, layers=3, patch=2, sample_size=8, pos_embed_max_size=12, out_channels=4)
+
+
+def _vch_ref(dtype=torch.float32, tag="vchm."):
+    ref = ref_loader.build_vchitect(dtype=dtype, **VCH_SMALL)
+    sd0 = {k: v.float() for k, v in ref.state_dict().items()}
+    sd = synth.fill_state_dict(sd0, tag)
+    sd["pos_embed.pos_embed"] = sd0["pos_embed.pos_embed"]  # the sin-cos table is not a weight
+    sd = {k: v.to(dtype) for k, v in sd.items()}
+    ref.load_state_dict(sd)
+    return ref, sd
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Fr", [5, 1])
+def test_vchitect_oracle_vs_reference_model(Fr, dtype):
+    """oracle/vchitect_oracle.transformer_forward against the reference's VchitectXLTransformerModel (vchitect_transformer_3d.py
+    executed unmodified on the reference's VchitectAttention; five diffusers leaf classes restated in oracle/ref_loader.py):
+    per-frame text broadcast in the first block, context_pre_only last block, the three attentions, norm_out, un-patchify."""
+    from oracle import vchitect_oracle as VO
+
+    ref, sd = _vch_ref(dtype)
+    lat = synth.normalish("vchm.lat", (1, Fr, 4, 12, 16)).to(dtype)
+    enc = synth.normalish("vchm.enc", (1, 9, 48)).to(dtype)
+    pooled = synth.normalish("vchm.pool", (1, 40)).to(dtype)
+    ts = torch.tensor([500.0])
+    with torch.no_grad():
+        want = ref(lat, encoder_hidden_states=enc, pooled_projections=pooled, timestep=ts, return_dict=False)[0]
+        got = VO.transformer_forward(sd, VCH_SMALL_O, lat, enc, pooled, ts)
+    assert got.shape == want.shape
+    if dtype == torch.float32:
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+    else:
+        print(f"[pin] vchitect oracle bf16 vs reference: bit-equal {(got == want).float().mean().item()*100:.1f} %")
+        assert torch.equal(got, want)
+
+
+def test_vchitect_mirror_vs_reference_model(monkeypatch):
+    """videosys_b200's VchitectXLTransformerModel (kernel entries = torch stand-ins) against the reference model: strict
+    state-dict compatibility, fp32 forward, and 8 steps with the three PAB gates on both sides."""
+    from tests import kernels_emul
+    from videosys_b200.core.pab import pab_mgr as ours
+    from videosys_b200.models.transformers.vchitect_transformer_3d import VchitectXLTransformerModel
+
+    kernels_emul.emulate(monkeypatch)
+    ref, sd = _vch_ref()
+    net = VchitectXLTransformerModel(**VCH_SMALL)
+    net.load_state_dict(sd)  # strict
+    net.eval()
+    enc = synth.normalish("vchm.enc", (1, 9, 48))
+    pooled = synth.normalish("vchm.pool", (1, 40))
+    P = ref_loader.load().pab_mgr
+    kw = dict(spatial_broadcast=True, spatial_threshold=[100, 800], spatial_range=2, temporal_broadcast=True,
+              temporal_threshold=[100, 800], temporal_range=3, cross_broadcast=True, cross_threshold=[100, 800], cross_range=4)
+    for pab in (False, True):
+        steps = [900, 700, 650, 600, 550, 500, 450, 50] if pab else [500]
+        if pab:
+            P.set_pab_manager(P.PABConfig(**kw))
+            P.update_steps(len(steps))
+            ours.set_pab_manager(ours.PABConfig(**kw))
+            ours.update_steps(len(steps))
+            net.reset_pab_state()
+        try:
+            for step, tv in enumerate(steps):
+                lat = synth.normalish(f"vchm.lat{step}", (1, 4, 4, 12, 16))
+                ts = torch.tensor([float(tv)])
+                with torch.no_grad():
+                    want = ref(lat, encoder_hidden_states=enc, pooled_projections=pooled, timestep=ts, return_dict=False)[0]
+                got = net(lat, enc, pooled, ts, return_dict=False)[0]
+                assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (pab, step, (got - want).abs().max())
+        finally:
+            P.PAB_MANAGER = None
+            ours.set_pab_manager(None)

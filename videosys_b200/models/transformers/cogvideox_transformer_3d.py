@@ -120,9 +120,8 @@ class CogVideoXBlockStack(nn.Module):
         ``n_video`` the unpadded global row count.  Everything but the attention core is row-wise and runs on the local
         rows; the joint attention runs on H / sp heads over every row after the head-scatter exchange (reference
         :112-122, :138-143, :162-165), pad rows excluded as keys (:58-62) and zero in the output (:66-72)."""
-        if not hidden.is_cuda or hidden.dtype not in (torch.bfloat16, torch.float16):
-            raise RuntimeError("videosys_b200 CogVideoX blocks run on sm_100a CUDA devices in fp16 / bf16 only (no CPU path)")
         K = kernels
+        K.require_cuda(hidden, "CogVideoX blocks", half_only=True)
         B, Nv, C = hidden.shape
         Nt = enc.shape[1]
         N = Nt + Nv
@@ -294,9 +293,8 @@ class CogVideoXTransformer3DModel(nn.Module):
     def forward(self, hidden_states, encoder_hidden_states, timestep, timestep_cond=None, image_rotary_emb=None,
                 return_dict=True, ts_int=None):
         """hidden_states [B, F, C, H, W] latents, encoder_hidden_states [B, 226, 4096], timestep [B]."""
-        if not hidden_states.is_cuda:
-            raise RuntimeError("videosys_b200 CogVideoX runs on sm_100a CUDA devices only (no CPU path)")
         K = kernels
+        K.require_cuda(hidden_states, "CogVideoX")
         dt = self.proj_out.weight.dtype
         pm = self.parallel_manager
         cp = pm is not None and pm.cp_size > 1

@@ -329,8 +329,7 @@ class LatteT2V(nn.Module):
                 class_labels=None, cross_attention_kwargs=None, attention_mask=None, encoder_attention_mask=None,
                 use_image_num: int = 0, enable_temporal_attentions: bool = True, return_dict: bool = True, ts_int=None):
         """hidden_states [B, C, F, H, W] latents, timestep [B], encoder_hidden_states [B, L, 4096] (reference :1144-1466)."""
-        if not hidden_states.is_cuda:
-            raise RuntimeError("videosys_b200 LatteT2V runs on sm_100a CUDA devices only (no CPU path)")
+        kernels.require_cuda(hidden_states, "LatteT2V")
         if attention_mask is not None or encoder_attention_mask is not None or use_image_num or not enable_temporal_attentions:
             raise NotImplementedError("masks / joint image training / spatial-only mode are outside the inference path "
                                       "(the reference pipeline never passes them: pipeline_latte.py:854-862)")

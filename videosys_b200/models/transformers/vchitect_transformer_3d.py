@@ -24,8 +24,9 @@ exactly the tensors the reference caches.
 
 The diffusers pieces (PatchEmbed with the cropped sin-cos table, CombinedTimestepTextProjEmbeddings, AdaLayerNormZero,
 AdaLayerNormContinuous, GELU feed-forward) are restated from their published semantics (diffusers==0.30.0, not
-installed): parity unpinned for those; the attention class + processor are pinned against the reference's own code
-(tests/test_oracle_vs_reference.py::test_vchitect_attention_vs_reference).
+installed).  Pinning: tests/test_oracle_vs_reference.py runs this front end (kernel entries = torch stand-ins) against the
+reference's transformer file executed unmodified (test_vchitect_mirror_vs_reference_model, incl. PAB), and the oracle
+against the reference's attention class + processor bit for bit.
 
 The reference pipeline calls the transformer with batch 1 (pipeline_vchitect.py:925-941); with a larger batch its
 ``temb.repeat(F, 1)`` pairs frames with the wrong sample's conditioning, so batch > 1 is rejected here.
