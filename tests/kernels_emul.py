@@ -191,3 +191,10 @@ def emulate(monkeypatch):
     g = globals()
     for n in NAMES:
         monkeypatch.setattr(kernels, n, g[n])
+
+
+def emulate_global():
+    """The same for a spawned worker process (no monkeypatch fixture there; the process ends with the test)."""
+    g = globals()
+    for n in NAMES:
+        setattr(kernels, n, g[n])

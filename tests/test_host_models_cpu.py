@@ -168,3 +168,79 @@ def test_osp_pipeline_generate_host_logic(monkeypatch):
     assert pipe.scheduler.counter == len(pipe.scheduler.timesteps) == 12 + 2  # 4 Runge-Kutta steps x 3 evaluations + 2 multi-step
     assert torch.equal(pipe.generate("Sunset over the sea.", **kw).video, out)
     assert OpenSoraPlanPipeline.latent_frames(65) == 17 and OpenSoraPlanPipeline.latent_frames(221) == 56
+
+
+# ---- sequence / CFG parallelism of the model front ends over gloo, world_size 2 (kernel entries = torch stand-ins) -------------
+def _sp_worker(rank, world, port, which, enable_cp, q):
+    import os
+    import traceback
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    try:
+        import torch.distributed as dist
+
+        from oracle import osp_cases as OC
+        from videosys_b200.core.distributed.parallel_mgr import initialize
+
+        kernels_emul.emulate_global()
+        initialize(rank, world)
+        if which == "osp_v110":
+            from videosys_b200.models.transformers.open_sora_plan_v110_transformer_3d import LatteT2V
+
+            net = LatteT2V(**OC.CASES["small_rope"][0])
+            net.load_state_dict(OC.weights(net.state_dict(), "small_rope", torch.float32))
+            x, enc, m, tt = OC.inputs("small_rope", torch.float32)
+            call = lambda: net(x, timestep=tt, all_timesteps=[900, 500], encoder_hidden_states=enc, encoder_attention_mask=m,  # noqa: E731
+                               return_dict=False)[0]
+        elif which == "latte":
+            from videosys_b200.models.transformers.latte_transformer_3d import LatteT2V
+
+            net = LatteT2V(num_attention_heads=2, attention_head_dim=72, in_channels=4, out_channels=8, num_layers=2, sample_size=8,
+                           caption_channels=32, video_length=5, cross_attention_dim=144)
+            net.load_state_dict(synth.fill_state_dict(net.state_dict(), "spl."))
+            x = synth.normalish("spl.x", (2, 4, 5, 8, 8))
+            enc = synth.normalish("spl.enc", (2, 7, 32))
+            tt = torch.tensor([500, 500])
+            call = lambda: net(x, timestep=tt, all_timesteps=[900, 500], encoder_hidden_states=enc, return_dict=False)[0]  # noqa: E731
+        else:
+            from videosys_b200.models.transformers.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+
+            net = CogVideoXTransformer3DModel(num_attention_heads=4, attention_head_dim=64, in_channels=4, out_channels=4,
+                                              time_embed_dim=64, text_embed_dim=48, num_layers=2, sample_width=16, sample_height=12,
+                                              sample_frames=9, max_text_seq_length=16)
+            net.load_state_dict(synth.fill_state_dict(net.state_dict(), "spc."))
+            lat = synth.normalish("spc.lat", (2, 3, 4, 12, 14))  # 6 x 7 = 42 patches per frame: 126 video rows, odd chunking
+            txt = synth.normalish("spc.txt", (2, 16, 48))
+            tt = torch.tensor([499, 499])
+            call = lambda: net(lat, txt, tt, return_dict=False)[0]  # noqa: E731
+        net.eval()
+        want = call()  # unsharded (parallel_manager None)
+        net.enable_parallel(1, world, enable_cp)
+        got = call()
+        q.put((rank, float((got - want).abs().max()), float(want.abs().max()), tuple(got.shape) == tuple(want.shape), None))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # pragma: no cover
+        q.put((rank, None, None, None, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("which,enable_cp", [("osp_v110", False), ("osp_v110", True), ("latte", False), ("cogvideox", False),
+                                             ("cogvideox", True)])
+def test_model_parallelism_gloo_world2(which, enable_cp):
+    """Two ranks: frame-sharded DSP (Latte / Open-Sora-Plan v1.1.0: temporal blocks switch to a patch shard, with the RoPE
+    tables following the switch), head-scatter sequence parallelism (CogVideoX) or CFG parallelism reproduce the single-rank
+    forward on every rank (fp32; the exchanges move data, the per-sequence arithmetic is unchanged)."""
+    import multiprocessing as mp
+    import os
+
+    world, port = 2, 30100 + (os.getpid() % 300) + 7 * ["osp_v110", "latte", "cogvideox"].index(which) + int(enable_cp)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_sp_worker, args=(r, world, port, which, enable_cp, q)) for r in range(world)]
+    [p.start() for p in procs]
+    for _ in range(world):
+        r, err_abs, scale, same_shape, tb = q.get(timeout=300)
+        assert tb is None, tb
+        assert same_shape and err_abs <= 1e-4 * max(scale, 1.0), (which, r, err_abs, scale)
+    [p.join(timeout=60) for p in procs]

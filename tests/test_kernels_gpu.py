@@ -731,10 +731,12 @@ def test_patch_embed(B, Cin, T, H, W, C, ph, pw, dt):
     tok = conv.permute(0, 2, 3, 4, 1).reshape(B, T, S, C)
     mid = (tok.float().to(dt).float() + bias.float()).to(dt)
     want = (mid.float() + pos.float()).to(dt)
-    # one ulp of the largest rounded intermediate (conv, conv + bias) or of the result: where conv + bias + pos cancels, a
-    # rounding-edge flip of an intermediate (fp32 vs float64 summation of the 16 products) is many ulps OF THE SUM
+    # ulps are measured at the largest magnitude in the chain (conv, conv + bias, result): where conv + bias + pos cancels, a
+    # rounding-edge flip of an intermediate (fp32 vs float64 summation of the 16 products) is many ulps OF THE SUM.  A flipped
+    # conv (one ulp) can push each of the two later roundings over an edge too: <= 3 such ulps on the rare (< 0.2 %) elements
+    # that differ at all (measured on B200: 99.99 - 100 % bit-equal, max 2)
     inter = torch.maximum(tok.float().abs(), mid.float().abs())
-    _ulp_report(f"patch_embed {dt} [{B},{Cin},{T},{H},{W}]->{C}", got, want, min_equal=0.998, max_ulps=1.0,
+    _ulp_report(f"patch_embed {dt} [{B},{Cin},{T},{H},{W}]->{C}", got, want, min_equal=0.998, max_ulps=3.0,
                 bits=8 if dt == torch.bfloat16 else 11, mag_floor=inter)
     # the rank-local form: 3 ranks, the last one's tail columns are padding (zeros)
     world = 3
@@ -746,5 +748,5 @@ def test_patch_embed(B, Cin, T, H, W, C, ph, pw, dt):
     # and the torch / cuDNN chain on the same GPU (different accumulation order: equal up to rare one-ulp flips)
     conv_g = torch.nn.functional.conv3d(zp.to(dt).to(dev), w.to(dev), bias.to(dev), stride=(1, ph, pw))
     eager = conv_g.flatten(2).transpose(1, 2).reshape(B, T, S, C) + pos.to(dev)
-    _ulp_report(f"patch_embed {dt} vs cuDNN chain", got, eager, min_equal=0.99, max_ulps=1.0, bits=8 if dt == torch.bfloat16 else 11,
+    _ulp_report(f"patch_embed {dt} vs cuDNN chain", got, eager, min_equal=0.99, max_ulps=3.0, bits=8 if dt == torch.bfloat16 else 11,
                 mag_floor=inter)

@@ -634,3 +634,81 @@ def test_vchitect_mirror_vs_reference_model(monkeypatch):
         finally:
             P.PAB_MANAGER = None
             ours.set_pab_manager(None)
+
+
+def _vch_sp_worker(rank, world, port, Fr, q):
+    import os
+    import traceback
+    import types
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    try:
+        import torch.distributed as dist
+
+        from tests import kernels_emul
+        from videosys_b200.core.distributed.parallel_mgr import initialize
+        from videosys_b200.models.transformers.vchitect_transformer_3d import VchitectXLTransformerModel
+
+        kernels_emul.emulate_global()
+        initialize(rank, world)
+
+        def a2a(out_list, in_list, group=None):  # gloo has no all_to_all: the same exchange through all_to_all_single
+            send = torch.stack([t.contiguous() for t in in_list])
+            recv = torch.empty_like(send)
+            dist.all_to_all_single(recv, send, group=group)
+            for o, r in zip(out_list, recv.unbind(0)):
+                o.copy_(r)
+
+        dist.all_to_all = a2a
+        RC = ref_loader.load().comm
+
+        def gather_cpu(input_, pg, dim, pad):  # the reference's _gather_sequence_func (comm.py:170-190) minus its CUDA assert
+            parts = [torch.empty_like(input_.contiguous()) for _ in range(dist.get_world_size(pg))]
+            dist.all_gather(parts, input_.contiguous(), group=pg)
+            out = torch.cat(parts, dim=dim)
+            return out.narrow(dim, 0, out.size(dim) - pad) if pad > 0 else out
+
+        RC._gather_sequence_func = gather_cpu
+        ref, sd = _vch_ref()
+        pm = types.SimpleNamespace(sp_size=world, sp_group=dist.group.WORLD, cp_size=1, sp_rank=rank)
+        ref.parallel_manager = pm
+        for mod in ref.modules():
+            if hasattr(mod, "parallel_manager"):
+                mod.parallel_manager = pm
+        net = VchitectXLTransformerModel(**VCH_SMALL)
+        net.load_state_dict(sd)
+        net.eval()
+        net.enable_parallel(1, world, False)
+        lat = synth.normalish("vchsp.lat", (1, Fr, 4, 12, 16))
+        enc = synth.normalish("vchsp.enc", (1, 9, 48))
+        pooled = synth.normalish("vchsp.pool", (1, 40))
+        ts = torch.tensor([500.0])
+        with torch.no_grad():
+            want = ref(lat, encoder_hidden_states=enc, pooled_projections=pooled, timestep=ts, return_dict=False)[0]
+        got = net(lat, enc, pooled, ts, return_dict=False)[0]
+        q.put((rank, float((got - want).abs().max()), float(want.abs().max()), tuple(got.shape) == tuple(want.shape), None))
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:  # pragma: no cover
+        q.put((rank, None, None, None, traceback.format_exc()))
+
+
+@pytest.mark.parametrize("Fr", [4, 5, 2])  # 5 frames: a zero frame pads the last rank; 2: one frame per rank (temporal branch * 0)
+def test_vchitect_sequence_parallel_vs_reference_gloo_world2(Fr):
+    """Two gloo ranks, both running the UNMODIFIED reference transformer and videosys_b200's (kernel entries = torch stand-ins)
+    under frame-sharded sequence parallelism: same output on every rank, incl. the reference's quirks under sp (cross attention
+    against the text keys of the rank's own first frame, cur_frame == 1 judged on the local frame count)."""
+    import multiprocessing as mp
+    import os
+
+    world, port = 2, 30700 + (os.getpid() % 250) + Fr
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_vch_sp_worker, args=(r, world, port, Fr, q)) for r in range(world)]
+    [p.start() for p in procs]
+    for _ in range(world):
+        r, err_abs, scale, same_shape, tb = q.get(timeout=300)
+        assert tb is None, tb
+        assert same_shape and err_abs <= 1e-4 * max(scale, 1.0), (r, err_abs, scale)
+    [p.join(timeout=60) for p in procs]

@@ -230,14 +230,14 @@ class VchitectXLTransformerModel(nn.Module):
         return build_from_pretrained(cls, path, subfolder, **config_overrides)
 
     def enable_parallel(self, dp_size=None, sp_size=None, enable_cp=None):
-        """reference :318-329.  The blocks of this build run on one GPU per sample (sequence parallelism over frames,
-        processor :725-727, :758-759, is not built)."""
+        """reference :318-329.  Sequence parallelism shards the FRAMES (:545-549); the temporal attention switches its q / k /
+        v to a token shard holding every frame and switches the result back (processor :725-727, :758-759, :929-949; NCCL
+        all-to-all).  As in the reference, ``enable_cp`` only takes a factor 2 out of sp_size: the forward never uses the cp
+        group (the pipeline runs the two CFG branches one after the other)."""
         dp_size, sp_size = dp_size or 1, sp_size or 1
         cp_size = 1
         if enable_cp and sp_size % 2 == 0:
             sp_size, cp_size = sp_size // 2, 2
-        if sp_size > 1:
-            raise NotImplementedError("videosys_b200 Vchitect: frame-sharded sequence parallelism is not built (1 GPU per sample)")
         self.parallel_manager = ParallelManager(dp_size, cp_size, sp_size)
 
     def reset_pab_state(self):
@@ -255,8 +255,11 @@ class VchitectXLTransformerModel(nn.Module):
         return self._rope[key]
 
     # ---- the attention of one block (VchitectAttnProcessor.__call__) ----
-    def _attention(self, a: VchitectAttention, nh, ne, Fr, S, L, ts_int):
-        """nh [Fr, S, C] / ne [Fr, L, C]: the modulated video / text tokens.  Returns (video [Fr*S, C], text [Fr*L, C])."""
+    def _attention(self, a: VchitectAttention, nh, ne, Fr, S, L, ts_int, sp_group=None, Fg=None):
+        """nh [Fr, S, C] / ne [Fr, L, C]: the modulated video / text tokens.  Returns (video [Fr*S, C], text [Fr*L, C]).
+        sp_group: Fr = this rank's frames, Fg = the video's frames; the temporal attention runs on a token shard with all Fg
+        frames (cross attention then uses the text keys of this rank's first frame, cur_frame == 1 is judged on the local
+        frame count: the reference's behaviour under sequence parallelism, processor :830-832, :785-786, :906-907)."""
         K = kernels
         C, H = self.inner_dim, a.heads
         D = C // H
@@ -278,15 +281,25 @@ class VchitectXLTransformerModel(nn.Module):
             jt = torch.empty(Fr, N, 3 * C, dtype=dt, device=dev)
             jt[:, :S] = K.gemm_bias_act(nh.view(Fr * S, C), w, b).view(Fr, S, 3 * C)
             jt[:, S:] = eqkv
-            cos, sin = self._rope_tables(Fr, dev)
-            if Fr <= 32:
-                ot = K.attn_short(jt.view(-1, 3, H, D), None, None, cos, sin, 1, N, Fr * N, 1, N, Fr, H, D, scale, flags=3)
+            Ft, Nt = Fr, N  # frames / tokens the temporal attention sees
+            if sp_group is not None:  # frame shard -> token shard (scatter the tokens, gather the frames)
+                comm.set_pad("spatial", N, sp_group)
+                jt = comm.all_to_all_with_pad(jt.view(1, Fr, N, 3 * C), sp_group, scatter_dim=2, gather_dim=1,
+                                              scatter_pad=comm.get_pad("spatial"), gather_pad=comm.get_pad("temporal")).contiguous()
+                Ft, Nt = jt.shape[1], jt.shape[2]
+                jt = jt.view(Ft, Nt, 3 * C)
+            cos, sin = self._rope_tables(Ft, dev)
+            if Ft <= 32:
+                ot = K.attn_short(jt.view(-1, 3, H, D), None, None, cos, sin, 1, Nt, Ft * Nt, 1, Nt, Ft, H, D, scale, flags=3)
             else:
-                K.qk_rmsnorm_(jt, None, None, H, D, rope_cos=cos, rope_sin=sin, pos_div=N, pos_mod=Fr)
-                ot = torch.empty(Fr * N, C, dtype=dt, device=dev)
-                q3 = jt.view(Fr * N, 3, C)
-                K.attn_flash(q3[:, 0], q3[:, 1], q3[:, 2], N, Fr, Fr, H, D, N * 3 * C, 3 * C, N * 3 * C, 3 * C, scale,
-                             out=ot, out_row_stride=N * C, out_batch_stride=C)
+                K.qk_rmsnorm_(jt, None, None, H, D, rope_cos=cos, rope_sin=sin, pos_div=Nt, pos_mod=Ft)
+                ot = torch.empty(Ft * Nt, C, dtype=dt, device=dev)
+                q3 = jt.view(Ft * Nt, 3, C)
+                K.attn_flash(q3[:, 0], q3[:, 1], q3[:, 2], Nt, Ft, Ft, H, D, Nt * 3 * C, 3 * C, Nt * 3 * C, 3 * C, scale,
+                             out=ot, out_row_stride=Nt * C, out_batch_stride=C)
+            if sp_group is not None:  # token shard -> frame shard
+                ot = comm.all_to_all_with_pad(ot.view(1, Ft, Nt, C), sp_group, scatter_dim=1, gather_dim=2,
+                                              scatter_pad=comm.get_pad("temporal"), gather_pad=comm.get_pad("spatial")).contiguous()
             ot = ot.view(Fr, N, C)
             hid_t = K.gemm_bias_act(ot[:, :S].contiguous().view(Fr * S, C), a.to_out_temporal.weight, a.to_out_temporal.bias)
             enc_t = ot[:, S:].contiguous().view(Fr * L, C)
@@ -344,7 +357,7 @@ class VchitectXLTransformerModel(nn.Module):
         """linear(silu(temb)) laid out as the [1, 1, rows, C] table the modulate / gate kernels read."""
         return kernels.gemm_bias_act(F.silu(temb), nz.linear.weight, nz.linear.bias).view(1, 1, nz.rows, self.inner_dim)
 
-    def _run_block(self, blk: JointTransformerBlock, hid, enc, temb, Fr, S, L, ts_int):
+    def _run_block(self, blk: JointTransformerBlock, hid, enc, temb, Fr, S, L, ts_int, sp_group=None, Fg=None):
         """hid [Fr*S, C]; enc [Fr*L, C] (or [L, C] before the first block); returns the two streams."""
         K = kernels
         C = self.inner_dim
@@ -358,7 +371,7 @@ class VchitectXLTransformerModel(nn.Module):
         else:
             cmod = self._mod(blk.norm1_context, temb)
             ne = K.ln_modulate(enc, cmod, None, 0, 1, 1, Fr, L, eps=1e-6)
-        hv, he = self._attention(blk.attn, nh.view(Fr, S, C), ne.view(Fr, L, C), Fr, S, L, ts_int)
+        hv, he = self._attention(blk.attn, nh.view(Fr, S, C), ne.view(Fr, L, C), Fr, S, L, ts_int, sp_group, Fg)
         hid = K.gate_residual(hid, hv, mod, None, 2, 1, Fr, S)
         nh = K.ln_modulate(hid, mod, None, 3, 4, 1, Fr, S, eps=1e-6)
         f = K.gemm_bias_act(K.gemm_bias_act(nh, blk.ff.net[0].proj.weight, blk.ff.net[0].proj.bias, act=1),
@@ -396,14 +409,25 @@ class VchitectXLTransformerModel(nn.Module):
         temb = self.time_text_embed(timestep, pooled_projections.to(dt))  # [1, C] (M = 1 rows: torch)
         enc = K.gemm_bias_act(encoder_hidden_states.to(dt).contiguous(), self.context_embedder.weight, self.context_embedder.bias)
         L = enc.shape[1]
+        pm = self.parallel_manager
+        sp_group = pm.sp_group if (pm is not None and pm.sp_size > 1) else None
+        Fg = Fr
+        if sp_group is not None:  # reference :545-549: this rank's frames (zero frames pad the last rank)
+            comm.set_pad("temporal", Fr, sp_group)
+            hid = comm.split_sequence(hid.view(1, Fr, S, C), sp_group, dim=1, pad=comm.get_pad("temporal")).contiguous()
+            Fr = hid.shape[1]
         hid, enc = hid.view(Fr * S, C), enc.view(L, C)
         if ts_int is None and pab_mgr.enable_pab():
             ts_int = int(timestep[0])
         for blk in self.transformer_blocks:
-            hid, enc = self._run_block(blk, hid, enc, temb, Fr, S, L, ts_int)
+            hid, enc = self._run_block(blk, hid, enc, temb, Fr, S, L, ts_int, sp_group, Fg)
         omod = self._mod(self.norm_out, temb)  # AdaLayerNormContinuous: rows scale, shift
         hid = K.ln_modulate(hid, omod, None, 1, 0, 1, Fr, S, eps=1e-6)
         out = K.gemm_bias_act(hid, self.proj_out.weight, self.proj_out.bias)  # [F*S, p*p*Cout]
+        if sp_group is not None:  # the head is row-wise: gather its narrow output (the reference gathers the C-wide rows, :563-564)
+            out = comm.gather_sequence(out.view(1, Fr, S, -1), sp_group, dim=1, pad=comm.get_pad("temporal"))
+            Fr = Fg
+            out = out.reshape(Fr * S, -1)
         Co, h, w = self.out_channels, Hh // p, Ww // p
         out = out.view(Fr, h, w, p, p, Co).permute(0, 5, 1, 3, 2, 4).reshape(Fr, Co, h * p, w * p)  # nhwpqc -> nchpwq
         return (out,) if not return_dict else type("Out", (), {"sample": out})()
