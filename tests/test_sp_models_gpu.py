@@ -1,4 +1,4 @@
-"""CogVideoX and Latte under the reference's multi-GPU modes, on 2 real GPUs (run with
+"""CogVideoX, Latte and Open-Sora-Plan v1.1.0 under the reference's multi-GPU modes, on 2 real GPUs (run with
 `gpurun --gpus 2 -- python -m pytest tests/test_sp_models_gpu.py -m gpu`):
 
   * CogVideoX head-scatter sequence parallelism (reference cogvideox_transformer_3d.py:44-165, :531-564) with and without
@@ -27,6 +27,9 @@ LATTE = dict(num_attention_heads=4, attention_head_dim=72, in_channels=4, out_ch
 # (name, latent shape): CogVideoX [B, F, C, H, W] -> F*(H/2)*(W/2) video rows; Latte [B, C, F, H, W]
 COGX_CASES = {"even": (2, 3, 4, 12, 16), "padded": (2, 3, 4, 6, 10)}  # 144 rows / 45 rows (pad 1 at sp = 2)
 LATTE_CASES = {"even": (2, 4, 6, 16, 16), "padded": (2, 4, 5, 16, 16)}  # 6 frames / 5 frames (pad 1 at sp = 2)
+# Open-Sora-Plan v1.1.0 (RoPE tables must follow the temporal blocks' switch to a patch shard): 5 frames -> pad 1 at sp = 2
+OSP = dict(num_attention_heads=4, attention_head_dim=72, in_channels=4, out_channels=8, num_layers=2, cross_attention_dim=288,
+           sample_size=(16, 16), caption_channels=64, video_length=5, use_rope=True)
 PAB_STEPS = [900, 880, 860]
 
 
@@ -62,8 +65,13 @@ def _run_all(dev, mode=None):
     dt = torch.float16  # the reference's dtype for both models
     res = {}
     cogx, latte = _cogx_net(dev, dt), _latte_net(dev, dt)
+    from videosys_b200.models.transformers.open_sora_plan_v110_transformer_3d import LatteT2V as OspT2V
+
+    osp = OspT2V(**OSP).to(dt)
+    osp.load_state_dict(synth.fill_state_dict(osp.state_dict(), "sposp."))
+    osp = osp.to(dev).eval()
     if mode is not None:
-        for net in (cogx, latte):
+        for net in (cogx, latte, osp):
             net.enable_parallel(1, 2, enable_cp=(mode == "cp"))
             pm = net.parallel_manager
             assert (pm.sp_size, pm.cp_size) == ((1, 2) if mode == "cp" else (2, 1))
@@ -77,6 +85,13 @@ def _run_all(dev, mode=None):
         txt = synth.normalish("splatte.txt", (shape[0], 20, 64)).to(dt).to(dev)
         ts = torch.tensor([999] * shape[0], dtype=torch.int64, device=dev)
         res["latte." + name] = latte(lat, timestep=ts, encoder_hidden_states=txt, return_dict=False)[0].cpu()
+    lat = synth.normalish("sposp.lat", (2, 4, 5, 16, 16)).to(dt).to(dev)
+    txt = synth.normalish("sposp.txt", (2, 1, 20, 64)).to(dt).to(dev)
+    msk = torch.ones(2, 1, 20)
+    msk[1, 0, 13:] = 0
+    ts = torch.tensor([500, 500], dtype=torch.int64, device=dev)
+    res["osp_v110.padded"] = osp(lat, timestep=ts, all_timesteps=[900, 500], encoder_hidden_states=txt,
+                                 encoder_attention_mask=msk, return_dict=False)[0].cpu()
     # PAB: caches live in the sharded layout (CogVideoX: the attention output of the local rows; Latte: gated outputs of
     # the local frames, MLP outputs through the manager)
     from videosys_b200.pipelines.latte.pipeline_latte import LattePABConfig
