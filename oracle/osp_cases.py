@@ -38,3 +38,32 @@ def inputs(name, dtype, step=None):
     m = torch.ones(shape[0], 1, L)
     m[shape[0] - 1, 0, L - max(2, L // 4):] = 0  # tokenizer padding on the last sample
     return x, enc, m, torch.tensor([t] * shape[0])
+
+
+# ---- Open-Sora-Plan v1.2.0 (OpenSoraT2V) ------------------------------------------------------------------------------------------
+BASE12 = dict(in_channels=4, out_channels=8, attention_bias=True, patch_size=2, patch_size_t=1, activation_fn="gelu-approximate",
+              norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6, attention_mode="math", downsampler=None)
+CASES12 = {
+    "small_rope": (dict(BASE12, num_attention_heads=2, attention_head_dim=96, num_layers=2, cross_attention_dim=192, sample_size=(8, 8),
+                        sample_size_t=5, caption_channels=32, interpolation_scale_h=1.0, interpolation_scale_w=2.0,
+                        interpolation_scale_t=1.5, use_rope=True), (2, 4, 5, 8, 8), 7, 500),
+    "small_abspos": (dict(BASE12, num_attention_heads=2, attention_head_dim=96, num_layers=2, cross_attention_dim=192,
+                          sample_size=(8, 8), sample_size_t=5, caption_channels=32, use_rope=False), (2, 4, 5, 8, 8), 7, 500),
+    # the released model's width (24 heads x 96 = 2304, 4096-wide captions), 2 of its 32 layers, 4 latent frames of 12 x 16
+    # latent pixels (48 patches per frame: 192 tokens; 29x480p would be 8 x 30 x 40 = 9600)
+    "wide_rope": (dict(BASE12, num_attention_heads=24, attention_head_dim=96, num_layers=2, cross_attention_dim=2304,
+                       sample_size=(12, 16), sample_size_t=4, caption_channels=4096, interpolation_scale_h=1.0,
+                       interpolation_scale_w=1.0, interpolation_scale_t=1.0, use_rope=True), (2, 4, 4, 12, 16), 40, 300),
+}
+PAB12_KW = dict(spatial_broadcast=True, spatial_threshold=[100, 850], spatial_range=2, cross_broadcast=True,
+                cross_threshold=[100, 850], cross_range=3)
+
+
+def inputs12(name, dtype, step=None):
+    cfg, shape, L, t = CASES12[name]
+    tag = f"ospg12.{name}." + ("" if step is None else f"s{step}.")
+    x = synth.normalish(tag + "x", shape).to(dtype)
+    enc = synth.normalish(tag + "enc", (shape[0], 1, L, cfg["caption_channels"])).to(dtype)
+    m = torch.ones(shape[0], 1, L)
+    m[shape[0] - 1, 0, L - max(2, L // 4):] = 0
+    return x, enc, m, torch.tensor([t] * shape[0])

@@ -472,3 +472,50 @@ def build_vchitect(dtype=torch.float32, **cfg):
         if hasattr(mod, "parallel_manager"):
             mod.parallel_manager = SingleRankPM()
     return net
+
+
+def load_osp_v120():
+    """The reference's models/transformers/open_sora_plan_v120_transformer_3d.py (RoPE3D, PatchEmbed2D, Attention +
+    AttnProcessor2_0, BasicTransformerBlock, OpenSoraT2V), imported unmodified.  diffusers leaves: ``Attention`` (base class)
+    = the reference's vendored copy in the v1.1.0 file, ``FeedForward`` / ``AdaLayerNormSingle`` / ``PixArtAlphaTextProjection``
+    = the vendored copies there (FeedForward, AdaLayerNormSingle, CaptionProjection), plus the three restated leaves."""
+    if "osp_v120" in _LOADED:
+        return _LOADED["osp_v120"]
+    O = load_osp_v110()
+
+    class FeedForward(O.FeedForward):
+        def __init__(self, dim, dropout=0.0, activation_fn="geglu", final_dropout=False, inner_dim=None, bias=True, **kw):
+            assert inner_dim is None and bias, "the vendored copy is the 4x / bias-on configuration"
+            super().__init__(dim, dropout=dropout, activation_fn=activation_fn, final_dropout=final_dropout)
+
+    class PixArtAlphaTextProjection(O.CaptionProjection):
+        def __init__(self, in_features, hidden_size, **kw):
+            super().__init__(in_features, hidden_size)
+            del self._buffers["y_embedding"]
+
+    ph = lambda name: type(name, (nn.Module,), {})  # noqa: E731
+    _mod("diffusers.models.attention", FeedForward=FeedForward, GatedSelfAttentionDense=ph("GatedSelfAttentionDense"),
+         Attention=sys.modules["diffusers.models.attention"].Attention if hasattr(sys.modules.get("diffusers.models.attention"), "Attention") else object)
+    sys.modules["diffusers.models.attention_processor"].Attention = O.Attention
+    emb = sys.modules["diffusers.models.embeddings"]
+    emb.PixArtAlphaTextProjection = PixArtAlphaTextProjection
+    norm = sys.modules["diffusers.models.normalization"]
+    norm.AdaLayerNormSingle = O.AdaLayerNormSingle
+    if not hasattr(norm, "AdaLayerNormContinuous"):
+        norm.AdaLayerNormContinuous = ph("AdaLayerNormContinuous")
+    sys.modules["diffusers.utils"].is_torch_version = lambda *a, **k: True
+    _mod("diffusers.pipelines")
+    _mod("diffusers.pipelines.pipeline_utils", DiffusionPipeline=type("DiffusionPipeline", (), {"__init__": lambda s: None}))
+    m = importlib.import_module("videosys.models.transformers.open_sora_plan_v120_transformer_3d")
+    _LOADED["osp_v120"] = m
+    return m
+
+
+def build_osp_v120(dtype=torch.float32, **cfg):
+    M = load_osp_v120()
+    net = M.OpenSoraT2V(**cfg).eval().to(dtype)
+    net.parallel_manager = SingleRankPM()
+    for mod in net.modules():
+        if hasattr(mod, "parallel_manager"):
+            mod.parallel_manager = SingleRankPM()
+    return net

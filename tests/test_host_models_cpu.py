@@ -193,6 +193,13 @@ def _sp_worker(rank, world, port, which, enable_cp, q):
             x, enc, m, tt = OC.inputs("small_rope", torch.float32)
             call = lambda: net(x, timestep=tt, all_timesteps=[900, 500], encoder_hidden_states=enc, encoder_attention_mask=m,  # noqa: E731
                                return_dict=False)[0]
+        elif which == "osp_v120":
+            from videosys_b200.models.transformers.open_sora_plan_v120_transformer_3d import OpenSoraT2V
+
+            net = OpenSoraT2V(**OC.CASES12["small_rope"][0])
+            net.load_state_dict(OC.weights(net.state_dict(), "v120.small_rope", torch.float32))
+            x, enc, m, tt = OC.inputs12("small_rope", torch.float32)
+            call = lambda: net(x, timestep=tt, encoder_hidden_states=enc, encoder_attention_mask=m, return_dict=False)[0]  # noqa: E731
         elif which == "latte":
             from videosys_b200.models.transformers.latte_transformer_3d import LatteT2V
 
@@ -226,7 +233,7 @@ def _sp_worker(rank, world, port, which, enable_cp, q):
 
 
 @pytest.mark.parametrize("which,enable_cp", [("osp_v110", False), ("osp_v110", True), ("latte", False), ("cogvideox", False),
-                                             ("cogvideox", True)])
+                                             ("cogvideox", True), ("osp_v120", False)])
 def test_model_parallelism_gloo_world2(which, enable_cp):
     """Two ranks: frame-sharded DSP (Latte / Open-Sora-Plan v1.1.0: temporal blocks switch to a patch shard, with the RoPE
     tables following the switch), head-scatter sequence parallelism (CogVideoX) or CFG parallelism reproduce the single-rank
@@ -234,7 +241,7 @@ def test_model_parallelism_gloo_world2(which, enable_cp):
     import multiprocessing as mp
     import os
 
-    world, port = 2, 30100 + (os.getpid() % 300) + 7 * ["osp_v110", "latte", "cogvideox"].index(which) + int(enable_cp)
+    world, port = 2, 30100 + (os.getpid() % 300) + 7 * ["osp_v110", "latte", "cogvideox", "osp_v120"].index(which) + int(enable_cp)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_sp_worker, args=(r, world, port, which, enable_cp, q)) for r in range(world)]
@@ -244,3 +251,40 @@ def test_model_parallelism_gloo_world2(which, enable_cp):
         assert tb is None, tb
         assert same_shape and err_abs <= 1e-4 * max(scale, 1.0), (which, r, err_abs, scale)
     [p.join(timeout=60) for p in procs]
+
+
+@pytest.mark.parametrize("name", ["small_rope", "small_abspos"])
+def test_osp_v120_host_logic_vs_reference_golden(monkeypatch, golden_dir, name):
+    """OpenSoraT2V's front end on the torch stand-ins, fp32, against the fp32 output of the UNMODIFIED reference model stored
+    in tests/golden/osp_v120.pt."""
+    import os
+
+    from oracle import osp_cases as OC
+    from videosys_b200.models.transformers.open_sora_plan_v120_transformer_3d import OpenSoraT2V
+
+    kernels_emul.emulate(monkeypatch)
+    gold = torch.load(os.path.join(golden_dir, "osp_v120.pt"))
+    net = OpenSoraT2V(**OC.CASES12[name][0])
+    net.load_state_dict(OC.weights(net.state_dict(), "v120." + name, torch.float32))
+    x, enc, m, tt = OC.inputs12(name, torch.float32)
+    out = net.eval()(x, timestep=tt, encoder_hidden_states=enc, encoder_attention_mask=m, return_dict=False)[0]
+    assert torch.allclose(out, gold[f"{name}.fp32"], rtol=1e-4, atol=1e-5), (out - gold[f"{name}.fp32"]).abs().max()
+
+
+def test_osp_v120_pipeline_generate_host_logic(monkeypatch):
+    from oracle import osp_cases as OC
+    from videosys_b200 import OpenSoraPlanConfig, OpenSoraPlanPipeline
+    from videosys_b200.models.transformers.open_sora_plan_v120_transformer_3d import OpenSoraT2V
+    from videosys_b200.schedulers.scheduling_euler_ancestral import EulerAncestralDiscreteScheduler
+
+    kernels_emul.emulate(monkeypatch)
+    tc = OC.CASES12["small_rope"][0]
+    net = OpenSoraT2V(**tc)
+    net.load_state_dict(OC.weights(net.state_dict(), "v120.small_rope", torch.float32))
+    cfg = OpenSoraPlanConfig(version="v120", transformer_type="29x480p", transformer_config=tc)
+    pipe = _bare_pipeline(OpenSoraPlanPipeline, cfg, net.eval(), EulerAncestralDiscreteScheduler())
+    kw = dict(num_inference_steps=5, guidance_scale=7.5, seed=0, max_sequence_length=24)
+    out = pipe.generate("Sunset over the sea.", **kw).video
+    assert out.shape == (1, 4, 5, 8, 8) and torch.isfinite(out).all()
+    assert torch.equal(pipe.generate("Sunset over the sea.", **kw).video, out)  # the ancestral noise follows the seed
+    assert OpenSoraPlanPipeline.latent_frames(29) == 8 and OpenSoraPlanPipeline.latent_frames(93) == 24

@@ -712,3 +712,88 @@ def test_vchitect_sequence_parallel_vs_reference_gloo_world2(Fr):
         assert tb is None, tb
         assert same_shape and err_abs <= 1e-4 * max(scale, 1.0), (r, err_abs, scale)
     [p.join(timeout=60) for p in procs]
+
+
+# ---- Open-Sora-Plan v1.2.0: the product's host logic against the UNMODIFIED reference model --------------------------------
+OSP12_SMALL = dict(num_attention_heads=2, attention_head_dim=96, in_channels=4, out_channels=8, num_layers=2, cross_attention_dim=192,
+                   attention_bias=True, sample_size=(8, 8), sample_size_t=5, patch_size=2, patch_size_t=1,
+                   activation_fn="gelu-approximate", norm_type="ada_norm_single", norm_elementwise_affine=False, norm_eps=1e-6,
+                   caption_channels=32, interpolation_scale_h=1.0, interpolation_scale_w=2.0, interpolation_scale_t=1.5,
+                   attention_mode="math", downsampler=None, use_rope=True)
+
+
+def _osp12_pair(cfg, tag="osp12."):
+    from videosys_b200.models.transformers.open_sora_plan_v120_transformer_3d import OpenSoraT2V
+
+    ref = ref_loader.build_osp_v120(**cfg)
+    sd = synth.fill_state_dict(ref.state_dict(), tag)
+    ref.load_state_dict(sd)
+    net = OpenSoraT2V(**cfg)
+    net.load_state_dict(sd)  # strict
+    return ref, net.eval()
+
+
+def _osp12_call(ref, x, t, enc, m):
+    return ref(x, timestep=t, encoder_hidden_states=enc, attention_mask=torch.ones(x.shape[0], x.shape[2], x.shape[3], x.shape[4]),
+               encoder_attention_mask=m, return_dict=False)[0]
+
+
+@pytest.mark.parametrize("use_rope,HW", [(True, (8, 8)), (False, (8, 8)), (True, (12, 8))])
+def test_osp_v120_mirror_vs_reference_model(monkeypatch, use_rope, HW):
+    """videosys_b200's OpenSoraT2V (kernel entries = torch stand-ins) against the reference's own OpenSoraT2V executed
+    unmodified: RoPE3D tables with per-axis interpolation scales, absolute position tables when RoPE is off, text padding
+    mask, block order, output head / un-patchify."""
+    from tests import kernels_emul
+
+    kernels_emul.emulate(monkeypatch)
+    ref, net = _osp12_pair(dict(OSP12_SMALL, use_rope=use_rope))
+    x, enc, m = _osp_inputs(2, 5, HW, tag="osp12.")
+    t = torch.tensor([500, 500])
+    with torch.no_grad():
+        want = _osp12_call(ref, x, t, enc, m)
+    got = net(x, timestep=t, encoder_hidden_states=enc, encoder_attention_mask=m, return_dict=False)[0]
+    assert got.shape == want.shape
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+
+
+def test_osp_v120_pab_vs_reference_model(monkeypatch):
+    from tests import kernels_emul
+    from videosys_b200.core.pab import pab_mgr as ours
+
+    kernels_emul.emulate(monkeypatch)
+    P = ref_loader.load().pab_mgr
+    ref, net = _osp12_pair(OSP12_SMALL, "osp12p.")
+    ts = [900, 700, 650, 600, 550, 500, 450, 50]
+    kw = dict(spatial_broadcast=True, spatial_threshold=[100, 850], spatial_range=2, cross_broadcast=True,
+              cross_threshold=[100, 850], cross_range=3)
+    P.set_pab_manager(P.PABConfig(**kw))
+    P.update_steps(len(ts))
+    ours.set_pab_manager(ours.PABConfig(**kw))
+    ours.update_steps(len(ts))
+    net.reset_pab_state()
+    try:
+        for step, t in enumerate(ts):
+            x, enc, m = _osp_inputs(2, 5, (8, 8), tag=f"osp12p{step}.")
+            tt = torch.tensor([t, t])
+            with torch.no_grad():
+                want = _osp12_call(ref, x, tt, enc, m)
+            got = net(x, timestep=tt, encoder_hidden_states=enc, encoder_attention_mask=m, return_dict=False)[0]
+            assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (step, (got - want).abs().max())
+    finally:
+        P.PAB_MANAGER = None
+        ours.set_pab_manager(None)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_osp_v120_rope3d_tables_vs_reference_class(dtype):
+    from videosys_b200.models.transformers.open_sora_plan_v120_transformer_3d import rope3d_tables
+
+    M = ref_loader.load_osp_v120()
+    D, Hh, T, h, w = 96, 3, 4, 3, 5
+    q = synth.normalish("rope3.q", (2, Hh, T * h * w, D)).to(dtype)
+    pos = M.PositionGetter3D()(2, T, h, w, "cpu")
+    want = M.RoPE3D(interpolation_scale_thw=(1.5, 1.0, 2.0))(q, pos)
+    c, s, half = rope3d_tables(D, T, h, w, (1.5, 1.0, 2.0), dtype, "cpu")
+    assert half == 16
+    partner = q.reshape(*q.shape[:-1], D // (2 * half), 2, half).flip(-2).reshape(q.shape)
+    assert torch.equal(q * c.to(dtype) + partner * s.to(dtype), want)

@@ -45,6 +45,9 @@ struct AttnParams {
 int attn_flash_kt64_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, int q_tmem, cudaStream_t st);
 // attn_tcgen05_kvres.cu: nk <= 320, K/V resident in shared memory, 160-key score tiles.  tm key boxes have 160 rows.
 int attn_flash_kvres_launch(const CUtensorMap* tm, const AttnParams& prm, int D, cudaStream_t st);
+// attn_mma.cu: head dims other than 64 / 72 (96 = Open-Sora-Plan v1.2.0) on the warp-level tensor path; raw strided pointers.
+int attn_mma_launch(const bf16* q, const bf16* k, const bf16* v, long long kv_row_stride, long long kv_batch_stride,
+                    const AttnParams& prm, int D, cudaStream_t st);
 // attn_tcgen05_kt64p.cu: the same tiles under persistent CTAs.
 int attn_flash_kt64p_launch(const CUtensorMap* tm, const AttnParams& prm, int D, int poly, cudaStream_t st);
 

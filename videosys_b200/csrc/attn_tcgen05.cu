@@ -337,7 +337,7 @@ extern "C" int VSB_API(vsb_attn_flash_strided)(const vsb_bf16* q, const vsb_bf16
   if (!q || !k || !v || !out || nb <= 0 || nq <= 0 || nk <= 0 || H <= 0) return fail(VSB_ERR_INVALID, "attn_flash: bad args");
   if ((out_row_stride % 8) || (out_batch_stride % 8) || out_row_stride < (long long)H * D)
     return fail(VSB_ERR_UNSUPPORTED, "attn_flash: output strides must be multiples of 8 elements, rows >= H*D apart");
-  if (D != 72 && D != 64) return fail(VSB_ERR_UNSUPPORTED, "attn_flash: head_dim %d (72 or 64 only)", D);
+  if (D % 16 != 0 && D != 72) return fail(VSB_ERR_UNSUPPORTED, "attn_flash: head_dim %d", D);
   if ((q_row_stride % 8) || (q_batch_stride % 8) || (kv_row_stride % 8) || (kv_batch_stride % 8) || !aligned16(q) ||
       !aligned16(k) || !aligned16(v) || !aligned16(out))
     return fail(VSB_ERR_UNSUPPORTED, "attn_flash: strides must be multiples of 8 elements and pointers 16B-aligned");
@@ -366,6 +366,9 @@ extern "C" int VSB_API(vsb_attn_flash_strided)(const vsb_bf16* q, const vsb_bf16
       if (host_kv_lens[i] < 1 || host_kv_lens[i] > nk) return fail(VSB_ERR_INVALID, "attn_flash: kv_lens[%d]=%d", i, host_kv_lens[i]);
       prm.lens[i] = host_kv_lens[i];
     }
+  if (D != 72 && D != 64)  // no tcgen05 layout for this head_dim: the mma.sync kernel (attn_mma.cu)
+    return attn_mma_launch((const bf16*)q, (const bf16*)k, (const bf16*)v, kv_row_stride, kv_batch_stride, prm, D,
+                           (cudaStream_t)stream);
   // Two tensor maps per operand: the 64-wide SWIZZLE_128B chunk and (head_dim 72 only) the 16-wide SWIZZLE_32B
   // chunk at d = 64..79.  The inner extent is D, so TMA zero-fills 72..79 and rows past nq / nk.
   // auto: text cross-attention (a handful of key tiles per query pair) is dominated by per-CTA fixed costs

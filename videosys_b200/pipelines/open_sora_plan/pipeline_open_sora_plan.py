@@ -2,10 +2,11 @@
 OpenSoraPlanV110PABConfig :41-100, OpenSoraPlanV120PABConfig :103-120, OpenSoraPlanConfig :123-226,
 OpenSoraPlanPipeline.generate :962-1180) around the B200 transformer.
 
-Version v110 (``LatteT2V``, 65 or 221 frames at 512 x 512, head_dim 72) runs on the kernels: CFG batch of 2, PNDM steps
-(incl. its Runge-Kutta warm-up: the transformer is evaluated at every entry of ``scheduler.timesteps``), learned-sigma split,
-PAB with the MLP skip.  Version v120 (``OpenSoraT2V``, head_dim 96, 3-D RoPE) is rejected: the tcgen05 flash kernels are built
-for head_dim 64 and 72 only.  Out of scope as for the other pipelines: T5 encoder and the
+Version v110 (``LatteT2V``, 65 or 221 frames at 512 x 512, head_dim 72): CFG batch of 2, PNDM steps (incl. its Runge-Kutta
+warm-up: the transformer is evaluated at every entry of ``scheduler.timesteps``), learned-sigma split, PAB with the MLP skip.
+Version v120 (``OpenSoraT2V``, 29 or 93 frames at 480p / 720p, head_dim 96, 3-D RoPE): ancestral Euler steps (the latent is
+scaled by the scheduler before every forward, :1097), PAB with the spatial and the cross gate; its attention runs on the
+warp-level kernel of csrc/attn_mma.cu (the tcgen05 flash kernels are laid out for head_dim 64 / 72: DESIGN.md).  Out of scope as for the other pipelines: T5 encoder and the
 causal VAE -- pass ``prompt_embeds`` (+ masks) or a ``text_encoder_fn``; without a ``vae_decode_fn`` the LATENTS are returned.
 dtype fp16 as the reference (:262).
 """
@@ -17,6 +18,8 @@ import torch
 
 from ...core.pab.pab_mgr import PABConfig, enable_pab, set_pab_manager, update_steps
 from ...models.transformers.open_sora_plan_v110_transformer_3d import LatteT2V
+from ...models.transformers.open_sora_plan_v120_transformer_3d import OpenSoraT2V
+from ...schedulers.scheduling_euler_ancestral import EulerAncestralDiscreteScheduler
 from ...schedulers.scheduling_pndm import PNDMScheduler
 from .._common import ParallelPipelineMixin
 from ..open_sora.pipeline_open_sora import VideoSysPipelineOutput
@@ -77,22 +80,23 @@ class OpenSoraPlanPipeline(ParallelPipelineMixin):
     def __init__(self, config: OpenSoraPlanConfig, device=None, dtype: torch.dtype = torch.float16):
         if not torch.cuda.is_available():
             raise RuntimeError("videosys_b200 pipelines need an sm_100a GPU (no CPU path)")
-        if config.version != "v110":
-            raise NotImplementedError("videosys_b200: Open-Sora-Plan v1.2.0 (OpenSoraT2V: head_dim 96, 3-D RoPE) is not built -- the "
-                                      "tcgen05 flash-attention kernels cover head_dim 64 and 72; use version='v110'")
         import os
 
         self._config, self._dtype = config, dtype
         self._device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         tc = config.transformer_config
+        cls = LatteT2V if config.version == "v110" else OpenSoraT2V
         if tc is None and config.state_dict is None and os.path.isdir(str(config.transformer)):
-            self.transformer = LatteT2V.from_pretrained(config.transformer, subfolder=config.transformer_type).to(dtype)
-        else:
+            self.transformer = cls.from_pretrained(config.transformer, subfolder=config.transformer_type).to(dtype)
+        elif config.version == "v110":
             self.transformer = LatteT2V(**(tc or dict(video_length=self.latent_frames(config.num_frames)))).to(dtype)
+        else:
+            hw = (60, 80) if config.transformer_type.endswith("480p") else (90, 160)  # latent height x width of 480p / 720p
+            self.transformer = OpenSoraT2V(**(tc or dict(sample_size=hw, sample_size_t=self.latent_frames(config.num_frames)))).to(dtype)
         if config.state_dict is not None:
             self.transformer.load_state_dict(config.state_dict)
         self.transformer = self.transformer.to(self._device).eval()
-        self.scheduler = PNDMScheduler()
+        self.scheduler = PNDMScheduler() if config.version == "v110" else EulerAncestralDiscreteScheduler()
         if config.enable_pab:
             set_pab_manager(config.pab_config)
         self._set_parallel()
@@ -121,7 +125,12 @@ class OpenSoraPlanPipeline(ParallelPipelineMixin):
                  callback_steps: int = 1, clean_caption: bool = True, mask_feature: bool = True,
                  enable_temporal_attentions: bool = True, verbose: bool = True, max_sequence_length: int = 300,
                  height: int = 512, width: int = 512):
-        """height / width are fixed to 512 by the reference (:1005-1007); arguments here so that the tests can run a small model."""
+        """height / width follow the transformer's sample size in the reference (:1005-1007: 512 x 512 for v110, the 480p / 720p
+        grid for v120; the arguments are used by v110 only, so that the tests can run a small model)."""
+        v120 = self._config.version == "v120"
+        if v120:
+            height = self.transformer.config.sample_size[0] * self.vae_scale_factor[1]
+            width = self.transformer.config.sample_size[1] * self.vae_scale_factor[2]
         update_steps(num_inference_steps)
         self.transformer.reset_pab_state()
         self._maybe_seed(seed)
@@ -135,21 +144,26 @@ class OpenSoraPlanPipeline(ParallelPipelineMixin):
             pe = torch.cat([negative_prompt_embeds.to(dev, dt), pe], dim=0)
             pm = torch.cat([negative_prompt_attention_mask, prompt_attention_mask], dim=0)
         self.scheduler.set_timesteps(num_inference_steps, dev)
-        ts = [int(v) for v in self.scheduler.timesteps.tolist()]
+        ts = [(float(v) if v120 else int(v)) for v in self.scheduler.timesteps.tolist()]
         cin = self.transformer.config.in_channels
-        Fr = self.latent_frames(self._config.num_frames) if self._config.transformer_config is None else self.transformer.video_length
+        if self._config.transformer_config is None:
+            Fr = self.latent_frames(self._config.num_frames)
+        else:
+            Fr = self.transformer.config.sample_size_t if v120 else self.transformer.video_length
         if latents is None:
             latents = torch.randn(prompt_embeds.shape[0], cin, Fr, height // self.vae_scale_factor[1],
                                   width // self.vae_scale_factor[2], device=dev, dtype=dt)
         lat = latents.to(dev, dt) * self.scheduler.init_noise_sigma
         for t in ts:
             inp = torch.cat([lat] * 2) if do_cfg else lat
-            tt = torch.full((inp.shape[0],), t, device=dev, dtype=torch.int64)
+            if v120:
+                inp = self.scheduler.scale_model_input(inp, t).to(dt)
+            tt = torch.full((inp.shape[0],), t, device=dev, dtype=torch.float32 if v120 else torch.int64)
             noise = self.transformer(inp, timestep=tt, all_timesteps=ts, encoder_hidden_states=pe.unsqueeze(1),
                                      added_cond_kwargs={"resolution": None, "aspect_ratio": None},
                                      enable_temporal_attentions=enable_temporal_attentions,
                                      encoder_attention_mask=pm.unsqueeze(1), return_dict=False,
-                                     ts_int=t if enable_pab() else None)[0]
+                                     ts_int=int(t) if enable_pab() else None)[0]
             if do_cfg:
                 un, tx = noise.chunk(2)
                 noise = un + guidance_scale * (tx - un)
