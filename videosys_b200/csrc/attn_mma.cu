@@ -7,10 +7,11 @@
 // (strided q / k / v views, per-batch key counts, strided output), same arithmetic contract (fp32 scores, softmax scale
 // folded into exp2, P rounded to the 16-bit dtype before P V, fp32 accumulation), FlashAttention-2 schedule:
 //
-//   CTA = 4 warps = 64 query rows of one (batch, head); a warp owns 16 rows (one m16 tile), its Q fragments live in registers.
-//   Loop over 64-key tiles: K / V tile -> shared memory (16-byte loads, rows padded by 16 bytes: conflict-free ldmatrix),
+//   CTA = 8 warps = 128 query rows of one (batch, head); a warp owns 16 rows (one m16 tile), its Q fragments live in registers.
+//   Loop over 64-key tiles: K / V tile -> shared memory (cp.async into two buffers: the next tile loads while this one is
+//   multiplied; rows padded by 16 bytes: conflict-free ldmatrix; B fragments fetched two tiles per ldmatrix.x4),
 //   S = Q K^T (mma.sync m16n8k16, fp32), online softmax on the accumulator fragments (row max / sum across the 4 lanes of a
-//   row), P re-packed as A fragments, O += P V (V fragments by ldmatrix.trans).  Rows beyond the sequence are zero (Q) or
+//   row), P re-packed as A fragments, O += P V (V fragments by ldmatrix.x4.trans).  Rows beyond the sequence are zero (Q) or
 //   masked to -inf (keys); V rows beyond the key count are zero so that 0 * garbage cannot produce NaN.
 //
 // mma.sync reaches a fraction of the tcgen05 rate: this is the functional path for those shapes, not a roofline kernel.
@@ -23,14 +24,17 @@ __device__ __forceinline__ void mm_ldsm_x4(uint32_t (&r)[4], const void* p) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(smem_u32(p)));
 }
-__device__ __forceinline__ void mm_ldsm_x2(uint32_t (&r)[2], const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void mm_ldsm_x2_trans(uint32_t (&r)[2], const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];"
-               : "=r"(r[0]), "=r"(r[1])
+__device__ __forceinline__ void mm_ldsm_x4_trans(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
                : "r"(smem_u32(p)));
 }
+// 16-byte asynchronous copy global -> shared; src_bytes = 0 writes zeros (rows past the key count)
+__device__ __forceinline__ void mm_cp_async16(void* dst, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void mm_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void mm_cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void mm_mma_k16(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile(
       "mma.sync.aligned.m16n8k16.row.col.f32." VSB_MMA_T "." VSB_MMA_T ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -38,21 +42,22 @@ __device__ __forceinline__ void mm_mma_k16(float (&c)[4], const uint32_t (&a)[4]
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-constexpr int kMmQ = 64;   // query rows per CTA
-constexpr int kMmK = 64;   // keys per tile
+constexpr int kMmQ = 128;        // query rows per CTA (8 warps x 16): every K / V tile staged in shared memory serves 128 rows
+constexpr int kMmK = 64;         // keys per tile
+constexpr int kMmThreads = 256;
 
 template <int D>
-__global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
+__global__ void __launch_bounds__(kMmThreads) attn_mma_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k,
                                                        const bf16* __restrict__ v, long long kv_row_stride,
                                                        long long kv_batch_stride, const __grid_constant__ AttnParams p) {
   constexpr int LD = D + 8;   // smem row pitch in elements (16 bytes of padding)
   constexpr int VPR = D / 8;  // 16-byte vectors per row
   constexpr int KS = D / 16;  // k16 steps of Q K^T
   constexpr int ND = D / 8;   // n8 tiles of O
+  static_assert(ND % 2 == 0, "output tiles are loaded in pairs");
   extern __shared__ __align__(16) unsigned char mm_smem[];
   bf16* sQ = reinterpret_cast<bf16*>(mm_smem);
-  bf16* sK = sQ + kMmQ * LD;
-  bf16* sV = sK + kMmK * LD;
+  bf16* sKV = sQ + kMmQ * LD;  // [2 buffers][K tile | V tile]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kMmQ, h = blockIdx.y, b = blockIdx.z;
   const int kv_len = p.has_lens ? p.lens[b] : p.nk;
@@ -62,7 +67,7 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ 
   const bf16* vb = v + (size_t)b * kv_batch_stride + (size_t)h * D;
 
   // ---- Q tile -> shared memory (rows past nq are zero), then this warp's A fragments -> registers ----
-  for (int i = threadIdx.x; i < kMmQ * VPR; i += 128) {
+  for (int i = threadIdx.x; i < kMmQ * VPR; i += kMmThreads) {
     const int r = i / VPR, c = i - r * VPR;
     uint4 val = make_uint4(0, 0, 0, 0);
     if (q0 + r < p.nq) val = *reinterpret_cast<const uint4*>(qb + (size_t)(q0 + r) * p.q_row_stride + c * 8);
@@ -79,20 +84,29 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ 
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;  // rows g and g + 8 of this warp's tile
   const int t = lane & 3;
 
-  for (int kt = 0; kt < n_tiles; ++kt) {
-    __syncthreads();  // every warp is done with the previous K / V tile
+  // K / V tiles travel by cp.async into two buffers: tile kt + 1 is in flight while tile kt is multiplied
+  auto prefetch = [&](int kt) {
     const int k0 = kt * kMmK;
-    for (int i = threadIdx.x; i < kMmK * VPR; i += 128) {
+    bf16* dK = sKV + (size_t)(kt & 1) * 2 * kMmK * LD;
+    bf16* dV = dK + kMmK * LD;
+    for (int i = threadIdx.x; i < kMmK * VPR; i += kMmThreads) {
       const int r = i / VPR, c = i - r * VPR;
-      uint4 kv4 = make_uint4(0, 0, 0, 0), vv4 = make_uint4(0, 0, 0, 0);
-      if (k0 + r < kv_len) {
-        kv4 = *reinterpret_cast<const uint4*>(kb + (size_t)(k0 + r) * kv_row_stride + c * 8);
-        vv4 = *reinterpret_cast<const uint4*>(vb + (size_t)(k0 + r) * kv_row_stride + c * 8);
-      }
-      *reinterpret_cast<uint4*>(sK + r * LD + c * 8) = kv4;
-      *reinterpret_cast<uint4*>(sV + r * LD + c * 8) = vv4;
+      const bool ok = k0 + r < kv_len;
+      const size_t off = (size_t)(ok ? k0 + r : 0) * kv_row_stride + c * 8;  // a valid address even when nothing is read
+      mm_cp_async16(dK + r * LD + c * 8, kb + off, ok ? 16 : 0);
+      mm_cp_async16(dV + r * LD + c * 8, vb + off, ok ? 16 : 0);
     }
-    __syncthreads();
+    mm_cp_async_commit();
+  };
+  prefetch(0);
+
+  for (int kt = 0; kt < n_tiles; ++kt) {
+    mm_cp_async_wait0();
+    __syncthreads();  // tile kt has landed for every thread; every warp is done with tile kt - 1 (the buffer refilled next)
+    if (kt + 1 < n_tiles) prefetch(kt + 1);
+    const int k0 = kt * kMmK;
+    const bf16* sK = sKV + (size_t)(kt & 1) * 2 * kMmK * LD;
+    const bf16* sV = sK + kMmK * LD;
 
     // ---- S = Q K^T: 16 rows x 64 keys per warp ----
     float sacc[8][4];
@@ -101,10 +115,12 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ 
 #pragma unroll
     for (int ks = 0; ks < KS; ++ks) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        uint32_t bfr[2];
-        mm_ldsm_x2(bfr, sK + (j * 8 + (lane & 7)) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
-        mm_mma_k16(sacc[j], qf[ks], bfr);
+      for (int j = 0; j < 8; j += 2) {  // one ldmatrix.x4 = the B fragments of key tiles j and j + 1
+        uint32_t bfr[4];
+        mm_ldsm_x4(bfr, sK + ((j + (lane >> 4)) * 8 + (lane & 7)) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
+        const uint32_t b0[2] = {bfr[0], bfr[1]}, b1[2] = {bfr[2], bfr[3]};
+        mm_mma_k16(sacc[j], qf[ks], b0);
+        mm_mma_k16(sacc[j + 1], qf[ks], b1);
       }
     }
     // ---- online softmax (base 2, scale folded); key column of sacc[j][e] = k0 + 8j + 2t + (e & 1) ----
@@ -159,10 +175,12 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ 
       pa[2] = pack_bf16x2(sacc[2 * kb4 + 1][0], sacc[2 * kb4 + 1][1]);
       pa[3] = pack_bf16x2(sacc[2 * kb4 + 1][2], sacc[2 * kb4 + 1][3]);
 #pragma unroll
-      for (int jd = 0; jd < ND; ++jd) {
-        uint32_t bfr[2];
-        mm_ldsm_x2_trans(bfr, sV + (kb4 * 16 + (lane & 15)) * LD + jd * 8);
-        mm_mma_k16(oacc[jd], pa, bfr);
+      for (int jd = 0; jd < ND; jd += 2) {  // one ldmatrix.x4.trans = the B fragments of output tiles jd and jd + 1
+        uint32_t bfr[4];
+        mm_ldsm_x4_trans(bfr, sV + (kb4 * 16 + (lane & 15)) * LD + (jd + (lane >> 4)) * 8);
+        const uint32_t b0[2] = {bfr[0], bfr[1]}, b1[2] = {bfr[2], bfr[3]};
+        mm_mma_k16(oacc[jd], pa, b0);
+        mm_mma_k16(oacc[jd + 1], pa, b1);
       }
     }
   }
@@ -184,7 +202,7 @@ __global__ void __launch_bounds__(128) attn_mma_kernel(const bf16* __restrict__ 
 template <int D>
 static int launch_mma(const bf16* q, const bf16* k, const bf16* v, long long kv_row_stride, long long kv_batch_stride,
                       const AttnParams& prm, cudaStream_t st) {
-  constexpr size_t smem = (size_t)(kMmQ + 2 * kMmK) * (D + 8) * sizeof(bf16);
+  constexpr size_t smem = (size_t)(kMmQ + 4 * kMmK) * (D + 8) * sizeof(bf16);  // Q + two (K | V) buffers
   static bool attr = false;
   if (!attr && smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(attn_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -192,7 +210,7 @@ static int launch_mma(const bf16* q, const bf16* k, const bf16* v, long long kv_
     attr = true;
   }
   dim3 grid((prm.nq + kMmQ - 1) / kMmQ, prm.H, prm.nb);
-  attn_mma_kernel<D><<<grid, 128, smem, st>>>(q, k, v, kv_row_stride, kv_batch_stride, prm);
+  attn_mma_kernel<D><<<grid, kMmThreads, smem, st>>>(q, k, v, kv_row_stride, kv_batch_stride, prm);
   return check_launch("attn_mma");
 }
 
