@@ -66,7 +66,7 @@ int vsb_debug_attn_trace(void* device_buffer);
  * replaces norm1/norm2 + t2i_modulate + t_mask_select: models/transformers/open_sora_transformer_3d.py:47-48,
  * :152-160, :196-200, :260-264.  Rounds to bf16 at the same points as the eager chain (after LN, after 1+scale,
  * after the multiply, after the add).
- *   x, out   [B, T, S, C] bf16 (out may alias x)
+ *   x, out   [B, T, S, C] bf16 (out may alias x); C % 8 == 0, C <= 2304
  *   mod      [2, B, 6, C] bf16: mod[0] = scale_shift_table + t, mod[1] = table + t0 (see vsb_modulation_table)
  *   x_mask   [B, T] uint8 (nonzero -> use mod[0]) or NULL (always mod[0])
  *   shift_row/scale_row: which of the 6 rows (0,1 for attention; 3,4 for the MLP) */
@@ -172,7 +172,9 @@ int vsb_gemm_bias_residual(const vsb_bf16* A, const vsb_bf16* W, const vsb_bf16*
  * replaces F.scaled_dot_product_attention at attentions.py:100 and :268 (bool key mask = per-batch key count).
  * q/k/v are strided views: element (b, n, h, d) at base + b*batch_stride + n*row_stride + h*D + d (strides in
  * elements, multiples of 8).  out [nb, nq, H*D] contiguous.  kv_lens (host int array, nullable) = valid keys per
- * batch (<= nk, nb <= 64 when given).  D must be 72 or 64. */
+ * batch (<= nk, nb <= 64 when given).  head_dim 72 / 64: the tcgen05 kernels; 96 (Open-Sora-Plan v1.2.0,
+ * open_sora_plan_v120_transformer_3d.py:929-931), 128, 80, 48, 32: the same contract on the warp-level tensor path
+ * (mma.sync, FlashAttention-2 schedule, csrc/attn_mma.cu). */
 int vsb_attn_flash(const vsb_bf16* q, const vsb_bf16* k, const vsb_bf16* v, vsb_bf16* out, int nb, int nq, int nk,
                    int H, int D, long long q_row_stride, long long q_batch_stride, long long kv_row_stride,
                    long long kv_batch_stride, const int* host_kv_lens, float scale, void* stream);
