@@ -37,6 +37,12 @@ for g in "$@"; do
     kernels) run kernels 900 tests/test_kernels_gpu.py ;;
     cogx) run cogx 600 tests/test_cogvideox_gpu.py ;;
     latte) run latte 600 tests/test_latte_gpu.py ;;
+    vch) run vch 600 tests/test_vchitect_gpu.py ;;
+    osp) run osp 600 tests/test_osp_gpu.py ;;
+    benchvch) timeout 600 python bench.py --workload vchitect_2b_40f_288x480_100step $BENCH_ARGS > gpurun_out/bench_vchitect.json 2> gpurun_out/bench_vchitect.err
+           echo "benchvch exit $? : $(tail -c 400 gpurun_out/bench_vchitect.json)" | tee -a gpurun_out/summary.txt ;;
+    mmabench) timeout 300 python tools/attn_mma_bench.py > gpurun_out/attn_mma_bench.json 2> gpurun_out/attn_mma_bench.err
+           echo "mmabench exit $? : $(tail -c 500 gpurun_out/attn_mma_bench.json)" | tee -a gpurun_out/summary.txt ;;
     benchcogx) timeout 900 python bench.py --workload cogvideox_2b_49f_480x720_50step $BENCH_ARGS > gpurun_out/benchcogx.json 2> gpurun_out/benchcogx.err
            echo "benchcogx exit $? : $(tail -c 500 gpurun_out/benchcogx.json)" | tee -a gpurun_out/summary.txt; tail -n 3 gpurun_out/benchcogx.err ;;
     kbench) timeout 600 python tools/kernel_bench.py > gpurun_out/kernel_bench.log 2>&1; echo "kbench exit $?" | tee -a gpurun_out/summary.txt; cat gpurun_out/kernel_bench.log | tail -12 ;;
