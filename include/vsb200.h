@@ -115,10 +115,10 @@ int vsb_qk_rmsnorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t
                    void* stream);
 /* Same, followed by RoPE on q and k (attentions.py:76-78 -> rotary_embedding_torch rotate_queries_or_keys: interleaved
  * pairs, fp32 math, cast back): the pre-pass of TEMPORAL attention over >= 30 frames, where the reference leaves
- * native_attention for F.scaled_dot_product_attention (attentions.py:95-100) and vsb_attn_short's 32-token limit is
- * exceeded.  rope_cos / rope_sin [pos_mod, D] fp32; token row r sits at position (r / pos_div) % pos_mod
+ * native_attention for F.scaled_dot_product_attention (attentions.py:95-100).  rope_cos / rope_sin [pos_mod, D] fp32;
+ * token row r sits at position (r / pos_div) % pos_mod
  * (token-major [B, T, S] activation: pos_div = S, pos_mod = T).
- * wq == wk == NULL: RoPE only (q / k stay un-normalised): the temporal attention of Vchitect beyond 32 frames
+ * wq == wk == NULL: RoPE only (q / k stay un-normalised): the temporal attention of Vchitect beyond 64 frames
  * (attentions.py:688-701 apply_rotary_emb, complex multiply on the same interleaved pairs; no q/k norm). */
 int vsb_qk_rmsnorm_rope(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* wk, size_t rows, int H, int D, float eps,
                         const float* rope_cos, const float* rope_sin, int pos_div, int pos_mod, void* stream);
@@ -143,6 +143,8 @@ int vsb_qk_layernorm(vsb_bf16* qkv, const vsb_bf16* wq, const vsb_bf16* bq, cons
  * (bf16(q*scale), bf16 scores, fp32 softmax, bf16 probs).  Reads the packed qkv of the token-major activation
  * without any rearrange: sequence (o,i) token j lives at row o*outer_stride + i*inner_stride + j*tok_stride.
  *   qkv [rows,3,H,D] bf16; out [rows,H*D] bf16; rope_cos/rope_sin [n, D] fp32 or NULL; n == 1 copies v (:65-66).
+ *   n <= 64: two instantiations, up to 32 tokens (OpenSora's 15 .. 20 frames) and 33 .. 64 (Vchitect's 40-frame temporal
+ *   attention, models/modules/attentions.py:707-768, with flags = 3 and RoPE tables from freqs_cis).
  *   flags: bit 0 = no q/k RMSNorm (wq, wk may be NULL): diffusers Attention as used by Latte
  *          (models/transformers/latte_transformer_3d.py:259-268,611-619); bit 1 = SDPA rounding (fp32 scores, scale
  *          inside the softmax) instead of native_attention's bf16 intermediate steps. */

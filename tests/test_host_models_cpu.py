@@ -24,7 +24,7 @@ def _vchitect(tag="vch."):
     return net.eval(), sd
 
 
-@pytest.mark.parametrize("Fr", [5, 1, 34])  # 34 frames: RoPE pre-pass + flash attention on strided views
+@pytest.mark.parametrize("Fr", [5, 1, 34, 66])  # 66 frames: RoPE pre-pass + flash attention on strided views
 def test_vchitect_forward_host_logic(monkeypatch, Fr):
     from oracle import vchitect_oracle as VO
 

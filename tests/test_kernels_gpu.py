@@ -131,7 +131,10 @@ def _rope_tables(n, D, dtype=BF):
                                                 (2, 3, 12, 4, 72, False), (1, 1, 6, 4, 72, True),
                                                 # every warp walks several items (TMA ring phases), row-pad edges
                                                 (2, 20, 700, 16, 72, True), (1, 32, 40, 4, 72, True), (1, 17, 33, 4, 72, True),
-                                                (1, 24, 10, 4, 72, True), (3, 2, 31, 4, 72, False)])
+                                                (1, 24, 10, 4, 72, True), (3, 2, 31, 4, 72, False),
+                                                # the 64-token instantiation (33 .. 64 tokens)
+                                                (1, 40, 70, 4, 72, True), (2, 64, 9, 4, 72, True), (1, 33, 20, 16, 72, True),
+                                                (2, 2, 48, 4, 72, False)])
 def test_attn_short(B, T, S, H, D, temporal):
     """Temporal self-attention core (RMSNorm -> RoPE -> native_attention), token-major in / out, no rearrange."""
     from videosys_b200 import kernels as K
@@ -166,7 +169,8 @@ def test_attn_short(B, T, S, H, D, temporal):
                        None if cos is None else cos.to(dev), None if sin is None else sin.to(dev), *args, H, D, D**-0.5)
     # more keys per row = more fp32-vs-bf16 accumulation-order noise against the eager oracle (n > 24 is outside the
     # OpenSora range; 20 keys stay within 2 ulp)
-    _ulp_report(f"attn_short T={T} S={S} temporal={temporal}", got, want, min_equal=0.97, max_ulps=2.0 if n <= 24 else 3.0, row_floor=0.5)
+    _ulp_report(f"attn_short T={T} S={S} temporal={temporal}", got, want, min_equal=0.97 if n <= 32 else 0.95,
+                max_ulps=2.0 if n <= 24 else (3.0 if n <= 32 else 4.0), row_floor=0.5)
 
 
 def _gemm_check(name, M, N, K_, act, BF=BF):
@@ -608,6 +612,36 @@ def test_attn_short_f16():
     err = (got.cpu().double() - exact).abs()
     print(f"[parity] f16 attn_short: max|err| vs fp64 {err.max().item():.3e}")
     assert (err <= 2.0**-9 * exact.abs().clamp_min(0.02) + 1e-3).all()
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("T,N,H,D", [(40, 100, 6, 64), (64, 33, 3, 64), (34, 50, 4, 72)])
+def test_attn_short_64_tokens_rope_sdpa(T, N, H, D, dt):
+    """The 64-token instantiation as Vchitect's temporal attention uses it (attentions.py:707-768): no q/k norm, RoPE on
+    interleaved pairs from fp32 tables, SDPA rounding; sequences of T frames read in place from the [T, N, 3, H, D] joint buffer."""
+    from videosys_b200 import kernels as K
+
+    dev = _dev()
+    C = H * D
+    qkv = synth.normalish(f"as64.{T}.{N}.{D}", (T, N, 3, H, D)).to(dt)
+    ang = torch.outer(torch.arange(T, dtype=torch.float32), 1.0 / (1e6 ** (torch.arange(0, D, 2).float() / D)))
+    cos, sin = ang.cos().repeat_interleave(2, 1).contiguous(), ang.sin().repeat_interleave(2, 1).contiguous()
+    q, k, v = (qkv[:, :, i].permute(1, 2, 0, 3) for i in range(3))  # [N, H, T, D]
+
+    def rope(x):
+        xf = x.float()
+        x1, x2 = xf[..., 0::2], xf[..., 1::2]
+        rot = torch.stack((-x2, x1), -1).flatten(-2)
+        return (xf * cos[None, None] + rot * sin[None, None]).to(dt)
+
+    exact = torch.nn.functional.scaled_dot_product_attention(rope(q).double(), rope(k).double(), v.double())
+    exact = exact.permute(2, 0, 1, 3).reshape(T * N, C)
+    got = K.attn_short(qkv.to(dev).reshape(-1, 3, H, D), None, None, cos.to(dev), sin.to(dev), 1, N, T * N, 1, N, T, H, D, D**-0.5,
+                       flags=3).cpu()
+    err = (got.double() - exact).abs()
+    tol = (2.0**-7 if dt == torch.bfloat16 else 2.0**-9) * exact.abs().clamp_min(0.02) + (4e-3 if dt == torch.bfloat16 else 1e-3)
+    print(f"[parity] attn_short 64-token {dt} T={T} N={N} D={D}: max|err| vs fp64 {err.max().item():.3e}")
+    assert (err <= tol).all()
 
 
 # ---- determinism: no kernel's result may depend on timing (CTA scheduling order, which warp wins a race, ...) ---------

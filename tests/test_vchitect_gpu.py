@@ -37,7 +37,8 @@ def _net(cfg, dt, tag):
 
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
 @pytest.mark.parametrize("cfg,ocfg,shape,L", [(SMALL, SMALL_O, (1, 5, 4, 12, 16), 9),       # 5 frames: vsb_attn_short
-                                             (SMALL, SMALL_O, (1, 34, 4, 12, 16), 9),      # 34 frames: RoPE pre-pass + flash
+                                             (SMALL, SMALL_O, (1, 34, 4, 12, 16), 9),      # 34 frames: vsb_attn_short's 64-token instantiation
+                                             (SMALL, SMALL_O, (1, 66, 4, 12, 16), 9),      # 66 frames: RoPE pre-pass + flash on strided views
                                              (SMALL, SMALL_O, (1, 1, 4, 12, 16), 9),       # one frame: temporal branch * 0
                                              (WIDE, WIDE_O, (1, 8, 16, 36, 60), 333)])     # 288 x 480, 77 + 256 text tokens
 def test_vchitect_forward(cfg, ocfg, shape, L, dt):

@@ -21,7 +21,8 @@
 
 namespace vsb {
 
-constexpr int kMaxN = 32;
+constexpr int kMaxN = 32;   // the OpenSora instantiation (temporal sequences of 15..20 frames; limit 32)
+constexpr int kMaxN2 = 64;  // second instantiation for 33..64 tokens (Vchitect: 40 frames; OpenSora 102..204-frame videos)
 constexpr int kMaxWarps = 16;
 
 union Vec8s {
@@ -57,7 +58,7 @@ __device__ __forceinline__ void mma_k8(float (&c)[4], const uint32_t (&a)[2], ui
                : "r"(a[0]), "r"(a[1]), "r"(b));
 }
 
-template <int D>
+template <int D, int MAXN = kMaxN>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
     const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
     const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_o, const bf16* __restrict__ wq,
@@ -67,6 +68,8 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
   constexpr int K16 = D / 16;       // full k16 steps of Q K^T
   constexpr bool K8 = (D % 16) != 0;  // one trailing k8 step (D = 72)
   constexpr int ND = D / 8;         // n8 tiles of the output
+  constexpr int NT = MAXN / 8;      // key n8 tiles of a score row
+  constexpr int KK = MAXN / 16;     // key k16 steps of P V = query m16 tiles
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem_raw = smem_dyn + ((128u - (smem_u32(smem_dyn) & 127u)) & 127u);  // keeps the shared address space
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -77,7 +80,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
   // rope table, one float4 per rotated pair (2i, 2i+1) of a position: (cos[2i], cos[2i+1], sin[2i], sin[2i+1])
   float4* s_rope = reinterpret_cast<float4*>(smem_raw + 128);
-  bf16* sq = reinterpret_cast<bf16*>(s_rope + kMaxN * (D / 2)) + (size_t)warp * (2 * rq + kMaxN) * D;
+  bf16* sq = reinterpret_cast<bf16*>(s_rope + MAXN * (D / 2)) + (size_t)warp * (2 * rq + MAXN) * D;
   bf16* sk = sq + (size_t)rq * D;
   bf16* sv = sk + (size_t)rq * D;
   uint64_t* bar = &bars[warp];
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
       s_rope[i] = make_float4(rope_cos[2 * i], rope_cos[2 * i + 1], rope_sin[2 * i], rope_sin[2 * i + 1]);
   }
   // zero V's padding rows once (P is 0 there, but 0 * garbage could be NaN); the TMA boxes never touch them
-  for (int i = lane; i < (kMaxN - n) * VPR; i += 32)
+  for (int i = lane; i < (MAXN - n) * VPR; i += 32)
     *reinterpret_cast<uint4*>(sv + (size_t)n * D + i * 8) = make_uint4(0, 0, 0, 0);
   if (lane == 0) {
     mbar_init(bar, 1);
@@ -202,18 +205,18 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
 
     // ---- 3. S = Q K^T (bf16 out), softmax fp32, P bf16, O = P V ----
 #pragma unroll 1
-    for (int mt = 0; mt < 2; ++mt) {
+    for (int mt = 0; mt < KK; ++mt) {
       if (mt * 16 >= n) break;
-      float sacc[4][4];
+      float sacc[NT][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
+      for (int j = 0; j < NT; ++j) sacc[j][0] = sacc[j][1] = sacc[j][2] = sacc[j][3] = 0.f;
       const bf16* qa = sq + (size_t)(mt * 16 + (lane & 15)) * D + (lane >> 4) * 8;
 #pragma unroll
       for (int ks = 0; ks < K16; ++ks) {
         uint32_t a[4];
         ldsm_x4(a, qa + ks * 16);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NT; ++j) {
           if (j < nt) {
             uint32_t b[2];
             ldsm_x2(b, sk + (size_t)(j * 8 + (lane & 7)) * D + ks * 16 + ((lane >> 3) & 1) * 8);
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
         uint32_t a[2];
         ldsm_x2(a, sq + (size_t)(mt * 16 + (lane & 15)) * D + K16 * 16);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        for (int j = 0; j < NT; ++j) {
           if (j < nt) {
             uint32_t b;
             ldsm_x1(b, sk + (size_t)(j * 8 + (lane & 7)) * D + K16 * 16);
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
       // rows g (c0,c1) and g+8 (c2,c3) of this m-tile; columns 8j + 2t, +1
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NT; ++j) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = j * 8 + 2 * t + (e & 1);
@@ -253,7 +256,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
       float d0 = 0.f, d1 = 0.f;
       const bool rows_hi = mt * 16 + 8 < n;  // rows g + 8 of this m-tile exist (warp-uniform): else their P stays unused
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NT; ++j) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           // exp(-inf) = 0 for masked keys; key tiles beyond the sequence and absent rows skip the exponential
@@ -269,9 +272,9 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
       // P (bf16) as A fragments of the two k16 steps
       // one correctly rounded reciprocal per row, then a multiply (vs p / d: <= 1.5 fp32 ulp before the bf16 rounding of P)
       const float i0 = 1.f / d0, i1 = rows_hi ? 1.f / d1 : 0.f;
-      uint32_t pa[2][4];
+      uint32_t pa[KK][4];
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
+      for (int kb = 0; kb < KK; ++kb) {
         pa[kb][0] = pack_bf16x2(sacc[2 * kb][0] * i0, sacc[2 * kb][1] * i0);
         pa[kb][1] = pack_bf16x2(sacc[2 * kb][2] * i1, sacc[2 * kb][3] * i1);
         pa[kb][2] = pack_bf16x2(sacc[2 * kb + 1][0] * i0, sacc[2 * kb + 1][1] * i0);
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
 #pragma unroll
       for (int jd = 0; jd < ND; ++jd) oacc[jd][0] = oacc[jd][1] = oacc[jd][2] = oacc[jd][3] = 0.f;
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb) {
+      for (int kb = 0; kb < KK; ++kb) {
         if (kb < kk) {
 #pragma unroll
           for (int jd = 0; jd < ND; ++jd) {
@@ -318,21 +321,21 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1) attn_short_kernel(
   if (lane == 0) tma_store_wait0();
 }
 
-template <int D>
+template <int D, int MAXN>
 static int launch_short(const bf16* qkv, bf16* out, const bf16* wq, const bf16* wk, const float* rc, const float* rs,
                         int n_outer, int n_inner, long long os, long long is, long long ts, int n, int H, float eps,
                         float scale, int flags, cudaStream_t st) {
   const int C = H * D;
   const int rq = (n + 7) & ~7;
-  const size_t fixed = 128 + 128 + 2 * kMaxN * D * sizeof(float);  // alignment slack, mbarriers, rope tables
-  const size_t per_warp = (size_t)(2 * rq + kMaxN) * D * sizeof(bf16);
+  const size_t fixed = 128 + 128 + 2 * MAXN * D * sizeof(float);  // alignment slack, mbarriers, rope tables
+  const size_t per_warp = (size_t)(2 * rq + MAXN) * D * sizeof(bf16);
   int warps = int((227 * 1024 - fixed) / per_warp);
   warps = warps >= kMaxWarps ? kMaxWarps : (warps & ~3);
   if (warps < 4) return fail(VSB_ERR_UNSUPPORTED, "attn_short: shared memory");
   const size_t smem = fixed + warps * per_warp;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(attn_short_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attn_short_kernel<D, MAXN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e != cudaSuccess) return fail(VSB_ERR_CUDA, "attn_short: smem attr: %s", cudaGetErrorString(e));
     attr = true;
   }
@@ -357,7 +360,7 @@ static int launch_short(const bf16* qkv, bf16* out, const bf16* wq, const bf16* 
   if (total >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "attn_short: %lld (sequence, head) items", total);
   long long blocks = (total + warps - 1) / warps;
   if (blocks > num_sms()) blocks = num_sms();  // persistent: one CTA per SM, each warp walks its share of the items
-  attn_short_kernel<D><<<(int)blocks, warps * 32, smem, st>>>(tm[0], tm[1], tm[2], tm[3], wq, wk, rc, rs, n_outer, n_inner,
+  attn_short_kernel<D, MAXN><<<(int)blocks, warps * 32, smem, st>>>(tm[0], tm[1], tm[2], tm[3], wq, wk, rc, rs, n_outer, n_inner,
                                                                n, H, eps, scale, flags);
   return check_launch("attn_short");
 }
@@ -373,15 +376,21 @@ extern "C" int VSB_API(vsb_attn_short)(const vsb_bf16* qkv, vsb_bf16* out, const
   if (!qkv || !out || n_outer <= 0 || n_inner <= 0 || n <= 0 || H <= 0)
     return fail(VSB_ERR_INVALID, "attn_short: bad args");
   if ((flags & 1) == 0 && (!wq || !wk)) return fail(VSB_ERR_INVALID, "attn_short: q/k norm weights required (or flag 1)");
-  if (n > kMaxN) return fail(VSB_ERR_UNSUPPORTED, "attn_short: n=%d > %d (use vsb_attn_flash)", n, kMaxN);
+  if (n > kMaxN2) return fail(VSB_ERR_UNSUPPORTED, "attn_short: n=%d > %d (use vsb_attn_flash)", n, kMaxN2);
   if ((rope_cos == nullptr) != (rope_sin == nullptr)) return fail(VSB_ERR_INVALID, "attn_short: rope tables");
   if (!aligned16(qkv) || !aligned16(out)) return fail(VSB_ERR_UNSUPPORTED, "attn_short: alignment");
   cudaStream_t st = (cudaStream_t)stream;
-  if (D == 72)
-    return launch_short<72>((const bf16*)qkv, (bf16*)out, (const bf16*)wq, (const bf16*)wk, rope_cos, rope_sin, n_outer,
-                            n_inner, outer_stride, inner_stride, tok_stride, n, H, eps, scale, flags, st);
-  if (D == 64)
-    return launch_short<64>((const bf16*)qkv, (bf16*)out, (const bf16*)wq, (const bf16*)wk, rope_cos, rope_sin, n_outer,
-                            n_inner, outer_stride, inner_stride, tok_stride, n, H, eps, scale, flags, st);
+#define VSB_SHORT(DD, MM)                                                                                                  \
+  return launch_short<DD, MM>((const bf16*)qkv, (bf16*)out, (const bf16*)wq, (const bf16*)wk, rope_cos, rope_sin, n_outer, \
+                              n_inner, outer_stride, inner_stride, tok_stride, n, H, eps, scale, flags, st)
+  if (D == 72) {
+    if (n <= kMaxN) VSB_SHORT(72, kMaxN);
+    VSB_SHORT(72, kMaxN2);
+  }
+  if (D == 64) {
+    if (n <= kMaxN) VSB_SHORT(64, kMaxN);
+    VSB_SHORT(64, kMaxN2);
+  }
+#undef VSB_SHORT
   return fail(VSB_ERR_UNSUPPORTED, "attn_short: head_dim %d (72 or 64 only)", D);
 }

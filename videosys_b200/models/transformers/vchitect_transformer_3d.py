@@ -10,8 +10,8 @@ and three attentions over the concatenated ``[video | text]`` tokens of a frame 
 
   * temporal (:707-768): every token attends over the F frames at its position, RoPE from ``freqs_cis[:F]``
     (complex multiply on interleaved pairs = the pairing of ``vsb_attn_short`` / ``vsb_qk_rmsnorm_rope``), SDPA rounding,
-    no q/k norm: ``vsb_attn_short`` (flags 3) on the token-major tensor, or the RoPE pre-pass + ``vsb_attn_flash`` on
-    strided views beyond 32 frames;
+    no q/k norm: ``vsb_attn_short`` (flags 3; its 64-token instantiation carries the reference's 40-frame example) on the
+    token-major tensor, or the RoPE pre-pass + ``vsb_attn_flash`` on strided views beyond 64 frames;
   * cross (:770-803): every token of every frame against the text keys / values of FRAME 0: ``vsb_attn_flash`` (the
     K/V-resident schedule for <= 320 keys);
   * spatial (:663-705): per frame over its S + L tokens: ``vsb_attn_flash``, head_dim 64.
@@ -289,7 +289,7 @@ class VchitectXLTransformerModel(nn.Module):
                 Ft, Nt = jt.shape[1], jt.shape[2]
                 jt = jt.view(Ft, Nt, 3 * C)
             cos, sin = self._rope_tables(Ft, dev)
-            if Ft <= 32:
+            if Ft <= 64:
                 ot = K.attn_short(jt.view(-1, 3, H, D), None, None, cos, sin, 1, Nt, Ft * Nt, 1, Nt, Ft, H, D, scale, flags=3)
             else:
                 K.qk_rmsnorm_(jt, None, None, H, D, rope_cos=cos, rope_sin=sin, pos_div=Nt, pos_mod=Ft)
