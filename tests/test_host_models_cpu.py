@@ -288,3 +288,32 @@ def test_osp_v120_pipeline_generate_host_logic(monkeypatch):
     assert out.shape == (1, 4, 5, 8, 8) and torch.isfinite(out).all()
     assert torch.equal(pipe.generate("Sunset over the sea.", **kw).video, out)  # the ancestral noise follows the seed
     assert OpenSoraPlanPipeline.latent_frames(29) == 8 and OpenSoraPlanPipeline.latent_frames(93) == 24
+
+
+def test_widened_models_from_pretrained_local_snapshot(tmp_path):
+    """Vchitect / Open-Sora-Plan v1.1.0 / v1.2.0 load hub-style LOCAL snapshots (config.json with list-valued sample sizes and
+    the library's bookkeeping keys + safetensors) strictly under the reference's parameter names (the layouts
+    pipeline_vchitect.py:222-225 and pipeline_open_sora_plan.py:294-300 read: ``<root>/transformer`` and ``<root>/<type>``)."""
+    import json
+
+    from safetensors.torch import save_file
+
+    from oracle import osp_cases as OC
+    from videosys_b200.models.transformers.open_sora_plan_v110_transformer_3d import LatteT2V
+    from videosys_b200.models.transformers.open_sora_plan_v120_transformer_3d import OpenSoraT2V
+    from videosys_b200.models.transformers.vchitect_transformer_3d import VchitectXLTransformerModel
+
+    def lists(cfg):
+        return {k: (list(v) if isinstance(v, tuple) else v) for k, v in cfg.items()}
+
+    for cls, cfg, sub in ((VchitectXLTransformerModel, VCH, "transformer"),
+                          (LatteT2V, OC.CASES["small_rope"][0], "65x512x512"),
+                          (OpenSoraT2V, OC.CASES12["small_rope"][0], "29x480p")):
+        src = cls(**cfg)
+        d = tmp_path / cls.__name__ / sub
+        d.mkdir(parents=True)
+        (d / "config.json").write_text(json.dumps(dict(lists(cfg), _class_name=cls.__name__, _diffusers_version="0.30.0")))
+        save_file({k: v.contiguous() for k, v in src.state_dict().items()}, str(d / "diffusion_pytorch_model.safetensors"))
+        got = cls.from_pretrained(str(tmp_path / cls.__name__), subfolder=sub)
+        assert set(got.state_dict()) == set(src.state_dict())
+        assert all(torch.equal(got.state_dict()[k], v) for k, v in src.state_dict().items()), cls.__name__
