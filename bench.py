@@ -42,6 +42,8 @@ MODEL = dict(hidden_size=1152, num_heads=16, depth=28, caption_channels=4096, mo
 COGVIDEOX = dict(frames=49, steps=50, h=480, w=720, lat=(13, 16, 60, 90), text=(226, 4096), heads=30, head_dim=64, layers=30)
 # not a BASELINE.json config (SURVEY section 8 (f)4 widening): Vchitect-2.0-2B, the reference's example call (40 frames 288x480,
 # 100 steps, pipeline_vchitect.py:84-93), bf16, 1 GPU
+# not a BASELINE.json config either: Open-Sora-Plan v1.2.0 29x480p (480 x 640 video -> 8 x 60 x 80 latent), 100 ancestral Euler steps
+OSP_V120 = dict(frames=29, steps=100, lat=(4, 8, 60, 80), sample_size=(60, 80), text=(512, 4096), layers=32)
 VCHITECT = dict(frames=40, steps=100, h=288, w=480, lat=(40, 16, 36, 60), text=(333, 4096), pooled=2048, heads=24, head_dim=64,
                 layers=24)
 
@@ -755,61 +757,25 @@ def run_cogvideox(args):
         os._exit(0)
 
 
-def run_vchitect(args):
-    """One denoising step of Vchitect-2.0-2B as the reference runs it (pipeline_vchitect.py:916-954): the unconditional and
-    the text forward (batch 1 each) through VchitectXLTransformerModel (24 MMDiT blocks, three joint attentions each),
-    cosine-ramped guidance, flow-match Euler update.  1 GPU."""
-    import videosys_b200  # noqa: F401
+def _simple_bench(args, name, net, one, n_sched, z_host, dt, frames, steps, config, roof_kind, roof_label, dtype_str, first):
+    """Timing / profiling / JSON tail shared by the single-GPU workloads of the widened models: ``one(z, k)`` is one denoising
+    step on a resident latent (schedule index k); the e2e variant copies the latent in from pinned host memory and the result
+    back out inside the timed region."""
     from videosys_b200 import kernels
     from videosys_b200.core.pab import pab_mgr
-    from videosys_b200.models.transformers.vchitect_transformer_3d import VchitectXLTransformerModel
-    from videosys_b200.pipelines.vchitect.pipeline_vchitect import VchitectPABConfig
-    from videosys_b200.schedulers.scheduling_flow_match_euler import FlowMatchEulerDiscreteScheduler
 
-    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", 1)) != 1:
-        raise SystemExit("the Vchitect workload runs on 1 GPU (frame-sharded sequence parallelism is not built)")
-    W = VCHITECT
     dev = torch.device("cuda", 0)
-    torch.cuda.set_device(0)
-    dt = torch.bfloat16
-    torch.manual_seed(0)
-    layers = args.depth or W["layers"]
-    net = VchitectXLTransformerModel(num_layers=layers, num_attention_heads=W["heads"], attention_head_dim=W["head_dim"],
-                                     caption_projection_dim=W["heads"] * W["head_dim"])
-    for prm in net.parameters():  # random-init weights of the named architecture (incl. the three zero-initialised projections)
-        if prm.ndim >= 2:
-            torch.nn.init.normal_(prm, std=0.02)
-    net = net.to(dt).to(dev).eval()
-    sched = FlowMatchEulerDiscreteScheduler(shift=3.0)
-    sched.set_timesteps(W["steps"], dev)
-    ts = [float(v) for v in sched.timesteps.tolist()]
-    if args.pab:
-        pab_mgr.set_pab_manager(VchitectPABConfig())
-        pab_mgr.update_steps(W["steps"])
-    g = torch.Generator(device="cpu").manual_seed(1)
-    z_host = torch.randn(1, *W["lat"], generator=g).pin_memory()
-    pe = [torch.randn(1, *W["text"], generator=g).to(dev, dt) for _ in range(2)]
-    pp = [torch.randn(1, W["pooled"], generator=g).to(dev, dt) for _ in range(2)]
-    first = args.first_step if args.first_step >= 0 else (20 if args.pab else 0)
     state = {"z": z_host.to(dev, dt)}
 
-    def one(z, k):
-        t = ts[k]
-        tt = sched.timesteps[k].expand(1)
-        un, tx = (net(z, encoder_hidden_states=e, pooled_projections=p, timestep=tt, return_dict=False,
-                      ts_int=int(t) if args.pab else None)[0] for e, p in zip(pe, pp))
-        sched._step_index = k
-        return sched.step(un + 7.5 * (tx - un), t, z)[0]
-
     def step_resident(i):
-        state["z"] = one(state["z"], (first + i) % len(ts))
+        state["z"] = one(state["z"], (first + i) % n_sched)
 
-    out_host = torch.empty(1, *W["lat"], dtype=torch.float32).pin_memory()
-    zdev = torch.empty(1, *W["lat"], device=dev, dtype=torch.float32)
+    out_host = torch.empty(z_host.shape, dtype=torch.float32).pin_memory()
+    zdev = torch.empty(z_host.shape, device=dev, dtype=torch.float32)
 
     def step_e2e(i):
         zdev.copy_(z_host, non_blocking=True)
-        out_host.copy_(one(zdev.to(dt), (first + i) % len(ts)).float(), non_blocking=True)
+        out_host.copy_(one(zdev.to(dt), (first + i) % n_sched).float(), non_blocking=True)
 
     def timed(fn, n):
         torch.cuda.synchronize()
@@ -847,29 +813,21 @@ def run_vchitect(args):
     shares = kernel_fractions({k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[2] / args.steps,
                                    "achieved": v[1] / (v[0] * 1e-3) / (1e12 if k in tf else 1e9),
                                    "unit": "TFLOP/s" if k in tf else "GB/s"} for k, v in by.items()}, peaks)
-    gm = by.get("gemm", [1e-9, 0.0, 1])
-    g_tf = gm[1] / (gm[0] * 1e-3) / 1e12
+    rk = by.get(roof_kind, [1e-9, 0.0, 1])
+    r_tf = rk[1] / (rk[0] * 1e-3) / 1e12
     per = sec / args.steps
-    S, L = (W["h"] // 16) * (W["w"] // 16), W["text"][0]
     line = {
-        "metric": "frames/sec", "value": W["frames"] / (W["steps"] * per), "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
+        "metric": "frames/sec", "value": frames / (steps * per), "unit": "frames/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": "vchitect_2b_40f_288x480_100step", "resolution": "288x480", "frames": 40, "sampling_steps": 100,
-                   "latent": list(W["lat"]), "forwards_per_step": 2, "text_tokens": L, "tokens_per_frame": S + L,
-                   "architecture": "Vchitect-2.0-2B transformer (hidden 1536, 24 heads x 64, 24 MMDiT blocks)",
-                   "pab": bool(args.pab), "parallelism": "single", "first_schedule_index": first,
-                   "l2": "per-step working set (107 MB per joint activation tensor, 24 blocks) exceeds what stays in the 126 MB L2 "
-                         "across a block; no flush needed"},
-        "e2e": {"value": W["frames"] / (W["steps"] * sec_e2e / args.steps), "unit": "frames/s",
-                "h2d_bytes_per_step": z_host.numel() * 4, "d2h_bytes_per_step": out_host.numel() * 4,
-                "ms_per_step": sec_e2e / args.steps * 1e3},
+        "dtype": dtype_str, "data": "synthetic", "config": dict(config, workload=name, pab=bool(args.pab), parallelism="single",
+                                                                first_schedule_index=first),
+        "e2e": {"value": frames / (steps * sec_e2e / args.steps), "unit": "frames/s", "h2d_bytes_per_step": z_host.numel() * 4,
+                "d2h_bytes_per_step": out_host.numel() * 4, "ms_per_step": sec_e2e / args.steps * 1e3},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "gemm2_bf16_tn_kernel / gemm_bf16_tn_kernel (every Linear of the two forwards)", "bound": "tensor",
-                     "achieved": g_tf, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": g_tf / peaks["tflops"], "traffic": None,
-                     "peak_source": peaks["src"], "launches_timed": gm[2],
+        "roofline": {"kernel": roof_label, "bound": "tensor", "achieved": r_tf, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                     "frac": r_tf / peaks["tflops"], "traffic": None, "peak_source": peaks["src"], "launches_timed": rk[2],
                      "timed_in": "a second pass of the same steps with CUDA-event pairs around every launch",
-                     "share_of_step": gm[0] / (sec_prof * 1e3)},
+                     "share_of_step": rk[0] / (sec_prof * 1e3)},
         "kernels": shares, "cpu_baseline": None,
         "cpu_baseline_note": "not sampled for this workload (not a BASELINE.json config); the headline workload carries the CPU arm",
         "clocks": clocks, "cuda_graph": False,
@@ -881,13 +839,124 @@ def run_vchitect(args):
     pab_mgr.set_pab_manager(None)
 
 
+def run_vchitect(args):
+    """One denoising step of Vchitect-2.0-2B as the reference runs it (pipeline_vchitect.py:916-954): the unconditional and
+    the text forward (batch 1 each) through VchitectXLTransformerModel (24 MMDiT blocks, three joint attentions each),
+    cosine-ramped guidance, flow-match Euler update.  1 GPU."""
+    import videosys_b200  # noqa: F401
+    from videosys_b200.core.pab import pab_mgr
+    from videosys_b200.models.transformers.vchitect_transformer_3d import VchitectXLTransformerModel
+    from videosys_b200.pipelines.vchitect.pipeline_vchitect import VchitectPABConfig
+    from videosys_b200.schedulers.scheduling_flow_match_euler import FlowMatchEulerDiscreteScheduler
+
+    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", 1)) != 1:
+        raise SystemExit("the Vchitect workload is a 1-GPU bench line (the model's frame-sharded parallelism has no bench leg)")
+    W = VCHITECT
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    dt = torch.bfloat16
+    torch.manual_seed(0)
+    net = VchitectXLTransformerModel(num_layers=args.depth or W["layers"], num_attention_heads=W["heads"],
+                                     attention_head_dim=W["head_dim"], caption_projection_dim=W["heads"] * W["head_dim"])
+    for prm in net.parameters():  # random-init weights of the named architecture (incl. the three zero-initialised projections)
+        if prm.ndim >= 2:
+            torch.nn.init.normal_(prm, std=0.02)
+    net = net.to(dt).to(dev).eval()
+    sched = FlowMatchEulerDiscreteScheduler(shift=3.0)
+    sched.set_timesteps(W["steps"], dev)
+    ts = [float(v) for v in sched.timesteps.tolist()]
+    if args.pab:
+        pab_mgr.set_pab_manager(VchitectPABConfig())
+        pab_mgr.update_steps(W["steps"])
+    g = torch.Generator(device="cpu").manual_seed(1)
+    z_host = torch.randn(1, *W["lat"], generator=g).pin_memory()
+    pe = [torch.randn(1, *W["text"], generator=g).to(dev, dt) for _ in range(2)]
+    pp = [torch.randn(1, W["pooled"], generator=g).to(dev, dt) for _ in range(2)]
+
+    def one(z, k):
+        t = ts[k]
+        tt = sched.timesteps[k].expand(1)
+        un, tx = (net(z, encoder_hidden_states=e, pooled_projections=p, timestep=tt, return_dict=False,
+                      ts_int=int(t) if args.pab else None)[0] for e, p in zip(pe, pp))
+        sched._step_index = k
+        return sched.step(un + 7.5 * (tx - un), t, z)[0]
+
+    S, L = (W["h"] // 16) * (W["w"] // 16), W["text"][0]
+    config = {"resolution": "288x480", "frames": 40, "sampling_steps": 100, "latent": list(W["lat"]), "forwards_per_step": 2,
+              "text_tokens": L, "tokens_per_frame": S + L,
+              "architecture": "Vchitect-2.0-2B transformer (hidden 1536, 24 heads x 64, 24 MMDiT blocks)",
+              "l2": "per-step working set (107 MB per joint activation tensor, 24 blocks) exceeds what stays in the 126 MB L2 "
+                    "across a block; no flush needed"}
+    _simple_bench(args, "vchitect_2b_40f_288x480_100step", net, one, len(ts), z_host, dt, W["frames"], W["steps"], config, "gemm",
+                  "gemm2_bf16_tn_kernel / gemm_bf16_tn_kernel (every Linear of the two forwards)", "bf16",
+                  args.first_step if args.first_step >= 0 else (20 if args.pab else 0))
+
+
+def run_osp_v120(args):
+    """One denoising step of Open-Sora-Plan v1.2.0 29x480p (pipeline_open_sora_plan.py:1095-1160): the CFG pair through
+    OpenSoraT2V (32 blocks, full 3-D attention over 8 x 30 x 40 = 9600 tokens, 24 heads x 96 -> csrc/attn_mma.cu), guidance,
+    ancestral Euler update.  fp16 as the reference, 1 GPU."""
+    import videosys_b200  # noqa: F401
+    from videosys_b200.core.pab import pab_mgr
+    from videosys_b200.models.transformers.open_sora_plan_v120_transformer_3d import OpenSoraT2V
+    from videosys_b200.pipelines.open_sora_plan.pipeline_open_sora_plan import OpenSoraPlanV120PABConfig
+    from videosys_b200.schedulers.scheduling_euler_ancestral import EulerAncestralDiscreteScheduler
+
+    if args.gpus != 1 or int(os.environ.get("WORLD_SIZE", 1)) != 1:
+        raise SystemExit("the Open-Sora-Plan workload is a 1-GPU bench line")
+    W = OSP_V120
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    dt = torch.float16
+    torch.manual_seed(0)
+    net = OpenSoraT2V(num_layers=args.depth or W["layers"], sample_size=W["sample_size"], sample_size_t=W["lat"][1],
+                      interpolation_scale_h=1.0, interpolation_scale_w=1.0, interpolation_scale_t=1.0)
+    for prm in net.parameters():  # random-init weights of the named architecture (small, so 32 blocks stay finite in fp16)
+        if prm.ndim >= 2:
+            torch.nn.init.normal_(prm, std=0.01)
+    net = net.to(dt).to(dev).eval()
+    sched = EulerAncestralDiscreteScheduler()
+    sched.set_timesteps(W["steps"], dev)
+    ts = [float(v) for v in sched.timesteps.tolist()]
+    if args.pab:
+        pab_mgr.set_pab_manager(OpenSoraPlanV120PABConfig())
+        pab_mgr.update_steps(W["steps"])
+    g = torch.Generator(device="cpu").manual_seed(1)
+    z_host = torch.randn(1, *W["lat"], generator=g).pin_memory()
+    pe = (0.1 * torch.randn(2, 1, *W["text"], generator=g)).to(dev, dt)
+    mask = torch.ones(2, 1, W["text"][0])
+    mask[0, 0, 1:] = 0   # the empty negative prompt
+    mask[1, 0, 60:] = 0  # a 60-token caption, the rest is tokenizer padding
+
+    def one(z, k):
+        t = ts[k]
+        sched._step_index = k
+        inp = sched.scale_model_input(torch.cat([z, z]), t).to(dt)
+        tt = torch.full((2,), t, device=dev, dtype=torch.float32)
+        noise = net(inp, timestep=tt, encoder_hidden_states=pe, encoder_attention_mask=mask, return_dict=False,
+                    ts_int=int(t) if args.pab else None)[0]
+        un, tx = noise.chunk(2)
+        noise = (un + 7.5 * (tx - un)).chunk(2, dim=1)[0]  # learned sigma: keep the mean prediction
+        return sched.step(noise, t, z)[0].to(dt)
+
+    config = {"resolution": "480x640", "frames": 29, "sampling_steps": 100, "latent": list(W["lat"]), "cfg_batch": 2,
+              "text_tokens": W["text"][0], "tokens": W["lat"][1] * (W["sample_size"][0] // 2) * (W["sample_size"][1] // 2),
+              "architecture": "OpenSoraT2V-ROPE-L/122 (hidden 2304, 24 heads x 96, 32 blocks, full 3-D attention)",
+              "l2": "per-step working set (88 MB per activation tensor, 32 blocks) exceeds what stays in the 126 MB L2 across a "
+                    "block; no flush needed"}
+    _simple_bench(args, "osp_v120_29f_480p_100step", net, one, len(ts), z_host, dt, W["frames"], W["steps"], config, "attn_flash",
+                  "attn_mma_kernel<96> behind vsb_attn_flash (3-D self attention over 9600 tokens + text cross attention)", "f16",
+                  args.first_step if args.first_step >= 0 else (20 if args.pab else 0))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="opensora_720p_68f_50step", choices=sorted(WORKLOADS) + ["cogvideox_2b_49f_480x720_50step", "vchitect_2b_40f_288x480_100step"])
+    ap.add_argument("--workload", default="opensora_720p_68f_50step", choices=sorted(WORKLOADS) + ["cogvideox_2b_49f_480x720_50step", "vchitect_2b_40f_288x480_100step",
+                                                                                           "osp_v120_29f_480p_100step"])
     ap.add_argument("--pab", action="store_true", help="enable Pyramid Attention Broadcast (config 5)")
     ap.add_argument("--cp", action="store_true", help="CogVideoX workload, N > 1: CFG parallelism instead of a factor 2 of sequence parallelism")
     ap.add_argument("--depth", type=int, default=0, help="debug only: fewer block pairs (marks the line invalid)")
@@ -902,11 +971,11 @@ def main():
             print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm is defined for the OpenSora workloads"}))
         else:
             run_cogvideox(args)
-    elif args.workload.startswith("vchitect"):
+    elif args.workload.startswith("vchitect") or args.workload.startswith("osp_"):
         if args.impl == "reference":
             print(json.dumps({"impl": "reference", "unavailable": "the CPU reference arm is defined for the OpenSora workloads"}))
         else:
-            run_vchitect(args)
+            (run_vchitect if args.workload.startswith("vchitect") else run_osp_v120)(args)
     elif args.impl == "reference":
         run_reference(args)
     else:
