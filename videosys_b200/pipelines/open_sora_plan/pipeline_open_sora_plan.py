@@ -139,6 +139,10 @@ class OpenSoraPlanPipeline(ParallelPipelineMixin):
             prompt_embeds, prompt_attention_mask, negative_prompt_embeds, negative_prompt_attention_mask = self._embeds(
                 prompt, negative_prompt, max_sequence_length)
         do_cfg = guidance_scale > 1.0
+        if prompt_attention_mask is None:  # caller-supplied embeddings without masks: every token is valid
+            prompt_attention_mask = torch.ones(prompt_embeds.shape[0], prompt_embeds.shape[-2], dtype=torch.int64)
+        if do_cfg and negative_prompt_attention_mask is None:
+            negative_prompt_attention_mask = torch.ones(negative_prompt_embeds.shape[0], negative_prompt_embeds.shape[-2], dtype=torch.int64)
         pe, pm = prompt_embeds.to(dev, dt), prompt_attention_mask
         if do_cfg:  # reference encode_prompt: [negative, positive]
             pe = torch.cat([negative_prompt_embeds.to(dev, dt), pe], dim=0)
