@@ -1,4 +1,4 @@
-"""CogVideoX, Latte and Open-Sora-Plan v1.1.0 under the reference's multi-GPU modes, on 2 real GPUs (run with
+"""CogVideoX, Latte and Open-Sora-Plan (v1.1.0, v1.2.0) under the reference's multi-GPU modes, on 2 real GPUs (run with
 `gpurun --gpus 2 -- python -m pytest tests/test_sp_models_gpu.py -m gpu`):
 
   * CogVideoX head-scatter sequence parallelism (reference cogvideox_transformer_3d.py:44-165, :531-564) with and without
@@ -30,6 +30,10 @@ LATTE_CASES = {"even": (2, 4, 6, 16, 16), "padded": (2, 4, 5, 16, 16)}  # 6 fram
 # Open-Sora-Plan v1.1.0 (RoPE tables must follow the temporal blocks' switch to a patch shard): 5 frames -> pad 1 at sp = 2
 OSP = dict(num_attention_heads=4, attention_head_dim=72, in_channels=4, out_channels=8, num_layers=2, cross_attention_dim=288,
            sample_size=(16, 16), caption_channels=64, video_length=5, use_rope=True)
+# Open-Sora-Plan v1.2.0: tokens split across the ranks, self-attention exchanges tokens for heads (head_dim 96: attn_mma)
+OSP12 = dict(num_attention_heads=4, attention_head_dim=96, in_channels=4, out_channels=8, num_layers=2, cross_attention_dim=384,
+             sample_size=(16, 16), sample_size_t=5, caption_channels=64, interpolation_scale_h=1.0, interpolation_scale_w=2.0,
+             interpolation_scale_t=1.5, use_rope=True)
 PAB_STEPS = [900, 880, 860]
 
 
@@ -70,7 +74,13 @@ def _run_all(dev, mode=None):
     osp = OspT2V(**OSP).to(dt)
     osp.load_state_dict(synth.fill_state_dict(osp.state_dict(), "sposp."))
     osp = osp.to(dev).eval()
+    from videosys_b200.models.transformers.open_sora_plan_v120_transformer_3d import OpenSoraT2V
+
+    osp12 = OpenSoraT2V(**OSP12).to(dt)
+    osp12.load_state_dict(synth.fill_state_dict(osp12.state_dict(), "sposp12."))
+    osp12 = osp12.to(dev).eval()
     if mode is not None:
+        osp12.enable_parallel(1, 2, enable_cp=(mode == "cp"))
         for net in (cogx, latte, osp):
             net.enable_parallel(1, 2, enable_cp=(mode == "cp"))
             pm = net.parallel_manager
@@ -92,6 +102,7 @@ def _run_all(dev, mode=None):
     ts = torch.tensor([500, 500], dtype=torch.int64, device=dev)
     res["osp_v110.padded"] = osp(lat, timestep=ts, all_timesteps=[900, 500], encoder_hidden_states=txt,
                                  encoder_attention_mask=msk, return_dict=False)[0].cpu()
+    res["osp_v120"] = osp12(lat, timestep=ts.float(), encoder_hidden_states=txt, encoder_attention_mask=msk, return_dict=False)[0].cpu()
     # PAB: caches live in the sharded layout (CogVideoX: the attention output of the local rows; Latte: gated outputs of
     # the local frames, MLP outputs through the manager)
     from videosys_b200.pipelines.latte.pipeline_latte import LattePABConfig
@@ -172,4 +183,4 @@ def test_cogvideox_and_latte_two_gpus(mode):
             assert torch.isfinite(v.float()).all(), k
             assert torch.equal(got[r][k], v), f"{mode}=2 differs from one GPU: {k} on rank {r} " \
                                               f"(max abs diff {(got[r][k].float() - v.float()).abs().max().item():.3e})"
-    print(f"[parity] CogVideoX + Latte under {mode}=2: {len(ref)} cases bit-identical to one GPU on both ranks")
+    print(f"[parity] CogVideoX + Latte + Open-Sora-Plan v1.1.0 / v1.2.0 under {mode}=2: {len(ref)} cases bit-identical to one GPU on both ranks")
