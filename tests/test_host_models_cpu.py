@@ -193,6 +193,16 @@ def _sp_worker(rank, world, port, which, enable_cp, q):
             x, enc, m, tt = OC.inputs("small_rope", torch.float32)
             call = lambda: net(x, timestep=tt, all_timesteps=[900, 500], encoder_hidden_states=enc, encoder_attention_mask=m,  # noqa: E731
                                return_dict=False)[0]
+        elif which == "stdit3":  # OpenSora: S-sharded resident layout, spatial blocks switch to a frame shard (NCCL transport here)
+            from oracle import cases
+            from videosys_b200.models.transformers.open_sora_transformer_3d import STDiT3, STDiT3Config
+
+            os.environ["VSB_DSP_P2P"] = "0"  # the peer-memory windows need CUDA IPC; all_to_all_single carries the switch
+            net = STDiT3(STDiT3Config(**cases.small_model_cfg(depth=2))).to(torch.bfloat16)
+            net.load_state_dict(synth.fill_state_dict(net.state_dict(), "spstd."))
+            inp = cases.forward_inputs(torch.bfloat16)
+            call = lambda: net(inp["x"], inp["timestep"], inp["y"], mask=inp["mask"], x_mask=inp["x_mask"], fps=inp["fps"],  # noqa: E731
+                               height=inp["height"], width=inp["width"]).float()
         elif which == "osp_v120":
             from videosys_b200.models.transformers.open_sora_plan_v120_transformer_3d import OpenSoraT2V
 
@@ -233,7 +243,7 @@ def _sp_worker(rank, world, port, which, enable_cp, q):
 
 
 @pytest.mark.parametrize("which,enable_cp", [("osp_v110", False), ("osp_v110", True), ("latte", False), ("cogvideox", False),
-                                             ("cogvideox", True), ("osp_v120", False)])
+                                             ("cogvideox", True), ("osp_v120", False), ("stdit3", False)])
 def test_model_parallelism_gloo_world2(which, enable_cp):
     """Two ranks: frame-sharded DSP (Latte / Open-Sora-Plan v1.1.0: temporal blocks switch to a patch shard, with the RoPE
     tables following the switch), head-scatter sequence parallelism (CogVideoX) or CFG parallelism reproduce the single-rank
@@ -241,7 +251,7 @@ def test_model_parallelism_gloo_world2(which, enable_cp):
     import multiprocessing as mp
     import os
 
-    world, port = 2, 30100 + (os.getpid() % 300) + 7 * ["osp_v110", "latte", "cogvideox", "osp_v120"].index(which) + int(enable_cp)
+    world, port = 2, 30100 + (os.getpid() % 300) + 7 * ["osp_v110", "latte", "cogvideox", "osp_v120", "stdit3"].index(which) + int(enable_cp)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_sp_worker, args=(r, world, port, which, enable_cp, q)) for r in range(world)]

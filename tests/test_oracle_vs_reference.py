@@ -797,3 +797,65 @@ def test_osp_v120_rope3d_tables_vs_reference_class(dtype):
     assert half == 16
     partner = q.reshape(*q.shape[:-1], D // (2 * half), 2, half).flip(-2).reshape(q.shape)
     assert torch.equal(q * c.to(dtype) + partner * s.to(dtype), want)
+
+
+def test_stdit3_mirror_vs_reference_model(monkeypatch):
+    """The headline model's front end (videosys_b200 STDiT3, kernel entries = torch stand-ins, bf16 as it insists) against
+    the reference STDiT3 executed unmodified: within the reference's own bf16-vs-fp32 error, with PAB off and over 6 PAB
+    steps (hoisted text projections, modulation tables, per-frame mask select, final layer on the shard, un-patchify)."""
+    from tests import kernels_emul
+    from videosys_b200.core.pab import pab_mgr as ours
+    from videosys_b200.models.transformers.open_sora_transformer_3d import STDiT3, STDiT3Config
+
+    kernels_emul.emulate(monkeypatch)
+    c = cases.small_model_cfg(depth=2)
+    ref16 = ref_loader.build_stdit3(dtype=torch.bfloat16, **c)
+    sd = synth.fill_state_dict(ref16.state_dict(), "stde.")
+    ref16.load_state_dict(sd)
+    ref32 = ref_loader.build_stdit3(dtype=torch.float32, **c)
+    ref32.load_state_dict({k: v.float() for k, v in sd.items()})
+    net = STDiT3(STDiT3Config(**c)).to(torch.bfloat16)
+    net.load_state_dict(sd)
+    net.eval()
+    P = ref_loader.load().pab_mgr
+
+    def rel(a, b):
+        return ((a.double() - b.double()).norm() / b.double().norm()).item()
+
+    def run(model, inp, dt):
+        f = lambda v: v.to(dt) if torch.is_tensor(v) and v.is_floating_point() else v  # noqa: E731
+        with torch.no_grad():
+            return model(f(inp["x"]), f(inp["timestep"]), f(inp["y"]), mask=inp["mask"], x_mask=inp["x_mask"], fps=f(inp["fps"]),
+                         height=f(inp["height"]), width=f(inp["width"]))
+
+    inp = cases.forward_inputs(torch.bfloat16)
+    got, w16, w32 = run(net, inp, torch.bfloat16), run(ref16, inp, torch.bfloat16), run(ref32, inp, torch.float32)
+    assert got.shape == w32.shape and rel(got, w32) <= 1.3 * rel(w16, w32) + 1e-4, (rel(got, w32), rel(w16, w32))
+    kw = dict(spatial_broadcast=True, spatial_threshold=[100, 930], spatial_range=2, temporal_broadcast=True,
+              temporal_threshold=[100, 930], temporal_range=3, cross_broadcast=True, cross_threshold=[100, 930], cross_range=4)
+    steps = [900.0, 800.0, 700.0, 600.0, 500.0, 50.0]
+    ours.set_pab_manager(ours.PABConfig(**kw))
+    ours.update_steps(len(steps))
+    net.reset_pab_state()
+    try:
+        outs = []
+        for t in steps:
+            inp["timestep"] = torch.tensor([t, t], dtype=torch.bfloat16)
+            outs.append(run(net, inp, torch.bfloat16))
+        for model, dt, name in ((ref16, torch.bfloat16, "w16"), (ref32, torch.float32, "w32")):
+            P.set_pab_manager(P.PABConfig(**kw))
+            P.update_steps(len(steps))
+            res = []
+            for t in steps:
+                inp["timestep"] = torch.tensor([t, t], dtype=torch.bfloat16)
+                res.append(run(model, inp, dt))
+            P.PAB_MANAGER = None
+            if name == "w16":
+                r16 = res
+            else:
+                r32 = res
+        for i in range(len(steps)):
+            assert rel(outs[i], r32[i]) <= 1.3 * rel(r16[i], r32[i]) + 1e-4, (i, rel(outs[i], r32[i]), rel(r16[i], r32[i]))
+    finally:
+        P.PAB_MANAGER = None
+        ours.set_pab_manager(None)

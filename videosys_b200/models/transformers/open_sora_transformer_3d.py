@@ -523,8 +523,7 @@ class STDiT3(nn.Module):
     @torch.no_grad()
     def forward(self, x, timestep, y, all_timesteps=None, mask=None, x_mask=None, fps=None, height=None, width=None,
                 **kwargs):
-        if not x.is_cuda:
-            raise RuntimeError("videosys_b200.STDiT3 runs on sm_100a CUDA devices only (no CPU path)")
+        kernels.require_cuda(x, "STDiT3")
         dtype = self.x_embedder.proj.weight.dtype
         if dtype != torch.bfloat16:
             raise RuntimeError("videosys_b200.STDiT3 kernels are bf16: call model.to(torch.bfloat16)")
