@@ -153,7 +153,7 @@ def _dsp_worker(rank, world, port, T, S, q):
         b = comm.all_to_all_with_pad(a, pm.sp_group, scatter_dim=2, gather_dim=1, scatter_pad=comm.get_pad("spatial"),
                                      gather_pad=comm.get_pad("temporal"))
         g = comm.gather_sequence(b, pm.sp_group, dim=2, pad=comm.get_pad("spatial"))
-        q.put((rank, x, a, b, g, None))
+        q.put((rank, x.numpy(), a.numpy(), b.numpy(), g.numpy(), None))  # by value: a tensor's shared-memory file dies with the worker
         dist.barrier()
         dist.destroy_process_group()
     except Exception as e:  # pragma: no cover
@@ -173,7 +173,7 @@ def test_dsp_comm_gloo_world2(T, S):
     for _ in range(world):
         r, x, a, b, g, err = q.get(timeout=120)
         assert err is None, err
-        res[r] = (x.clone(), a.clone(), b.clone(), g.clone())
+        res[r] = tuple(torch.from_numpy(v).clone() for v in (x, a, b, g))
     [p.join(timeout=60) for p in procs]
     B, C = 2, 16
     full = synth.normalish(f"gloo{T}{S}", (B, T, S, C))
@@ -203,7 +203,7 @@ def _ulysses_worker(rank, world, port, q):
         a = comm.ulysses_scatter_heads(mine, Nt, pm.sp_group)  # every row, my heads
         o = a[:, :, 0].reshape(B, Nt + Nv, -1).contiguous()    # stand-in attention output: my heads of q
         back = comm.ulysses_gather_heads(o, Nt, pm.sp_group)    # my rows, every head
-        q.put((rank, a, back, None))
+        q.put((rank, a.contiguous().numpy(), back.contiguous().numpy(), None))  # by value
         dist.barrier()
         dist.destroy_process_group()
     except Exception:  # pragma: no cover
@@ -224,7 +224,7 @@ def test_ulysses_head_scatter_gloo_world2():
     for _ in range(world):
         r, a, back, err = q.get(timeout=120)
         assert err is None, err
-        res[r] = (a.clone(), back.clone())
+        res[r] = (torch.from_numpy(a).clone(), torch.from_numpy(back).clone())
     [p.join(timeout=60) for p in procs]
     B, Nt, Nv, H, D = 2, 3, 8, 4, 2
     full = synth.normalish("ulysses", (B, Nt + Nv, 3, H, D))
