@@ -66,7 +66,7 @@ int vsb_debug_attn_trace(void* device_buffer);
  * replaces norm1/norm2 + t2i_modulate + t_mask_select: models/transformers/open_sora_transformer_3d.py:47-48,
  * :152-160, :196-200, :260-264.  Rounds to bf16 at the same points as the eager chain (after LN, after 1+scale,
  * after the multiply, after the add).
- *   x, out   [B, T, S, C] bf16 (out may alias x); C % 8 == 0, C <= 2304
+ *   x, out   [B, T, S, C] bf16 (out may alias x); C % 8 == 0, C <= 3072
  *   mod      [2, B, 6, C] bf16: mod[0] = scale_shift_table + t, mod[1] = table + t0 (see vsb_modulation_table)
  *   x_mask   [B, T] uint8 (nonzero -> use mod[0]) or NULL (always mod[0])
  *   shift_row/scale_row: which of the 6 rows (0,1 for attention; 3,4 for the MLP) */

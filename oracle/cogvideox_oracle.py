@@ -36,8 +36,46 @@ def layer_norm_zero(sd: Dict[str, Tensor], p: str, hidden: Tensor, enc: Tensor, 
     return hs, es, gate[:, None, :], e_gate[:, None, :]
 
 
-def joint_attention(sd, p: str, hidden: Tensor, enc: Tensor, heads: int):
-    """CogVideoXAttnProcessor2_0.__call__ with sp_size == 1, no mask, no rotary: cogvideox_transformer_3d.py:88-175."""
+def apply_rotary_emb(x: Tensor, cos: Tensor, sin: Tensor) -> Tensor:
+    """models/modules/embeddings.py:367-412 (use_real, unbind dim -1): interleaved pairs, fp32 math, cast back."""
+    xr, xi = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)
+    rot = torch.stack([-xi, xr], dim=-1).flatten(3)
+    return (x.float() * cos[None, None] + rot.float() * sin[None, None]).to(x.dtype)
+
+
+def rotary_3d(embed_dim: int, crops_coords, grid_size, temporal_size: int, theta: float = 10000.0):
+    """get_3d_rotary_pos_embed (models/modules/embeddings.py:283-364): (cos, sin) [T*H*W, embed_dim]; a quarter of the
+    channels for the frame, three eighths each for the (cropped, resized) row and column coordinate."""
+    (s0, s1), (e0, e1) = crops_coords
+    lin = lambda a, b, n: torch.from_numpy(__import__("numpy").linspace(a, b, n, endpoint=False, dtype="float32")).float()  # noqa: E731
+    gh, gw, gt = lin(s0, e0, grid_size[0]), lin(s1, e1, grid_size[1]), lin(0, temporal_size, temporal_size)
+    dt_, dh = embed_dim // 4, embed_dim // 8 * 3
+
+    def fr(g, d):
+        f = 1.0 / (theta ** (torch.arange(0, d, 2).float() / d))
+        return torch.einsum("n,f->nf", g, f).repeat_interleave(2, dim=-1)
+
+    ft, fh, fw = fr(gt, dt_), fr(gh, dh), fr(gw, dh)
+    T, H, W = temporal_size, grid_size[0], grid_size[1]
+    freqs = torch.cat([ft[:, None, None, :].expand(T, H, W, -1), fh[None, :, None, :].expand(T, H, W, -1),
+                       fw[None, None, :, :].expand(T, H, W, -1)], dim=-1).reshape(T * H * W, -1)
+    return freqs.cos(), freqs.sin()
+
+
+def resize_crop_region_for_grid(src, tgt_width, tgt_height):
+    """pipelines/cogvideox/pipeline_cogvideox.py:758-773."""
+    h, w = src
+    if h / w > tgt_height / tgt_width:
+        rh, rw = tgt_height, int(round(tgt_height / h * w))
+    else:
+        rw, rh = tgt_width, int(round(tgt_width / w * h))
+    top, left = int(round((tgt_height - rh) / 2.0)), int(round((tgt_width - rw) / 2.0))
+    return (top, left), (top + rh, left + rw)
+
+
+def joint_attention(sd, p: str, hidden: Tensor, enc: Tensor, heads: int, rotary=None):
+    """CogVideoXAttnProcessor2_0.__call__ with sp_size == 1, no mask: cogvideox_transformer_3d.py:88-175; rotary = (cos, sin)
+    of the video tokens (:146-155, CogVideoX-5b) or None."""
     text_len = enc.size(1)
     x = torch.cat([enc, hidden], dim=1)
     B, N, C = x.shape
@@ -50,6 +88,10 @@ def joint_attention(sd, p: str, hidden: Tensor, enc: Tensor, heads: int):
     v = v.view(B, -1, heads, D).transpose(1, 2)
     q = F.layer_norm(q, (D,), sd[p + "norm_q.weight"], sd[p + "norm_q.bias"], 1e-6)
     k = F.layer_norm(k, (D,), sd[p + "norm_k.weight"], sd[p + "norm_k.bias"], 1e-6)
+    if rotary is not None:
+        n = rotary[0].shape[0]
+        q[:, :, text_len : text_len + n] = apply_rotary_emb(q[:, :, text_len : text_len + n], *rotary)
+        k[:, :, text_len : text_len + n] = apply_rotary_emb(k[:, :, text_len : text_len + n], *rotary)
     o = F.scaled_dot_product_attention(q, k, v, attn_mask=None, dropout_p=0.0, is_causal=False)
     o = o.transpose(1, 2).reshape(B, -1, C)
     o = F.linear(o, sd[p + "to_out.0.weight"], sd[p + "to_out.0.bias"])
@@ -68,7 +110,8 @@ class BlockPAB:
         self.last_attn = None
 
 
-def block(sd, p: str, hidden: Tensor, enc: Tensor, temb: Tensor, heads: int, pab=None, pab_state=None, timestep_int=None):
+def block(sd, p: str, hidden: Tensor, enc: Tensor, temb: Tensor, heads: int, pab=None, pab_state=None, timestep_int=None,
+          rotary=None):
     """CogVideoXBlock.forward: cogvideox_transformer_3d.py:268-312 (PAB: spatial gate only, :284-295)."""
     text_len = enc.size(1)
     nh, ne, gate, e_gate = layer_norm_zero(sd, p + "norm1.", hidden, enc, temb)
@@ -78,7 +121,7 @@ def block(sd, p: str, hidden: Tensor, enc: Tensor, temb: Tensor, heads: int, pab
     if reuse:
         ah, ae = pab_state.last_attn
     else:
-        ah, ae = joint_attention(sd, p + "attn1.", nh, ne, heads)
+        ah, ae = joint_attention(sd, p + "attn1.", nh, ne, heads, rotary)
         if pab is not None and pab.enabled():
             pab_state.last_attn = (ah, ae)
     hidden = hidden + gate * ah
@@ -117,7 +160,7 @@ def timestep_sinusoid(timesteps: Tensor, dim: int, flip_sin_to_cos=True, freq_sh
     return torch.cat([emb[:, half:], emb[:, :half]], dim=-1) if flip_sin_to_cos else emb
 
 
-def transformer_forward(sd, cfg: dict, hidden: Tensor, enc: Tensor, timestep: Tensor, pab=None, pab_states=None):
+def transformer_forward(sd, cfg: dict, hidden: Tensor, enc: Tensor, timestep: Tensor, pab=None, pab_states=None, rotary=None):
     """CogVideoXTransformer3DModel.forward (:479-589), 2B configuration; cfg: heads, head_dim, layers, patch,
     max_text, sample_width/height/frames, spatial_scale, temporal_scale, out_channels, eps."""
     dt = sd["proj_out.weight"].dtype
@@ -136,11 +179,12 @@ def transformer_forward(sd, cfg: dict, hidden: Tensor, enc: Tensor, timestep: Te
     pos = torch.zeros(1, cfg["max_text"] + (cfg["sample_height"] // p) * (cfg["sample_width"] // p) * frames, C)
     pos[:, cfg["max_text"]:] = sincos_3d(C, (cfg["sample_width"] // p, cfg["sample_height"] // p), frames,
                                          cfg.get("spatial_scale", 1.875), cfg.get("temporal_scale", 1.0)).flatten(0, 1)
-    x = x + pos[:, : x.shape[1]].to(dt)
+    if rotary is None:  # use_rotary_positional_embeddings (CogVideoX-5b) adds no table (:519-524)
+        x = x + pos[:, : x.shape[1]].to(dt)
     e, h = x[:, :Nt], x[:, Nt:]
     ts_int = int(timestep[0]) if pab is not None else None
     for i in range(cfg["layers"]):
-        h, e = block(sd, f"transformer_blocks.{i}.", h, e, emb, heads, pab, pab_states[i] if pab_states else None, ts_int)
+        h, e = block(sd, f"transformer_blocks.{i}.", h, e, emb, heads, pab, pab_states[i] if pab_states else None, ts_int, rotary)
     eps = cfg.get("eps", 1e-5)
     h = F.layer_norm(h, (C,), sd["norm_final.weight"], sd["norm_final.bias"], eps)
     shift, scale = F.linear(F.silu(emb), sd["norm_out.linear.weight"], sd["norm_out.linear.bias"]).chunk(2, dim=1)

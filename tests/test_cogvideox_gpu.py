@@ -127,6 +127,40 @@ def test_cogvideox_transformer_forward(dt):
     assert e_ours <= 1.3 * e_ref + 1e-4
 
 
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_cogvideox_rotary_forward(dt):
+    """use_rotary_positional_embeddings=True (CogVideoX-5b; its dtype is bf16): no position table, q / k of the video tokens
+    rotated by the 3-D rotary tables through vsb_qk_rmsnorm_rope's RoPE-only mode (identity rows for the text tokens); the oracle
+    is pinned bit for bit against the reference model (tests/test_oracle_vs_reference.py)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from videosys_b200.models.transformers.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+
+    dev = torch.device("cuda:0")
+    net = CogVideoXTransformer3DModel(**dict(SMALL, use_rotary_positional_embeddings=True)).to(dt)
+    sd = _fill(net)
+    for k in sd:
+        if k.endswith("norm_final.weight") or k.endswith("norm_out.norm.weight"):
+            sd[k] = (1.0 + 0.2 * synth.uniform("cogxr." + k, tuple(sd[k].shape))).to(dt)
+    net.load_state_dict(sd)
+    net = net.to(dev).eval()
+    B, Fr, H, W = 2, 3, 12, 16
+    lat = synth.normalish("cogxr.lat", (B, Fr, 4, H, W)).to(dt)
+    txt = synth.normalish("cogxr.txt", (B, 16, 48)).to(dt)
+    ts = torch.tensor([499, 499], dtype=torch.int64)
+    rot = CO.rotary_3d(64, CO.resize_crop_region_for_grid((6, 8), 45, 30), (6, 8), Fr)
+    out = net(lat.to(dev), txt.to(dev), ts.to(dev), image_rotary_emb=(rot[0].to(dev), rot[1].to(dev)), return_dict=False)[0].cpu()
+    with torch.no_grad():
+        r16 = CO.transformer_forward(sd, SMALL_O, lat, txt, ts, rotary=rot)
+        r32 = CO.transformer_forward({k: v.float() for k, v in sd.items()}, SMALL_O, lat.float(), txt.float(), ts, rotary=rot)
+        plain = CO.transformer_forward({k: v.float() for k, v in sd.items()}, SMALL_O, lat.float(), txt.float(), ts)
+    e_ours, e_ref = _rel(out, r32), _rel(r16, r32)
+    print(f"[parity] cogvideox rotary forward {dt}: ours-vs-fp32 {e_ours:.3e}, oracle 16-bit-vs-fp32 {e_ref:.3e}, "
+          f"rotary-vs-table model {_rel(plain, r32):.3e}")
+    assert e_ours <= 1.3 * e_ref + 1e-4
+    assert _rel(plain, r32) > 10 * e_ref, "the rotary path must matter in this test"
+
+
 def test_cogvideox_joint_attention_real_length():
     """The joint text + video attention at cfg4's real sequence length (226 + 17 550 = 17 776 tokens, head_dim 64, fp16),
     two heads of the 30: flash kernel vs fp64 attention on a subsample of query rows."""

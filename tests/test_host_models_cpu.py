@@ -221,16 +221,19 @@ def _sp_worker(rank, world, port, which, enable_cp, q):
             tt = torch.tensor([500, 500])
             call = lambda: net(x, timestep=tt, all_timesteps=[900, 500], encoder_hidden_states=enc, return_dict=False)[0]  # noqa: E731
         else:
+            from oracle import cogvideox_oracle as CO
             from videosys_b200.models.transformers.cogvideox_transformer_3d import CogVideoXTransformer3DModel
 
+            rope = which == "cogvideox_rope"  # CogVideoX-5b: rotary tables follow the head-scatter exchange (pad rows = identity)
             net = CogVideoXTransformer3DModel(num_attention_heads=4, attention_head_dim=64, in_channels=4, out_channels=4,
                                               time_embed_dim=64, text_embed_dim=48, num_layers=2, sample_width=16, sample_height=12,
-                                              sample_frames=9, max_text_seq_length=16)
+                                              sample_frames=9, max_text_seq_length=16, use_rotary_positional_embeddings=rope)
             net.load_state_dict(synth.fill_state_dict(net.state_dict(), "spc."))
             lat = synth.normalish("spc.lat", (2, 3, 4, 12, 14))  # 6 x 7 = 42 patches per frame: 126 video rows, odd chunking
             txt = synth.normalish("spc.txt", (2, 16, 48))
             tt = torch.tensor([499, 499])
-            call = lambda: net(lat, txt, tt, return_dict=False)[0]  # noqa: E731
+            rot = CO.rotary_3d(64, CO.resize_crop_region_for_grid((6, 7), 45, 30), (6, 7), 3) if rope else None
+            call = lambda: net(lat, txt, tt, image_rotary_emb=rot, return_dict=False)[0]  # noqa: E731
         net.eval()
         want = call()  # unsharded (parallel_manager None)
         net.enable_parallel(1, world, enable_cp)
@@ -243,7 +246,8 @@ def _sp_worker(rank, world, port, which, enable_cp, q):
 
 
 @pytest.mark.parametrize("which,enable_cp", [("osp_v110", False), ("osp_v110", True), ("latte", False), ("cogvideox", False),
-                                             ("cogvideox", True), ("osp_v120", False), ("stdit3", False)])
+                                             ("cogvideox", True), ("osp_v120", False), ("stdit3", False),
+                                             ("cogvideox_rope", False)])
 def test_model_parallelism_gloo_world2(which, enable_cp):
     """Two ranks: frame-sharded DSP (Latte / Open-Sora-Plan v1.1.0: temporal blocks switch to a patch shard, with the RoPE
     tables following the switch), head-scatter sequence parallelism (CogVideoX) or CFG parallelism reproduce the single-rank
@@ -251,7 +255,7 @@ def test_model_parallelism_gloo_world2(which, enable_cp):
     import multiprocessing as mp
     import os
 
-    world, port = 2, 30100 + (os.getpid() % 300) + 7 * ["osp_v110", "latte", "cogvideox", "osp_v120", "stdit3"].index(which) + int(enable_cp)
+    world, port = 2, 30100 + (os.getpid() % 300) + 7 * ["osp_v110", "latte", "cogvideox", "osp_v120", "stdit3", "cogvideox_rope"].index(which) + int(enable_cp)
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     procs = [ctx.Process(target=_sp_worker, args=(r, world, port, which, enable_cp, q)) for r in range(world)]

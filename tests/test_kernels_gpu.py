@@ -53,7 +53,8 @@ def _mask_u8(x_mask, dev):
     return x_mask.to(torch.uint8).contiguous().to(dev)
 
 
-@pytest.mark.parametrize("B,T,S,C", [(2, 5, 36, 288), (2, 3, 50, 1152), (1, 2, 7, 1920)])
+@pytest.mark.parametrize("B,T,S,C", [(2, 5, 36, 288), (2, 3, 50, 1152), (1, 2, 7, 1920),
+                                     (2, 2, 9, 2304), (1, 3, 11, 3072)])  # Open-Sora-Plan v1.2.0 / CogVideoX-5b widths
 def test_ln_modulate(B, T, S, C):
     from videosys_b200 import kernels as K
 

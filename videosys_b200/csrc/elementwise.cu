@@ -480,8 +480,8 @@ static int ln_modulate_launch(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* 
                               int S, int C, float eps, const LnDspArgs* dsp, void* stream) {
   if ((gamma == nullptr) != (beta == nullptr)) return fail(VSB_ERR_INVALID, "ln_modulate: gamma and beta go together");
   if (!x || (!out && !dsp) || !mod || B <= 0 || T <= 0 || S <= 0 || C <= 0) return fail(VSB_ERR_INVALID, "ln_modulate: bad args");
-  if (C % 8 || C > 2304 || (dsp && C > 2048) || !aligned16(x) || !aligned16(out) || !aligned16(mod))
-    return fail(VSB_ERR_UNSUPPORTED, "ln_modulate: need C %% 8 == 0, C <= 2304 (2048 with the fused reshard), 16B-aligned pointers (C=%d)", C);
+  if (C % 8 || C > 3072 || (dsp && C > 2048) || !aligned16(x) || !aligned16(out) || !aligned16(mod))
+    return fail(VSB_ERR_UNSUPPORTED, "ln_modulate: need C %% 8 == 0, C <= 3072 (2048 with the fused reshard), 16B-aligned pointers (C=%d)", C);
   if (shift_row < 0 || shift_row > 5 || scale_row < 0 || scale_row > 5) return fail(VSB_ERR_INVALID, "ln_modulate: row");
   long long rows = (long long)B * T * S;
   if (rows >= (1ll << 31)) return fail(VSB_ERR_UNSUPPORTED, "ln_modulate: %lld rows", rows);
@@ -499,8 +499,10 @@ static int ln_modulate_launch(const vsb_bf16* x, vsb_bf16* out, const vsb_bf16* 
     if (g_opt_ln_occupancy >= 4) VSB_LN_LAUNCH(5, false, 4, none); else VSB_LN_LAUNCH(5, false, 3, none);
   } else if (C <= 2048) {
     VSB_LN_LAUNCH(8, false, 2, none);
-  } else {  // hidden 2304 (Open-Sora-Plan v1.2.0: 24 heads x 96)
+  } else if (C <= 2304) {  // hidden 2304 (Open-Sora-Plan v1.2.0: 24 heads x 96)
     VSB_LN_LAUNCH(9, false, 2, none);
+  } else {  // hidden 3072 (CogVideoX-5b: 48 heads x 64): the row still lives in registers, one block per SM slot
+    VSB_LN_LAUNCH(12, false, 1, none);
   }
 #undef VSB_LN_LAUNCH
   return check_launch("ln_modulate");

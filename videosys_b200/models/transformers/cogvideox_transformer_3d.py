@@ -113,13 +113,16 @@ class CogVideoXBlockStack(nn.Module):
 
     @torch.no_grad()
     def forward(self, hidden: torch.Tensor, enc: torch.Tensor, temb: torch.Tensor, timestep=None, ts_int=None,
-                sp_group=None, n_video: int = None):
+                sp_group=None, n_video: int = None, rope=None):
         """hidden [B, Nv, C], enc [B, Nt, C] (fp16 / bf16, CUDA), temb [B, time_embed_dim]; returns the two streams.
         ts_int: host integer timestep for the PAB gate (else one D2H read of timestep[0], as the reference does).
         sp_group: sequence-parallel group; ``hidden`` is then this rank's chunk of the (zero-padded) video rows and
         ``n_video`` the unpadded global row count.  Everything but the attention core is row-wise and runs on the local
         rows; the joint attention runs on H / sp heads over every row after the head-scatter exchange (reference
-        :112-122, :138-143, :162-165), pad rows excluded as keys (:58-62) and zero in the output (:66-72)."""
+        :112-122, :138-143, :162-165), pad rows excluded as keys (:58-62) and zero in the output (:66-72).
+        rope (CogVideoX-5b, :146-155): (cos, sin) fp32 tables [text + video rows, head_dim] of ``vsb_qk_rmsnorm_rope``'s RoPE-only
+        mode -- identity rows for the text tokens (and pad rows), the 3-D rotary angles for the video tokens; applied to q
+        and k after their LayerNorm, on the full sequence."""
         K = kernels
         K.require_cuda(hidden, "CogVideoX blocks", half_only=True)
         B, Nv, C = hidden.shape
@@ -145,12 +148,17 @@ class CogVideoXBlockStack(nn.Module):
                 at = blk.attn1
                 K.qk_layernorm_(qkv, at.norm_q.weight, at.norm_q.bias, at.norm_k.weight, at.norm_k.bias, H, D, eps=1e-6)
                 if sp_group is None:
+                    if rope is not None:
+                        K.qk_rmsnorm_(qkv, None, None, H, D, rope_cos=rope[0], rope_sin=rope[1], pos_div=1, pos_mod=N)
                     q3 = qkv.view(-1, 3, C)
                     o = K.attn_flash(q3[:, 0], q3[:, 1], q3[:, 2], B, N, N, H, D, 3 * C, N * 3 * C, 3 * C, N * 3 * C, D**-0.5)
                 else:
                     full = comm.ulysses_scatter_heads(qkv.view(B, N, 3, H, D), Nt, sp_group)  # every row, H / sp heads
                     Lf, Hn = full.shape[1], full.shape[3]
                     Cn, Lv = Hn * D, Nt + n_video
+                    if rope is not None:  # positions of the gathered sequence (the table covers the pad rows with identity)
+                        full = full.contiguous()
+                        K.qk_rmsnorm_(full, None, None, Hn, D, rope_cos=rope[0], rope_sin=rope[1], pos_div=1, pos_mod=Lf)
                     f3 = full.view(B * Lf, 3, Cn)
                     of = torch.empty(B, Lf, Cn, dtype=qkv.dtype, device=qkv.device)
                     if Lf > Lv:
@@ -225,7 +233,8 @@ class _AdaLayerNorm(nn.Module):
 class CogVideoXTransformer3DModel(nn.Module):
     """State-dict compatible with the reference / HF ``THUDM/CogVideoX-2b`` transformer (same module names), forward
     on the vsb200 kernels.  ``enable_parallel`` as the reference: head-scatter sequence parallelism (30 % sp == 0:
-    sp in {2, 3, 5, 6, ...}) and CFG parallelism (cp = 2)."""
+    sp in {2, 3, 5, 6, ...}) and CFG parallelism (cp = 2).  ``use_rotary_positional_embeddings`` (CogVideoX-5b: 48 heads x 64,
+    42 layers, bf16): no position table is added, ``image_rotary_emb`` rotates q and k of the video tokens."""
 
     def __init__(self, num_attention_heads=30, attention_head_dim=64, in_channels=16, out_channels=16, flip_sin_to_cos=True,
                  freq_shift=0, time_embed_dim=512, text_embed_dim=4096, num_layers=30, sample_width=90, sample_height=60,
@@ -233,13 +242,12 @@ class CogVideoXTransformer3DModel(nn.Module):
                  spatial_interpolation_scale=1.875, temporal_interpolation_scale=1.0,
                  use_rotary_positional_embeddings=False, **unused):
         super().__init__()
-        if use_rotary_positional_embeddings:
-            raise NotImplementedError("rotary position embeddings (CogVideoX-5b) are not built; the 2b model is the BASELINE config")
         dim = num_attention_heads * attention_head_dim
         self.config = type("Cfg", (), dict(in_channels=in_channels, out_channels=out_channels, patch_size=patch_size,
                                            max_text_seq_length=max_text_seq_length, sample_width=sample_width,
                                            sample_height=sample_height, sample_frames=sample_frames,
-                                           use_rotary_positional_embeddings=False, num_attention_heads=num_attention_heads,
+                                           use_rotary_positional_embeddings=bool(use_rotary_positional_embeddings),
+                                           num_attention_heads=num_attention_heads,
                                            attention_head_dim=attention_head_dim, time_embed_dim=time_embed_dim,
                                            text_embed_dim=text_embed_dim, num_layers=num_layers))()
         self.inner_dim, self.flip, self.freq_shift, self.eps = dim, flip_sin_to_cos, freq_shift, norm_eps
@@ -259,6 +267,23 @@ class CogVideoXTransformer3DModel(nn.Module):
         self.norm_out = _AdaLayerNorm(time_embed_dim, dim, norm_eps)
         self.proj_out = nn.Linear(dim, patch_size * patch_size * out_channels)
         self.parallel_manager = None
+        self._rope = None
+
+    def _rope_tables(self, image_rotary_emb, Nt, n_rows, device):
+        """(cos, sin) [n_rows, head_dim] fp32: identity for the Nt text rows and for rows past the rotary table (sequence-
+        parallel padding), the caller's 3-D rotary angles for the video rows (reference processor :146-155).  Cached on the
+        identity of the caller's tensors (the pipeline passes the same pair at every step)."""
+        cos, sin = image_rotary_emb
+        key = (id(cos), id(sin), cos._version, Nt, n_rows, str(device))
+        if self._rope is None or self._rope[0] != key:
+            D = self.config.attention_head_dim
+            c = torch.ones(n_rows, D, dtype=torch.float32, device=device)
+            s_ = torch.zeros(n_rows, D, dtype=torch.float32, device=device)
+            n = min(cos.shape[0], n_rows - Nt)
+            c[Nt : Nt + n] = cos[:n].to(device=device, dtype=torch.float32)
+            s_[Nt : Nt + n] = sin[:n].to(device=device, dtype=torch.float32)
+            self._rope = (key, (c.contiguous(), s_.contiguous()))
+        return self._rope[1]
 
     @classmethod
     def from_pretrained(cls, path, subfolder: str = "transformer", **config_overrides):
@@ -313,13 +338,21 @@ class CogVideoXTransformer3DModel(nn.Module):
         img = self.patch_embed.proj(hidden_states.to(dt).reshape(-1, Cin, H, W))  # conv: cuDNN (glue, once per step)
         img = img.view(B, Fr, C, -1).transpose(2, 3).flatten(1, 2)  # [B, F*h*w, C]
         Nt, Nv = txt.shape[1], img.shape[1]
-        pos = self.pos_embedding[:, : Nt + Nv].to(dt)
-        enc = txt + pos[:, :Nt]
-        hid = img + pos[:, Nt:]
+        if self.config.use_rotary_positional_embeddings:  # reference :519-524: no learned / sin-cos table is added
+            enc, hid = txt, img.contiguous()
+        else:
+            pos = self.pos_embedding[:, : Nt + Nv].to(dt)
+            enc = txt + pos[:, :Nt]
+            hid = img + pos[:, Nt:]
         if sp:  # reference :531-533: the video rows are split (zero-padded to a multiple of sp), the text rows replicated
             comm.set_pad("pad", Nv, pm.sp_group)
             hid = comm.split_sequence(hid, pm.sp_group, dim=1, pad=comm.get_pad("pad"))
-        hid, enc = self._stack[0](hid, enc, emb, timestep, ts_int=ts_int, sp_group=pm.sp_group if sp else None, n_video=Nv)
+        rope = None
+        if image_rotary_emb is not None:
+            n_rows = Nt + (hid.shape[1] * pm.sp_size if sp else Nv)  # every row of the gathered sequence, pad rows included
+            rope = self._rope_tables(image_rotary_emb, Nt, n_rows, hid.device)
+        hid, enc = self._stack[0](hid, enc, emb, timestep, ts_int=ts_int, sp_group=pm.sp_group if sp else None, n_video=Nv,
+                                  rope=rope)
         Nv_all, Nv = Nv, hid.shape[1]  # the output head is row-wise: it runs on the local rows, its 30x narrower
         # result is gathered (the reference gathers the C-wide rows first, :563-564: same values)
         # norm_final (plain affine LayerNorm = modulate with shift = scale = 0), then norm_out (AdaLayerNorm, chunk_dim 1:

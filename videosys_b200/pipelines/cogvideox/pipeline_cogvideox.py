@@ -59,7 +59,10 @@ class CogVideoXPipeline(ParallelPipelineMixin):
         if config.transformer_config is None and config.state_dict is None and os.path.isdir(str(config.model_path)):
             self.transformer = CogVideoXTransformer3DModel.from_pretrained(config.model_path, subfolder="transformer").to(dtype)
         else:
-            self.transformer = CogVideoXTransformer3DModel(**(config.transformer_config or {})).to(dtype)
+            tc = config.transformer_config
+            if tc is None and "5b" in str(config.model_path).lower():  # THUDM/CogVideoX-5b: 48 heads x 64, 42 blocks, rotary
+                tc = dict(num_attention_heads=48, num_layers=42, use_rotary_positional_embeddings=True)
+            self.transformer = CogVideoXTransformer3DModel(**(tc or {})).to(dtype)
         if config.state_dict is not None:
             self.transformer.load_state_dict(config.state_dict)
         self.transformer = self.transformer.to(self._device).eval()
@@ -83,6 +86,34 @@ class CogVideoXPipeline(ParallelPipelineMixin):
         if latents is None:
             latents = torch.randn(shape, device=device, dtype=dtype)
         return latents.to(device) * self.scheduler.init_noise_sigma
+
+    def _prepare_rotary_positional_embeddings(self, height: int, width: int, num_frames: int, device):
+        """Reference :449-474 (get_resize_crop_region_for_grid :758-773, get_3d_rotary_pos_embed models/modules/
+        embeddings.py:283-364): (cos, sin) [frames * grid_h * grid_w, head_dim] fp32 of the video tokens."""
+        import numpy as np
+
+        cfg = self.transformer.config
+        unit = self.vae_scale_factor_spatial * cfg.patch_size
+        gh, gw = height // unit, width // unit
+        tw, th = 720 // unit, 480 // unit
+        if gh / gw > th / tw:
+            rh, rw = th, int(round(th / gh * gw))
+        else:
+            rw, rh = tw, int(round(tw / gw * gh))
+        top, left = int(round((th - rh) / 2.0)), int(round((tw - rw) / 2.0))
+        D, theta = cfg.attention_head_dim, 10000.0
+        lin = lambda a, b, n: torch.from_numpy(np.linspace(a, b, n, endpoint=False, dtype=np.float32)).float()  # noqa: E731
+
+        def freqs(grid, d):
+            f = 1.0 / (theta ** (torch.arange(0, d, 2).float() / d))
+            return torch.einsum("n,f->nf", grid, f).repeat_interleave(2, dim=-1)
+
+        ft = freqs(lin(0, num_frames, num_frames), D // 4)
+        fh = freqs(lin(top, top + rh, gh), D // 8 * 3)
+        fw = freqs(lin(left, left + rw, gw), D // 8 * 3)
+        fr = torch.cat([ft[:, None, None, :].expand(num_frames, gh, gw, -1), fh[None, :, None, :].expand(num_frames, gh, gw, -1),
+                        fw[None, None, :, :].expand(num_frames, gh, gw, -1)], dim=-1).reshape(num_frames * gh * gw, -1)
+        return fr.cos().to(device), fr.sin().to(device)
 
     @torch.no_grad()
     def generate(self, prompt=None, negative_prompt=None, height: int = 480, width: int = 720, num_frames: int = 49,
@@ -112,12 +143,15 @@ class CogVideoXPipeline(ParallelPipelineMixin):
         ts_host = [int(v) for v in ts.tolist()]
         lat = self.prepare_latents(prompt_embeds.shape[0], self.transformer.config.in_channels, num_frames, height, width,
                                    dt, dev, latents)
+        rotary = None
+        if self.transformer.config.use_rotary_positional_embeddings:  # CogVideoX-5b (reference :669-673)
+            rotary = self._prepare_rotary_positional_embeddings(height, width, lat.size(1), dev)
         gs = guidance_scale
         for i, t in enumerate(ts_host):
             inp = torch.cat([lat] * 2) if do_cfg else lat
             tt = torch.full((inp.shape[0],), t, device=dev, dtype=torch.int64)
-            noise = self.transformer(hidden_states=inp, encoder_hidden_states=pe, timestep=tt, return_dict=False,
-                                     ts_int=t if enable_pab() else None)[0].float()
+            noise = self.transformer(hidden_states=inp, encoder_hidden_states=pe, timestep=tt, image_rotary_emb=rotary,
+                                     return_dict=False, ts_int=t if enable_pab() else None)[0].float()
             if use_dynamic_cfg:
                 gs = 1 + guidance_scale * ((1 - math.cos(math.pi * ((num_inference_steps - t) / num_inference_steps) ** 5.0)) / 2)
             if do_cfg:
