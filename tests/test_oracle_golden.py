@@ -81,3 +81,44 @@ def test_pab_gate_edges():
     assert g.gate("cross", 500, 1) == (False, 2)  # kind off, manager on: counter still advances
     off = pab_oracle.PABGate(steps=4)
     assert off.gate("spatial", 500, 3) == (False, 3)  # disabled wrapper leaves the count untouched
+
+
+# ---- Latte / CogVideoX / Vchitect oracles against outputs of the UNMODIFIED reference (tests/golden/models_small.pt, written by
+#      oracle/gen_golden_models.py); the reference tree is not needed here ------------------------------------------------------------
+@pytest.fixture(scope="module")
+def model_gold(golden_dir):
+    import os
+
+    return torch.load(os.path.join(golden_dir, "models_small.pt"))
+
+
+def _check(got, gold, name, dn):
+    want = gold[f"{name}.{dn}"]
+    assert got.shape == want.shape
+    if dn == "bf16":
+        assert torch.equal(got, want), f"{name}: oracle bf16 differs from the reference's bf16 output ({(got == want).float().mean().item()*100:.2f} % equal)"
+    else:
+        assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (name, (got - want).abs().max())
+
+
+@pytest.mark.parametrize("dtype,dn", [(torch.float32, "fp32"), (torch.bfloat16, "bf16")])
+def test_model_oracles_match_reference_golden(model_gold, dtype, dn):
+    from oracle import cogvideox_oracle as CO, latte_oracle as LO, model_cases as MC, vchitect_oracle as VO
+    from videosys_b200.models.transformers.cogvideox_transformer_3d import CogVideoXTransformer3DModel
+    from videosys_b200.models.transformers.latte_transformer_3d import LatteT2V
+    from videosys_b200.models.transformers.vchitect_transformer_3d import VchitectXLTransformerModel
+
+    with torch.no_grad():
+        # the state-dict templates come from the product's modules (same names / shapes as the reference's, strict-load tested)
+        sd = MC.weights(LatteT2V(**MC.LATTE).state_dict(), "latte", dtype)
+        x, t, enc = MC.latte_inputs(dtype)
+        _check(LO.transformer_forward(sd, MC.LATTE_O, x, t, enc), model_gold, "latte", dn)
+        for rot in (False, True):
+            tmpl = CogVideoXTransformer3DModel(**dict(MC.COGX, use_rotary_positional_embeddings=rot)).state_dict()
+            sd = MC.weights(tmpl, "cogx", dtype, norm_ones=True)
+            lat, txt, ts = MC.cogx_inputs(dtype)
+            got = CO.transformer_forward(sd, MC.COGX_O, lat, txt, ts, rotary=MC.cogx_rotary() if rot else None)
+            _check(got, model_gold, "cogx_rotary" if rot else "cogx", dn)
+        sd = MC.weights(VchitectXLTransformerModel(**MC.VCH).state_dict(), "vch", dtype, keep=("pos_embed.pos_embed",))
+        lat, enc, pooled, ts = MC.vch_inputs(dtype)
+        _check(VO.transformer_forward(sd, MC.VCH_O, lat, enc, pooled, ts), model_gold, "vchitect", dn)
